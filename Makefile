@@ -1,0 +1,49 @@
+# Build of the B200 engine.  `make` = the product (nvcc, sm_100a only).  `make simt` = the CPU unit-test build of the same kernel
+# sources (tests only, see tests/simt/simt.h).  `make oracle` = the CPU oracle and, when /root/reference exists, oracle/_ref.
+NVCC     ?= /usr/local/cuda/bin/nvcc
+CXX      ?= g++
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS  := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden,-Wall,-Wno-unknown-pragmas --expt-relaxed-constexpr
+CSRC     := mumemto_b200/csrc
+CU       := $(wildcard $(CSRC)/*.cu)
+HOSTCPP  := $(wildcard $(CSRC)/library_api.cpp)
+OBJ      := $(patsubst $(CSRC)/%.cu,build/%.o,$(CU)) $(patsubst $(CSRC)/%.cpp,build/%.o,$(HOSTCPP))
+LIB      := mumemto_b200/lib/libmumemto_b200.so
+BIN      := mumemto_b200/bin/mumemto_exec mumemto_b200/bin/anchor_merge
+HDRS     := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
+
+.PHONY: all lib simt oracle clean
+all: lib $(BIN)
+lib: $(LIB)
+
+build/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+build/%.o: $(CSRC)/%.cpp $(HDRS)
+	@mkdir -p build
+	$(CXX) -O2 -std=c++17 -fPIC -fvisibility=hidden -Wall -Iinclude -c $< -o $@
+
+$(LIB): $(OBJ)
+	@mkdir -p mumemto_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
+
+mumemto_b200/bin/mumemto_exec: $(CSRC)/cli_main.cpp $(LIB) $(HDRS)
+	@mkdir -p mumemto_b200/bin
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude $< -o $@ -Lmumemto_b200/lib -lmumemto_b200 -lz -Wl,-rpath,'$$ORIGIN/../lib'
+mumemto_b200/bin/anchor_merge: $(CSRC)/anchor_merge_main.cpp $(LIB) $(HDRS)
+	@mkdir -p mumemto_b200/bin
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude $< -o $@ -Lmumemto_b200/lib -lmumemto_b200 -Wl,-rpath,'$$ORIGIN/../lib'
+
+# ---- tests only -------------------------------------------------------------------------------------------------------------
+SIMT     := tests/simt/_build/libmumemto_b200_simt.so
+simt: $(SIMT)
+$(SIMT): $(CU) $(HOSTCPP) $(HDRS) tests/simt/simt.h tests/simt/simt.cpp
+	@mkdir -p tests/simt/_build
+	$(CXX) -O1 -g -std=c++17 -fPIC -shared -DMMB_SIMT -Itests/simt -Iinclude -Wall -Wno-unknown-pragmas -Wno-unused-function \
+	    $(foreach f,$(CU),-x c++ $(f)) -x c++ $(HOSTCPP) tests/simt/simt.cpp -o $@
+
+oracle:
+	$(MAKE) -C oracle port ref
+
+clean:
+	rm -rf build mumemto_b200/lib mumemto_b200/bin tests/simt/_build

@@ -1,0 +1,115 @@
+/* include/mumemto_b200.h -- C ABI of the B200 multi-MUM / multi-MEM engine (libmumemto_b200.so).
+ *
+ * This is the drop-in boundary for the reference's FASTA -> .mums/.mems hot path.  Plain pointers and sizes only; no CUDA, torch or
+ * C++ types.  Each entry point names the reference interface it stands in for (paths relative to the reference repository):
+ *
+ *   mmb_load_fasta / _device   RefBuilder::build_input_file            src/ref_builder.cpp:211-314
+ *   mmb_load_records           RefBuilder::build_input_file_lib        src/ref_builder.cpp:330-384
+ *   mmb_find                   the body of build_main after parsing    src/pfp_mum.cpp:76-94,116-145
+ *                              = gsacak_lcp / pf_parsing + pfp_lcp::process feeding mem_finder::update
+ *                              (include/direct_gsacak.hpp:50-116, include/pfp_lcp_mum.hpp:115-231, include/mem_finder.hpp:161-170)
+ *   mmb_options                BuildOptions + validate/set_parameters  include/pfp_mum.hpp:56-198
+ *   mmb_text / mmb_mum_* / mmb_mem_*   mem_finder::write_mum / write_mem / write_bums   include/mem_finder.hpp:210-263,357-428,460-503
+ *   mmb_thresholds             candidate_thresh (.athresh)             include/mem_finder.hpp:110-115,326-336
+ *   mmb_arrays                 -A array dump (.sa/.lcp/.bwt)           include/pfp_lcp_mum.hpp:323-369
+ *   mmb_anchor_merge           merge_partitions left fold              src/merge_candidates.cpp:106-157,208-219
+ *
+ * Every function returns 0 on success, a non-zero code otherwise; mmb_last_error() then holds the message (thread local).
+ * The library has no CPU implementation: creating an engine without a usable CUDA device fails with MMB_ERR_NO_DEVICE.
+ */
+#ifndef MUMEMTO_B200_H
+#define MUMEMTO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMB_API __attribute__((visibility("default")))
+
+enum {
+    MMB_OK = 0,
+    MMB_ERR_ARG = 1,          /* null / inconsistent argument */
+    MMB_ERR_NO_DEVICE = 2,    /* no CUDA device: there is no CPU fallback */
+    MMB_ERR_INPUT = 3,        /* bad input data (empty file, FASTQ, NUL byte, < 2 documents ...) */
+    MMB_ERR_PARAM = 4,        /* parameter combination the reference rejects (FATAL_ERROR) or the engine does not support */
+    MMB_ERR_CUDA = 5,
+    MMB_ERR_STATE = 6,        /* call order: results requested before mmb_find, ... */
+    MMB_ERR_INTERNAL = 7
+};
+
+typedef struct mmb_engine mmb_engine;
+
+/* Flags of the reference CLI that reach the hot path (defaults: include/pfp_mum.hpp:56-78). */
+typedef struct mmb_options {
+    uint32_t min_match_len;      /* -l, default 20 */
+    int32_t num_distinct_docs;   /* -k as typed (0, negative = relative to N); library callers pass the absolute count */
+    int32_t rare_freq;           /* -f, default 1 (1 = MUM mode, other = MEM mode) */
+    int32_t max_mem_freq;        /* -F, default 0 */
+    uint8_t merge;               /* -M */
+    uint8_t anchor_merge;        /* -n */
+    uint8_t cli_normalise;       /* 1: apply BuildOptions::validate/set_parameters; 0: library rules (mumemto_api.cpp:332-411) */
+    uint8_t want_text;           /* 1: also format the .mums/.mems bytes on the device */
+} mmb_options;
+
+typedef struct mmb_stats {
+    uint64_t text_symbols;       /* |T| */
+    uint64_t input_bases;        /* sum of forward bases */
+    uint64_t num_matches;
+    uint64_t kernel_launches;    /* launches issued by this library since the engine was created */
+    uint32_t sa_rounds;
+    uint64_t sa_sorted_elements;
+    float ms_text, ms_sa, ms_lcp, ms_detect, ms_emit, ms_total;   /* CUDA-event times of the last mmb_find (ms_text: last load) */
+} mmb_stats;
+
+MMB_API const char* mmb_last_error(void);
+MMB_API void mmb_default_options(mmb_options* o);
+
+/* cuda_stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL for the engine's own stream. */
+MMB_API int mmb_create(int device, void* cuda_stream, mmb_engine** out);
+MMB_API void mmb_destroy(mmb_engine* e);
+
+/* Input.  files[i] is the (decompressed) byte image of FASTA file i in host memory.  The copy to the device happens here. */
+MMB_API int mmb_load_fasta(mmb_engine* e, const uint8_t* const* files, const uint64_t* sizes, size_t nfiles, int use_revcomp);
+/* Same, but the images already sit in device memory at d_raw + offsets[i] (offsets multiples of 16). */
+MMB_API int mmb_load_fasta_device(mmb_engine* e, const void* d_raw, const uint64_t* offsets, const uint64_t* sizes, size_t nfiles, int use_revcomp);
+/* Library-style input: document d has n_records[d] NUL-terminated records, flattened in records[] (no FASTA syntax). */
+MMB_API int mmb_load_records(mmb_engine* e, const char* const* records, const size_t* n_records, size_t ndocs, int use_revcomp);
+
+/* The hot path.  Everything stays on the device until one of the copy functions below is called. */
+MMB_API int mmb_find(mmb_engine* e, const mmb_options* opts);
+MMB_API int mmb_get_stats(const mmb_engine* e, mmb_stats* out);
+
+/* Documents and FASTA records (for PREFIX.lengths, src/ref_builder.cpp:193-209). */
+MMB_API size_t mmb_num_docs(const mmb_engine* e);
+MMB_API int mmb_doc_lengths(const mmb_engine* e, uint64_t* lengths /* [num_docs] forward bases */);
+MMB_API size_t mmb_num_records(const mmb_engine* e, size_t doc);
+MMB_API int mmb_record(const mmb_engine* e, size_t doc, size_t rec, const char** name, uint64_t* length);
+
+/* Results of the last mmb_find. */
+MMB_API int mmb_is_mum_mode(const mmb_engine* e);
+MMB_API uint64_t mmb_num_matches(const mmb_engine* e);
+MMB_API uint64_t mmb_text_size(const mmb_engine* e);                 /* bytes of the .mums / .mems file */
+MMB_API int mmb_copy_text(mmb_engine* e, void* host_dst);            /* device -> host */
+MMB_API const void* mmb_text_device(const mmb_engine* e);            /* device pointer, valid until the next mmb_find */
+/* MUM table: lengths[n], offsets[n][num_docs] (-1 absent), strands[n][num_docs] (1 '+', 0 '-' or absent). NULL skips a field. */
+MMB_API int mmb_copy_mums(mmb_engine* e, uint32_t* lengths, int64_t* offsets, uint8_t* strands);
+/* .bumbl strand bits (MSB first, '+' = 1), (n * num_docs + 7) / 8 bytes. */
+MMB_API int mmb_copy_mum_strand_bits(mmb_engine* e, uint8_t* packed);
+/* MEM table in CSR form: first[n+1]; offsets/seq_ids/strands[total occurrences]. */
+MMB_API uint64_t mmb_num_mem_occurrences(const mmb_engine* e);
+MMB_API int mmb_copy_mems(mmb_engine* e, uint32_t* lengths, uint64_t* first, int64_t* offsets, uint64_t* seq_ids, uint8_t* strands);
+/* -M: 2 * (L_0 + 1) uint16 next-best thresholds; PREFIX.athresh is the first L_0 + 1 of them. */
+MMB_API uint64_t mmb_threshold_count(const mmb_engine* e);
+MMB_API int mmb_copy_thresholds(mmb_engine* e, uint16_t* dst);
+/* -A: the suffix stream, |T| + 1 entries each. NULL skips an array. */
+MMB_API int mmb_copy_arrays(mmb_engine* e, uint64_t* sa, uint64_t* lcp, uint8_t* bwt);
+/* The text T itself (|T| bytes), for tests. */
+MMB_API int mmb_copy_symbols(mmb_engine* e, uint8_t* dst);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUMEMTO_B200_H */

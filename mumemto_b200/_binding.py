@@ -1,0 +1,245 @@
+"""ctypes binding of include/mumemto_b200.h (libmumemto_b200.so, CUDA sm_100a).
+
+There is no CPU implementation behind this module: if the shared library has not been built, or no CUDA device is present,
+construction of an Engine raises.  (tests/ can inject the SIMT unit-test build of the same kernel sources through the private
+``_lib`` argument; nothing in the package does.)
+"""
+import ctypes as C
+import gzip
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmumemto_b200.so")
+
+u8p = C.POINTER(C.c_uint8)
+
+
+class Options(C.Structure):
+    _fields_ = [("min_match_len", C.c_uint32), ("num_distinct_docs", C.c_int32), ("rare_freq", C.c_int32), ("max_mem_freq", C.c_int32),
+                ("merge", C.c_uint8), ("anchor_merge", C.c_uint8), ("cli_normalise", C.c_uint8), ("want_text", C.c_uint8)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("text_symbols", C.c_uint64), ("input_bases", C.c_uint64), ("num_matches", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("sa_rounds", C.c_uint32), ("sa_sorted_elements", C.c_uint64),
+                ("ms_text", C.c_float), ("ms_sa", C.c_float), ("ms_lcp", C.c_float), ("ms_detect", C.c_float), ("ms_emit", C.c_float),
+                ("ms_total", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class MumemtoError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+_SIGNATURES = {
+    "mmb_last_error": (C.c_char_p, []),
+    "mmb_default_options": (None, [C.POINTER(Options)]),
+    "mmb_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mmb_destroy": (None, [C.c_void_p]),
+    "mmb_load_fasta": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_size_t, C.c_int]),
+    "mmb_load_fasta_device": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_size_t, C.c_int]),
+    "mmb_load_records": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t, C.c_int]),
+    "mmb_find": (C.c_int, [C.c_void_p, C.POINTER(Options)]),
+    "mmb_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "mmb_num_docs": (C.c_size_t, [C.c_void_p]),
+    "mmb_doc_lengths": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "mmb_num_records": (C.c_size_t, [C.c_void_p, C.c_size_t]),
+    "mmb_record": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64)]),
+    "mmb_is_mum_mode": (C.c_int, [C.c_void_p]),
+    "mmb_num_matches": (C.c_uint64, [C.c_void_p]),
+    "mmb_text_size": (C.c_uint64, [C.c_void_p]),
+    "mmb_copy_text": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mmb_text_device": (C.c_void_p, [C.c_void_p]),
+    "mmb_copy_mums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmb_copy_mum_strand_bits": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mmb_num_mem_occurrences": (C.c_uint64, [C.c_void_p]),
+    "mmb_copy_mems": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmb_threshold_count": (C.c_uint64, [C.c_void_p]),
+    "mmb_copy_thresholds": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mmb_copy_arrays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmb_copy_symbols": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mmb_anchor_merge": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint64]),
+    "mmb_merge_num_mums": (C.c_uint64, [C.c_void_p]),
+    "mmb_merge_num_docs": (C.c_uint64, [C.c_void_p]),
+    "mmb_merge_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmb_merge_text_size": (C.c_uint64, [C.c_void_p]),
+    "mmb_merge_copy_text": (C.c_int, [C.c_void_p, C.c_void_p]),
+}
+
+
+def declare(lib):
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+_lib_cache = None
+
+
+def load_library():
+    """The CUDA library, or a loud failure."""
+    global _lib_cache
+    if _lib_cache is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is not built: run `make` (nvcc, sm_100a). mumemto_b200 has no CPU fallback.")
+        _lib_cache = declare(C.CDLL(LIB_PATH))
+    return _lib_cache
+
+
+def read_fasta_image(path):
+    """File bytes as the reference sees them through gzopen/gzread (plain or .gz)."""
+    with open(path, "rb") as f:
+        head = f.read(2)
+    if head == b"\x1f\x8b":
+        with gzip.open(path, "rb") as f:
+            return f.read()
+    with open(path, "rb") as f:
+        return f.read()
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Engine:
+    def __init__(self, device=0, stream=None, _lib=None):
+        self.lib = _lib if _lib is not None else load_library()
+        h = C.c_void_p()
+        self._check(self.lib.mmb_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self._keep = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MumemtoError(rc, self.lib.mmb_last_error().decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mmb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ input
+    def load_fasta_bytes(self, images, revcomp=True):
+        """images: list of bytes-like / uint8 numpy arrays, one decompressed FASTA file each (host memory)."""
+        arrs = [np.frombuffer(b, dtype=np.uint8) if not isinstance(b, np.ndarray) else b for b in images]
+        n = len(arrs)
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data if a.size else None for a in arrs])
+        sizes = (C.c_uint64 * n)(*[a.size for a in arrs])
+        self._keep = arrs
+        self._check(self.lib.mmb_load_fasta(self.h, ptrs, sizes, n, int(revcomp)))
+
+    def load_fasta_files(self, paths, revcomp=True):
+        self.load_fasta_bytes([read_fasta_image(p) for p in paths], revcomp)
+
+    def load_fasta_device(self, dev_ptr, offsets, sizes, revcomp=True):
+        n = len(offsets)
+        self._check(self.lib.mmb_load_fasta_device(self.h, C.c_void_p(dev_ptr), (C.c_uint64 * n)(*offsets), (C.c_uint64 * n)(*sizes), n, int(revcomp)))
+
+    def load_records(self, docs, revcomp=True):
+        flat = [r.encode() if isinstance(r, str) else bytes(r) for d in docs for r in d]
+        recs = (C.c_char_p * max(1, len(flat)))(*flat)
+        counts = (C.c_size_t * max(1, len(docs)))(*[len(d) for d in docs])
+        self._check(self.lib.mmb_load_records(self.h, recs, counts, len(docs), int(revcomp)))
+
+    # ------------------------------------------------------------------ hot path
+    def find(self, min_match_len=20, num_distinct_docs=0, rare_freq=1, max_mem_freq=0, merge=False, anchor_merge=False, cli_normalise=True,
+             want_text=True):
+        o = Options(min_match_len, num_distinct_docs, rare_freq, max_mem_freq, int(merge), int(anchor_merge), int(cli_normalise), int(want_text))
+        self._check(self.lib.mmb_find(self.h, C.byref(o)))
+        return self.stats()
+
+    def stats(self):
+        s = Stats()
+        self._check(self.lib.mmb_get_stats(self.h, C.byref(s)))
+        return s.as_dict()
+
+    # ------------------------------------------------------------------ results
+    @property
+    def num_docs(self):
+        return self.lib.mmb_num_docs(self.h)
+
+    def doc_lengths(self):
+        a = np.zeros(self.num_docs, dtype=np.uint64)
+        self._check(self.lib.mmb_doc_lengths(self.h, a.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return a
+
+    def records(self, doc):
+        out = []
+        for r in range(self.lib.mmb_num_records(self.h, doc)):
+            name, length = C.c_char_p(), C.c_uint64()
+            self._check(self.lib.mmb_record(self.h, doc, r, C.byref(name), C.byref(length)))
+            out.append(((name.value or b"").decode(errors="replace"), length.value))
+        return out
+
+    @property
+    def mum_mode(self):
+        return bool(self.lib.mmb_is_mum_mode(self.h))
+
+    @property
+    def num_matches(self):
+        return self.lib.mmb_num_matches(self.h)
+
+    def text(self):
+        n = self.lib.mmb_text_size(self.h)
+        buf = np.empty(n, dtype=np.uint8)
+        self._check(self.lib.mmb_copy_text(self.h, _ptr(buf)))
+        return buf.tobytes()
+
+    def copy_text_into(self, host_array):
+        self._check(self.lib.mmb_copy_text(self.h, _ptr(host_array)))
+        return self.lib.mmb_text_size(self.h)
+
+    def mums(self):
+        n, N = self.num_matches, self.num_docs
+        lengths = np.empty(n, dtype=np.uint32); offsets = np.empty((n, N), dtype=np.int64); strands = np.empty((n, N), dtype=np.uint8)
+        self._check(self.lib.mmb_copy_mums(self.h, _ptr(lengths), _ptr(offsets), _ptr(strands)))
+        return lengths, offsets, strands
+
+    def mum_strand_bits(self):
+        bits = np.empty((self.num_matches * self.num_docs + 7) // 8, dtype=np.uint8)
+        self._check(self.lib.mmb_copy_mum_strand_bits(self.h, _ptr(bits)))
+        return bits
+
+    def mems(self):
+        n, occ = self.num_matches, self.lib.mmb_num_mem_occurrences(self.h)
+        lengths = np.empty(n, dtype=np.uint32); first = np.empty(n + 1, dtype=np.uint64)
+        offsets = np.empty(occ, dtype=np.int64); seq_ids = np.empty(occ, dtype=np.uint64); strands = np.empty(occ, dtype=np.uint8)
+        self._check(self.lib.mmb_copy_mems(self.h, _ptr(lengths), _ptr(first), _ptr(offsets), _ptr(seq_ids), _ptr(strands)))
+        return lengths, first, offsets, seq_ids, strands
+
+    def thresholds(self):
+        t = np.empty(self.lib.mmb_threshold_count(self.h), dtype=np.uint16)
+        self._check(self.lib.mmb_copy_thresholds(self.h, _ptr(t)))
+        return t
+
+    def arrays(self):
+        m = int(self.stats()["text_symbols"]) + 1
+        sa = np.empty(m, dtype=np.uint64); lcp = np.empty(m, dtype=np.uint64); bwt = np.empty(m, dtype=np.uint8)
+        self._check(self.lib.mmb_copy_arrays(self.h, _ptr(sa), _ptr(lcp), _ptr(bwt)))
+        return sa, lcp, bwt
+
+    def symbols(self):
+        t = np.empty(int(self.stats()["text_symbols"]), dtype=np.uint8)
+        self._check(self.lib.mmb_copy_symbols(self.h, _ptr(t)))
+        return t.tobytes()
+
+    def bumbl_bytes(self, partial):
+        """The .bumbl image the reference assembles in mem_finder::write_bums (include/mem_finder.hpp:451-503)."""
+        lengths, offsets, _ = self.mums()
+        flags = np.uint16(0x8000 | (0x2000 if partial else 0))
+        head = flags.tobytes() + np.uint64(self.num_docs).tobytes() + np.uint64(len(lengths)).tobytes()
+        return head + lengths.tobytes() + offsets.tobytes() + self.mum_strand_bits().tobytes()

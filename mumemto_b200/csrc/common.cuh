@@ -1,0 +1,89 @@
+// mumemto_b200/csrc/common.cuh -- shared definitions for the sm_100a engine.
+//
+// Everything under csrc/ is compiled by nvcc for sm_100a into libmumemto_b200.so.  The only other way these sources are ever
+// compiled is the unit-test build under tests/simt/ (-DMMB_SIMT), which runs the kernel bodies on CPU fibers so that index logic
+// can be tested in a container without a GPU; that build is never shipped or loaded by the product.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#ifdef MMB_SIMT
+#include "simt.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+namespace mmb {
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int64_t i64;
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+extern unsigned long long g_kernel_launches;   // every MMB_LAUNCH, for bench.py's "gpu_launches"
+
+inline void check(cudaError_t e, const char* what, const char* file, int line) {
+    if (e != cudaSuccess)
+        throw Error(10, std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + file + ":" + std::to_string(line) + " (" + what + ")");
+}
+#define MMB_CUDA(x) ::mmb::check((x), #x, __FILE__, __LINE__)
+
+#ifndef MMB_SIMT
+#define MMB_LAUNCH(kernel, grid, block, smem, stream, ...)                       \
+    do {                                                                         \
+        ++::mmb::g_kernel_launches;                                              \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);              \
+        ::mmb::check(cudaPeekAtLastError(), #kernel, __FILE__, __LINE__);        \
+    } while (0)
+#define MMB_DYN_SMEM(type, name)                                  \
+    extern __shared__ __align__(16) unsigned char name##_raw_[];  \
+    type* name = reinterpret_cast<type*>(name##_raw_)
+#endif
+
+inline u32 ceil_div(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
+
+// Stream-ordered device buffer.
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void alloc(size_t count, cudaStream_t stream) {
+        release();
+        s = stream; n = count;
+        void* q = nullptr;
+        MMB_CUDA(cudaMallocAsync(&q, (count ? count : 1) * sizeof(T), stream));
+        p = (T*)q;
+    }
+    void zero() { if (n) MMB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    void release() { if (p) { cudaFreeAsync(p, s); p = nullptr; n = 0; } }
+    size_t bytes() const { return n * sizeof(T); }
+    void swap(DevBuf& o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(s, o.s); }
+};
+
+template <class T>
+inline std::vector<T> to_host(const T* d, size_t n, cudaStream_t s) {
+    std::vector<T> h(n);
+    if (n) MMB_CUDA(cudaMemcpyAsync(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+    MMB_CUDA(cudaStreamSynchronize(s));
+    return h;
+}
+
+}  // namespace mmb

@@ -1,0 +1,410 @@
+// mumemto_b200/csrc/engine.cu -- host orchestration of the device pipeline and the C ABI declared in include/mumemto_b200.h.
+//
+// Pipeline of mmb_find (one CUDA stream, no host work between stages except scalar read-backs that size the next allocation):
+//   text (text.cu)  ->  suffix array (sa.cu)  ->  LCP + BWT (lcp.cu)  ->  interval detection (detect.cu)  ->  records + text (emit.cu)
+// which stands in for build_main's stages in the reference (src/pfp_mum.cpp:57-145).  Parameter normalisation follows
+// BuildOptions::validate / set_parameters (include/pfp_mum.hpp:80-198) for the CLI and mumemto::mumemto_mum / mumemto_mem
+// (mumemto_library/mumemto_api.cpp:332-411) for library callers.
+#include "../../include/mumemto_b200.h"
+#include "detect.h"
+#include "sa.h"
+#include "text.h"
+
+#include <cctype>
+
+namespace mmb {
+unsigned long long g_kernel_launches = 0;
+}
+
+using namespace mmb;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) { g_error = msg; return code; }
+
+int map_error(const Error& e) {
+    int c = e.code;
+    if (c == 10) return MMB_ERR_CUDA;
+    if (c == 13 || c == 21 || c == 40 || c == 41) return MMB_ERR_INPUT;
+    if (c == 12 || c == 20 || (c >= 30 && c <= 39) || (c >= 50 && c <= 59)) return MMB_ERR_PARAM;
+    return MMB_ERR_INTERNAL;
+}
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr; cudaStream_t s;
+    explicit Timer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    void start() { cudaEventRecord(a, s); }
+    float stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+};
+
+struct RecordInfo { std::string name; u64 length; };
+
+}  // namespace
+
+struct mmb_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    unsigned long long launches_at_create = 0;
+
+    bool loaded = false, found = false;
+    TextLayout text;
+    std::vector<std::vector<RecordInfo>> records;
+    DevBuf<u8> raw;                     // device copy of the input images (host-load path)
+
+    SuffixArray sa;
+    DevBuf<u32> lcp;
+    DevBuf<u8> bwt;
+    Reports reports;
+    MumTable mums;
+    MemTable mems;
+    DevBuf<u16> thresh;
+    u64 thresh_count = 0;
+    bool mum_mode = true;
+    DetectParams prm{};
+    mmb_stats stats{};
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------- parameters
+void normalise(const mmb_options& o, u32 N, DetectParams& p, bool& mum_mode, bool& merge) {
+    long n = (long)N, k = o.num_distinct_docs, f = o.rare_freq, F = o.max_mem_freq;
+    merge = o.merge || o.anchor_merge;
+    if (o.cli_normalise) {
+        if (f < 0) throw Error(50, "Per-sequence MEM frequency must be > 0 (or 0 for no limit).");
+        if (k < -n) k = 2; else if (k <= 0) k = n + k; else if (k == 1) k = 2; else if (k >= n) k = n;
+        if (merge && k != n) throw Error(51, "Merging not available for partial multi-MUM/MEMs");
+        if (merge && f != 1) throw Error(52, "Merging not available for multi-MEMs");
+        if (F < -n || F == 1) F = 0; else if (F < 0) F = n + F;
+        if (f > 0 && (F == 0 || F > f * n)) F = f * n;
+    } else {
+        if (k == 0) k = n;
+        if (f < 0 || F < 0 || k < 0) throw Error(53, "negative frequency / document count");
+    }
+    p.min_len = o.min_match_len; p.num_distinct = (u32)k; p.max_doc_freq = (u32)f; p.max_freq = (u32)F; p.ndocs = N; p.merge = merge ? 1 : 0;
+    mum_mode = (f == 1);
+}
+
+// name of the FASTA record whose header marker sits at img[at]: up to the first whitespace (kseq, include/kseq.h:186-187)
+std::string record_name(const u8* img, u64 size, u64 at) {
+    std::string s;
+    for (u64 i = at + 1; i < size && !isspace(img[i]); ++i) s += (char)img[i];
+    return s;
+}
+
+void finish_load(mmb_engine* e, const u8* const* host_imgs, const std::vector<u64>& off, const std::vector<u64>& size, bool raw_mode) {
+    u32 N = (u32)off.size();
+    for (u32 d = 0; d < N; ++d)
+        if (e->text.h_doc_len[d] == 0) throw Error(40, "Empty input file found (document " + std::to_string(d) + ")");
+    e->records.assign(N, {});
+    if (raw_mode) return;
+    // FASTA records: boundaries from the device scan, names from the host image when we have one
+    const auto& pos = e->text.h_rec_pos; const auto& before = e->text.h_rec_before;
+    u64 cum = 0; size_t r = 0;
+    for (u32 d = 0; d < N; ++d) {
+        u64 doc_end_bases = cum + e->text.h_doc_len[d];
+        while (r < pos.size() && pos[r] < off[d] + size[d]) {
+            u64 next = (r + 1 < pos.size() && pos[r + 1] < off[d] + size[d]) ? before[r + 1] : doc_end_bases;
+            RecordInfo ri; ri.length = next - before[r];
+            if (host_imgs) ri.name = record_name(host_imgs[d], size[d], pos[r] - off[d]);
+            e->records[d].push_back(std::move(ri));
+            ++r;
+        }
+        cum = doc_end_bases;
+    }
+}
+
+void load_common(mmb_engine* e, const u8* d_raw, const u8* const* host_imgs, const std::vector<u64>& off, const std::vector<u64>& size,
+                 bool revcomp, bool raw_mode) {
+    if (off.size() < 2) throw Error(41, "Multiple FASTA inputs required. Perhaps split a multi-FASTA into multiple files?");
+    e->found = false; e->loaded = false;
+    Timer t(e->stream); t.start();
+    build_text(d_raw, off, size, revcomp, raw_mode, e->text, e->stream);
+    e->stats.ms_text = t.stop();
+    finish_load(e, host_imgs, off, size, raw_mode);
+    e->stats.text_symbols = e->text.n; e->stats.input_bases = e->text.total_bases;
+    e->loaded = true;
+}
+
+void upload(mmb_engine* e, const u8* const* imgs, const u64* sizes, size_t n, std::vector<u64>& off, std::vector<u64>& size) {
+    u64 at = 0;
+    for (size_t i = 0; i < n; ++i) { off.push_back(at); size.push_back(sizes[i]); at += (sizes[i] + 15) & ~15ull; }
+    e->raw.alloc(at + 32, e->stream);
+    for (size_t i = 0; i < n; ++i)
+        if (sizes[i]) MMB_CUDA(cudaMemcpyAsync(e->raw.p + off[i], imgs[i], sizes[i], cudaMemcpyHostToDevice, e->stream));
+}
+
+template <class F>
+int guarded(F&& f) {
+    try { f(); return MMB_OK; }
+    catch (const Error& e) { return fail(map_error(e), e.what()); }
+    catch (const std::exception& e) { return fail(MMB_ERR_INTERNAL, e.what()); }
+    catch (...) { return fail(MMB_ERR_INTERNAL, "unknown exception"); }
+}
+
+template <class T>
+void copy_out(const T* d, T* h, u64 n, cudaStream_t s) {
+    if (h && n) MMB_CUDA(cudaMemcpyAsync(h, d, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+}
+
+__global__ void widen_u32(const u32* __restrict__ in, u64 n, u64* __restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+__global__ void strands_to_flags(const u8* __restrict__ in, u64 n, u8* __restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] == '+' ? 1 : 0;
+}
+__global__ void mem_widen(const u64* __restrict__ off, const u32* __restrict__ doc, u64 n, i64* __restrict__ off_out, u64* __restrict__ doc_out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { off_out[i] = (i64)off[i]; doc_out[i] = doc[i]; }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mmb_last_error(void) { return g_error.c_str(); }
+
+void mmb_default_options(mmb_options* o) {
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->min_match_len = 20; o->num_distinct_docs = 0; o->rare_freq = 1; o->max_mem_freq = 0; o->cli_normalise = 1; o->want_text = 1;
+}
+
+int mmb_create(int device, void* cuda_stream, mmb_engine** out) {
+    if (!out) return fail(MMB_ERR_ARG, "out must be non-null");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return fail(MMB_ERR_NO_DEVICE, "no usable CUDA device " + std::to_string(device) + ": this library has no CPU path");
+    }
+    return guarded([&] {
+        MMB_CUDA(cudaSetDevice(device));
+        auto* e = new mmb_engine();
+        e->device = device;
+        if (cuda_stream) e->stream = (cudaStream_t)cuda_stream;
+        else { MMB_CUDA(cudaStreamCreate(&e->stream)); e->own_stream = true; }
+#ifndef MMB_SIMT
+        cudaMemPool_t pool;                       // keep freed blocks cached: stages allocate and free in a steady pattern
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+#endif
+        e->launches_at_create = g_kernel_launches;
+        *out = e;
+    });
+}
+
+void mmb_destroy(mmb_engine* e) {
+    if (!e) return;
+    cudaStreamSynchronize(e->stream);
+    cudaStream_t s = e->stream; bool own = e->own_stream;
+    delete e;
+    if (own) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+}
+
+int mmb_load_fasta(mmb_engine* e, const uint8_t* const* files, const uint64_t* sizes, size_t nfiles, int use_revcomp) {
+    if (!e || !files || !sizes) return fail(MMB_ERR_ARG, "null argument");
+    return guarded([&] {
+        MMB_CUDA(cudaSetDevice(e->device));
+        std::vector<u64> off, size;
+        upload(e, files, sizes, nfiles, off, size);
+        load_common(e, e->raw.p, files, off, size, use_revcomp != 0, false);
+    });
+}
+
+int mmb_load_fasta_device(mmb_engine* e, const void* d_raw, const uint64_t* offsets, const uint64_t* sizes, size_t nfiles, int use_revcomp) {
+    if (!e || !d_raw || !offsets || !sizes) return fail(MMB_ERR_ARG, "null argument");
+    return guarded([&] {
+        MMB_CUDA(cudaSetDevice(e->device));
+        std::vector<u64> off(offsets, offsets + nfiles), size(sizes, sizes + nfiles);
+        load_common(e, (const u8*)d_raw, nullptr, off, size, use_revcomp != 0, false);
+    });
+}
+
+int mmb_load_records(mmb_engine* e, const char* const* records, const size_t* n_records, size_t ndocs, int use_revcomp) {
+    if (!e || (!records && ndocs) || !n_records) return fail(MMB_ERR_ARG, "null argument");
+    return guarded([&] {
+        MMB_CUDA(cudaSetDevice(e->device));
+        // concatenate the records of each document on the host (they are scattered C strings), then one copy per document
+        std::vector<std::string> docs(ndocs);
+        std::vector<std::vector<RecordInfo>> recs(ndocs);
+        size_t r = 0;
+        for (size_t d = 0; d < ndocs; ++d)
+            for (size_t i = 0; i < n_records[d]; ++i, ++r) {
+                const char* sp = records[r] ? records[r] : "";
+                docs[d] += sp;
+                recs[d].push_back(RecordInfo{"", (u64)strlen(sp)});
+            }
+        std::vector<const u8*> imgs; std::vector<u64> sizes;
+        for (auto& d : docs) { imgs.push_back((const u8*)d.data()); sizes.push_back(d.size()); }
+        std::vector<u64> off, size;
+        upload(e, imgs.data(), sizes.data(), ndocs, off, size);
+        MMB_CUDA(cudaStreamSynchronize(e->stream));       // the host strings die at the end of this scope
+        load_common(e, e->raw.p, nullptr, off, size, use_revcomp != 0, true);
+        e->records = std::move(recs);
+    });
+}
+
+int mmb_find(mmb_engine* e, const mmb_options* opts) {
+    if (!e || !opts) return fail(MMB_ERR_ARG, "null argument");
+    if (!e->loaded) return fail(MMB_ERR_STATE, "mmb_find before a successful mmb_load_*");
+    return guarded([&] {
+        MMB_CUDA(cudaSetDevice(e->device));
+        cudaStream_t s = e->stream;
+        e->found = false;
+        u32 N = (u32)e->text.h_doc_len.size();
+        bool merge = false;
+        normalise(*opts, N, e->prm, e->mum_mode, merge);
+        e->prm.revcomp = e->text.revcomp ? 1 : 0;
+
+        Timer total(s), t(s);
+        total.start();
+        t.start();
+        build_suffix_array(e->text.text.p, e->text.n, e->sa, s);
+        e->stats.ms_sa = t.stop();
+        t.start();
+        build_lcp_bwt(e->text.text.p, e->text.n, e->sa, e->lcp, e->bwt, s);
+        e->stats.ms_lcp = t.stop();
+        e->sa.isa.release();
+
+        t.start();
+        e->thresh_count = 0; e->thresh.release();
+        if (merge) {
+            e->thresh_count = 2 * (e->text.h_doc_len[0] + 1);       // candidate_thresh.resize(doc_lens[0] * 2), include/mem_finder.hpp:79-81
+            e->thresh.alloc(e->thresh_count, s); e->thresh.zero();
+        }
+        detect_intervals<u32>(e->lcp.p, e->sa.sa.p, e->bwt.p, e->sa.m, e->prm, e->text.doc_start.p, merge ? e->thresh.p : nullptr, e->reports, s);
+        MMB_CUDA(cudaStreamSynchronize(s));
+        e->stats.ms_detect = t.stop();
+
+        t.start();
+        if (e->mum_mode) emit_mums<u32>(e->reports, e->sa.sa.p, e->prm, e->text.doc_start.p, e->text.doc_len.p, opts->want_text != 0, e->mums, s);
+        else emit_mems<u32>(e->reports, e->sa.sa.p, e->prm, e->text.doc_start.p, e->text.doc_len.p, opts->want_text != 0, e->mems, s);
+        e->stats.ms_emit = t.stop();
+        e->stats.ms_total = total.stop();
+        e->stats.num_matches = e->mum_mode ? e->mums.count : e->mems.count;
+        e->stats.sa_rounds = e->sa.rounds; e->stats.sa_sorted_elements = e->sa.sorted_elements;
+        e->found = true;
+    });
+}
+
+int mmb_get_stats(const mmb_engine* e, mmb_stats* out) {
+    if (!e || !out) return fail(MMB_ERR_ARG, "null argument");
+    *out = e->stats;
+    out->kernel_launches = g_kernel_launches - e->launches_at_create;
+    return MMB_OK;
+}
+
+size_t mmb_num_docs(const mmb_engine* e) { return (e && e->loaded) ? e->text.h_doc_len.size() : 0; }
+int mmb_doc_lengths(const mmb_engine* e, uint64_t* lengths) {
+    if (!e || !lengths || !e->loaded) return fail(MMB_ERR_STATE, "no input loaded");
+    for (size_t d = 0; d < e->text.h_doc_len.size(); ++d) lengths[d] = e->text.h_doc_len[d];
+    return MMB_OK;
+}
+size_t mmb_num_records(const mmb_engine* e, size_t doc) { return (e && e->loaded && doc < e->records.size()) ? e->records[doc].size() : 0; }
+int mmb_record(const mmb_engine* e, size_t doc, size_t rec, const char** name, uint64_t* length) {
+    if (!e || !e->loaded || doc >= e->records.size() || rec >= e->records[doc].size()) return fail(MMB_ERR_ARG, "record index out of range");
+    if (name) *name = e->records[doc][rec].name.c_str();
+    if (length) *length = e->records[doc][rec].length;
+    return MMB_OK;
+}
+
+int mmb_is_mum_mode(const mmb_engine* e) { return e && e->mum_mode; }
+uint64_t mmb_num_matches(const mmb_engine* e) { return (e && e->found) ? (e->mum_mode ? e->mums.count : e->mems.count) : 0; }
+uint64_t mmb_text_size(const mmb_engine* e) { return (e && e->found) ? (e->mum_mode ? e->mums.text_bytes : e->mems.text_bytes) : 0; }
+const void* mmb_text_device(const mmb_engine* e) { return (e && e->found) ? (e->mum_mode ? (const void*)e->mums.text.p : (const void*)e->mems.text.p) : nullptr; }
+
+int mmb_copy_text(mmb_engine* e, void* host_dst) {
+    if (!e || !e->found) return fail(MMB_ERR_STATE, "no results: call mmb_find first");
+    return guarded([&] {
+        u64 n = mmb_text_size(e);
+        if (n && !host_dst) throw Error(1, "null destination");
+        copy_out((const u8*)mmb_text_device(e), (u8*)host_dst, n, e->stream);
+        MMB_CUDA(cudaStreamSynchronize(e->stream));
+    });
+}
+
+int mmb_copy_mums(mmb_engine* e, uint32_t* lengths, int64_t* offsets, uint8_t* strands) {
+    if (!e || !e->found || !e->mum_mode) return fail(MMB_ERR_STATE, "no MUM results");
+    return guarded([&] {
+        cudaStream_t s = e->stream;
+        u64 n = e->mums.count, cells = n * e->prm.ndocs;
+        copy_out(e->mums.len.p, lengths, n, s);
+        copy_out(e->mums.off.p, offsets, cells, s);
+        DevBuf<u8> flags;
+        if (strands && cells) {
+            flags.alloc(cells, s);
+            MMB_LAUNCH(strands_to_flags, ceil_div(cells, 256), 256, 0, s, e->mums.strand.p, cells, flags.p);
+            copy_out(flags.p, strands, cells, s);
+        }
+        MMB_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int mmb_copy_mum_strand_bits(mmb_engine* e, uint8_t* packed) {
+    if (!e || !e->found || !e->mum_mode) return fail(MMB_ERR_STATE, "no MUM results");
+    return guarded([&] {
+        u64 nbits = e->mums.count * e->prm.ndocs;
+        DevBuf<u8> bits;
+        pack_strands(e->mums.strand.p, nbits, bits, e->stream);
+        copy_out(bits.p, packed, (nbits + 7) / 8, e->stream);
+        MMB_CUDA(cudaStreamSynchronize(e->stream));
+    });
+}
+
+uint64_t mmb_num_mem_occurrences(const mmb_engine* e) { return (e && e->found && !e->mum_mode) ? e->mems.total_occ : 0; }
+
+int mmb_copy_mems(mmb_engine* e, uint32_t* lengths, uint64_t* first, int64_t* offsets, uint64_t* seq_ids, uint8_t* strands) {
+    if (!e || !e->found || e->mum_mode) return fail(MMB_ERR_STATE, "no MEM results");
+    return guarded([&] {
+        cudaStream_t s = e->stream;
+        u64 n = e->mems.count, occ = e->mems.total_occ;
+        copy_out(e->mems.len.p, lengths, n, s);
+        copy_out(e->mems.first.p, first, n + 1, s);
+        DevBuf<i64> o64; DevBuf<u64> d64; DevBuf<u8> flags;
+        if (occ && (offsets || seq_ids)) {
+            o64.alloc(occ, s); d64.alloc(occ, s);
+            MMB_LAUNCH(mem_widen, ceil_div(occ, 256), 256, 0, s, e->mems.off.p, e->mems.doc.p, occ, o64.p, d64.p);
+            copy_out(o64.p, offsets, occ, s); copy_out(d64.p, seq_ids, occ, s);
+        }
+        if (occ && strands) {
+            flags.alloc(occ, s);
+            MMB_LAUNCH(strands_to_flags, ceil_div(occ, 256), 256, 0, s, e->mems.strand.p, occ, flags.p);
+            copy_out(flags.p, strands, occ, s);
+        }
+        MMB_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+uint64_t mmb_threshold_count(const mmb_engine* e) { return (e && e->found) ? e->thresh_count : 0; }
+int mmb_copy_thresholds(mmb_engine* e, uint16_t* dst) {
+    if (!e || !e->found || !e->thresh_count) return fail(MMB_ERR_STATE, "no thresholds: run mmb_find with merge set");
+    return guarded([&] { copy_out(e->thresh.p, dst, e->thresh_count, e->stream); MMB_CUDA(cudaStreamSynchronize(e->stream)); });
+}
+
+int mmb_copy_arrays(mmb_engine* e, uint64_t* sa, uint64_t* lcp, uint8_t* bwt) {
+    if (!e || !e->found) return fail(MMB_ERR_STATE, "no results: call mmb_find first");
+    return guarded([&] {
+        cudaStream_t s = e->stream; u64 m = e->sa.m;
+        DevBuf<u64> wide; wide.alloc(m, s);
+        if (sa) { MMB_LAUNCH(widen_u32, ceil_div(m, 256), 256, 0, s, e->sa.sa.p, m, wide.p); copy_out(wide.p, sa, m, s); MMB_CUDA(cudaStreamSynchronize(s)); }
+        if (lcp) { MMB_LAUNCH(widen_u32, ceil_div(m, 256), 256, 0, s, e->lcp.p, m, wide.p); copy_out(wide.p, lcp, m, s); MMB_CUDA(cudaStreamSynchronize(s)); }
+        copy_out(e->bwt.p, bwt, m, s);
+        MMB_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int mmb_copy_symbols(mmb_engine* e, uint8_t* dst) {
+    if (!e || !e->loaded) return fail(MMB_ERR_STATE, "no input loaded");
+    return guarded([&] { copy_out(e->text.text.p, dst, e->text.n, e->stream); MMB_CUDA(cudaStreamSynchronize(e->stream)); });
+}
+
+}  // extern "C"
