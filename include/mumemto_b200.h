@@ -106,6 +106,23 @@ MMB_API uint64_t mmb_threshold_count(const mmb_engine* e);
 MMB_API int mmb_copy_thresholds(mmb_engine* e, uint16_t* dst);
 /* -A: the suffix stream, |T| + 1 entries each. NULL skips an array. */
 MMB_API int mmb_copy_arrays(mmb_engine* e, uint64_t* sa, uint64_t* lcp, uint8_t* bwt);
+/* Device pointers of the last MUM table (lengths u32[n], offsets i64[n][num_docs], strands u8[n][num_docs] as '+', '-', 0) and of
+ * the threshold array, e.g. to hand them to NCCL or to mmb_anchor_merge without leaving the GPU.  Valid until the next mmb_find. */
+MMB_API int mmb_mum_table_device(mmb_engine* e, const void** lengths, const void** offsets, const void** strands, const void** thresholds);
+
+/* Anchor-based merge of nparts partitions, folded left to right like `anchor_merge p1 p2 ...` (src/merge_candidates.cpp:208-219).
+ * Partition p: n_mums[p] strict MUMs over ndocs[p] sequences whose first sequence is the shared anchor; lengths[p] u32[n],
+ * offsets[p] i64[n][ndocs], strands[p] u8[n][ndocs] (1 or '+' = forward), thresholds[p] u16[anchor_len] (= PREFIX.athresh).
+ * inputs_on_device: 1 if all those pointers are device pointers (e.g. an all-gather result), 0 for host memory. */
+MMB_API int mmb_anchor_merge(mmb_engine* e, size_t nparts, const void* const* lengths, const uint64_t* n_mums, const void* const* offsets,
+                             const void* const* strands, const void* const* thresholds, const uint64_t* ndocs, uint64_t anchor_len,
+                             int inputs_on_device);
+MMB_API uint64_t mmb_merge_num_mums(const mmb_engine* e);
+MMB_API uint64_t mmb_merge_num_docs(const mmb_engine* e);
+MMB_API int mmb_merge_copy(mmb_engine* e, uint32_t* lengths, int64_t* offsets, uint8_t* strands /* 1 = '+' */, uint16_t* thresholds);
+MMB_API uint64_t mmb_merge_text_size(const mmb_engine* e);          /* merged .mums bytes (include/mumsio.hpp:283-296,318-326) */
+MMB_API int mmb_merge_copy_text(mmb_engine* e, void* host_dst);
+
 /* The text T itself (|T| bytes), for tests. */
 MMB_API int mmb_copy_symbols(mmb_engine* e, uint8_t* dst);
 

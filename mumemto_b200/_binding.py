@@ -64,8 +64,9 @@ _SIGNATURES = {
     "mmb_copy_thresholds": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mmb_copy_arrays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmb_copy_symbols": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mmb_mum_table_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "mmb_anchor_merge": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
-                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint64]),
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_uint64, C.c_int]),
     "mmb_merge_num_mums": (C.c_uint64, [C.c_void_p]),
     "mmb_merge_num_docs": (C.c_uint64, [C.c_void_p]),
     "mmb_merge_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -243,3 +244,34 @@ class Engine:
         flags = np.uint16(0x8000 | (0x2000 if partial else 0))
         head = flags.tobytes() + np.uint64(self.num_docs).tobytes() + np.uint64(len(lengths)).tobytes()
         return head + lengths.tobytes() + offsets.tobytes() + self.mum_strand_bits().tobytes()
+
+    # ------------------------------------------------------------------ partition merge
+    def mum_table_device(self):
+        """Device pointers (lengths, offsets, strands, thresholds) of the last MUM table, as ints."""
+        p = [C.c_void_p() for _ in range(4)]
+        self._check(self.lib.mmb_mum_table_device(self.h, *[C.byref(x) for x in p]))
+        return tuple(x.value for x in p)
+
+    def anchor_merge(self, parts, anchor_len, on_device=False):
+        """parts: per partition (lengths, offsets, strands, thresholds, n_mums, ndocs); host numpy arrays, or device pointers (ints)
+        when on_device.  Folded left to right like `anchor_merge p1 p2 ...`."""
+        k = len(parts)
+        def col(i):
+            return (C.c_void_p * k)(*[(p[i] if on_device else p[i].ctypes.data) for p in parts])
+        n = (C.c_uint64 * k)(*[int(p[4]) for p in parts])
+        nd = (C.c_uint64 * k)(*[int(p[5]) for p in parts])
+        self._keep = parts
+        self._check(self.lib.mmb_anchor_merge(self.h, k, col(0), n, col(1), col(2), col(3), nd, int(anchor_len), int(on_device)))
+        self._merge_anchor_len = int(anchor_len)
+
+    def merge_result(self):
+        n, nd = self.lib.mmb_merge_num_mums(self.h), self.lib.mmb_merge_num_docs(self.h)
+        lengths = np.empty(n, dtype=np.uint32); offsets = np.empty((n, nd), dtype=np.int64); strands = np.empty((n, nd), dtype=np.uint8)
+        thresholds = np.empty(self._merge_anchor_len, dtype=np.uint16)
+        self._check(self.lib.mmb_merge_copy(self.h, _ptr(lengths), _ptr(offsets), _ptr(strands), _ptr(thresholds)))
+        return lengths, offsets, strands, thresholds
+
+    def merge_text(self):
+        buf = np.empty(self.lib.mmb_merge_text_size(self.h), dtype=np.uint8)
+        self._check(self.lib.mmb_merge_copy_text(self.h, _ptr(buf)))
+        return buf.tobytes()

@@ -1,0 +1,254 @@
+// mumemto_b200/csrc/cli_main.cpp -- host C++ command line with the reference's flag table, on top of the C ABI.
+//
+// Mirrors src/pfp_mum.cpp of the reference: option table and parse_build_options (:255-313), BuildOptions::validate
+// (include/pfp_mum.hpp:80-147), the RefBuilder input checks (src/ref_builder.cpp:52-138: file-list, extensions, de-duplication,
+// at least two inputs), the output files of mem_finder (include/mem_finder.hpp:91-158,451-503) and PREFIX.lengths
+// (src/ref_builder.cpp:193-209).  Everything between reading the files and writing the results runs on the GPU through
+// include/mumemto_b200.h.  Stage files of the CPU algorithm (-p/-P/-K .dict/.parse, -a array input) have no counterpart here.
+#include <getopt.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "mumemto_b200.h"
+
+namespace fs = std::filesystem;
+
+#define MUMEMTO_B200_VERSION "1.4.0-b200"
+
+[[noreturn]] static void fatal(const std::string& msg) {
+    std::fprintf(stderr, "\n\033[31mError:\033[m %s\n\n", msg.c_str());
+    std::exit(1);
+}
+static void status(const char* what) { std::fprintf(stderr, "\033[32m[build_main] \033[m%s", what); }
+
+struct Options {
+    std::string input_list, output_prefix = "output";
+    std::vector<std::string> files;
+    bool use_rcomp = true, arrays_out = false, binary = false, merge = false, anchor_merge = false;
+    int num_distinct_docs = 0, max_mem_freq = 0, rare_freq = 1;
+    size_t min_match_len = 20;
+    int device = 0;
+};
+
+static bool ends_with(const std::string& s, const std::string& suf) { return s.size() >= suf.size() && !s.compare(s.size() - suf.size(), suf.size(), suf); }
+static bool is_fasta_name(const std::string& f) {
+    for (const char* e : {".fa", ".fasta", ".fna", ".fa.gz", ".fasta.gz", ".fna.gz"}) if (ends_with(f, e)) return true;
+    return false;
+}
+
+static int usage() {
+    std::fprintf(stderr,
+        "\nmumemto (B200 engine) - find maximal [unique | exact] matches on the GPU.\n"
+        "Usage: mumemto_exec [options] [input_fasta [...]]\n\n"
+        "I/O options:\n"
+        "\t-h, --help                      prints this usage message\n"
+        "\t-i, --input           [FILE]    path to a file-list of genomes to use (overrides positional args)\n"
+        "\t-o, --output          [PREFIX]  output prefix path\n"
+        "\t-r, --no-revcomp                do not include the reverse complement of the sequences\n"
+        "\t-b, --binary                    output binary format (multi-MUMs only)\n"
+        "\t-A, --arrays-out                write LCP, BWT, and SA to file\n"
+        "\t-M, --merge                     output extra metadata to enable merging multi-MUMs\n"
+        "\t-n, --anchor                    use anchor-based merging (uses first sequence as anchor)\n"
+        "Exact match parameters:\n"
+        "\t-l, --min-match-len   [INT]     minimum MUM or MEM length (default: 20)\n"
+        "\t-k, --minimum-genomes [INT]     find matches in at least k sequences (k < 0: relative to N)\n"
+        "\t-f, --per-seq-freq    [INT]     maximum number of occurences per sequence (default: 1)\n"
+        "\t-F, --max-total-freq  [INT]     maximum number of total occurences of match\n"
+        "Accepted for compatibility, no effect on results: -w, -m, -g, -s\n"
+        "Not available (stage files of the CPU algorithm): -p, -P, -K, -a\n"
+        "Engine: -d, --device [INT]\n\n");
+    return 0;
+}
+
+static std::string slurp(const std::string& path) {          // gzopen reads plain and gzip files alike, like the reference
+    gzFile f = gzopen(path.c_str(), "r");
+    if (!f) fatal("cannot open " + path);
+    gzbuffer(f, 1 << 20);
+    std::string out; std::vector<char> buf(1 << 22); int k;
+    while ((k = gzread(f, buf.data(), (unsigned)buf.size())) > 0) out.append(buf.data(), k);
+    gzclose(f);
+    return out;
+}
+
+static void put_file(const std::string& path, const void* p, size_t n) {
+    std::ofstream o(path, std::ios::binary);
+    if (!o) fatal("cannot write " + path);
+    o.write((const char*)p, (std::streamsize)n);
+}
+
+#define CHECK(call) do { if ((call) != 0) fatal(mmb_last_error()); } while (0)
+
+int main(int argc, char** argv) {
+    std::fprintf(stderr, "\033[1m\033[31m\nmumemto version: %s\033[m\033[0m\n", MUMEMTO_B200_VERSION);
+    if (argc == 1) { std::fprintf(stderr, "\nUsage: mumemto_exec [options] [input_fasta [...]]\n\t-h, --help   prints detailed usage message\n"); return 0; }
+    static struct option long_options[] = {
+        {"help", no_argument, nullptr, 'h'}, {"input", required_argument, nullptr, 'i'}, {"output", required_argument, nullptr, 'o'},
+        {"revcomp", no_argument, nullptr, 'r'}, {"minimum-genomes", required_argument, nullptr, 'k'}, {"no-overlap", no_argument, nullptr, 's'},
+        {"modulus", required_argument, nullptr, 'm'}, {"from-parse", no_argument, nullptr, 'p'}, {"only-parse", no_argument, nullptr, 'P'},
+        {"min-match-len", required_argument, nullptr, 'l'}, {"max-freq", required_argument, nullptr, 'F'}, {"arrays-out", no_argument, nullptr, 'A'},
+        {"arrays-in", required_argument, nullptr, 'a'}, {"keep-temp-files", no_argument, nullptr, 'K'}, {"window", required_argument, nullptr, 'w'},
+        {"rare", required_argument, nullptr, 'f'}, {"binary", no_argument, nullptr, 'b'}, {"merge", no_argument, nullptr, 'M'},
+        {"anchor", no_argument, nullptr, 'n'}, {"use-gsacak", no_argument, nullptr, 'g'}, {"device", required_argument, nullptr, 'd'},
+        {nullptr, 0, nullptr, 0}};
+    Options o;
+    int c;
+    while ((c = getopt_long(argc, argv, "hi:F:o:w:sl:ra:AKk:p:m:f:bgMnPd:", long_options, nullptr)) >= 0) {
+        switch (c) {
+            case 'h': usage(); return 0;
+            case 'i': o.input_list = optarg; break;
+            case 'o': o.output_prefix = optarg; break;
+            case 'w': case 'm': case 's': case 'g': break;          // PFP window / modulus / overlap / gsacak: results do not depend on them
+            case 'r': o.use_rcomp = false; break;
+            case 'k': o.num_distinct_docs = std::atoi(optarg); break;
+            case 'l': o.min_match_len = (size_t)std::atoi(optarg); break;
+            case 'F': o.max_mem_freq = std::atoi(optarg); break;
+            case 'A': o.arrays_out = true; break;
+            case 'f': o.rare_freq = std::atoi(optarg); break;
+            case 'b': o.binary = true; break;
+            case 'M': o.merge = true; break;
+            case 'n': o.anchor_merge = true; break;
+            case 'd': o.device = std::atoi(optarg); break;
+            case 'a': case 'p': case 'P': case 'K':
+                fatal("-p/-P/-K/-a use stage files of the CPU algorithm (.dict/.parse/.sa/.lcp/.bwt input); the GPU engine has no such stages");
+            default: usage(); return 1;
+        }
+    }
+    for (int i = optind; i < argc; ++i) o.files.push_back(argv[i]);
+
+    // BuildOptions::validate
+    if (!o.input_list.empty() && !fs::is_regular_file(o.input_list)) fatal("The provided file-list is not valid.");
+    if (!o.input_list.empty() && !o.files.empty()) { status("Using filelist, ignoring positional args\n"); o.files.clear(); }
+    if (o.input_list.empty() && o.files.empty()) fatal("Need to provide a file-list or files as positional args for processing.");
+    fs::path pp(o.output_prefix);
+    if (pp.parent_path().string().empty() && !pp.string().empty()) o.output_prefix = "./" + o.output_prefix;
+    else if (!fs::exists(pp.parent_path())) fs::create_directories(pp.parent_path());
+    if (o.anchor_merge) o.merge = true;
+    if (o.rare_freq < 0) fatal("Per-sequence MEM frequency must be > 0 (or 0 for no limit).");
+    if (o.binary && o.rare_freq != 1) { status("binary output is not supported for multi-MEMs, ignoring flag\n"); o.binary = false; }
+
+    // RefBuilder constructors: collect, check, de-duplicate
+    std::vector<std::string> inputs;
+    if (!o.input_list.empty()) {
+        std::ifstream in(o.input_list); std::string line;
+        while (std::getline(in, line)) {
+            std::istringstream ss(line); std::string w;
+            if (!(ss >> w)) continue;
+            if (!fs::is_regular_file(w)) fatal("The following path in the input list is not valid: " + w);
+            if (!is_fasta_name(w)) fatal("The following input-file is not a FASTA file: " + w);
+            inputs.push_back(w);
+        }
+        std::vector<std::string> u; std::unordered_set<std::string> seen;
+        for (auto& f : inputs) if (seen.insert(f).second) u.push_back(f);
+        inputs.swap(u);
+    } else {
+        std::unordered_set<std::string> seen;
+        for (auto& f : o.files) {
+            if (!fs::is_regular_file(f)) fatal("The following file path is not valid: " + f);
+            if (!is_fasta_name(f)) fatal("The following input-file is not a FASTA file: " + f);
+            std::string norm = fs::absolute(f).lexically_normal().string();
+            if (seen.insert(norm).second) inputs.push_back(norm);
+        }
+    }
+    if (inputs.size() <= 1) fatal("Multiple FASTA inputs required. Perhaps split a multi-FASTA into multiple files?");
+
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&]() { auto t = std::chrono::steady_clock::now(); double s = std::chrono::duration<double>(t - t0).count(); t0 = t; return s; };
+
+    status("parsing input files");
+    std::vector<std::string> images;
+    for (auto& f : inputs) images.push_back(slurp(f));
+    mmb_engine* e = nullptr;
+    CHECK(mmb_create(o.device, nullptr, &e));
+    std::vector<const uint8_t*> ptrs; std::vector<uint64_t> sizes;
+    for (auto& im : images) { ptrs.push_back((const uint8_t*)im.data()); sizes.push_back(im.size()); }
+    if (mmb_load_fasta(e, ptrs.data(), sizes.data(), ptrs.size(), o.use_rcomp) != 0)
+        fatal(std::string(mmb_last_error()) + "\nPlease check the input files and ensure that it contains valid FASTA files.");
+    std::fprintf(stderr, " done.  (%.3f sec)\n", lap());
+    {   // PREFIX.lengths
+        std::ofstream L(o.output_prefix + ".lengths");
+        for (size_t d = 0; d < inputs.size(); ++d) {
+            std::string cp = fs::canonical(inputs[d]).string();
+            uint64_t total = 0; size_t nr = mmb_num_records(e, d);
+            for (size_t r = 0; r < nr; ++r) { uint64_t len; mmb_record(e, d, r, nullptr, &len); total += len; }
+            L << cp << " * " << total << std::endl;
+            for (size_t r = 0; r < nr; ++r) { const char* name; uint64_t len; mmb_record(e, d, r, &name, &len); L << cp << " " << name << " " << len << std::endl; }
+        }
+    }
+
+    mmb_options mo; mmb_default_options(&mo);
+    mo.min_match_len = (uint32_t)o.min_match_len; mo.num_distinct_docs = o.num_distinct_docs; mo.rare_freq = o.rare_freq; mo.max_mem_freq = o.max_mem_freq;
+    mo.merge = o.merge; mo.anchor_merge = o.anchor_merge; mo.cli_normalise = 1; mo.want_text = o.binary ? 0 : 1;
+    bool mum_mode = (o.rare_freq == 1);
+    status(mum_mode ? "finding multi-MUMs on the GPU" : "finding multi-MEMs on the GPU");
+    CHECK(mmb_find(e, &mo));
+    std::fprintf(stderr, " done.  (%.3f sec)\n", lap());
+
+    size_t N = mmb_num_docs(e);
+    uint64_t count = mmb_num_matches(e);
+    if (!mum_mode || !o.binary) {
+        std::vector<char> text(mmb_text_size(e));
+        CHECK(mmb_copy_text(e, text.data()));
+        put_file(o.output_prefix + (mum_mode ? ".mums" : ".mems"), text.data(), text.size());
+    } else {
+        if (count == 0) fatal("no multi-MUMs found: nothing to write in binary format");
+        long n = (long)N, k = o.num_distinct_docs;
+        k = k < -n ? 2 : (k <= 0 ? n + k : (k == 1 ? 2 : std::min(k, n)));
+        uint16_t flags = (uint16_t)(0x8000 | (k < n ? 0x2000 : 0));
+        uint64_t ns = N, nm = count;
+        std::vector<uint32_t> len(nm); std::vector<int64_t> off(nm * ns); std::vector<uint8_t> bits((nm * ns + 7) / 8);
+        CHECK(mmb_copy_mums(e, len.data(), off.data(), nullptr));
+        CHECK(mmb_copy_mum_strand_bits(e, bits.data()));
+        std::ofstream b(o.output_prefix + ".bumbl", std::ios::binary);
+        b.write((char*)&flags, 2); b.write((char*)&ns, 8); b.write((char*)&nm, 8);
+        b.write((char*)len.data(), nm * 4); b.write((char*)off.data(), nm * ns * 8); b.write((char*)bits.data(), bits.size());
+    }
+    if (o.merge) {
+        std::vector<uint16_t> t(mmb_threshold_count(e));
+        CHECK(mmb_copy_thresholds(e, t.data()));
+        if (o.anchor_merge) put_file(o.output_prefix + ".athresh", t.data(), t.size());          // first L_0 + 1 entries = half of the bytes
+        else {
+            // string-based merge metadata, include/mem_finder.hpp:116-157: thresholds re-laid per MUM in anchor order
+            std::vector<uint32_t> len(count); std::vector<int64_t> off(count * N);
+            CHECK(mmb_copy_mums(e, len.data(), off.data(), nullptr));
+            std::vector<std::pair<uint64_t, uint64_t>> pos;
+            for (uint64_t i = 0; i < count; ++i) pos.push_back({(uint64_t)off[i * N], len[i]});
+            std::sort(pos.begin(), pos.end(), [](auto& a, auto& b) { return a.first < b.first; });
+            std::vector<uint16_t> f, r; uint64_t half = t.size() / 2;
+            for (auto& [at, l] : pos) {
+                uint64_t rev = 2 * half - at - l - 1;
+                for (uint64_t x = 0; x < l; ++x) { f.push_back(t[at + x] < l - x ? t[at + x] : 0); r.push_back(t.at(rev + x) < l - x ? t[rev + x] : 0); }
+                f.push_back(0); r.push_back(0);
+            }
+            put_file(o.output_prefix + ".thresh", f.data(), f.size() * 2);
+            put_file(o.output_prefix + ".thresh_rev", r.data(), r.size() * 2);
+        }
+    }
+    if (o.arrays_out) {
+        mmb_stats st; mmb_get_stats(e, &st);
+        uint64_t m = st.text_symbols + 1;
+        std::vector<uint64_t> sa(m), lcp(m); std::vector<uint8_t> bwt(m);
+        CHECK(mmb_copy_arrays(e, sa.data(), lcp.data(), bwt.data()));
+        FILE* fa = std::fopen((o.output_prefix + ".sa").c_str(), "wb"); FILE* fl = std::fopen((o.output_prefix + ".lcp").c_str(), "wb");
+        if (!fa || !fl) fatal("cannot write array files");
+        for (uint64_t i = 0; i < m; ++i) { std::fwrite(&sa[i], 5, 1, fa); std::fwrite(&lcp[i], 5, 1, fl); }     // SSABYTES = THRBYTES = 5
+        std::fclose(fa); std::fclose(fl);
+        put_file(o.output_prefix + ".bwt", bwt.data(), bwt.size());
+    }
+    mmb_stats st; mmb_get_stats(e, &st);
+    status(""); std::fprintf(stderr, "Found %llu matches!\n", (unsigned long long)count);
+    std::fprintf(stderr, "\tdevice time: text %.2f ms, suffix array %.2f ms (%u rounds), LCP/BWT %.2f ms, detection %.2f ms, output %.2f ms; %llu kernel launches\n\n",
+                 st.ms_text, st.ms_sa, st.sa_rounds, st.ms_lcp, st.ms_detect, st.ms_emit, (unsigned long long)st.kernel_launches);
+    mmb_destroy(e);
+    return 0;
+}

@@ -134,7 +134,9 @@ void dispatch_planes(const u32* lcp, const SAT* sa, const u8* bwt, u64 m, const 
 template <class SAT>
 void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, u64 m, const DetectParams& prm, const u64* d_doc_start, u16* thresh,
                       Reports& out, cudaStream_t s) {
-    if (prm.max_freq == 0) throw Error(31, "unbounded total frequency (-f 0 with -F 0) is not supported by the windowed interval scan");
+    // the leftward walk is bounded by max_freq, or else by max_doc_freq * ndocs (a document overflows); with neither it is unbounded
+    if (prm.max_freq == 0 && prm.max_doc_freq == 0)
+        throw Error(31, "unbounded total frequency (-f 0 with -F 0) is not supported by the windowed interval scan");
     if (prm.max_freq >= (1u << 20)) throw Error(32, "maximum total frequency must be below 2^20");
     if (prm.ndocs > 1024) throw Error(33, "more than 1024 input sequences are not supported");
     out.count = 0;

@@ -7,6 +7,7 @@
 // (mumemto_library/mumemto_api.cpp:332-411) for library callers.
 #include "../../include/mumemto_b200.h"
 #include "detect.h"
+#include "merge.h"
 #include "sa.h"
 #include "text.h"
 
@@ -66,6 +67,11 @@ struct mmb_engine {
     bool mum_mode = true;
     DetectParams prm{};
     mmb_stats stats{};
+
+    MergePartition merged;              // result of the last mmb_anchor_merge
+    DevBuf<u8> merged_text;
+    u64 merged_text_bytes = 0, merged_anchor_len = 0;
+    bool has_merged = false;
 };
 
 namespace {
@@ -400,6 +406,77 @@ int mmb_copy_arrays(mmb_engine* e, uint64_t* sa, uint64_t* lcp, uint8_t* bwt) {
         copy_out(e->bwt.p, bwt, m, s);
         MMB_CUDA(cudaStreamSynchronize(s));
     });
+}
+
+int mmb_mum_table_device(mmb_engine* e, const void** lengths, const void** offsets, const void** strands, const void** thresholds) {
+    if (!e || !e->found || !e->mum_mode) return fail(MMB_ERR_STATE, "no MUM results");
+    if (lengths) *lengths = e->mums.len.p;
+    if (offsets) *offsets = e->mums.off.p;
+    if (strands) *strands = e->mums.strand.p;
+    if (thresholds) *thresholds = e->thresh_count ? e->thresh.p : nullptr;
+    return MMB_OK;
+}
+
+int mmb_anchor_merge(mmb_engine* e, size_t nparts, const void* const* lengths, const uint64_t* n_mums, const void* const* offsets,
+                     const void* const* strands, const void* const* thresholds, const uint64_t* ndocs, uint64_t anchor_len, int inputs_on_device) {
+    if (!e || !lengths || !n_mums || !offsets || !strands || !thresholds || !ndocs) return fail(MMB_ERR_ARG, "null argument");
+    if (nparts < 2) return fail(MMB_ERR_ARG, "requires at least two partitions");
+    return guarded([&] {
+        MMB_CUDA(cudaSetDevice(e->device));
+        cudaStream_t s = e->stream;
+        e->has_merged = false;
+        auto prepare = [&](size_t p, MergePartition& out) {
+            u64 n = n_mums[p], nd = ndocs[p];
+            if (nd < 2 || nd > 0xffffffffull) throw Error(61, "a partition needs at least two sequences");
+            if (inputs_on_device) {
+                merge_prepare((const u32*)lengths[p], (const i64*)offsets[p], (const u8*)strands[p], n, (u32)nd, (const u16*)thresholds[p], anchor_len, out, s);
+                return;
+            }
+            DevBuf<u32> l; DevBuf<i64> o; DevBuf<u8> st; DevBuf<u16> t;
+            l.alloc(n, s); o.alloc(n * nd, s); st.alloc(n * nd, s); t.alloc(anchor_len, s);
+            if (n) {
+                MMB_CUDA(cudaMemcpyAsync(l.p, lengths[p], n * 4, cudaMemcpyHostToDevice, s));
+                MMB_CUDA(cudaMemcpyAsync(o.p, offsets[p], n * nd * 8, cudaMemcpyHostToDevice, s));
+                MMB_CUDA(cudaMemcpyAsync(st.p, strands[p], n * nd, cudaMemcpyHostToDevice, s));
+            }
+            if (anchor_len) MMB_CUDA(cudaMemcpyAsync(t.p, thresholds[p], anchor_len * 2, cudaMemcpyHostToDevice, s));
+            merge_prepare(l.p, o.p, st.p, n, (u32)nd, t.p, anchor_len, out, s);
+            MMB_CUDA(cudaStreamSynchronize(s));
+        };
+        MergePartition acc, next, res;
+        prepare(0, acc);
+        for (size_t p = 1; p < nparts; ++p) {
+            prepare(p, next);
+            merge_fold(acc, next, anchor_len, res, s);
+            std::swap(acc, res);
+        }
+        e->merged = std::move(acc);
+        e->merged_anchor_len = anchor_len;
+        merge_text(e->merged, e->merged_text, e->merged_text_bytes, s);
+        MMB_CUDA(cudaStreamSynchronize(s));
+        e->has_merged = true;
+    });
+}
+
+uint64_t mmb_merge_num_mums(const mmb_engine* e) { return (e && e->has_merged) ? e->merged.n : 0; }
+uint64_t mmb_merge_num_docs(const mmb_engine* e) { return (e && e->has_merged) ? e->merged.ndocs : 0; }
+uint64_t mmb_merge_text_size(const mmb_engine* e) { return (e && e->has_merged) ? e->merged_text_bytes : 0; }
+
+int mmb_merge_copy(mmb_engine* e, uint32_t* lengths, int64_t* offsets, uint8_t* strands, uint16_t* thresholds) {
+    if (!e || !e->has_merged) return fail(MMB_ERR_STATE, "no merge result");
+    return guarded([&] {
+        cudaStream_t s = e->stream; u64 n = e->merged.n, cells = n * e->merged.ndocs;
+        copy_out(e->merged.len.p, lengths, n, s);
+        copy_out(e->merged.off.p, offsets, cells, s);
+        copy_out(e->merged.plus.p, strands, cells, s);
+        copy_out(e->merged.nb.p, thresholds, e->merged_anchor_len, s);
+        MMB_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int mmb_merge_copy_text(mmb_engine* e, void* host_dst) {
+    if (!e || !e->has_merged) return fail(MMB_ERR_STATE, "no merge result");
+    return guarded([&] { copy_out(e->merged_text.p, (u8*)host_dst, e->merged_text_bytes, e->stream); MMB_CUDA(cudaStreamSynchronize(e->stream)); });
 }
 
 int mmb_copy_symbols(mmb_engine* e, uint8_t* dst) {

@@ -1,0 +1,150 @@
+"""Parity tests proper: the nvcc-built CUDA library, called through the C ABI (include/mumemto_b200.h), against the committed golden
+vectors (reference build outputs) and the CPU oracle on seeded inputs.  Bit-exact: everything on this path is integer/byte work."""
+import os
+
+import numpy as np
+import pytest
+
+import util
+from mumemto_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+T2 = dict(N=5, L=20000, seed=42, identical_ends=True)
+T2_FLAGS = {"strict": [], "partial": ["-k", "-1"], "mem": ["-f", "3", "-F", "100"], "bumbl": ["-b"], "partial_bumbl": ["-k", "-1", "-b"],
+            "anchor": ["-M", "-n"], "arrays": ["-A"], "norc": ["-r"], "short": ["-l", "12"], "mem2": ["-k", "3", "-f", "2"],
+            "memF": ["-f", "0", "-F", "7", "-k", "2"]}
+
+
+def run_gpu(cuda_lib, paths, prefix, flags):
+    return api.find_files(paths, prefix, _lib=cuda_lib, **util.flags_to_kwargs(flags))
+
+
+@pytest.fixture(scope="module")
+def t2(tmp_path_factory):
+    d = tmp_path_factory.mktemp("t2")
+    return str(d), util.appendix_a(str(d), **T2), util.load_golden_table()["t2"]
+
+
+@pytest.fixture(scope="module")
+def c1(tmp_path_factory):
+    d = tmp_path_factory.mktemp("c1")
+    return str(d), util.appendix_a(str(d), N=5, L=1000000, seed=1), util.load_golden_table()["t7"]
+
+
+@pytest.mark.parametrize("name", sorted(T2_FLAGS))
+def test_t2_golden(cuda_lib, t2, name):
+    d, paths, table = t2
+    run_gpu(cuda_lib, paths, os.path.join(d, "g_" + name), T2_FLAGS[name])
+    got = {ext: util.md5(b) for ext, b in util.outputs(os.path.join(d, "g_" + name)).items()}
+    assert got == table["outputs"][name]["md5"]
+
+
+@pytest.mark.parametrize("name", ["strict", "partial", "mem", "anchor"])
+def test_c1_golden(cuda_lib, c1, name):
+    """BASELINE configs[0]: 5 x 1 Mbp synthetic haplotypes (1 % SNP); 18 070 strict MUMs, 48 393 partial, 36 139 MEMs."""
+    d, paths, table = c1
+    st = run_gpu(cuda_lib, paths, os.path.join(d, "g_" + name), table["outputs"][name]["flags"])
+    got = {ext: util.md5(b) for ext, b in util.outputs(os.path.join(d, "g_" + name)).items()}
+    assert got == table["outputs"][name]["md5"]
+    assert st["text_symbols"] == 10000010 and st["input_bases"] == 5000000
+
+
+def test_edge_inputs_vs_oracle(cuda_lib, oracle_bin, tmp_path):
+    rng = np.random.default_rng(5)
+    core = util.random_dna(rng, 7000)
+    p = []
+    p.append(util.write_fasta(str(tmp_path / "multi.fa"), [("c1 desc", core[:2500]), ("c2", core[2500:4800]), ("c3", core[4800:])], width=50))
+    p.append(util.write_fasta(str(tmp_path / "lower.fasta"), [("x", util.mutate(rng, core, 0.02).lower())], width=61))
+    p.append(util.write_fasta(str(tmp_path / "iupac.fna"), [("y", util.mutate(rng, core, 0.01)[:3000] + "NNNNNRYKMSWBDHVNU" + core[3017:])], width=50, newline="\r\n"))
+    with open(tmp_path / "odd.fa", "w") as f:
+        f.write("junk before header\n\n>z some comment > with marker\n" + core[:1000] + "\n\n" + core[1000:3333] + "\n>empty\n>tail\n" + core[3333:])
+    p.append(str(tmp_path / "odd.fa"))
+    for i, flags in enumerate(([], ["-f", "2"], ["-k", "-1", "-l", "10"], ["-r"], ["-M", "-n"], ["-f", "5", "-l", "8"])):
+        o, g = str(tmp_path / f"o{i}"), str(tmp_path / f"g{i}")
+        util.run_cli(oracle_bin, ["-o", o, *flags, *p])
+        run_gpu(cuda_lib, p, g, flags)
+        assert util.outputs(g) == util.outputs(o), flags
+        assert open(g + ".lengths").read() == open(o + ".lengths").read()
+
+
+@pytest.mark.parametrize("seed,N,L,snp", [(21, 2, 50000, 0.001), (22, 9, 30000, 0.03), (23, 33, 8000, 0.01), (24, 70, 3000, 0.02)])
+def test_random_collections_vs_oracle(cuda_lib, oracle_bin, tmp_path, seed, N, L, snp):
+    """N = 2 ... 70 documents (70 exercises the multi-word document counters), shallow and deep LCPs."""
+    paths = util.appendix_a(str(tmp_path), N=N, L=L, seed=seed, snp=snp)
+    for i, flags in enumerate(([], ["-k", "-2"], ["-f", "2", "-k", "2"], ["-M", "-n"])):
+        o, g = str(tmp_path / f"o{i}"), str(tmp_path / f"g{i}")
+        util.run_cli(oracle_bin, ["-o", o, *flags, *paths])
+        run_gpu(cuda_lib, paths, g, flags)
+        assert util.outputs(g) == util.outputs(o), flags
+
+
+def test_quirk_last_rank_and_saturation(cuda_lib, oracle_bin, tmp_path):
+    rng = np.random.default_rng(3)
+    S = "TTTTGACGTCAGCTAGCTAGCATCGA"
+    a = util.random_dna(rng, 50, "ACG") + "G" + S + "A" + util.random_dna(rng, 50, "ACG")
+    b = util.random_dna(rng, 50, "ACG") + "A" + S + "C" + util.random_dna(rng, 50, "ACG")
+    p = [util.write_fasta(str(tmp_path / "a.fa"), [("a", a)]), util.write_fasta(str(tmp_path / "b.fa"), [("b", b)])]
+    run_gpu(cuda_lib, p, str(tmp_path / "q6"), ["-r"])
+    assert open(tmp_path / "q6.mums").read() == ""
+    X = util.random_dna(np.random.default_rng(9), 70000)
+    p = [util.write_fasta(str(tmp_path / "d0.fa"), [("d0", X + "A" + X[:66000])], width=80), util.write_fasta(str(tmp_path / "d1.fa"), [("d1", X)], width=80)]
+    util.run_cli(oracle_bin, ["-o", str(tmp_path / "o"), "-M", "-n", "-r", *p])
+    run_gpu(cuda_lib, p, str(tmp_path / "g"), ["-M", "-n", "-r"])
+    assert util.outputs(str(tmp_path / "g")) == util.outputs(str(tmp_path / "o"))
+    assert np.frombuffer(util.outputs(str(tmp_path / "g"))[".athresh"], dtype=np.uint16).max() == 65535
+
+
+def test_library_mirror(cuda_lib, oracle_bin, tmp_path):
+    r = api.mem([["ACGTACGT"], ["TACGTAAA"]], min_match_len=3, max_doc_freq=2, _lib=cuda_lib)
+    assert len(r) == 2
+    l, off, ids, st = r.match_at(0)
+    assert (l, off.tolist(), ids.tolist(), st.tolist()) == (5, [0, 1, 0, 4], [1, 1, 0, 0], [0, 1, 1, 0])
+    assert len(api.mum([["ACGTACGT"], ["TACGTAAA"]], min_match_len=3, _lib=cuda_lib)) == 0
+    rng = np.random.default_rng(2)
+    core = util.random_dna(rng, 15000)
+    docs = [[core[:7000], core[7000:]], [util.mutate(rng, core, 0.02)], [util.mutate(rng, core, 0.02)[:8000], util.mutate(rng, core, 0.01)[8000:]]]
+    paths = [util.write_fasta(str(tmp_path / f"d{i}.fa"), [(f"r{j}", s) for j, s in enumerate(d)]) for i, d in enumerate(docs)]
+    util.run_cli(oracle_bin, ["-o", str(tmp_path / "o"), "-k", "2", *paths])
+    res = api.mum(docs, num_distinct=2, _lib=cuda_lib)
+    lines = []
+    for i in range(len(res)):
+        l, off, st = res.match_at(i)
+        lines.append(f"{l}\t" + ",".join("" if o < 0 else str(o) for o in off) + "\t" + ",".join("" if o < 0 else ("+" if s else "-") for o, s in zip(off, st)) + "\n")
+    assert "".join(lines) == open(tmp_path / "o.mums").read()
+
+
+def test_size_independent_properties(cuda_lib, tmp_path):
+    """At a size the oracle is not run on here (8 x 2 Mbp): SA is a permutation, LCP agrees with direct comparison on sampled ranks,
+    every reported MUM really occurs at its coordinates, and document order / strand rules hold."""
+    from mumemto_b200 import Engine
+    paths = util.appendix_a(str(tmp_path), N=8, L=2000000, seed=77, snp=0.005)
+    e = Engine(_lib=cuda_lib)
+    e.load_fasta_files(paths)
+    st = e.find()
+    T = np.frombuffer(e.symbols(), dtype=np.uint8)
+    sa, lcp, bwt = e.arrays()
+    m = len(T) + 1
+    assert len(sa) == m and sa[0] == len(T)
+    seen = np.zeros(m, dtype=bool); seen[sa] = True
+    assert seen.all()
+    rng = np.random.default_rng(0)
+    for r in rng.integers(1, m, 2000):
+        a, b, l = int(sa[r - 1]), int(sa[r]), int(lcp[r])
+        x, y = T[a:a + l + 1], T[b:b + l + 1]
+        assert (x[:l] == y[:l]).all() and (len(x) <= l or len(y) <= l or x[l] != y[l])
+        assert bytes(x[:l + 1]) < bytes(y[:l + 1]) or len(x) < len(y)
+        assert bwt[r] == (T[b - 1] if b else 0)
+    lengths, offsets, strands = e.mums()
+    assert st["num_matches"] == len(lengths) > 1000
+    docs = [np.frombuffer(open(p, "rb").read().split(b"\n", 1)[1].replace(b"\n", b""), dtype=np.uint8) for p in paths]
+    comp = np.zeros(256, dtype=np.uint8); comp[list(b"ACGT")] = list(b"TGCA")
+    for i in rng.integers(0, len(lengths), 300):
+        l = int(lengths[i]); assert l >= 20 and strands[i][0] == 1
+        ref = docs[0][offsets[i][0]:offsets[i][0] + l]
+        for d in range(1, 8):
+            seg = docs[d][offsets[i][d]:offsets[i][d] + l]
+            if not strands[i][d]:
+                seg = comp[seg[::-1]]
+            assert (seg == ref).all()
+    e.close()

@@ -1,0 +1,142 @@
+"""Kernel logic of the engine, executed through the SIMT unit-test build (tests/simt) and compared byte-for-byte with the CPU oracle.
+CPU only: this checks index arithmetic, halo handling and host orchestration of the sm_100a sources before they reach a GPU; the
+parity tests proper are tests/test_gpu_parity.py (-m gpu), which run the nvcc build through the same C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+import util
+from mumemto_b200 import api
+
+FLAGSETS = {"strict": [], "partial": ["-k", "-1"], "mem": ["-f", "3", "-F", "100"], "bumbl": ["-b"], "partial_bumbl": ["-k", "-2", "-b"],
+            "anchor": ["-M", "-n"], "arrays": ["-A"], "norc": ["-r"], "short": ["-l", "9"], "mem2": ["-k", "3", "-f", "2"],
+            "memF": ["-f", "0", "-F", "7", "-k", "2"], "k1": ["-k", "1"], "kbig": ["-k", "99"], "kneg": ["-k", "-99"], "F1": ["-F", "1", "-f", "2"],
+            "Fneg": ["-f", "2", "-F", "-1", "-k", "2"], "f5": ["-f", "5", "-l", "10"]}
+
+
+def both(simt_lib, oracle_bin, tmp, paths, flags):
+    o, g = os.path.join(tmp, "o"), os.path.join(tmp, "g")
+    util.run_cli(oracle_bin, ["-o", o, *flags, *paths])
+    api.find_files(paths, g, _lib=simt_lib, **util.flags_to_kwargs(flags))
+    assert util.outputs(g) == util.outputs(o)
+    assert open(g + ".lengths").read() == open(o + ".lengths").read()
+    return util.outputs(g)
+
+
+@pytest.fixture(scope="module")
+def small(tmp_path_factory):
+    d = tmp_path_factory.mktemp("small")
+    return util.appendix_a(str(d), N=4, L=2500, seed=11, identical_ends=True, snp=0.02, width=70)
+
+
+@pytest.mark.parametrize("name", sorted(FLAGSETS))
+def test_simt_equals_oracle(simt_lib, oracle_bin, small, tmp_path, name):
+    outs = both(simt_lib, oracle_bin, str(tmp_path), small, FLAGSETS[name])
+    assert any(len(b) > 0 for b in outs.values())
+
+
+def test_simt_edge_inputs(simt_lib, oracle_bin, tmp_path):
+    """Multi-record FASTA, CRLF line ends, lower case, N runs, IUPAC codes, blank lines, leading junk before the first header."""
+    rng = np.random.default_rng(5)
+    core = util.random_dna(rng, 700)
+    p = []
+    p.append(util.write_fasta(str(tmp_path / "multi.fa"), [("c1 desc", core[:250]), ("c2", core[250:480]), ("c3", core[480:])], width=50))
+    p.append(util.write_fasta(str(tmp_path / "lower.fasta"), [("x", util.mutate(rng, core, 0.02).lower())], width=61))
+    p.append(util.write_fasta(str(tmp_path / "iupac.fna"), [("y", util.mutate(rng, core, 0.01)[:300] + "NNNNNRYKMSWBDHVNU" + core[317:])], width=50, newline="\r\n"))
+    with open(tmp_path / "odd.fa", "w") as f:
+        f.write("junk before header\n\n>z some comment > with marker\n" + core[:100] + "\n\n" + core[100:333] + "\n>empty\n>tail\n" + core[333:])   # no final newline
+    p.append(str(tmp_path / "odd.fa"))
+    for flags in ([], ["-f", "2"], ["-k", "-1", "-l", "10"], ["-r"]):
+        both(simt_lib, oracle_bin, str(tmp_path), p, flags)
+
+
+def test_simt_gz_and_duplicates(simt_lib, oracle_bin, small, tmp_path):
+    import gzip, shutil
+    gz = str(tmp_path / "h0.fa.gz")
+    with open(small[0], "rb") as a, gzip.open(gz, "wb") as b:
+        shutil.copyfileobj(a, b)
+    both(simt_lib, oracle_bin, str(tmp_path), [gz, small[1], small[1], small[2]], [])       # duplicate path is dropped
+
+
+def test_simt_last_rank_interval_is_lost(simt_lib, oracle_bin, tmp_path):
+    """Q6: no flush at end of stream -- a MUM whose interval reaches the last suffix-array rank is never reported."""
+    rng = np.random.default_rng(3)
+    S = "TTTTGACGTCAGCTAGCTAGCATCGA"
+    a = util.random_dna(rng, 50, "ACG") + "G" + S + "A" + util.random_dna(rng, 50, "ACG")
+    b = util.random_dna(rng, 50, "ACG") + "A" + S + "C" + util.random_dna(rng, 50, "ACG")
+    p = [util.write_fasta(str(tmp_path / "a.fa"), [("a", a)]), util.write_fasta(str(tmp_path / "b.fa"), [("b", b)])]
+    outs = both(simt_lib, oracle_bin, str(tmp_path), p, ["-r"])
+    assert outs[".mums"] == b""
+
+
+def test_simt_threshold_saturation(simt_lib, oracle_bin, tmp_path):
+    """-M with LCP values above 65535: thresholds saturate at 65535 (include/mem_finder.hpp:299,328).  X occurs once per document and
+    its 66000-symbol prefix once more in document 0, so the MUM intervals of X's suffixes have a neighbour sharing up to 66000."""
+    rng = np.random.default_rng(9)
+    X = util.random_dna(rng, 70000)
+    docs = [X + "A" + X[:66000], X]
+    p = [util.write_fasta(str(tmp_path / f"d{i}.fa"), [(f"d{i}", s)], width=80) for i, s in enumerate(docs)]
+    outs = both(simt_lib, oracle_bin, str(tmp_path), p, ["-M", "-n", "-r"])
+    t = np.frombuffer(outs[".athresh"], dtype=np.uint16)
+    assert t.max() == 65535 and (t == 65535).sum() > 100
+
+
+def test_simt_library_mirror(simt_lib, oracle_bin, tmp_path):
+    """mumemto.mum / mumemto.mem of the reference's Python bindings, on the README toy and on random documents."""
+    r = api.mem([["ACGTACGT"], ["TACGTAAA"]], min_match_len=3, max_doc_freq=2, _lib=simt_lib)
+    assert len(r) == 2
+    l, off, ids, st = r.match_at(0)
+    assert (l, off.tolist(), ids.tolist(), st.tolist()) == (5, [0, 1, 0, 4], [1, 1, 0, 0], [0, 1, 1, 0])      # -,+,+,- with the +1 quirk
+    assert len(api.mum([["ACGTACGT"], ["TACGTAAA"]], min_match_len=3, _lib=simt_lib)) == 0
+    with pytest.raises(ValueError):
+        api.mem([["ACGT"], ["ACGT"]], max_doc_freq=1, _lib=simt_lib)
+    # multi-record documents against the oracle's text output
+    rng = np.random.default_rng(2)
+    core = util.random_dna(rng, 1500)
+    docs = [[core[:700], core[700:]], [util.mutate(rng, core, 0.02)], [util.mutate(rng, core, 0.02)[:800], util.mutate(rng, core, 0.01)[800:]]]
+    paths = [util.write_fasta(str(tmp_path / f"d{i}.fa"), [(f"r{j}", s) for j, s in enumerate(d)]) for i, d in enumerate(docs)]
+    util.run_cli(oracle_bin, ["-o", str(tmp_path / "o"), "-k", "2", *paths])
+    res = api.mum(docs, num_distinct=2, _lib=simt_lib)
+    lines = []
+    for i in range(len(res)):
+        l, off, st = res.match_at(i)
+        lines.append(f"{l}\t" + ",".join("" if o < 0 else str(o) for o in off) + "\t" + ",".join("" if o < 0 else ("+" if s else "-") for o, s in zip(off, st)) + "\n")
+    assert "".join(lines) == open(tmp_path / "o.mums").read()
+    assert res.record_lengths == [[700, 800], [1500], [800, 700]]
+
+
+def test_simt_errors(simt_lib, tmp_path):
+    from mumemto_b200 import MumemtoError
+    p = util.appendix_a(str(tmp_path), N=2, L=300, seed=1)
+    with pytest.raises(MumemtoError, match="Merging not available for partial"):
+        api.find_files([p[0], p[1], util.write_fasta(str(tmp_path / "c.fa"), [("c", "ACGT" * 50)])], str(tmp_path / "x"), num_distinct_docs=-1, merge=True, _lib=simt_lib)
+    with pytest.raises(MumemtoError, match="Merging not available for multi-MEMs"):
+        api.find_files(p, str(tmp_path / "x"), rare_freq=2, merge=True, _lib=simt_lib)
+    with pytest.raises(MumemtoError, match="Multiple FASTA inputs required"):
+        api.find_files([p[0], p[0]], str(tmp_path / "x"), _lib=simt_lib)
+    open(tmp_path / "empty.fa", "w").write(">only a header\n")
+    with pytest.raises(MumemtoError, match="Empty input file"):
+        api.find_files([p[0], str(tmp_path / "empty.fa")], str(tmp_path / "x"), _lib=simt_lib)
+    with pytest.raises(MumemtoError, match="not supported"):
+        api.find_files(p, str(tmp_path / "x"), rare_freq=0, max_mem_freq=0, _lib=simt_lib)
+
+
+@pytest.mark.parametrize("parts", [[[0, 1, 2], [0, 3]], [[0, 1], [0, 2], [0, 3]], [[0, 3, 1], [0, 2]]])
+def test_simt_anchor_merge(simt_lib, oracle_bin, small, tmp_path, parts):
+    """Partition -> merge (row J): the device fold equals the oracle's fold, and (as a set) the direct run on the union."""
+    names_o, names_g = [], []
+    for i, idx in enumerate(parts):
+        sel = [small[j] for j in idx]
+        o, g = str(tmp_path / f"o{i}"), str(tmp_path / f"g{i}")
+        util.run_cli(oracle_bin, ["-o", o, "-M", "-n", *sel])
+        api.find_files(sel, g, merge=True, anchor_merge=True, _lib=simt_lib)
+        assert util.outputs(g) == util.outputs(o)
+        names_o.append(o + ".mums"); names_g.append(g + ".mums")
+    util.run_cli(oracle_bin, ["merge", *names_o, "-o", str(tmp_path / "om")])
+    api.merge_files(names_g, str(tmp_path / "gm"), _lib=simt_lib)
+    assert util.outputs(str(tmp_path / "gm")) == util.outputs(str(tmp_path / "om"))
+    if sorted(j for idx in parts for j in idx[1:]) == [1, 2, 3] and [j for idx in parts for j in idx[1:]] == [1, 2, 3]:
+        util.run_cli(oracle_bin, ["-o", str(tmp_path / "all"), "-M", "-n", *small])
+        assert sorted(open(tmp_path / "gm.mums").read().splitlines()) == sorted(open(tmp_path / "all.mums").read().splitlines())
+        assert open(tmp_path / "gm.athresh", "rb").read() == open(tmp_path / "all.athresh", "rb").read()
