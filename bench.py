@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- input bases/sec of the FASTA -> .mums hot path on B200 (BASELINE.json metric), one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|...] [--impl ours|reference]
+
+A step = one pass of the hot path over one synthetic collection:
+  value : FASTA bytes already resident in HBM -> text build -> suffix array -> LCP/BWT -> interval detection -> formatted .mums bytes
+          (left on the device); timed per step with CUDA events on the stream the kernels are launched on, L2 flushed between steps.
+  e2e   : the same through the reference-facing call with HOST buffers: pinned FASTA images -> H2D -> hot path -> D2H of the .mums bytes.
+N > 1 (torchrun): every rank owns one partition (shared anchor h0 + its own haplotypes, -M -n), no collective on the data path
+(scaling "weak"); the partition tables are then exchanged with one NCCL all-gather and folded by the merge kernels (reported aside).
+--impl reference times the reference's own CPU implementation (oracle/_ref/mumemto_exec = reference sources compiled unmodified,
+single-threaded because the reference has no threads) on the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (N docs, L bases per doc, generator, description)
+    "c1": dict(N=5, L=1_000_000, kind="independent", snp=0.01, desc="5x1 Mbp synthetic haplotypes (1% SNP), strict multi-MUMs [BASELINE configs[0]]"),
+    "c1x4": dict(N=5, L=4_000_000, kind="independent", snp=0.01, desc="5x4 Mbp synthetic haplotypes (1% SNP), strict multi-MUMs"),
+    "h64_1m": dict(N=64, L=1_000_000, kind="pangenome", desc="64x1 Mbp human-chr-like haplotypes, strict multi-MUMs"),
+    "h64_4m": dict(N=64, L=4_000_000, kind="pangenome", desc="64x4 Mbp human-chr-like haplotypes, strict multi-MUMs"),
+    "h64_16m": dict(N=64, L=16_000_000, kind="pangenome", desc="64x16 Mbp human-chr-like haplotypes, strict multi-MUMs"),
+    "c2": dict(N=64, L=100_000_000, kind="pangenome", desc="64x100 Mbp synthetic human-chr-like haplotypes, strict multi-MUMs [BASELINE configs[1]]"),
+}
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def fasta_image(name, codes, width=80):
+    """uint8 codes 0..3 -> FASTA file image (header + 80-column lines) as a uint8 array, vectorised."""
+    L = len(codes)
+    seq = ACGT[codes]
+    nfull, rem = divmod(L, width)
+    head = f">{name}\n".encode()
+    body = np.empty(L + nfull + (1 if rem else 0), dtype=np.uint8)
+    if nfull:
+        blk = body[: nfull * (width + 1)].reshape(nfull, width + 1)
+        blk[:, :width] = seq[: nfull * width].reshape(nfull, width)
+        blk[:, width] = 10
+    if rem:
+        body[nfull * (width + 1): nfull * (width + 1) + rem] = seq[nfull * width:]
+        body[-1] = 10
+    return np.concatenate([np.frombuffer(head, dtype=np.uint8), body])
+
+
+def make_collection(spec, seed, anchor_seed=None, first_index=0):
+    """Synthetic collection as a list of FASTA images.
+    independent: SURVEY.md Appendix A generator (base + independent per-haplotype SNPs; seed 1 reproduces the golden C1 files).
+    pangenome  : ancestral sequence (GC ~ 0.41), segregating sites at density 1/300 with derived-allele frequency ~ 1/x on [1/64, 1]
+                 shared across haplotypes, plus 0.01 % private SNPs per haplotype."""
+    N, L = spec["N"], spec["L"]
+    imgs = []
+    if spec["kind"] == "independent":
+        rng = np.random.default_rng(seed)
+        base = rng.integers(0, 4, L)
+        for i in range(N):
+            s = base.copy()
+            m = rng.random(L) < spec["snp"]
+            s[m] = (s[m] + rng.integers(1, 4, m.sum())) % 4
+            imgs.append(fasta_image(f"h{i}", s.astype(np.uint8)))
+        return imgs
+    arng = np.random.default_rng(seed if anchor_seed is None else anchor_seed)
+    anc = arng.choice(4, size=L, p=[0.295, 0.205, 0.205, 0.295]).astype(np.uint8)
+    nsites = L // 300
+    sites = np.sort(arng.choice(L, size=nsites, replace=False))
+    u = arng.random(nsites)
+    freq = (1.0 / 64) * (64.0 ** u)                       # density ~ 1/x on [1/64, 1]
+    alt = ((anc[sites] + arng.integers(1, 4, nsites)) % 4).astype(np.uint8)
+    rng = np.random.default_rng(seed)
+    for i in range(N):
+        s = anc.copy()
+        if not (anchor_seed is not None and i == 0):      # document 0 of a partition is the shared anchor = the ancestral haplotype pattern
+            carry = rng.random(nsites) < freq
+            s[sites[carry]] = alt[carry]
+            priv = rng.random(L) < 1e-4
+            s[priv] = (s[priv] + rng.integers(1, 4, int(priv.sum()))) % 4
+        else:
+            carry = np.random.default_rng(anchor_seed + 1).random(nsites) < freq
+            s[sites[carry]] = alt[carry]
+        imgs.append(fasta_image(f"h{first_index + i}", s))
+    return imgs
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.smax, self.reasons = index, False, [], 0, set()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.sm.append(float(out[0])); self.smax = max(self.smax, float(out[1]))
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax or None, "reasons": sorted(self.reasons)}
+
+
+def reference_arm(args, spec, rank):
+    """The reference's own CPU implementation of the path, timed on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    exe = os.path.join(ROOT, "oracle", "_ref", "mumemto_exec")
+    kind = "reference"
+    if not os.path.exists(exe):
+        exe, kind = os.path.join(ROOT, "oracle", "_build", "mumemto_oracle"), "port"
+        if not os.path.exists(exe):
+            subprocess.run(["make", "port"], cwd=os.path.join(ROOT, "oracle"), check=True, capture_output=True)
+    sample = spec
+    imgs = make_collection(sample, seed=1)
+    bases = sample["N"] * sample["L"]
+    with tempfile.TemporaryDirectory() as d:
+        paths = []
+        for i, im in enumerate(imgs):
+            p = os.path.join(d, f"h{i}.fa"); im.tofile(p); paths.append(p)
+        times = []
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            subprocess.run([exe, "-o", os.path.join(d, "ref"), *paths], check=True, capture_output=True)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    t = float(np.mean(times))
+    v = bases / t
+    line = {"impl": "reference", "metric": "input bases/sec end-to-end (FASTA->.mums)", "value": v, "unit": "bases/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": {"workload": sample["desc"]},
+            "cpu_baseline": {"value": v, "unit": "bases/s", "cores": 1, "kind": kind,
+                             "sample": "whole workload; reference sources compiled unmodified with sdsl/gsacak stand-ins (oracle/ref_shims), 1 thread: the reference has no threads"},
+            "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline_sample(spec):
+    """Bounded CPU run beside the GPU number (rank 0, N = 1): the reference build on (a sample of) the workload."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "mumemto_exec")
+    kind = "reference"
+    if not os.path.exists(exe):
+        exe, kind = os.path.join(ROOT, "oracle", "_build", "mumemto_oracle"), "port"
+    sample = dict(spec)
+    budget_bases = 8_000_000          # ~ 15 s at ~0.5 Mbases/s
+    note = "whole workload"
+    if spec["N"] * spec["L"] > budget_bases:
+        sample["L"] = max(10_000, budget_bases // spec["N"])
+        note = f"{spec['N']}x{sample['L']} bp prefix-sized sample of the same generator (CPU time grows linearly in input size)"
+    imgs = make_collection(sample, seed=1)
+    with tempfile.TemporaryDirectory() as d:
+        paths = []
+        for i, im in enumerate(imgs):
+            p = os.path.join(d, f"h{i}.fa"); im.tofile(p); paths.append(p)
+        t0 = time.perf_counter()
+        subprocess.run([exe, "-o", os.path.join(d, "ref"), *paths], check=True, capture_output=True)
+        dt = time.perf_counter() - t0
+    return {"value": sample["N"] * sample["L"] / dt, "unit": "bases/s", "cores": 1, "kind": kind,
+            "sample": note + "; 1 thread (the reference is single-threaded); sdsl/gsacak replaced by stand-ins", "seconds": dt}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("MMB_WORKLOAD", "c1"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    spec = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, spec, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mumemto_b200 import Engine
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream()
+    eng = Engine(device=local, stream=stream.cuda_stream)
+
+    # ---- synthetic input: N = 1 -> the named collection; N > 1 -> one partition per rank sharing the anchor document
+    multi = world > 1
+    imgs = make_collection(spec, seed=1 + 1000 * rank, anchor_seed=(12345 if (multi and spec["kind"] == "pangenome") else None),
+                           first_index=0) if not (multi and spec["kind"] == "independent") else make_collection(spec, seed=1)
+    if multi and spec["kind"] == "independent":
+        # partitions of the Appendix-A collection cannot share an anchor unless it is the same h0: rank r keeps h0 + its own variants
+        rng = np.random.default_rng(1)
+        base = rng.integers(0, 4, spec["L"])
+        def variant(seed):
+            r2 = np.random.default_rng(seed); s = base.copy(); m = r2.random(spec["L"]) < spec["snp"]
+            s[m] = (s[m] + r2.integers(1, 4, m.sum())) % 4
+            return s.astype(np.uint8)
+        imgs = [fasta_image("h0", variant(7))] + [fasta_image(f"h{rank * 100 + i}", variant(1000 * rank + i + 11)) for i in range(1, spec["N"])]
+    bases_rank = spec["N"] * spec["L"]
+    new_bases_rank = bases_rank if not multi else (spec["N"] - 1) * spec["L"]      # the anchor is counted once
+    total_bases = bases_rank if not multi else spec["L"] + world * new_bases_rank
+
+    sizes = [int(im.size) for im in imgs]
+    offsets, at = [], 0
+    for s in sizes:
+        offsets.append(at); at += (s + 15) & ~15
+    host = torch.empty(at + 32, dtype=torch.uint8).pin_memory()
+    hv = host.numpy()
+    for o, im in zip(offsets, imgs):
+        hv[o:o + im.size] = im
+    dev = host.cuda(non_blocking=False)
+    pinned_imgs = [hv[o:o + s] for o, s in zip(offsets, sizes)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
+    opts = dict(merge=multi, anchor_merge=multi)
+
+    def step_device():
+        eng.load_fasta_device(dev.data_ptr(), offsets, sizes)
+        return eng.find(want_text=True, **opts)
+
+    out_host = None
+
+    def step_e2e():
+        nonlocal out_host
+        eng.load_fasta_bytes(pinned_imgs)
+        eng.find(want_text=True, **opts)
+        n = eng.lib.mmb_text_size(eng.h)
+        if out_host is None or out_host.numel() < n:
+            out_host = torch.empty(max(n, 1), dtype=torch.uint8).pin_memory()
+        eng.copy_text_into(out_host.numpy())
+        return n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_(); step_device()
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    launches0 = eng.stats()["kernel_launches"]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage = {k: 0.0 for k in ("ms_text", "ms_sa", "ms_lcp", "ms_detect", "ms_emit")}
+    st = None
+    t_wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.zero_()
+        a.record(stream)
+        st = step_device()
+        b.record(stream)
+        for k in stage:
+            stage[k] += st[k]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = eng.stats()["kernel_launches"] - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    ms = float(np.mean(step_ms))
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = total_bases / (ms_max * 1e-3)
+
+    # ---- end to end through the host-buffer call
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    out_bytes = 0
+    for _ in range(args.steps):
+        out_bytes = step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_bases / float(te.item())
+    sampler.stop_flag = True; sampler.join(timeout=2)
+
+    # ---- partition merge (N > 1): one NCCL all-gather of the partition tables, then the merge kernels on every rank
+    merge_info = None
+    if multi:
+        merge_info = partition_merge(eng, dist, world, rank, spec)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak = peaks.get("hbm_gbs", 6650.0)
+        algo_bytes = 60.0 * bases_rank                       # 30 B per suffix, 2 suffixes per input base
+        achieved = algo_bytes / (ms * 1e-3) / 1e9
+        line = {"metric": "input bases/sec end-to-end (FASTA->.mums)", "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic", "config": {"workload": spec["desc"], "name": args.workload, "l2": "flushed between steps (256 MiB write)",
+                                                "partitioning": "1 collection" if not multi else f"{world} partitions sharing anchor h0, -M -n, 1 per GPU"},
+                "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(sum(sizes)), "d2h_bytes_per_step": int(out_bytes)},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "whole hot path (text+SA+LCP+detect+emit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+                "stages_ms": {k: v / args.steps for k, v in stage.items()},
+                "matches": int(st["num_matches"]), "sa_rounds": int(st["sa_rounds"]), "sa_sorted_elements": int(st["sa_sorted_elements"]),
+                "text_symbols": int(st["text_symbols"]), "wall_s_timed_region": t_wall, "clocks": sampler.summary()}
+        if merge_info:
+            line["partition_merge"] = merge_info
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample(spec)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def partition_merge(eng, dist, world, rank, spec):
+    """All ranks exchange (lengths, offsets, strands, thresholds) with NCCL all-gathers and fold them with the merge kernels."""
+    import torch
+    lengths, offsets, strands = eng.mums()
+    thr = eng.thresholds()
+    anchor_len = len(thr) // 2
+    n = torch.tensor([len(lengths)], device="cuda", dtype=torch.int64)
+    counts = [torch.zeros(1, device="cuda", dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    nmax, N = max(counts + [1]), spec["N"]
+    def gather(arr, shape, dtype):
+        t = torch.zeros(shape, dtype=dtype, device="cuda")
+        src = torch.from_numpy(arr).cuda()
+        t.view(-1)[: src.numel()] = src.view(-1)
+        out = [torch.empty_like(t) for _ in range(world)]
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        dist.all_gather(out, t)
+        torch.cuda.synchronize()
+        return out, time.perf_counter() - t0
+    gl, t1 = gather(lengths.view(np.int32), (nmax,), torch.int32)
+    go, t2 = gather(offsets, (nmax, N), torch.int64)
+    gs, t3 = gather(strands, (nmax, N), torch.uint8)
+    gt, t4 = gather(thr[:anchor_len].view(np.int16), (anchor_len,), torch.int16)
+    parts = [(gl[r].data_ptr(), go[r].data_ptr(), gs[r].data_ptr(), gt[r].data_ptr(), counts[r], N) for r in range(world)]
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    eng.anchor_merge(parts, anchor_len, on_device=True)
+    torch.cuda.synchronize(); tm = time.perf_counter() - t0
+    return {"allgather_s": t1 + t2 + t3 + t4, "merge_s": tm, "merged_mums": int(eng.lib.mmb_merge_num_mums(eng.h)),
+            "merged_columns": int(eng.lib.mmb_merge_num_docs(eng.h)), "partition_mums": counts}
+
+
+if __name__ == "__main__":
+    main()
