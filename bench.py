@@ -287,8 +287,12 @@ def main():
     barrier()
     t0 = time.perf_counter()
     out_bytes = 0
+    e2e_stage = {k: 0.0 for k in stage}
     for _ in range(args.steps):
         out_bytes = step_e2e()
+        s2 = eng.stats()
+        for k in e2e_stage:
+            e2e_stage[k] += s2[k] / args.steps
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.steps
     te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
@@ -320,7 +324,7 @@ def main():
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "whole hot path (text+SA+LCP+detect+emit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-                "stages_ms": {k: v / args.steps for k, v in stage.items()},
+                "stages_ms": {k: v / args.steps for k, v in stage.items()}, "step_ms": step_ms, "e2e_stages_ms": e2e_stage,
                 "matches": int(st["num_matches"]), "sa_rounds": int(st["sa_rounds"]), "sa_sorted_elements": int(st["sa_sorted_elements"]),
                 "text_symbols": int(st["text_symbols"]), "wall_s_timed_region": t_wall, "clocks": sampler.summary()}
         if merge_info:

@@ -297,7 +297,7 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
         e->stats.ms_emit = t.stop();
         e->stats.ms_total = total.stop();
         e->stats.num_matches = e->mum_mode ? e->mums.count : e->mems.count;
-        e->stats.sa_rounds = e->sa.rounds; e->stats.sa_sorted_elements = e->sa.sorted_elements;
+        e->stats.sa_rounds = e->sa.stats.rounds; e->stats.sa_sorted_elements = e->sa.stats.groups_sorted;
         e->found = true;
     });
 }

@@ -1,15 +1,22 @@
-// mumemto_b200/csrc/sa.cu -- suffix array of the text (plus the smallest sentinel suffix) by prefix doubling with group filtering.
+// mumemto_b200/csrc/sa.cu -- suffix sorting by prefix doubling with group-local sorts.
 //
-// Replaces the reference's gsacak() call on the whole text (include/direct_gsacak.hpp:56-67; third-party gsa-is) and defines the
-// same stream the PFP enumeration produces (include/pfp_lcp_mum.hpp:115-231): ranks 0..n over T followed by a sentinel smaller
-// than every symbol, rank 0 being the sentinel suffix (SA = n).  Rows C/D of SURVEY.md section 8.
+// Replaces the reference's gsacak() / sacak_int() calls (include/direct_gsacak.hpp:56-67, include/dictionary.hpp:133,
+// include/parse.hpp:85; third-party gsa-is) -- rows C/D of SURVEY.md section 8.  Three users share one refinement engine:
+//   build_suffix_array      the text itself (direct route): ranks 0..n over T followed by a smallest sentinel, rank 0 = the sentinel
+//   (pfp.cu)                the dictionary (suffixes end at their phrase's terminator and may TIE) and the parse (integer alphabet)
 //
-// Layout in HBM (m = n + 1 suffixes, 32-bit indices, direct mode requires m < 2^32):
-//   sa[m]   current order            isa[m]  rank of the first member of the suffix's group ("head rank")
-//   round-local: pos[A] (ranks still in multi-member groups), key[A] = head<<32 | rank(suffix+h)+1, val[A] = suffix
-// Round h: gather keys for the A active ranks (2 random 4 B reads each), radix sort (key,val), write sa back through pos, flag new
-// group starts, max-scan them into head ranks, update isa, drop singletons.  Stops when no multi-member group is left.
-// Initial order: the first `cpk` symbols packed `bits` per symbol into one 64-bit key (21 symbols for DNA + '$' + N).
+// State in HBM (m suffixes, 32-bit indices): sa[m] current order, isa[m] = rank of the first member of the suffix's group
+// ("head rank"), nh[m] scratch for the new head ranks of one round, and a list of the groups that still have >1 member,
+// each packed as head << 32 | size.
+// Round h (all suffixes already ordered by their first h symbols): every listed group is sorted by key = isa[suffix + h] + 1
+// (0 = nothing left to compare) by a kernel chosen by group size:
+//   size <= 256   sub-warp / warp rank sort in registers (4/8/16/32 lanes per group, up to 8 elements per lane): each element
+//                 counts the smaller and the equal keys of its group through shuffles, which gives its slot AND its new head
+//                 rank in one go; the first element of each run of equal keys appends the run as a group of the next round
+//   size <= 4096  one block, bitonic sort in shared memory
+//   larger        flat list + device-wide radix sort (prims.h), as in round 1's first version
+// New head ranks are written to nh[] and applied to isa[] by a second kernel, so that no group reads a rank of this round.
+// Traffic per listed suffix per round: sa 4 B read + 4 B written, isa one random 4 B read and one random 4 B write, nh 4+4 B.
 #include "sa.h"
 #include "prims.h"
 
@@ -18,7 +25,45 @@ namespace mmb {
 namespace {
 
 constexpr u32 TPB = 256;
+constexpr u32 FULL = 0xffffffffu;
+constexpr u32 BLOCK_SORT_MAX = 4096;      // elements one block sorts in shared memory
+constexpr int NCLASS = 9;                 // size classes: <=4, <=8, <=16, <=32, <=64, <=128, <=256, <=BLOCK_SORT_MAX, larger
 
+typedef u64 Group;                        // head << 32 | size
+__device__ __forceinline__ u32 g_head(Group g) { return (u32)(g >> 32); }
+__device__ __forceinline__ u32 g_size(Group g) { return (u32)g; }
+__device__ __forceinline__ int size_class(u32 size) {
+    if (size <= 32) return size <= 4 ? 0 : (size <= 8 ? 1 : (size <= 16 ? 2 : 3));
+    if (size <= 256) return size <= 64 ? 4 : (size <= 128 ? 5 : 6);
+    return size <= BLOCK_SORT_MAX ? 7 : 8;
+}
+
+// Next round's groups, one list per size class (so that no binning pass is needed).
+struct GroupLists {
+    Group* list[NCLASS];
+    u32* count;                 // NCLASS counters
+};
+
+// Append groups from a converged warp: lanes that want to append are matched by class and one lane per class reserves the slots.
+__device__ __forceinline__ void append_group_warp(bool want, u32 head, u32 size, const GroupLists& L) {
+    unsigned wanting = __ballot_sync(FULL, want);
+    if (!want) return;
+    int cls = size_class(size);
+    unsigned peers = __match_any_sync(wanting, cls);
+    u32 lane = threadIdx.x & 31;
+    int leader = __ffs((int)peers) - 1;
+    u32 base = 0;
+    if ((int)lane == leader) base = atomicAdd(&L.count[cls], (u32)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    L.list[cls][base + __popc(peers & ((1u << lane) - 1))] = ((u64)head << 32) | size;
+}
+// Same from divergent code (few callers per block).
+__device__ __forceinline__ void append_group_single(u32 head, u32 size, const GroupLists& L) {
+    int cls = size_class(size);
+    L.list[cls][atomicAdd(&L.count[cls], 1u)] = ((u64)head << 32) | size;
+}
+
+// ------------------------------------------------------------------------------------------------ initial order
 __global__ void __launch_bounds__(TPB) symbol_histogram(const u8* __restrict__ text, u64 n, u32* __restrict__ hist) {
     __shared__ u32 h[256];
     h[threadIdx.x] = 0;
@@ -29,8 +74,8 @@ __global__ void __launch_bounds__(TPB) symbol_histogram(const u8* __restrict__ t
     if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
 }
 
-__global__ void __launch_bounds__(TPB) pack_keys(const u8* __restrict__ text, u64 n, const u8* __restrict__ lut, u32 bits, u32 cpk,
-                                                 u64* __restrict__ keys, u32* __restrict__ vals) {
+__global__ void __launch_bounds__(TPB) pack_text_keys(const u8* __restrict__ text, u64 n, const u8* __restrict__ lut, u32 bits, u32 cpk,
+                                                      u64* __restrict__ keys, u32* __restrict__ vals) {
     __shared__ u8 code[256];
     code[threadIdx.x] = lut[threadIdx.x];
     __syncthreads();
@@ -46,80 +91,322 @@ __global__ void __launch_bounds__(TPB) pack_keys(const u8* __restrict__ text, u6
     vals[i] = (u32)i;
 }
 
-// After a sort of all m suffixes: group starts, and which ranks sit in multi-member groups.
-__global__ void __launch_bounds__(TPB) first_flags(const u64* __restrict__ keys, u32 m, u32* __restrict__ head_cand, u32* __restrict__ active) {
+// group starts / head-rank candidates after the initial sort
+__global__ void __launch_bounds__(TPB) first_flags(const u64* __restrict__ keys, u32 m, u32* __restrict__ head_cand) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= m) return;
-    u64 k = keys[p];
-    bool start = (p == 0) || keys[p - 1] != k;
-    bool next_start = (p + 1 == m) || keys[p + 1] != k;
-    head_cand[p] = start ? p : 0u;
-    active[p] = (start && next_start) ? 0u : 1u;
+    head_cand[p] = (p == 0 || keys[p - 1] != keys[p]) ? p : 0u;
 }
 
-__global__ void __launch_bounds__(TPB) first_ranks(const u32* __restrict__ sa, const u32* __restrict__ head, u32 m, u32* __restrict__ isa) {
+// isa from head ranks; the last member of every multi-member group appends the group (limit: see refine_by_doubling)
+__global__ void __launch_bounds__(TPB) first_ranks(const u64* __restrict__ keys, const u32* __restrict__ sa, const u32* __restrict__ head, u32 m, u32 h0,
+                                                   const u32* __restrict__ limit, u32* __restrict__ isa, GroupLists L) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < m) isa[sa[p]] = head[p];
+    bool want = false; u32 hd = 0;
+    if (p < m) {
+        hd = head[p];
+        isa[sa[p]] = hd;
+        bool last = (p + 1 == m) || keys[p + 1] != keys[p];
+        want = last && hd != p;
+        if (want && limit && limit[sa[hd]] <= h0) want = false;   // the whole (terminated) suffix is inside the key: equal strings, final tie
+    }
+    append_group_warp(want, hd, p - hd + 1, L);
 }
 
-__global__ void __launch_bounds__(TPB) compact_first(const u32* __restrict__ active, const u32* __restrict__ idx, u32 m, u32* __restrict__ pos) {
-    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < m && active[p]) pos[idx[p]] = p;
-}
-
-__global__ void __launch_bounds__(TPB) gather_keys(const u32* __restrict__ pos, const u32* __restrict__ sa, const u32* __restrict__ isa, u32 h, u32 m,
-                                                   u32 A, u64* __restrict__ keys, u32* __restrict__ vals) {
-    u32 a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= A) return;
-    u32 s = sa[pos[a]];
+// key of suffix s for the round with offset h: rank of the suffix h symbols further on (+1), 0 when there is nothing further
+__device__ __forceinline__ u32 round_key(u32 s, u32 h, u32 m, const u32* __restrict__ isa, const u32* __restrict__ limit) {
+    if (limit && limit[s] <= h) return 0u;
     u64 t = (u64)s + h;
-    u32 r2 = (t < m) ? isa[t] + 1u : 0u;
-    keys[a] = ((u64)isa[s] << 32) | r2;
-    vals[a] = s;
+    return t < m ? isa[t] + 1u : 0u;
 }
 
-__global__ void __launch_bounds__(TPB) scatter_sorted(const u32* __restrict__ pos, const u64* __restrict__ keys, const u32* __restrict__ vals, u32 A,
-                                                      u32* __restrict__ sa, u32* __restrict__ head_cand, u32* __restrict__ still) {
+// ------------------------------------------------------------------------------------------------ (sub-)warp rank sort
+// WIDTH lanes per group, K elements per lane (K > 1 only with WIDTH = 32).
+template <int WIDTH, int K>
+__global__ void __launch_bounds__(TPB) sort_groups_warp(const Group* __restrict__ groups, u32 ngroups, u32 h, u32 m, u32* __restrict__ sa,
+                                                        const u32* __restrict__ isa, const u32* __restrict__ limit, u32* __restrict__ nh,
+                                                        GroupLists next) {
+    u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 gi = tid / WIDTH, lane = tid % WIDTH;
+    bool have = gi < ngroups;
+    Group g = have ? groups[gi] : 0;
+    u32 head = g_head(g), size = have ? g_size(g) : 0u;
+    u32 s[K], key[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        u32 e = lane + (u32)WIDTH * k;
+        s[k] = 0; key[k] = 0;
+        if (e < size) { s[k] = sa[head + e]; key[k] = round_key(s[k], h, m, isa, limit); }
+    }
+    u32 lt[K], eq[K], before[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { lt[k] = 0; eq[k] = 0; before[k] = 0; }
+#pragma unroll
+    for (int k2 = 0; k2 < K; ++k2) {
+        for (int j = 0; j < WIDTH; ++j) {
+            u32 kj = __shfl_sync(FULL, key[k2], j, WIDTH);
+            u32 ej = (u32)j + (u32)WIDTH * k2;
+            if (ej < size) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    u32 e = lane + (u32)WIDTH * k;
+                    lt[k] += kj < key[k];
+                    eq[k] += kj == key[k];
+                    before[k] += (kj == key[k]) && (ej < e);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        u32 e = lane + (u32)WIDTH * k;
+        bool valid = e < size;
+        if (valid) {
+            u32 slot = head + lt[k] + before[k];
+            sa[slot] = s[k];
+            nh[slot] = head + lt[k];
+        }
+        append_group_warp(valid && before[k] == 0 && eq[k] > 1 && key[k] != 0, head + lt[k], eq[k], next);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ block bitonic sort
+__global__ void __launch_bounds__(TPB) sort_groups_block(const Group* __restrict__ groups, u32 h, u32 m, u32* __restrict__ sa, const u32* __restrict__ isa,
+                                                         const u32* __restrict__ limit, u32* __restrict__ nh, GroupLists next) {
+    __shared__ u64 item[BLOCK_SORT_MAX];          // key << 32 | suffix
+    __shared__ u16 start_of[BLOCK_SORT_MAX];      // 1 + index of the first element of the run each element belongs to (<= 4096)
+    Group g = groups[blockIdx.x];
+    u32 head = g_head(g), size = g_size(g);
+    u32 n2 = 1; while (n2 < size) n2 <<= 1;
+    for (u32 e = threadIdx.x; e < n2; e += blockDim.x) {
+        u64 v = ~0ull;
+        if (e < size) { u32 s = sa[head + e]; v = ((u64)round_key(s, h, m, isa, limit) << 32) | s; }
+        item[e] = v;
+    }
+    __syncthreads();
+    for (u32 k = 2; k <= n2; k <<= 1) {
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            for (u32 e = threadIdx.x; e < n2; e += blockDim.x) {
+                u32 partner = e ^ j;
+                if (partner > e) {
+                    u64 a = item[e], b = item[partner];
+                    bool up = (e & k) == 0;
+                    if ((a > b) == up) { item[e] = b; item[partner] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // run starts -> for every element the index of the first element of its run (block-wide inclusive max-scan, stored +1)
+    __shared__ u32 slice_max[TPB];
+    u32 per = (size + blockDim.x - 1) / blockDim.x;
+    u32 lo = min(threadIdx.x * per, size), hi = min(lo + per, size);
+    u32 run = 0;
+    for (u32 e = lo; e < hi; ++e) {
+        if (e == 0 || (u32)(item[e] >> 32) != (u32)(item[e - 1] >> 32)) run = e + 1;
+        start_of[e] = (u16)run;
+    }
+    slice_max[threadIdx.x] = run;
+    __syncthreads();
+    for (u32 d = 1; d < blockDim.x; d <<= 1) {
+        u32 v = (threadIdx.x >= d) ? slice_max[threadIdx.x - d] : 0u;
+        __syncthreads();
+        slice_max[threadIdx.x] = max(slice_max[threadIdx.x], v);
+        __syncthreads();
+    }
+    u32 carry = threadIdx.x ? slice_max[threadIdx.x - 1] : 0u;
+    for (u32 e = lo; e < hi; ++e) {
+        u32 st = max((u32)start_of[e], carry) - 1;
+        u32 key = (u32)(item[e] >> 32);
+        sa[head + e] = (u32)item[e];
+        nh[head + e] = head + st;
+        bool last = (e + 1 == size) || (u32)(item[e + 1] >> 32) != key;
+        if (last && e != st && key != 0) append_group_single(head + st, e - st + 1, next);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ applying new head ranks
+template <int WIDTH, int K>
+__global__ void __launch_bounds__(TPB) apply_groups_warp(const Group* __restrict__ groups, u32 ngroups, const u32* __restrict__ sa,
+                                                         const u32* __restrict__ nh, u32* __restrict__ isa) {
+    u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 gi = tid / WIDTH, lane = tid % WIDTH;
+    if (gi >= ngroups) return;
+    Group g = groups[gi];
+    u32 head = g_head(g), size = g_size(g);
+#pragma unroll
+    for (int k = 0; k < K; ++k) { u32 e = lane + (u32)WIDTH * k; if (e < size) isa[sa[head + e]] = nh[head + e]; }
+}
+__global__ void __launch_bounds__(TPB) apply_groups_block(const Group* __restrict__ groups, const u32* __restrict__ sa, const u32* __restrict__ nh,
+                                                          u32* __restrict__ isa) {
+    Group g = groups[blockIdx.x];
+    u32 head = g_head(g), size = g_size(g);
+    for (u32 e = threadIdx.x; e < size; e += blockDim.x) isa[sa[head + e]] = nh[head + e];
+}
+
+// ------------------------------------------------------------------------------------------------ large groups: flat list + radix sort
+__global__ void large_sizes(const Group* __restrict__ groups, u32 n, u32* __restrict__ sizes) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sizes[i] = g_size(groups[i]);
+    if (i == n) sizes[i] = 0;
+}
+__global__ void __launch_bounds__(TPB) large_gather(const Group* __restrict__ groups, const u32* __restrict__ base, u32 h, u32 m,
+                                                    const u32* __restrict__ sa, const u32* __restrict__ isa, const u32* __restrict__ limit,
+                                                    u64* __restrict__ keys, u32* __restrict__ vals, u32* __restrict__ pos) {
+    Group g = groups[blockIdx.x];
+    u32 head = g_head(g), size = g_size(g), b = base[blockIdx.x];
+    for (u32 e = blockIdx.y * blockDim.x + threadIdx.x; e < size; e += gridDim.y * blockDim.x) {
+        u32 s = sa[head + e];
+        keys[b + e] = ((u64)head << 32) | round_key(s, h, m, isa, limit);
+        vals[b + e] = s;
+        pos[b + e] = head + e;
+    }
+}
+__global__ void __launch_bounds__(TPB) large_scatter(const u32* __restrict__ pos, const u64* __restrict__ keys, const u32* __restrict__ vals, u32 A,
+                                                     u32* __restrict__ sa, u32* __restrict__ head_cand) {
     u32 a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= A) return;
-    u64 k = keys[a];
-    bool start = (a == 0) || keys[a - 1] != k;
-    bool next_start = (a + 1 == A) || keys[a + 1] != k;
-    u32 p = pos[a];
-    sa[p] = vals[a];
-    head_cand[a] = start ? p : 0u;
-    still[a] = (start && next_start) ? 0u : 1u;
+    sa[pos[a]] = vals[a];
+    head_cand[a] = (a == 0 || keys[a - 1] != keys[a]) ? pos[a] : 0u;
 }
-
-__global__ void __launch_bounds__(TPB) update_ranks(const u32* __restrict__ vals, const u32* __restrict__ head, u32 A, u32* __restrict__ isa) {
+__global__ void __launch_bounds__(TPB) large_finish(const u32* __restrict__ pos, const u64* __restrict__ keys, const u32* __restrict__ head, u32 A,
+                                                    u32* __restrict__ nh, GroupLists next) {
     u32 a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a < A) isa[vals[a]] = head[a];
+    bool want = false; u32 hd = 0, p = 0;
+    if (a < A) {
+        hd = head[a]; p = pos[a];
+        nh[p] = hd;
+        bool last = (a + 1 == A) || keys[a + 1] != keys[a];
+        want = last && hd != p && (u32)keys[a] != 0;
+    }
+    append_group_warp(want, hd, p - hd + 1, next);
 }
-
-__global__ void __launch_bounds__(TPB) compact_active(const u32* __restrict__ pos, const u32* __restrict__ still, const u32* __restrict__ idx, u32 A,
-                                                      u32* __restrict__ pos_out) {
+__global__ void __launch_bounds__(TPB) large_apply(const u32* __restrict__ pos, u32 A, const u32* __restrict__ sa, const u32* __restrict__ nh,
+                                                   u32* __restrict__ isa) {
     u32 a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a < A && still[a]) pos_out[idx[a]] = pos[a];
+    if (a < A) isa[sa[pos[a]]] = nh[pos[a]];
 }
 
 u32 bits_for(u64 x) { u32 b = 1; while ((1ull << b) <= x && b < 63) ++b; return b; }   // bits to represent values 0..x
 
-u32 read_count(const u32* idx, const u32* flag, u32 count, cudaStream_t s) {
-    u32 h[2] = {0, 0};
-    if (count == 0) return 0;
-    MMB_CUDA(cudaMemcpyAsync(&h[0], idx + count - 1, 4, cudaMemcpyDeviceToHost, s));
-    MMB_CUDA(cudaMemcpyAsync(&h[1], flag + count - 1, 4, cudaMemcpyDeviceToHost, s));
-    MMB_CUDA(cudaStreamSynchronize(s));
-    return h[0] + h[1];
+template <int WIDTH, int K>
+void launch_warp_class(const Group* groups, u32 n, u32 h, u32 m, u32* sa, u32* isa, const u32* limit, u32* nh, const GroupLists& next, cudaStream_t s) {
+    if (!n) return;
+    auto k = sort_groups_warp<WIDTH, K>;
+    MMB_LAUNCH(k, ceil_div((u64)n * WIDTH, TPB), TPB, 0, s, groups, n, h, m, sa, (const u32*)isa, limit, nh, next);
+}
+template <int WIDTH, int K>
+void launch_apply_class(const Group* groups, u32 n, const u32* sa, const u32* nh, u32* isa, cudaStream_t s) {
+    if (!n) return;
+    auto k = apply_groups_warp<WIDTH, K>;
+    MMB_LAUNCH(k, ceil_div((u64)n * WIDTH, TPB), TPB, 0, s, groups, n, sa, nh, isa);
 }
 
+const u32 kClassMinSize[NCLASS] = {2, 5, 9, 17, 33, 65, 129, 257, BLOCK_SORT_MAX + 1};
+
 }  // namespace
+
+void GroupStore::alloc(u32 m, cudaStream_t s) {
+    u64 total = 0;
+    for (int c = 0; c < NCLASS; ++c) { first[c] = total; total += (u64)m / kClassMinSize[c] + 1; }
+    first[NCLASS] = total;
+    groups.alloc(total, s); counts.alloc(NCLASS, s); counts.zero();
+}
+
+static GroupLists lists_of(GroupStore& g) {
+    GroupLists L;
+    for (int c = 0; c < NCLASS; ++c) L.list[c] = g.groups.p + g.first[c];
+    L.count = g.counts.p;
+    return L;
+}
+
+// Refine an order that is already sorted by the first h0 symbols (sa, isa = head ranks, cur = multi-member groups by size class,
+// all on the device) until every group is a single suffix or a set of suffixes that are equal up to their `limit` (dictionary mode).
+void refine_by_doubling(u32* sa, u32* isa, u32 m, u32 h0, const u32* limit, GroupStore& cur, SaStats& st, cudaStream_t s) {
+    GroupStore nxt; nxt.alloc(m, s);
+    DevBuf<u32> nh; nh.alloc(m, s);
+    int sort_bits = 32 + (int)bits_for(m);
+    for (u64 h = h0;; h *= 2) {
+        std::vector<u32> cnt = to_host(cur.counts.p, NCLASS, s);
+        u64 total = 0;
+        for (int c = 0; c < NCLASS; ++c) {
+            if ((u64)cnt[c] > cur.first[c + 1] - cur.first[c]) throw Error(23, "internal: group list overflow");
+            total += cnt[c];
+        }
+        if (getenv("MMB_DEBUG")) {
+            fprintf(stderr, "[sa] m=%u h=%llu classes:", m, (unsigned long long)h);
+            for (int c = 0; c < NCLASS; ++c) fprintf(stderr, " %u", cnt[c]);
+            fprintf(stderr, "\n");
+        }
+        if (total == 0) break;
+        if (h >= 2 * (u64)m) throw Error(22, "internal: prefix doubling did not converge");
+        u32 hh = (u32)std::min<u64>(h, m);
+        nxt.counts.zero();
+        GroupLists next = lists_of(nxt);
+        const Group* G[NCLASS];
+        for (int c = 0; c < NCLASS; ++c) G[c] = cur.groups.p + cur.first[c];
+        launch_warp_class<4, 1>(G[0], cnt[0], hh, m, sa, isa, limit, nh.p, next, s);
+        launch_warp_class<8, 1>(G[1], cnt[1], hh, m, sa, isa, limit, nh.p, next, s);
+        launch_warp_class<16, 1>(G[2], cnt[2], hh, m, sa, isa, limit, nh.p, next, s);
+        launch_warp_class<32, 1>(G[3], cnt[3], hh, m, sa, isa, limit, nh.p, next, s);
+        launch_warp_class<32, 2>(G[4], cnt[4], hh, m, sa, isa, limit, nh.p, next, s);
+        launch_warp_class<32, 4>(G[5], cnt[5], hh, m, sa, isa, limit, nh.p, next, s);
+        launch_warp_class<32, 8>(G[6], cnt[6], hh, m, sa, isa, limit, nh.p, next, s);
+        if (cnt[7]) MMB_LAUNCH(sort_groups_block, cnt[7], TPB, 0, s, G[7], hh, m, sa, (const u32*)isa, limit, nh.p, next);
+        DevBuf<u32> lpos; u32 A = 0;
+        if (cnt[8]) {
+            u32 nl = cnt[8];
+            DevBuf<u32> sizes, base, lval_a, lval_b, cand, head; DevBuf<u64> lkey_a, lkey_b, by_head;
+            sizes.alloc(nl + 1, s); base.alloc(nl + 1, s);
+            // Groups were appended in arbitrary (atomic) order; the flat list below must follow suffix-array order, because after the
+            // radix sort (head in the high key bits) the a-th pair belongs at the a-th listed position.
+            by_head.alloc(nl, s); lval_a.alloc(nl, s); lval_b.alloc(nl, s);
+            MMB_CUDA(cudaMemsetAsync(lval_a.p, 0, (size_t)nl * 4, s));
+            prim::sort_pairs(G[8], by_head.p, lval_a.p, lval_b.p, nl, 32, 64, s);
+            G[8] = by_head.p;
+            MMB_LAUNCH(large_sizes, ceil_div(nl + 1, TPB), TPB, 0, s, G[8], nl, sizes.p);
+            prim::exclusive_sum(sizes.p, base.p, nl + 1, s);
+            A = to_host(base.p + nl, 1, s)[0];
+            lpos.alloc(A, s); lkey_a.alloc(A, s); lkey_b.alloc(A, s); lval_a.alloc(A, s); lval_b.alloc(A, s); cand.alloc(A, s); head.alloc(A, s);
+            dim3 grid(nl, 32);
+            MMB_LAUNCH(large_gather, grid, TPB, 0, s, G[8], (const u32*)base.p, hh, m, (const u32*)sa, (const u32*)isa, limit, lkey_a.p, lval_a.p, lpos.p);
+            prim::sort_pairs(lkey_a.p, lkey_b.p, lval_a.p, lval_b.p, A, 0, sort_bits, s);
+            MMB_LAUNCH(large_scatter, ceil_div(A, TPB), TPB, 0, s, (const u32*)lpos.p, (const u64*)lkey_b.p, (const u32*)lval_b.p, A, sa, cand.p);
+            prim::inclusive_max(cand.p, head.p, A, s);
+            MMB_LAUNCH(large_finish, ceil_div(A, TPB), TPB, 0, s, (const u32*)lpos.p, (const u64*)lkey_b.p, (const u32*)head.p, A, nh.p, next);
+        }
+        launch_apply_class<4, 1>(G[0], cnt[0], sa, nh.p, isa, s);
+        launch_apply_class<8, 1>(G[1], cnt[1], sa, nh.p, isa, s);
+        launch_apply_class<16, 1>(G[2], cnt[2], sa, nh.p, isa, s);
+        launch_apply_class<32, 1>(G[3], cnt[3], sa, nh.p, isa, s);
+        launch_apply_class<32, 2>(G[4], cnt[4], sa, nh.p, isa, s);
+        launch_apply_class<32, 4>(G[5], cnt[5], sa, nh.p, isa, s);
+        launch_apply_class<32, 8>(G[6], cnt[6], sa, nh.p, isa, s);
+        if (cnt[7]) MMB_LAUNCH(apply_groups_block, cnt[7], TPB, 0, s, G[7], (const u32*)sa, (const u32*)nh.p, isa);
+        if (A) MMB_LAUNCH(large_apply, ceil_div(A, TPB), TPB, 0, s, (const u32*)lpos.p, A, (const u32*)sa, (const u32*)nh.p, isa);
+        cur.groups.swap(nxt.groups); cur.counts.swap(nxt.counts);
+        ++st.rounds; st.groups_sorted += total; st.large_elements += A;
+    }
+}
+
+// Sort (key, suffix) pairs, derive head ranks and the first group lists.  keys are consumed.
+void order_by_initial_keys(u64* keys_in, u64* keys_tmp, u32* vals_in, u32 m, int key_bits, u32 h0, const u32* limit, u32* sa, u32* isa,
+                           GroupStore& groups, cudaStream_t s) {
+    DevBuf<u32> cand, head;
+    cand.alloc(m, s); head.alloc(m, s);
+    groups.alloc(m, s);
+    prim::sort_pairs(keys_in, keys_tmp, vals_in, sa, m, 0, key_bits, s);
+    MMB_LAUNCH(first_flags, ceil_div(m, TPB), TPB, 0, s, (const u64*)keys_tmp, m, cand.p);
+    prim::inclusive_max(cand.p, head.p, m, s);
+    MMB_LAUNCH(first_ranks, ceil_div(m, TPB), TPB, 0, s, (const u64*)keys_tmp, (const u32*)sa, (const u32*)head.p, m, h0, limit, isa, lists_of(groups));
+}
 
 void build_suffix_array(const u8* text, u64 n, SuffixArray& out, cudaStream_t s) {
     if (n + 1 >= 0xfffffff0ull) throw Error(20, "text too long for the direct (32-bit) suffix array builder");
     u32 m = (u32)(n + 1);
     out.m = m;
     out.sa.alloc(m, s); out.isa.alloc(m, s);
+    out.stats = SaStats{};
 
     // symbol codes: 1 + rank among the symbols present, 0 is the padding / sentinel code
     DevBuf<u32> d_hist; d_hist.alloc(256, s); d_hist.zero();
@@ -133,37 +420,14 @@ void build_suffix_array(const u8* text, u64 n, SuffixArray& out, cudaStream_t s)
     DevBuf<u8> d_lut; d_lut.alloc(256, s);
     MMB_CUDA(cudaMemcpyAsync(d_lut.p, lut.data(), 256, cudaMemcpyHostToDevice, s));
 
-    DevBuf<u64> key_a, key_b; DevBuf<u32> val_a, val_b, pos_a, pos_b, cand, head, flag, idx;
-    key_a.alloc(m, s); key_b.alloc(m, s); val_a.alloc(m, s); val_b.alloc(m, s);
-    cand.alloc(m, s); head.alloc(m, s); flag.alloc(m, s); idx.alloc(m, s);
-
-    MMB_LAUNCH(pack_keys, ceil_div(m, TPB), TPB, 0, s, text, n, d_lut.p, bits, cpk, key_a.p, val_a.p);
-    prim::sort_pairs(key_a.p, key_b.p, val_a.p, out.sa.p, m, 0, (int)(bits * cpk), s);
-    MMB_LAUNCH(first_flags, ceil_div(m, TPB), TPB, 0, s, key_b.p, m, cand.p, flag.p);
-    prim::inclusive_max(cand.p, head.p, m, s);
-    MMB_LAUNCH(first_ranks, ceil_div(m, TPB), TPB, 0, s, out.sa.p, head.p, m, out.isa.p);
-    prim::exclusive_sum(flag.p, idx.p, m, s);
-    u32 A = read_count(idx.p, flag.p, m, s);
-    pos_a.alloc(A, s); pos_b.alloc(A, s);
-    if (A) MMB_LAUNCH(compact_first, ceil_div(m, TPB), TPB, 0, s, flag.p, idx.p, m, pos_a.p);
-
-    int sort_bits = 32 + (int)bits_for(m);
-    out.rounds = 0; out.sorted_elements = m;
-    for (u64 h = cpk; A > 0; h *= 2) {
-        if (h >= 2 * (u64)m) throw Error(22, "internal: prefix doubling did not converge");
-        u32 g = ceil_div(A, TPB);
-        MMB_LAUNCH(gather_keys, g, TPB, 0, s, pos_a.p, out.sa.p, out.isa.p, (u32)std::min<u64>(h, m), m, A, key_a.p, val_a.p);
-        prim::sort_pairs(key_a.p, key_b.p, val_a.p, val_b.p, A, 0, sort_bits, s);
-        MMB_LAUNCH(scatter_sorted, g, TPB, 0, s, pos_a.p, key_b.p, val_b.p, A, out.sa.p, cand.p, flag.p);
-        prim::inclusive_max(cand.p, head.p, A, s);
-        MMB_LAUNCH(update_ranks, g, TPB, 0, s, val_b.p, head.p, A, out.isa.p);
-        prim::exclusive_sum(flag.p, idx.p, A, s);
-        u32 A2 = read_count(idx.p, flag.p, A, s);
-        if (A2) MMB_LAUNCH(compact_active, g, TPB, 0, s, pos_a.p, flag.p, idx.p, A, pos_b.p);
-        pos_a.swap(pos_b);
-        out.sorted_elements += A;
-        A = A2; ++out.rounds;
+    GroupStore groups;
+    {
+        DevBuf<u64> key_a, key_b; DevBuf<u32> val_a;
+        key_a.alloc(m, s); key_b.alloc(m, s); val_a.alloc(m, s);
+        MMB_LAUNCH(pack_text_keys, ceil_div(m, TPB), TPB, 0, s, text, n, (const u8*)d_lut.p, bits, cpk, key_a.p, val_a.p);
+        order_by_initial_keys(key_a.p, key_b.p, val_a.p, m, (int)(bits * cpk), cpk, nullptr, out.sa.p, out.isa.p, groups, s);
     }
+    refine_by_doubling(out.sa.p, out.isa.p, m, cpk, nullptr, groups, out.stats, s);
 }
 
 }  // namespace mmb

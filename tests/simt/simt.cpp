@@ -8,11 +8,13 @@ uint3 g_threadIdx, g_blockIdx;
 dim3 g_blockDim, g_gridDim;
 unsigned char* g_dyn_smem = nullptr;
 unsigned long long g_launches = 0;
+int g_block_order = 0;
 
 namespace {
 constexpr size_t kStack = 256 * 1024;
 struct Fiber { ucontext_t ctx; bool done; uint3 tid; unsigned warp; };
-struct Warp { unsigned long long slot[32]; unsigned count; unsigned long gen; unsigned lanes; };
+struct MaskBarrier { unsigned mask; unsigned count; unsigned long gen; };
+struct Warp { unsigned long long slot[32]; unsigned lanes; std::vector<MaskBarrier> bar; };
 std::vector<Fiber> fibers;
 std::vector<char*> stacks;
 std::vector<Warp> warps;
@@ -38,12 +40,17 @@ void block_barrier() {
     while (bar_gen == g) yield_to_scheduler();
 }
 
+// Disjoint lane sets of one warp may run collectives at the same time (divergent code), so barriers are keyed by their mask.
 void warp_barrier(unsigned mask) {
     Warp& w = warps[fibers[cur].warp];
-    unsigned expected = (unsigned)__builtin_popcount(mask & w.lanes);
-    unsigned long g = w.gen;
-    if (++w.count >= expected) { w.count = 0; ++w.gen; ++progress; return; }
-    while (w.gen == g) yield_to_scheduler();
+    mask &= w.lanes;
+    size_t i = 0;
+    while (i < w.bar.size() && w.bar[i].mask != mask) ++i;
+    if (i == w.bar.size()) w.bar.push_back(MaskBarrier{mask, 0, 0});
+    unsigned expected = (unsigned)__builtin_popcount(mask);
+    unsigned long g = w.bar[i].gen;
+    if (++w.bar[i].count >= expected) { w.bar[i].count = 0; ++w.bar[i].gen; ++progress; return; }
+    while (w.bar[i].gen == g) yield_to_scheduler();      // entries are only appended within a block, so index i stays valid
 }
 
 unsigned long long* warp_slot(unsigned lane) { return &warps[fibers[cur].warp].slot[lane & 31]; }
@@ -60,8 +67,19 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& fn)
     body = &fn;
     fibers.resize(nthreads);
     warps.resize((nthreads + 31) / 32);
-    for (unsigned bz = 0; bz < grid.z; ++bz) for (unsigned by = 0; by < grid.y; ++by) for (unsigned bx = 0; bx < grid.x; ++bx) {
-        for (auto& w : warps) { w.count = 0; w.gen = 0; w.lanes = 0; }
+    // Blocks of a real grid run in no particular order; tests switch between forward, reverse and a scrambled order so that code
+    // relying on the order of e.g. atomic appends does not pass by accident.
+    size_t nblocks = (size_t)grid.x * grid.y * grid.z;
+    for (size_t bi = 0; bi < nblocks; ++bi) {
+        size_t b = bi;
+        if (g_block_order == 1) b = nblocks - 1 - bi;
+        else if (g_block_order == 2) {                   // bijection on [0, nblocks): multiply by an odd constant modulo the next power of two, cycle-walk
+            size_t p2 = 1; while (p2 < nblocks) p2 <<= 1;
+            b = bi;
+            do { b = (b * 0x9E3779B1ull + 12345) & (p2 - 1); } while (b >= nblocks);
+        }
+        unsigned bx = (unsigned)(b % grid.x), by = (unsigned)((b / grid.x) % grid.y), bz = (unsigned)(b / ((size_t)grid.x * grid.y));
+        for (auto& w : warps) { w.bar.clear(); w.lanes = 0; }
         size_t t = 0;
         for (unsigned tz = 0; tz < block.z; ++tz) for (unsigned ty = 0; ty < block.y; ++ty) for (unsigned tx = 0; tx < block.x; ++tx, ++t) {
             Fiber& f = fibers[t];
@@ -87,3 +105,5 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& fn)
 }
 
 }  // namespace simt
+
+extern "C" __attribute__((visibility("default"))) void simt_set_block_order(int mode) { simt::g_block_order = mode; }

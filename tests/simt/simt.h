@@ -53,6 +53,7 @@ void block_barrier();
 void warp_barrier(unsigned mask);
 unsigned long long* warp_slot(unsigned lane);   // per-warp exchange buffer of the calling fiber's warp
 extern unsigned long long g_launches;
+extern int g_block_order;      // 0 forward, 1 reverse, 2 scrambled
 }  // namespace simt
 
 #define threadIdx simt::g_threadIdx
@@ -103,6 +104,16 @@ inline unsigned __ballot_sync(unsigned mask, int pred) {
     simt::warp_barrier(mask);
     unsigned r = 0;
     for (unsigned l = 0; l < 32; ++l) if ((mask >> l & 1) && *simt::warp_slot(l)) r |= 1u << l;
+    simt::warp_barrier(mask);
+    return r;
+}
+template <class T> inline unsigned __match_any_sync(unsigned mask, T v) {
+    static_assert(sizeof(T) <= 8, "match payload");
+    unsigned long long raw = 0; memcpy(&raw, &v, sizeof(T));
+    *simt::warp_slot(simt::lane_id()) = raw;
+    simt::warp_barrier(mask);
+    unsigned r = 0;
+    for (unsigned l = 0; l < 32; ++l) if ((mask >> l & 1) && *simt::warp_slot(l) == raw) r |= 1u << l;
     simt::warp_barrier(mask);
     return r;
 }

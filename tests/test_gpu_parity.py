@@ -95,6 +95,24 @@ def test_quirk_last_rank_and_saturation(cuda_lib, oracle_bin, tmp_path):
     assert np.frombuffer(util.outputs(str(tmp_path / "g"))[".athresh"], dtype=np.uint16).max() == 65535
 
 
+def test_repeats_all_group_size_classes(cuda_lib, oracle_bin, tmp_path):
+    """Low-complexity / tandem-repeat inputs: every group-size class of the doubling rounds (sub-warp ... block sort, radix fallback)."""
+    rng = np.random.default_rng(17)
+    unit = util.random_dna(rng, 37)
+    body = util.random_dna(rng, 30000)
+    docs = [
+        "A" * 9000 + body + unit * 300 + "ACGT" * 400 + body[:7000] + "G" * 4500,
+        "A" * 300 + util.mutate(rng, body, 0.01) + unit * 260 + "C" * 150 + body[2000:9000],
+        util.mutate(rng, body, 0.02) + "AC" * 2700 + unit * 120 + "A" * 1000,
+    ]
+    p = [util.write_fasta(str(tmp_path / f"d{i}.fa"), [(f"d{i}", s)], width=77) for i, s in enumerate(docs)]
+    for i, flags in enumerate(([], ["-k", "2"], ["-f", "4", "-k", "2", "-l", "15"], ["-f", "0", "-F", "40", "-k", "2"], ["-r", "-f", "2"])):
+        o, g = str(tmp_path / f"o{i}"), str(tmp_path / f"g{i}")
+        util.run_cli(oracle_bin, ["-o", o, *flags, *p])
+        run_gpu(cuda_lib, p, g, flags)
+        assert util.outputs(g) == util.outputs(o), flags
+
+
 def test_library_mirror(cuda_lib, oracle_bin, tmp_path):
     r = api.mem([["ACGTACGT"], ["TACGTAAA"]], min_match_len=3, max_doc_freq=2, _lib=cuda_lib)
     assert len(r) == 2

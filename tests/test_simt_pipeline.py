@@ -124,6 +124,7 @@ def test_simt_errors(simt_lib, tmp_path):
 
 @pytest.mark.parametrize("parts", [[[0, 1, 2], [0, 3]], [[0, 1], [0, 2], [0, 3]], [[0, 3, 1], [0, 2]]])
 def test_simt_anchor_merge(simt_lib, oracle_bin, small, tmp_path, parts):
+    simt_lib.simt_set_block_order(len(parts) % 3)
     """Partition -> merge (row J): the device fold equals the oracle's fold, and (as a set) the direct run on the union."""
     names_o, names_g = [], []
     for i, idx in enumerate(parts):
@@ -140,3 +141,24 @@ def test_simt_anchor_merge(simt_lib, oracle_bin, small, tmp_path, parts):
         util.run_cli(oracle_bin, ["-o", str(tmp_path / "all"), "-M", "-n", *small])
         assert sorted(open(tmp_path / "gm.mums").read().splitlines()) == sorted(open(tmp_path / "all.mums").read().splitlines())
         assert open(tmp_path / "gm.athresh", "rb").read() == open(tmp_path / "all.athresh", "rb").read()
+
+
+@pytest.mark.parametrize("block_order", [0, 1, 2])
+def test_simt_repeats_all_group_size_classes(simt_lib, oracle_bin, tmp_path, block_order):
+    """Low-complexity and tandem-repeat inputs: the doubling rounds see groups of every size class (sub-warp ... warp x8, block sort,
+    device-wide fallback above 4096), and matches with many occurrences exercise -f / -F limits."""
+    rng = np.random.default_rng(17)
+    unit = util.random_dna(rng, 37)
+    body = util.random_dna(rng, 1500)
+    docs = [
+        "A" * 5200 + body + unit * 90 + "ACGT" * 40 + body[:700],
+        "A" * 300 + util.mutate(rng, body, 0.01) + unit * 60 + "C" * 150 + body[200:900],
+        util.mutate(rng, body, 0.02) + "AC" * 700 + unit * 20 + "A" * 100,
+    ]
+    p = [util.write_fasta(str(tmp_path / f"d{i}.fa"), [(f"d{i}", s)], width=77) for i, s in enumerate(docs)]
+    simt_lib.simt_set_block_order(block_order)       # real grids run their blocks in no particular order
+    try:
+        for flags in ([], ["-f", "4", "-k", "2", "-l", "15"], ["-r", "-f", "2"]) if block_order else ([], ["-k", "2"], ["-f", "4", "-k", "2", "-l", "15"], ["-f", "0", "-F", "40", "-k", "2"], ["-r", "-f", "2"]):
+            both(simt_lib, oracle_bin, str(tmp_path), p, flags)
+    finally:
+        simt_lib.simt_set_block_order(0)
