@@ -8,8 +8,16 @@
 //   v > lcp[j] and v >= min_len.  Document multiplicities accumulate in bit-sliced counters as the walk widens, the BWT
 //   left-maximality flag is the OR of bwt[k] != bwt[k-1] over the pairs absorbed so far, and the next-best threshold of -M is
 //   max(lcp[k], lcp[j]).  Intervals that never close (they touch the last rank) are never reported, like the reference (no flush).
-// Reports are appended with an atomic counter and sorted afterwards by (closing rank, order in chain) = the reference's order.
-// Traffic per suffix: lcp 4 B + bwt 1 B + sa 4/8 B for walked ranks (L1/L2 hits between neighbouring threads).
+// Reports are appended with an atomic counter and sorted afterwards by (closing rank, interval size) = the reference's order.
+//
+// Two kernels implement this:
+//   detect_window_kernel  (used when at most 64 interval sizes can qualify, i.e. F - k < 64: strict / partial MUMs, bounded MEMs).
+//       An interval of size m closing at j is [j-m, j-1]; it exists iff v = min(lcp[j-m+1 .. j-1]) exceeds both lcp[j-m] and lcp[j],
+//       and its length is v.  Each block stages a tile of lcp (1024 closing ranks + halo F) in shared memory with one TMA bulk copy,
+//       builds power-of-two window minima there, and every thread tests its closing ranks in O(1) per size.  The few survivors are
+//       verified by the whole warp: document bitmask by OR-reduction, BWT left-maximality by neighbour comparison.
+//       Traffic per suffix: lcp 4 B; sa (+ text for the BWT symbol) only for surviving candidates.
+//   detect_walk_kernel    (any other parameters) the leftward walk described above, one thread per closing rank.
 #include "detect.h"
 #include "prims.h"
 
@@ -57,9 +65,17 @@ struct DocCounter {
     }
 };
 
+// symbol preceding the suffix at rank r
+template <class SAT>
+__device__ __forceinline__ u8 bwt_at(const u8* __restrict__ bwt, const u8* __restrict__ text, const SAT* __restrict__ sa, u64 r) {
+    if (bwt) return bwt[r];
+    u64 p = (u64)sa[r];
+    return p ? text[p - 1] : (u8)0;
+}
+
 template <class SAT, int W, int P>
-__global__ void __launch_bounds__(TPB) detect_kernel(const u32* __restrict__ lcp, const SAT* __restrict__ sa, const u8* __restrict__ bwt, u64 m,
-                                                     DetectParams prm, const u64* __restrict__ doc_start_g, Report* __restrict__ reports, u32 cap,
+__global__ void __launch_bounds__(TPB) detect_walk_kernel(const u32* __restrict__ lcp, const SAT* __restrict__ sa, const u8* __restrict__ bwt,
+                                                          const u8* __restrict__ text, u64 m, DetectParams prm, const u64* __restrict__ doc_start_g, Report* __restrict__ reports, u32 cap,
                                                      u32* __restrict__ count, u16* __restrict__ thresh) {
     MMB_DYN_SMEM(u64, doc_start);
     for (u32 i = threadIdx.x; i <= prm.ndocs; i += blockDim.x) doc_start[i] = doc_start_g[i];
@@ -72,7 +88,7 @@ __global__ void __launch_bounds__(TPB) detect_kernel(const u32* __restrict__ lcp
     DocCounter<W, P> docs; docs.clear();
     u64 k = j - 1;                  // lowest rank inside the current interval
     u64 anchor_sa = ~0ull;          // SA of the lowest-ranked document-0 suffix seen
-    u32 size = 1, order = 0;
+    u32 size = 1;
     bool left_differs = false;
     {
         u64 p = (u64)sa[k]; u32 d = find_doc(doc_start, prm.ndocs, p);
@@ -81,7 +97,7 @@ __global__ void __launch_bounds__(TPB) detect_kernel(const u32* __restrict__ lcp
     }
     for (;;) {
         while (lcp[k] >= v) {       // rank k-1 shares v symbols with rank k: absorb it (k >= 2 here because lcp[0] = lcp[1] = 0 < v)
-            left_differs |= (bwt[k] != bwt[k - 1]);
+            left_differs |= (bwt_at(bwt, text, sa, k) != bwt_at(bwt, text, sa, k - 1));
             --k; ++size;
             if (prm.max_freq && size > prm.max_freq) return;
             u64 p = (u64)sa[k]; u32 d = find_doc(doc_start, prm.ndocs, p);
@@ -93,12 +109,204 @@ __global__ void __launch_bounds__(TPB) detect_kernel(const u32* __restrict__ lcp
             if (prm.merge && anchor_sa != ~0ull) thresh[anchor_sa] = (u16)min(max(before, cur), 65535u);
             if (left_differs) {
                 u32 slot = atomicAdd(count, 1u);
-                if (slot < cap) { Report r; r.key = (j << 20) | order; r.s = k; r.len = v; r.pad = 0; reports[slot] = r; }
-                ++order;
+                if (slot < cap) { Report r; r.key = (j << 20) | size; r.s = k; r.len = v; r.pad = 0; reports[slot] = r; }
             }
         }
         v = before;
         if (v <= cur || v < prm.min_len) return;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ windowed-minimum detector
+constexpr u32 DW_TPB = 256, DW_JPT = 4, DW_TILE = DW_TPB * DW_JPT;
+constexpr u32 DW_MAX_SIZES = 64;
+
+struct WindowPlan {
+    u32 size_lo, size_hi;       // interval sizes that can qualify
+    u32 lev_lo, lev_hi;         // floor(log2(size-1)) over that range: window-minimum levels kept in shared memory
+    u32 nkept;                  // number of levels >= 1 kept (lev_hi - max(lev_lo, 1) + 1, or 0)
+    u32 halo;                   // ranks staged to the left of the tile (multiple of 4, >= size_hi)
+    u32 span;                   // halo + DW_TILE
+};
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+// One TMA bulk copy global -> shared, completion on an mbarrier (cp.async.bulk; UBLKCP in SASS).  bytes and both addresses are
+// multiples of 16.  Thread 0 issues, everybody waits.
+__device__ __forceinline__ void tma_load_tile(void* dst, const void* src, u32 bytes, u64* bar) {
+#ifdef MMB_SIMT
+    if (threadIdx.x == 0) memcpy(dst, src, bytes);
+    (void)bar;
+    __syncthreads();
+#else
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                     "r"(smem_u32(bar))
+                     : "memory");
+    }
+    u32 done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar))
+            : "memory");
+    }
+#endif
+}
+
+template <class SAT, int W, int P>
+__global__ void __launch_bounds__(DW_TPB) detect_window_kernel(const u32* __restrict__ lcp, const SAT* __restrict__ sa, const u8* __restrict__ bwt,
+                                                              const u8* __restrict__ text, u64 m, DetectParams prm, WindowPlan plan,
+                                                              const u64* __restrict__ doc_start_g, Report* __restrict__ reports, u32 cap,
+                                                              u32* __restrict__ count, u16* __restrict__ thresh) {
+    MMB_DYN_SMEM(u64, smem64);
+    u64* bar = smem64;                                  // 16 bytes reserved
+    u64* doc_start = smem64 + 2;                        // ndocs + 1 (+1 pad to keep 16-byte alignment)
+    u32* lc = reinterpret_cast<u32*>(doc_start + ((prm.ndocs + 2) & ~1u));      // level 0: the lcp tile itself
+    u32* lev = lc + plan.span;                          // levels lev_lo' .. lev_hi, each plan.span entries (level 0 lives in lc)
+    const u32 span = plan.span, halo = plan.halo;
+    const u64 tile0 = (u64)blockIdx.x * DW_TILE;        // first closing rank handled by this block
+    const i64 origin = (i64)tile0 - (i64)halo;          // rank held by lc[0]
+
+    for (u32 i = threadIdx.x; i <= prm.ndocs; i += blockDim.x) doc_start[i] = doc_start_g[i];
+    // stage lcp[origin .. origin + span): ranks below 0 or at/after m read as 0 (an lcp of 0 closes everything)
+    {
+        u64 lo = origin < 0 ? 0 : (u64)origin, hi = min((u64)(origin + span), m);
+        u32 skip = (u32)((i64)lo - origin);
+        for (u32 i = threadIdx.x; i < skip; i += blockDim.x) lc[i] = 0;
+        u32 have = hi > lo ? (u32)(hi - lo) : 0u, padded = (have + 3) & ~3u;      // lcp is allocated with slack past m (engine)
+        if (padded) tma_load_tile(lc + skip, lcp + lo, padded * 4, bar); else __syncthreads();
+        for (u32 i = skip + have + threadIdx.x; i < span; i += blockDim.x) lc[i] = 0;
+    }
+    __syncthreads();
+    // window minima: level t holds min(lc[i .. i + 2^t - 1]); built by doubling, levels lev_lo..lev_hi are kept
+    {
+        constexpr u32 PER = 6;                          // span <= DW_TPB * PER is checked on the host
+        u32 v[PER];
+#pragma unroll
+        for (u32 q = 0; q < PER; ++q) { u32 i = threadIdx.x + q * DW_TPB; v[q] = i < span ? lc[i] : 0u; }
+        u32* work = lev + (size_t)plan.nkept * span;      // scratch level after the kept ones
+        for (u32 t = 1; t <= plan.lev_hi; ++t) {
+            const u32* prev = (t == 1) ? lc : work;
+            u32 stride = 1u << (t - 1);
+            u32 nv[PER];
+#pragma unroll
+            for (u32 q = 0; q < PER; ++q) {
+                u32 i = threadIdx.x + q * DW_TPB;
+                nv[q] = v[q];
+                if (i < span && i + stride < span) nv[q] = min(v[q], prev[i + stride]);
+            }
+            __syncthreads();
+#pragma unroll
+            for (u32 q = 0; q < PER; ++q) {
+                u32 i = threadIdx.x + q * DW_TPB;
+                v[q] = nv[q];
+                if (i < span) { work[i] = nv[q]; if (t >= plan.lev_lo) lev[(size_t)(t - max(plan.lev_lo, 1u)) * span + i] = nv[q]; }
+            }
+            __syncthreads();
+        }
+    }
+    const u32 lane = threadIdx.x & 31;
+    const u32 lev_base = max(plan.lev_lo, 1u);
+    auto window_min = [&](u32 idx_j, u32 size) -> u32 {      // min(lc[idx_j - size + 1 .. idx_j - 1]), size >= 2
+        u32 w = size - 1;
+        u32 t = 31 - __clz((int)w), pw = 1u << t;
+        const u32* L = t ? lev + (size_t)(t - lev_base) * span : lc;
+        return min(L[idx_j - size + 1], L[idx_j - pw]);
+    };
+
+    for (u32 q = 0; q < DW_JPT; ++q) {
+        u32 idx = halo + q * DW_TPB + threadIdx.x;          // position of rank j in lc
+        u64 j = tile0 + q * DW_TPB + threadIdx.x;
+        bool active = j >= 1 && j < m;
+        u32 cur = lc[idx];
+        u32 size = plan.size_lo;
+        if (active) {                                       // the smallest window has the largest minimum: cheap rejection
+            u32 v0 = (j >= size) ? window_min(idx, size) : 0u;
+            if (v0 <= cur || v0 < prm.min_len) active = false;
+        }
+        for (;;) {                                          // warp-uniform: one candidate per lane per turn
+            bool have = false; u32 v = 0;
+            while (active && size <= plan.size_hi) {
+                if (j < size) { active = false; break; }
+                v = window_min(idx, size);
+                if (v <= cur || v < prm.min_len) { active = false; break; }
+                if (lc[idx - size] < v) { have = true; break; }
+                ++size;
+            }
+            if (!have) active = false;
+            unsigned cand = __ballot_sync(0xffffffffu, have);
+            if (!cand) break;
+            if (P == 1 && prm.max_doc_freq == 1) {
+                // MUM modes: the warp verifies each candidate together
+                while (cand) {
+                    int src = __ffs((int)cand) - 1; cand &= cand - 1;
+                    u64 cj = __shfl_sync(0xffffffffu, j, src);
+                    u32 cs = __shfl_sync(0xffffffffu, size, src), cv = __shfl_sync(0xffffffffu, v, src), ccur = __shfl_sync(0xffffffffu, cur, src);
+                    u32 cbefore = __shfl_sync(0xffffffffu, lc[idx - (have ? size : 0)], src);
+                    u64 s0 = cj - cs;
+                    u64 bits[W];
+#pragma unroll
+                    for (int w = 0; w < W; ++w) bits[w] = 0;
+                    u64 anchor = ~0ull; bool differs = false; u32 carry = 0;
+                    for (u32 t0 = 0; t0 < cs; t0 += 32) {
+                        u32 t = t0 + lane;
+                        u32 sym = 0;
+                        if (t < cs) {
+                            u64 r = s0 + t; u64 p = (u64)sa[r];
+                            u32 d = find_doc(doc_start, prm.ndocs, p);
+                            bits[(W == 1) ? 0 : (d >> 6)] |= 1ull << (d & 63);
+                            if (d == 0) anchor = p;
+                            sym = bwt ? bwt[r] : (p ? text[p - 1] : (u8)0);
+                        }
+                        u32 left = __shfl_up_sync(0xffffffffu, sym, 1);
+                        if (lane == 0) left = carry;
+                        if (t < cs && t > 0 && left != sym) differs = true;
+                        carry = __shfl_sync(0xffffffffu, sym, 31);
+                    }
+                    u32 distinct = 0;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        u64 b = bits[w];
+#pragma unroll
+                        for (u32 d = 16; d > 0; d >>= 1) b |= __shfl_xor_sync(0xffffffffu, b, d);
+                        distinct += (u32)__popcll(b);
+                    }
+                    differs = __any_sync(0xffffffffu, differs);
+                    if (distinct == cs && distinct >= prm.num_distinct) {          // every document at most once
+                        if (prm.merge && anchor != ~0ull) thresh[anchor] = (u16)min(max(cbefore, ccur), 65535u);
+                        if (differs && lane == 0) {
+                            u32 slot = atomicAdd(count, 1u);
+                            if (slot < cap) { Report r; r.key = (cj << 20) | cs; r.s = s0; r.len = cv; r.pad = 0; reports[slot] = r; }
+                        }
+                    }
+                }
+            } else if (have) {
+                // MEM modes: the owning thread counts documents itself
+                DocCounter<W, P> docs; docs.clear();
+                u64 s0 = j - size; bool ok = true, differs = false;
+                u8 prev_sym = 0;
+                for (u32 t = 0; t < size && ok; ++t) {
+                    u64 r = s0 + t; u64 p = (u64)sa[r];
+                    ok = docs.add(find_doc(doc_start, prm.ndocs, p), prm.max_doc_freq);
+                    u8 sym = bwt ? bwt[r] : (p ? text[p - 1] : (u8)0);
+                    if (t > 0 && sym != prev_sym) differs = true;
+                    prev_sym = sym;
+                }
+                if (ok && docs.distinct >= prm.num_distinct && differs) {
+                    u32 slot = atomicAdd(count, 1u);
+                    if (slot < cap) { Report r; r.key = (j << 20) | size; r.s = s0; r.len = v; r.pad = 0; reports[slot] = r; }
+                }
+            }
+            if (have) ++size;
+        }
     }
 }
 
@@ -111,45 +319,79 @@ __global__ void report_gather(const Report* __restrict__ rep, const u32* __restr
     if (i < n) out[i] = rep[idx[i]];
 }
 
+struct DetectArgs {
+    const u32* lcp; const u8* bwt; const u8* text; u64 m; DetectParams prm; const u64* d_doc_start; Report* rep; u32 cap; u32* count; u16* thresh;
+    bool use_window; WindowPlan plan;
+};
+
 template <class SAT, int W, int P>
-void launch_detect(const u32* lcp, const SAT* sa, const u8* bwt, u64 m, const DetectParams& prm, const u64* d_doc_start, Report* rep, u32 cap,
-                   u32* count, u16* thresh, cudaStream_t s) {
-    auto k = detect_kernel<SAT, W, P>;
-    size_t smem = (size_t)(prm.ndocs + 1) * sizeof(u64);
-    MMB_LAUNCH(k, ceil_div(m - 1, TPB), TPB, smem, s, lcp, sa, bwt, m, prm, d_doc_start, rep, cap, count, thresh);
+void launch_detect(const SAT* sa, const DetectArgs& a, cudaStream_t s) {
+    if (a.use_window) {
+        auto k = detect_window_kernel<SAT, W, P>;
+        size_t smem = 16 + (size_t)((a.prm.ndocs + 2) & ~1u) * 8 + (size_t)a.plan.span * 4 * (2 + a.plan.nkept);
+#ifndef MMB_SIMT
+        if (smem > 48 * 1024) MMB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+        MMB_LAUNCH(k, ceil_div(a.m, DW_TILE), DW_TPB, smem, s, a.lcp, sa, a.bwt, a.text, a.m, a.prm, a.plan, a.d_doc_start, a.rep, a.cap, a.count, a.thresh);
+    } else {
+        auto k = detect_walk_kernel<SAT, W, P>;
+        size_t smem = (size_t)(a.prm.ndocs + 1) * sizeof(u64);
+        MMB_LAUNCH(k, ceil_div(a.m - 1, TPB), TPB, smem, s, a.lcp, sa, a.bwt, a.text, a.m, a.prm, a.d_doc_start, a.rep, a.cap, a.count, a.thresh);
+    }
 }
 
 template <class SAT, int W>
-void dispatch_planes(const u32* lcp, const SAT* sa, const u8* bwt, u64 m, const DetectParams& prm, const u64* d_doc_start, Report* rep, u32 cap,
-                     u32* count, u16* thresh, cudaStream_t s) {
-    u32 f = prm.max_doc_freq;
-    if (f <= 1) launch_detect<SAT, W, 1>(lcp, sa, bwt, m, prm, d_doc_start, rep, cap, count, thresh, s);
-    else if (f <= 3) launch_detect<SAT, W, 2>(lcp, sa, bwt, m, prm, d_doc_start, rep, cap, count, thresh, s);
-    else if (f <= 255) launch_detect<SAT, W, 8>(lcp, sa, bwt, m, prm, d_doc_start, rep, cap, count, thresh, s);
+void dispatch_planes(const SAT* sa, const DetectArgs& a, cudaStream_t s) {
+    u32 f = a.prm.max_doc_freq;
+    if (f <= 1) launch_detect<SAT, W, 1>(sa, a, s);
+    else if (f <= 3) launch_detect<SAT, W, 2>(sa, a, s);
+    else if (f <= 255) launch_detect<SAT, W, 8>(sa, a, s);
     else throw Error(30, "per-sequence frequency limits above 255 are not supported");
+}
+
+u32 floor_log2(u32 x) { u32 t = 0; while ((2u << t) <= x) ++t; return t; }
+
+// Which interval sizes can qualify, and whether the windowed kernel covers them.  Returns false if nothing can qualify at all.
+bool make_plan(const DetectParams& prm, bool& use_window, WindowPlan& pl) {
+    u64 hi = prm.max_freq;
+    if (prm.max_doc_freq) { u64 bound = (u64)prm.max_doc_freq * prm.ndocs; hi = hi ? std::min(hi, bound) : bound; }
+    u64 lo = std::max<u64>(2, prm.num_distinct);
+    if (hi < lo) return false;
+    use_window = false;
+    if (hi - lo + 1 > DW_MAX_SIZES) return true;
+    pl.size_lo = (u32)lo; pl.size_hi = (u32)hi;
+    pl.halo = ((u32)hi + 3) & ~3u; pl.span = pl.halo + DW_TILE;
+    if (pl.span > DW_TPB * 6) return true;
+    pl.lev_lo = floor_log2(pl.size_lo - 1); pl.lev_hi = floor_log2(pl.size_hi - 1);
+    pl.nkept = pl.lev_hi >= 1 ? pl.lev_hi - std::max(pl.lev_lo, 1u) + 1 : 0;
+    use_window = !getenv("MMB_FORCE_WALK");
+    return true;
 }
 
 }  // namespace
 
 template <class SAT>
-void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, u64 m, const DetectParams& prm, const u64* d_doc_start, u16* thresh,
-                      Reports& out, cudaStream_t s) {
+void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, const u8* text, u64 m, const DetectParams& prm, const u64* d_doc_start,
+                      u16* thresh, Reports& out, cudaStream_t s) {
     // the leftward walk is bounded by max_freq, or else by max_doc_freq * ndocs (a document overflows); with neither it is unbounded
     if (prm.max_freq == 0 && prm.max_doc_freq == 0)
         throw Error(31, "unbounded total frequency (-f 0 with -F 0) is not supported by the windowed interval scan");
     if (prm.max_freq >= (1u << 20)) throw Error(32, "maximum total frequency must be below 2^20");
     if (prm.ndocs > 1024) throw Error(33, "more than 1024 input sequences are not supported");
     out.count = 0;
-    if (m < 2) { out.rep.alloc(0, s); return; }
+    DetectArgs a;
+    a.lcp = lcp; a.bwt = bwt; a.text = text; a.m = m; a.prm = prm; a.d_doc_start = d_doc_start; a.thresh = thresh;
+    if (m < 2 || !make_plan(prm, a.use_window, a.plan)) { out.rep.alloc(0, s); return; }
     DevBuf<u32> d_count; d_count.alloc(1, s);
     u64 cap = std::max<u64>(1u << 16, m / 64);
     DevBuf<Report> raw;
     for (;;) {
         if (cap > 0xfffffff0ull) throw Error(34, "too many matches for one pass");
         raw.alloc(cap, s); d_count.zero();
-        if (prm.ndocs <= 64) dispatch_planes<SAT, 1>(lcp, sa, bwt, m, prm, d_doc_start, raw.p, (u32)cap, d_count.p, thresh, s);
-        else if (prm.ndocs <= 256) dispatch_planes<SAT, 4>(lcp, sa, bwt, m, prm, d_doc_start, raw.p, (u32)cap, d_count.p, thresh, s);
-        else dispatch_planes<SAT, 16>(lcp, sa, bwt, m, prm, d_doc_start, raw.p, (u32)cap, d_count.p, thresh, s);
+        a.rep = raw.p; a.cap = (u32)cap; a.count = d_count.p;
+        if (prm.ndocs <= 64) dispatch_planes<SAT, 1>(sa, a, s);
+        else if (prm.ndocs <= 256) dispatch_planes<SAT, 4>(sa, a, s);
+        else dispatch_planes<SAT, 16>(sa, a, s);
         u32 got = to_host(d_count.p, 1, s)[0];
         if (got <= cap) { out.count = got; break; }
         cap = (u64)got + 1024;          // the counter kept counting past the capacity: one retry with the exact size
@@ -164,7 +406,7 @@ void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, u64 m, const
     MMB_LAUNCH(report_gather, ceil_div(n, 256), 256, 0, s, raw.p, ib.p, n, out.rep.p);
 }
 
-template void detect_intervals<u32>(const u32*, const u32*, const u8*, u64, const DetectParams&, const u64*, u16*, Reports&, cudaStream_t);
-template void detect_intervals<u64>(const u32*, const u64*, const u8*, u64, const DetectParams&, const u64*, u16*, Reports&, cudaStream_t);
+template void detect_intervals<u32>(const u32*, const u32*, const u8*, const u8*, u64, const DetectParams&, const u64*, u16*, Reports&, cudaStream_t);
+template void detect_intervals<u64>(const u32*, const u64*, const u8*, const u8*, u64, const DetectParams&, const u64*, u16*, Reports&, cudaStream_t);
 
 }  // namespace mmb

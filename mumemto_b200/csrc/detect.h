@@ -28,10 +28,11 @@ struct Reports {
     u64 count = 0;
 };
 
-// thresh: 2*(L_0+1) zero-initialised uint16 (only when prm.merge), else nullptr.
+// thresh: 2*(L_0+1) zero-initialised uint16 (only when prm.merge), else nullptr.  bwt may be nullptr: the preceding symbol is then
+// read from text[sa - 1] for the few ranks that need it.  lcp must be readable (zero) for 64 entries past m.
 template <class SAT>
-void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, u64 m, const DetectParams& prm, const u64* d_doc_start, u16* thresh,
-                      Reports& out, cudaStream_t s);
+void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, const u8* text, u64 m, const DetectParams& prm, const u64* d_doc_start,
+                      u16* thresh, Reports& out, cudaStream_t s);
 
 struct MumTable {           // strict / partial multi-MUMs that survive the strand rules, in output order
     u64 count = 0;

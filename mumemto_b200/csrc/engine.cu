@@ -277,7 +277,8 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
         build_suffix_array(e->text.text.p, e->text.n, e->sa, s);
         e->stats.ms_sa = t.stop();
         t.start();
-        build_lcp_bwt(e->text.text.p, e->text.n, e->sa, e->lcp, e->bwt, s);
+        build_lcp(e->text.text.p, e->text.n, e->sa, e->lcp, s);
+        e->bwt.release();
         e->stats.ms_lcp = t.stop();
         e->sa.isa.release();
 
@@ -287,7 +288,7 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
             e->thresh_count = 2 * (e->text.h_doc_len[0] + 1);       // candidate_thresh.resize(doc_lens[0] * 2), include/mem_finder.hpp:79-81
             e->thresh.alloc(e->thresh_count, s); e->thresh.zero();
         }
-        detect_intervals<u32>(e->lcp.p, e->sa.sa.p, e->bwt.p, e->sa.m, e->prm, e->text.doc_start.p, merge ? e->thresh.p : nullptr, e->reports, s);
+        detect_intervals<u32>(e->lcp.p, e->sa.sa.p, (const u8*)nullptr, e->text.text.p, e->sa.m, e->prm, e->text.doc_start.p, merge ? e->thresh.p : nullptr, e->reports, s);
         MMB_CUDA(cudaStreamSynchronize(s));
         e->stats.ms_detect = t.stop();
 
@@ -403,7 +404,7 @@ int mmb_copy_arrays(mmb_engine* e, uint64_t* sa, uint64_t* lcp, uint8_t* bwt) {
         DevBuf<u64> wide; wide.alloc(m, s);
         if (sa) { MMB_LAUNCH(widen_u32, ceil_div(m, 256), 256, 0, s, e->sa.sa.p, m, wide.p); copy_out(wide.p, sa, m, s); MMB_CUDA(cudaStreamSynchronize(s)); }
         if (lcp) { MMB_LAUNCH(widen_u32, ceil_div(m, 256), 256, 0, s, e->lcp.p, m, wide.p); copy_out(wide.p, lcp, m, s); MMB_CUDA(cudaStreamSynchronize(s)); }
-        copy_out(e->bwt.p, bwt, m, s);
+        if (bwt) { if (!e->bwt.p) build_bwt(e->text.text.p, e->sa, e->bwt, s); copy_out(e->bwt.p, bwt, m, s); }
         MMB_CUDA(cudaStreamSynchronize(s));
     });
 }

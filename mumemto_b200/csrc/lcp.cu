@@ -1,4 +1,4 @@
-// mumemto_b200/csrc/lcp.cu -- LCP array and BWT from (text, SA, ISA).
+// mumemto_b200/csrc/lcp.cu -- LCP array from (text, SA, ISA); BWT from (text, SA) when the arrays are dumped (-A).
 //
 // The reference obtains LCP from gsacak (include/direct_gsacak.hpp:62) or, on the PFP path, from lcpD / s_lcp_T range minima
 // (include/pfp_lcp_mum.hpp:145,179,284-321); both equal the plain LCP of adjacent suffixes of T with '$' as an ordinary symbol.
@@ -61,12 +61,17 @@ __global__ void __launch_bounds__(256) gather_bwt(const u8* __restrict__ text, c
 
 }  // namespace
 
-void build_lcp_bwt(const u8* text, u64 n, const SuffixArray& sa, DevBuf<u32>& lcp, DevBuf<u8>& bwt, cudaStream_t s) {
+void build_lcp(const u8* text, u64 n, const SuffixArray& sa, DevBuf<u32>& lcp, cudaStream_t s) {
     u32 m = sa.m;
-    lcp.alloc(m, s); bwt.alloc(m, s);
+    lcp.alloc((u64)m + 64, s);                       // 64 zero entries of slack: tile loads of the detector round up to 16 bytes
+    MMB_CUDA(cudaMemsetAsync(lcp.p + m, 0, 64 * sizeof(u32), s));
     u64 threads = ((u64)m + CHUNK - 1) / CHUNK;
     MMB_LAUNCH(plcp_chunks, ceil_div(threads, TPB), TPB, 0, s, text, n, sa.sa.p, sa.isa.p, m, lcp.p);
-    MMB_LAUNCH(gather_bwt, ceil_div(m, 256), 256, 0, s, text, sa.sa.p, m, bwt.p);
+}
+
+void build_bwt(const u8* text, const SuffixArray& sa, DevBuf<u8>& bwt, cudaStream_t s) {
+    bwt.alloc(sa.m, s);
+    MMB_LAUNCH(gather_bwt, ceil_div(sa.m, 256), 256, 0, s, text, sa.sa.p, sa.m, bwt.p);
 }
 
 }  // namespace mmb

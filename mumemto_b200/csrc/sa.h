@@ -36,7 +36,9 @@ void order_by_initial_keys(u64* keys_in, u64* keys_tmp, u32* vals_in, u32 m, int
                            GroupStore& groups, cudaStream_t s);
 void refine_by_doubling(u32* sa, u32* isa, u32 m, u32 h0, const u32* limit, GroupStore& groups, SaStats& st, cudaStream_t s);
 
-// lcp[r] = longest common prefix of suffixes sa[r-1] and sa[r] (lcp[0] = 0); bwt[r] = text[sa[r]-1] (0 when sa[r] = 0).
-void build_lcp_bwt(const u8* text, u64 n, const SuffixArray& sa, DevBuf<u32>& lcp, DevBuf<u8>& bwt, cudaStream_t s);
+// lcp[r] = longest common prefix of suffixes sa[r-1] and sa[r] (lcp[0] = 0), followed by 64 zero entries.
+void build_lcp(const u8* text, u64 n, const SuffixArray& sa, DevBuf<u32>& lcp, cudaStream_t s);
+// bwt[r] = text[sa[r]-1] (0 when sa[r] = 0)
+void build_bwt(const u8* text, const SuffixArray& sa, DevBuf<u8>& bwt, cudaStream_t s);
 
 }  // namespace mmb

@@ -162,3 +162,10 @@ def test_simt_repeats_all_group_size_classes(simt_lib, oracle_bin, tmp_path, blo
             both(simt_lib, oracle_bin, str(tmp_path), p, flags)
     finally:
         simt_lib.simt_set_block_order(0)
+
+
+@pytest.mark.parametrize("flags", [[], ["-f", "3", "-k", "2"], ["-M", "-n"]])
+def test_simt_walk_kernel_fallback(simt_lib, oracle_bin, small, tmp_path, flags, monkeypatch):
+    """The leftward-walk detector (used when more than 64 interval sizes can qualify) must agree with the windowed one."""
+    monkeypatch.setenv("MMB_FORCE_WALK", "1")
+    both(simt_lib, oracle_bin, str(tmp_path), small, flags)
