@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("MMB_WORKLOAD", "c1"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--route", default=os.environ.get("MMB_ROUTE", "auto"), choices=["auto", "direct", "pfp"])
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     spec = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -231,7 +233,7 @@ def main():
     dev = host.cuda(non_blocking=False)
     pinned_imgs = [hv[o:o + s] for o, s in zip(offsets, sizes)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
-    opts = dict(merge=multi, anchor_merge=multi)
+    opts = dict(merge=multi, anchor_merge=multi, route=args.route)
 
     def step_device():
         eng.load_fasta_device(dev.data_ptr(), offsets, sizes)
@@ -282,19 +284,19 @@ def main():
     value = total_bases / (ms_max * 1e-3)
 
     # ---- end to end through the host-buffer call
-    for _ in range(2):
+    for _ in range(0 if args.no_e2e else 2):
         step_e2e()
     barrier()
     t0 = time.perf_counter()
     out_bytes = 0
     e2e_stage = {k: 0.0 for k in stage}
-    for _ in range(args.steps):
+    for _ in range(1 if args.no_e2e else args.steps):
         out_bytes = step_e2e()
         s2 = eng.stats()
         for k in e2e_stage:
             e2e_stage[k] += s2[k] / args.steps
     barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
+    e2e_s = (time.perf_counter() - t0) / (1 if args.no_e2e else args.steps)
     te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -326,7 +328,8 @@ def main():
                              "frac": achieved / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
                 "stages_ms": {k: v / args.steps for k, v in stage.items()}, "step_ms": step_ms, "e2e_stages_ms": e2e_stage,
                 "matches": int(st["num_matches"]), "sa_rounds": int(st["sa_rounds"]), "sa_sorted_elements": int(st["sa_sorted_elements"]),
-                "text_symbols": int(st["text_symbols"]), "wall_s_timed_region": t_wall, "clocks": sampler.summary()}
+                "text_symbols": int(st["text_symbols"]), "wall_s_timed_region": t_wall, "clocks": sampler.summary(),
+                "route": int(st["route"]), "pfp": {k: int(st[k]) for k in ("pfp_phrases", "pfp_distinct_phrases", "pfp_dict_bytes", "pfp_tiles")}}
         if merge_info:
             line["partition_merge"] = merge_info
         if world == 1 and not args.no_cpu_baseline:

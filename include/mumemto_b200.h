@@ -52,6 +52,10 @@ typedef struct mmb_options {
     uint8_t anchor_merge;        /* -n */
     uint8_t cli_normalise;       /* 1: apply BuildOptions::validate/set_parameters; 0: library rules (mumemto_api.cpp:332-411) */
     uint8_t want_text;           /* 1: also format the .mums/.mems bytes on the device */
+    uint8_t route;               /* 0 auto; 1 direct suffix sorting of the text (|T| < 2^31); 2 prefix-free parse (dictionary + parse), any |T| < 2^40 */
+    uint8_t keep_arrays;         /* 1: keep SA/LCP of the whole stream for mmb_copy_arrays even on the tiled (route 2) path */
+    uint8_t reserved[6];
+    uint64_t tile_ranks;         /* route 2: ranks per stream tile, 0 = default (2^26) */
 } mmb_options;
 
 typedef struct mmb_stats {
@@ -62,6 +66,8 @@ typedef struct mmb_stats {
     uint32_t sa_rounds;
     uint64_t sa_sorted_elements;
     float ms_text, ms_sa, ms_lcp, ms_detect, ms_emit, ms_total;   /* CUDA-event times of the last mmb_find (ms_text: last load) */
+    uint32_t route;              /* route taken by the last mmb_find (1 direct, 2 prefix-free parse) */
+    uint32_t pfp_phrases, pfp_distinct_phrases, pfp_dict_bytes, pfp_tiles;
 } mmb_stats;
 
 MMB_API const char* mmb_last_error(void);

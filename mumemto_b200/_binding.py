@@ -18,14 +18,16 @@ u8p = C.POINTER(C.c_uint8)
 
 class Options(C.Structure):
     _fields_ = [("min_match_len", C.c_uint32), ("num_distinct_docs", C.c_int32), ("rare_freq", C.c_int32), ("max_mem_freq", C.c_int32),
-                ("merge", C.c_uint8), ("anchor_merge", C.c_uint8), ("cli_normalise", C.c_uint8), ("want_text", C.c_uint8)]
+                ("merge", C.c_uint8), ("anchor_merge", C.c_uint8), ("cli_normalise", C.c_uint8), ("want_text", C.c_uint8),
+                ("route", C.c_uint8), ("keep_arrays", C.c_uint8), ("reserved", C.c_uint8 * 6), ("tile_ranks", C.c_uint64)]
 
 
 class Stats(C.Structure):
     _fields_ = [("text_symbols", C.c_uint64), ("input_bases", C.c_uint64), ("num_matches", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("sa_rounds", C.c_uint32), ("sa_sorted_elements", C.c_uint64),
                 ("ms_text", C.c_float), ("ms_sa", C.c_float), ("ms_lcp", C.c_float), ("ms_detect", C.c_float), ("ms_emit", C.c_float),
-                ("ms_total", C.c_float)]
+                ("ms_total", C.c_float), ("route", C.c_uint32), ("pfp_phrases", C.c_uint32), ("pfp_distinct_phrases", C.c_uint32),
+                ("pfp_dict_bytes", C.c_uint32), ("pfp_tiles", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -157,9 +159,12 @@ class Engine:
         self._check(self.lib.mmb_load_records(self.h, recs, counts, len(docs), int(revcomp)))
 
     # ------------------------------------------------------------------ hot path
+    ROUTES = {"auto": 0, "direct": 1, "pfp": 2}
+
     def find(self, min_match_len=20, num_distinct_docs=0, rare_freq=1, max_mem_freq=0, merge=False, anchor_merge=False, cli_normalise=True,
-             want_text=True):
-        o = Options(min_match_len, num_distinct_docs, rare_freq, max_mem_freq, int(merge), int(anchor_merge), int(cli_normalise), int(want_text))
+             want_text=True, route="auto", keep_arrays=False, tile_ranks=0):
+        o = Options(min_match_len, num_distinct_docs, rare_freq, max_mem_freq, int(merge), int(anchor_merge), int(cli_normalise), int(want_text),
+                    self.ROUTES[route], int(keep_arrays), (C.c_uint8 * 6)(), int(tile_ranks))
         self._check(self.lib.mmb_find(self.h, C.byref(o)))
         return self.stats()
 

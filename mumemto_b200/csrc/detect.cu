@@ -75,13 +75,13 @@ __device__ __forceinline__ u8 bwt_at(const u8* __restrict__ bwt, const u8* __res
 
 template <class SAT, int W, int P>
 __global__ void __launch_bounds__(TPB) detect_walk_kernel(const u32* __restrict__ lcp, const SAT* __restrict__ sa, const u8* __restrict__ bwt,
-                                                          const u8* __restrict__ text, u64 m, DetectParams prm, const u64* __restrict__ doc_start_g, Report* __restrict__ reports, u32 cap,
+                                                          const u8* __restrict__ text, u64 m, u64 j_first, DetectParams prm, const u64* __restrict__ doc_start_g, Report* __restrict__ reports, u32 cap,
                                                      u32* __restrict__ count, u16* __restrict__ thresh) {
     MMB_DYN_SMEM(u64, doc_start);
     for (u32 i = threadIdx.x; i <= prm.ndocs; i += blockDim.x) doc_start[i] = doc_start_g[i];
     __syncthreads();
     u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (j >= m) return;
+    if (j >= m || j < j_first) return;
     u32 cur = lcp[j], v = lcp[j - 1];
     if (v <= cur || v < prm.min_len) return;
 
@@ -163,7 +163,7 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const void* src, u32 by
 
 template <class SAT, int W, int P>
 __global__ void __launch_bounds__(DW_TPB) detect_window_kernel(const u32* __restrict__ lcp, const SAT* __restrict__ sa, const u8* __restrict__ bwt,
-                                                              const u8* __restrict__ text, u64 m, DetectParams prm, WindowPlan plan,
+                                                              const u8* __restrict__ text, u64 m, u64 j_first, DetectParams prm, WindowPlan plan,
                                                               const u64* __restrict__ doc_start_g, Report* __restrict__ reports, u32 cap,
                                                               u32* __restrict__ count, u16* __restrict__ thresh) {
     MMB_DYN_SMEM(u64, smem64);
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(DW_TPB) detect_window_kernel(const u32* __rest
     for (u32 q = 0; q < DW_JPT; ++q) {
         u32 idx = halo + q * DW_TPB + threadIdx.x;          // position of rank j in lc
         u64 j = tile0 + q * DW_TPB + threadIdx.x;
-        bool active = j >= 1 && j < m;
+        bool active = j >= j_first && j >= 1 && j < m;
         u32 cur = lc[idx];
         u32 size = plan.size_lo;
         if (active) {                                       // the smallest window has the largest minimum: cheap rejection
@@ -320,7 +320,7 @@ __global__ void report_gather(const Report* __restrict__ rep, const u32* __restr
 }
 
 struct DetectArgs {
-    const u32* lcp; const u8* bwt; const u8* text; u64 m; DetectParams prm; const u64* d_doc_start; Report* rep; u32 cap; u32* count; u16* thresh;
+    const u32* lcp; const u8* bwt; const u8* text; u64 m; u64 j_first; DetectParams prm; const u64* d_doc_start; Report* rep; u32 cap; u32* count; u16* thresh;
     bool use_window; WindowPlan plan;
 };
 
@@ -332,11 +332,11 @@ void launch_detect(const SAT* sa, const DetectArgs& a, cudaStream_t s) {
 #ifndef MMB_SIMT
         if (smem > 48 * 1024) MMB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
-        MMB_LAUNCH(k, ceil_div(a.m, DW_TILE), DW_TPB, smem, s, a.lcp, sa, a.bwt, a.text, a.m, a.prm, a.plan, a.d_doc_start, a.rep, a.cap, a.count, a.thresh);
+        MMB_LAUNCH(k, ceil_div(a.m, DW_TILE), DW_TPB, smem, s, a.lcp, sa, a.bwt, a.text, a.m, a.j_first, a.prm, a.plan, a.d_doc_start, a.rep, a.cap, a.count, a.thresh);
     } else {
         auto k = detect_walk_kernel<SAT, W, P>;
         size_t smem = (size_t)(a.prm.ndocs + 1) * sizeof(u64);
-        MMB_LAUNCH(k, ceil_div(a.m - 1, TPB), TPB, smem, s, a.lcp, sa, a.bwt, a.text, a.m, a.prm, a.d_doc_start, a.rep, a.cap, a.count, a.thresh);
+        MMB_LAUNCH(k, ceil_div(a.m - 1, TPB), TPB, smem, s, a.lcp, sa, a.bwt, a.text, a.m, a.j_first, a.prm, a.d_doc_start, a.rep, a.cap, a.count, a.thresh);
     }
 }
 
@@ -371,8 +371,8 @@ bool make_plan(const DetectParams& prm, bool& use_window, WindowPlan& pl) {
 }  // namespace
 
 template <class SAT>
-void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, const u8* text, u64 m, const DetectParams& prm, const u64* d_doc_start,
-                      u16* thresh, Reports& out, cudaStream_t s) {
+void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, const u8* text, u64 m, u64 j_first, const DetectParams& prm,
+                      const u64* d_doc_start, u16* thresh, Reports& out, cudaStream_t s) {
     // the leftward walk is bounded by max_freq, or else by max_doc_freq * ndocs (a document overflows); with neither it is unbounded
     if (prm.max_freq == 0 && prm.max_doc_freq == 0)
         throw Error(31, "unbounded total frequency (-f 0 with -F 0) is not supported by the windowed interval scan");
@@ -380,10 +380,10 @@ void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, const u8* te
     if (prm.ndocs > 1024) throw Error(33, "more than 1024 input sequences are not supported");
     out.count = 0;
     DetectArgs a;
-    a.lcp = lcp; a.bwt = bwt; a.text = text; a.m = m; a.prm = prm; a.d_doc_start = d_doc_start; a.thresh = thresh;
+    a.lcp = lcp; a.bwt = bwt; a.text = text; a.m = m; a.j_first = j_first; a.prm = prm; a.d_doc_start = d_doc_start; a.thresh = thresh;
     if (m < 2 || !make_plan(prm, a.use_window, a.plan)) { out.rep.alloc(0, s); return; }
     DevBuf<u32> d_count; d_count.alloc(1, s);
-    u64 cap = std::max<u64>(1u << 16, m / 64);
+    u64 cap = std::max<u64>(1u << 16, (m - std::min(m, j_first)) / 64);
     DevBuf<Report> raw;
     for (;;) {
         if (cap > 0xfffffff0ull) throw Error(34, "too many matches for one pass");
@@ -406,7 +406,7 @@ void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, const u8* te
     MMB_LAUNCH(report_gather, ceil_div(n, 256), 256, 0, s, raw.p, ib.p, n, out.rep.p);
 }
 
-template void detect_intervals<u32>(const u32*, const u32*, const u8*, const u8*, u64, const DetectParams&, const u64*, u16*, Reports&, cudaStream_t);
-template void detect_intervals<u64>(const u32*, const u64*, const u8*, const u8*, u64, const DetectParams&, const u64*, u16*, Reports&, cudaStream_t);
+template void detect_intervals<u32>(const u32*, const u32*, const u8*, const u8*, u64, u64, const DetectParams&, const u64*, u16*, Reports&, cudaStream_t);
+template void detect_intervals<u64>(const u32*, const u64*, const u8*, const u8*, u64, u64, const DetectParams&, const u64*, u16*, Reports&, cudaStream_t);
 
 }  // namespace mmb

@@ -30,9 +30,11 @@ struct Reports {
 
 // thresh: 2*(L_0+1) zero-initialised uint16 (only when prm.merge), else nullptr.  bwt may be nullptr: the preceding symbol is then
 // read from text[sa - 1] for the few ranks that need it.  lcp must be readable (zero) for 64 entries past m.
+// The arrays are a view of the suffix stream (the whole stream, or one tile with a halo in front); only closing ranks j >= j_first
+// of the view are examined, and report keys / starts are view indices.
 template <class SAT>
-void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, const u8* text, u64 m, const DetectParams& prm, const u64* d_doc_start,
-                      u16* thresh, Reports& out, cudaStream_t s);
+void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, const u8* text, u64 m, u64 j_first, const DetectParams& prm,
+                      const u64* d_doc_start, u16* thresh, Reports& out, cudaStream_t s);
 
 struct MumTable {           // strict / partial multi-MUMs that survive the strand rules, in output order
     u64 count = 0;
@@ -61,6 +63,16 @@ void emit_mums(const Reports& rep, const SAT* sa, const DetectParams& prm, const
 template <class SAT>
 void emit_mems(const Reports& rep, const SAT* sa, const DetectParams& prm, const u64* d_doc_start, const u64* d_doc_len, bool want_text,
                MemTable& out, cudaStream_t s);
+
+// Rows only (mum_rows / mem_rows), text from rows (mum_text / mem_text), and concatenation of per-tile tables in stream order.
+template <class SAT>
+void mum_rows(const Reports& rep, const SAT* sa, const DetectParams& prm, const u64* d_doc_start, const u64* d_doc_len, MumTable& out, cudaStream_t s);
+void mum_text(MumTable& t, u32 ndocs, cudaStream_t s);
+template <class SAT>
+void mem_rows(const Reports& rep, const SAT* sa, const DetectParams& prm, const u64* d_doc_start, const u64* d_doc_len, MemTable& out, cudaStream_t s);
+void mem_text(MemTable& t, cudaStream_t s);
+void concat_mums(std::vector<MumTable>& parts, u32 ndocs, MumTable& out, cudaStream_t s);
+void concat_mems(std::vector<MemTable>& parts, MemTable& out, cudaStream_t s);
 
 // .bumbl strand bits: MSB-first, '+' = 1, bit index = row * ndocs + doc.
 void pack_strands(const u8* strand, u64 nbits, DevBuf<u8>& packed, cudaStream_t s);

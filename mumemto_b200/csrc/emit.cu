@@ -75,7 +75,7 @@ __global__ void compact_reports(const Report* __restrict__ rep, const u32* __res
 }
 
 template <class SAT>
-__global__ void __launch_bounds__(TPB) mum_rows(const Report* __restrict__ rep, u32 n, const SAT* __restrict__ sa, const u64* __restrict__ doc_start,
+__global__ void __launch_bounds__(TPB) mum_rows_kernel(const Report* __restrict__ rep, u32 n, const SAT* __restrict__ sa, const u64* __restrict__ doc_start,
                                                 const u64* __restrict__ doc_len, u32 ndocs, int revcomp, u32* __restrict__ len_out,
                                                 i64* __restrict__ off, u8* __restrict__ strand) {
     u32 lane = threadIdx.x & 31, r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -129,7 +129,7 @@ __global__ void mem_sizes(const Report* __restrict__ rep, u32 n, u64* __restrict
 }
 
 template <class SAT>
-__global__ void __launch_bounds__(TPB) mem_rows(const Report* __restrict__ rep, u32 n, const SAT* __restrict__ sa, const u64* __restrict__ doc_start,
+__global__ void __launch_bounds__(TPB) mem_rows_kernel(const Report* __restrict__ rep, u32 n, const SAT* __restrict__ sa, const u64* __restrict__ doc_start,
                                                 const u64* __restrict__ doc_len, u32 ndocs, int revcomp, const u64* __restrict__ first,
                                                 u32* __restrict__ len_out, u64* __restrict__ off, u32* __restrict__ doc, u8* __restrict__ strand) {
     u32 lane = threadIdx.x & 31, r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -184,16 +184,20 @@ __global__ void pack_strand_bits(const u8* __restrict__ strand, u64 nbits, u8* _
     packed[byte] = (u8)v;
 }
 
+__global__ void rebase_first(const u64* __restrict__ in, u64 n, u64 add, u64* __restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] + add;
+}
+
 u32 warps_grid(u32 n) { return ceil_div((u64)n * 32, TPB); }
 
 }  // namespace
 
 template <class SAT>
-void emit_mums(const Reports& rep, const SAT* sa, const DetectParams& prm, const u64* d_doc_start, const u64* d_doc_len, bool want_text,
-               MumTable& out, cudaStream_t s) {
+void mum_rows(const Reports& rep, const SAT* sa, const DetectParams& prm, const u64* d_doc_start, const u64* d_doc_len, MumTable& out, cudaStream_t s) {
     u32 n = (u32)rep.count, N = prm.ndocs;
-    out.count = 0; out.text_bytes = 0;
-    if (n == 0) { out.len.alloc(0, s); out.off.alloc(0, s); out.strand.alloc(0, s); out.text.alloc(0, s); return; }
+    out.count = 0; out.text_bytes = 0; out.text.alloc(0, s);
+    if (n == 0) { out.len.alloc(0, s); out.off.alloc(0, s); out.strand.alloc(0, s); return; }
     DevBuf<u32> valid, idx; valid.alloc(n, s); idx.alloc(n, s);
     auto kv = mum_validate<SAT>;
     MMB_LAUNCH(kv, warps_grid(n), TPB, 0, s, rep.rep.p, n, sa, d_doc_start, d_doc_len, N, prm.revcomp, valid.p);
@@ -205,14 +209,19 @@ void emit_mums(const Reports& rep, const SAT* sa, const DetectParams& prm, const
     u32 nv = tail[0] + tail[1];
     out.count = nv;
     out.len.alloc(nv, s); out.off.alloc((u64)nv * N, s); out.strand.alloc((u64)nv * N, s);
-    if (nv == 0) { out.text.alloc(0, s); return; }
+    if (nv == 0) return;
     DevBuf<Report> kept; kept.alloc(nv, s);
     MMB_LAUNCH(compact_reports, ceil_div(n, 256), 256, 0, s, rep.rep.p, valid.p, idx.p, n, kept.p);
     MMB_CUDA(cudaMemsetAsync(out.off.p, 0xff, out.off.bytes(), s));
     MMB_CUDA(cudaMemsetAsync(out.strand.p, 0, out.strand.bytes(), s));
-    auto kr = mum_rows<SAT>;
+    auto kr = mum_rows_kernel<SAT>;
     MMB_LAUNCH(kr, warps_grid(nv), TPB, 0, s, kept.p, nv, sa, d_doc_start, d_doc_len, N, prm.revcomp, out.len.p, out.off.p, out.strand.p);
-    if (!want_text) { out.text.alloc(0, s); return; }
+}
+
+void mum_text(MumTable& out, u32 N, cudaStream_t s) {
+    u32 nv = (u32)out.count;
+    out.text_bytes = 0;
+    if (nv == 0) { out.text.alloc(0, s); return; }
     DevBuf<u32> ll; DevBuf<u64> lo; ll.alloc(nv + 1, s); lo.alloc(nv + 1, s);
     MMB_CUDA(cudaMemsetAsync(ll.p + nv, 0, 4, s));
     auto k1 = mum_lines<false>; auto k2 = mum_lines<true>;
@@ -224,21 +233,32 @@ void emit_mums(const Reports& rep, const SAT* sa, const DetectParams& prm, const
 }
 
 template <class SAT>
-void emit_mems(const Reports& rep, const SAT* sa, const DetectParams& prm, const u64* d_doc_start, const u64* d_doc_len, bool want_text,
-               MemTable& out, cudaStream_t s) {
+void emit_mums(const Reports& rep, const SAT* sa, const DetectParams& prm, const u64* d_doc_start, const u64* d_doc_len, bool want_text,
+               MumTable& out, cudaStream_t s) {
+    mum_rows<SAT>(rep, sa, prm, d_doc_start, d_doc_len, out, s);
+    if (want_text) mum_text(out, prm.ndocs, s);
+}
+
+template <class SAT>
+void mem_rows(const Reports& rep, const SAT* sa, const DetectParams& prm, const u64* d_doc_start, const u64* d_doc_len, MemTable& out, cudaStream_t s) {
     u32 n = (u32)rep.count, N = prm.ndocs;
-    out.count = n; out.total_occ = 0; out.text_bytes = 0;
-    out.len.alloc(n, s); out.first.alloc(n + 1, s);
-    if (n == 0) { out.off.alloc(0, s); out.doc.alloc(0, s); out.strand.alloc(0, s); out.text.alloc(0, s); return; }
-    DevBuf<u64> occ; occ.alloc(n + 1, s);
+    out.count = n; out.total_occ = 0; out.text_bytes = 0; out.text.alloc(0, s);
+    out.len.alloc(n, s); out.first.alloc((u64)n + 1, s);
+    if (n == 0) { MMB_CUDA(cudaMemsetAsync(out.first.p, 0, 8, s)); out.off.alloc(0, s); out.doc.alloc(0, s); out.strand.alloc(0, s); return; }
+    DevBuf<u64> occ; occ.alloc((u64)n + 1, s);
     MMB_LAUNCH(mem_sizes, ceil_div(n + 1, 256), 256, 0, s, rep.rep.p, n, occ.p);
-    prim::exclusive_sum(occ.p, out.first.p, n + 1, s);
+    prim::exclusive_sum(occ.p, out.first.p, (u64)n + 1, s);
     out.total_occ = to_host(out.first.p + n, 1, s)[0];
     out.off.alloc(out.total_occ, s); out.doc.alloc(out.total_occ, s); out.strand.alloc(out.total_occ, s);
-    auto kr = mem_rows<SAT>;
+    auto kr = mem_rows_kernel<SAT>;
     MMB_LAUNCH(kr, warps_grid(n), TPB, 0, s, rep.rep.p, n, sa, d_doc_start, d_doc_len, N, prm.revcomp, out.first.p, out.len.p, out.off.p, out.doc.p,
                out.strand.p);
-    if (!want_text) { out.text.alloc(0, s); return; }
+}
+
+void mem_text(MemTable& out, cudaStream_t s) {
+    u32 n = (u32)out.count;
+    out.text_bytes = 0;
+    if (n == 0) { out.text.alloc(0, s); return; }
     DevBuf<u32> ll; DevBuf<u64> lo; ll.alloc(n + 1, s); lo.alloc(n + 1, s);
     MMB_CUDA(cudaMemsetAsync(ll.p + n, 0, 4, s));
     auto k1 = mem_lines<false>; auto k2 = mem_lines<true>;
@@ -249,12 +269,65 @@ void emit_mems(const Reports& rep, const SAT* sa, const DetectParams& prm, const
     MMB_LAUNCH(k2, warps_grid(n), TPB, 0, s, out.len.p, out.first.p, out.off.p, out.doc.p, out.strand.p, n, ll.p, lo.p, out.text.p);
 }
 
+template <class SAT>
+void emit_mems(const Reports& rep, const SAT* sa, const DetectParams& prm, const u64* d_doc_start, const u64* d_doc_len, bool want_text,
+               MemTable& out, cudaStream_t s) {
+    mem_rows<SAT>(rep, sa, prm, d_doc_start, d_doc_len, out, s);
+    if (want_text) mem_text(out, s);
+}
+
+void concat_mums(std::vector<MumTable>& parts, u32 N, MumTable& out, cudaStream_t s) {
+    u64 total = 0;
+    for (auto& p : parts) total += p.count;
+    if (total > 0xfffffff0ull) throw Error(35, "too many matches");
+    out.count = total; out.text_bytes = 0; out.text.alloc(0, s);
+    out.len.alloc(total, s); out.off.alloc(total * N, s); out.strand.alloc(total * N, s);
+    u64 at = 0;
+    for (auto& p : parts) {
+        if (!p.count) continue;
+        MMB_CUDA(cudaMemcpyAsync(out.len.p + at, p.len.p, p.count * 4, cudaMemcpyDeviceToDevice, s));
+        MMB_CUDA(cudaMemcpyAsync(out.off.p + at * N, p.off.p, p.count * N * 8, cudaMemcpyDeviceToDevice, s));
+        MMB_CUDA(cudaMemcpyAsync(out.strand.p + at * N, p.strand.p, p.count * N, cudaMemcpyDeviceToDevice, s));
+        at += p.count;
+    }
+    MMB_CUDA(cudaStreamSynchronize(s));
+    parts.clear();
+}
+
+void concat_mems(std::vector<MemTable>& parts, MemTable& out, cudaStream_t s) {
+    u64 total = 0, occ = 0;
+    for (auto& p : parts) { total += p.count; occ += p.total_occ; }
+    if (total > 0xfffffff0ull) throw Error(35, "too many matches");
+    out.count = total; out.total_occ = occ; out.text_bytes = 0; out.text.alloc(0, s);
+    out.len.alloc(total, s); out.first.alloc(total + 1, s); out.off.alloc(occ, s); out.doc.alloc(occ, s); out.strand.alloc(occ, s);
+    u64 at = 0, oat = 0;
+    for (auto& p : parts) {
+        if (p.count) {
+            MMB_CUDA(cudaMemcpyAsync(out.len.p + at, p.len.p, p.count * 4, cudaMemcpyDeviceToDevice, s));
+            MMB_LAUNCH(rebase_first, ceil_div(p.count, 256), 256, 0, s, (const u64*)p.first.p, p.count, oat, out.first.p + at);
+            if (p.total_occ) {
+                MMB_CUDA(cudaMemcpyAsync(out.off.p + oat, p.off.p, p.total_occ * 8, cudaMemcpyDeviceToDevice, s));
+                MMB_CUDA(cudaMemcpyAsync(out.doc.p + oat, p.doc.p, p.total_occ * 4, cudaMemcpyDeviceToDevice, s));
+                MMB_CUDA(cudaMemcpyAsync(out.strand.p + oat, p.strand.p, p.total_occ, cudaMemcpyDeviceToDevice, s));
+            }
+        }
+        at += p.count; oat += p.total_occ;
+    }
+    MMB_CUDA(cudaMemcpyAsync(out.first.p + total, &occ, 8, cudaMemcpyHostToDevice, s));
+    MMB_CUDA(cudaStreamSynchronize(s));
+    parts.clear();
+}
+
 void pack_strands(const u8* strand, u64 nbits, DevBuf<u8>& packed, cudaStream_t s) {
     u64 bytes = (nbits + 7) / 8;
     packed.alloc(bytes, s);
     if (bytes) MMB_LAUNCH(pack_strand_bits, ceil_div(bytes, 256), 256, 0, s, strand, nbits, packed.p);
 }
 
+template void mum_rows<u32>(const Reports&, const u32*, const DetectParams&, const u64*, const u64*, MumTable&, cudaStream_t);
+template void mum_rows<u64>(const Reports&, const u64*, const DetectParams&, const u64*, const u64*, MumTable&, cudaStream_t);
+template void mem_rows<u32>(const Reports&, const u32*, const DetectParams&, const u64*, const u64*, MemTable&, cudaStream_t);
+template void mem_rows<u64>(const Reports&, const u64*, const DetectParams&, const u64*, const u64*, MemTable&, cudaStream_t);
 template void emit_mums<u32>(const Reports&, const u32*, const DetectParams&, const u64*, const u64*, bool, MumTable&, cudaStream_t);
 template void emit_mums<u64>(const Reports&, const u64*, const DetectParams&, const u64*, const u64*, bool, MumTable&, cudaStream_t);
 template void emit_mems<u32>(const Reports&, const u32*, const DetectParams&, const u64*, const u64*, bool, MemTable&, cudaStream_t);

@@ -8,6 +8,7 @@
 #include "../../include/mumemto_b200.h"
 #include "detect.h"
 #include "merge.h"
+#include "pfp.h"
 #include "sa.h"
 #include "text.h"
 
@@ -67,6 +68,10 @@ struct mmb_engine {
     bool mum_mode = true;
     DetectParams prm{};
     mmb_stats stats{};
+
+    DevBuf<u64> full_sa;                // route 2 with keep_arrays: the whole stream
+    DevBuf<u32> full_lcp;
+    u32 route = 1;
 
     MergePartition merged;              // result of the last mmb_anchor_merge
     DevBuf<u8> merged_text;
@@ -160,6 +165,10 @@ void copy_out(const T* d, T* h, u64 n, cudaStream_t s) {
 __global__ void widen_u32(const u32* __restrict__ in, u64 n, u64* __restrict__ out) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i];
+}
+__global__ void bwt_from_sa64(const u8* __restrict__ text, const u64* __restrict__ sa, u64 m, u8* __restrict__ bwt) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < m) { u64 p = sa[r]; bwt[r] = p ? text[p - 1] : (u8)0; }
 }
 __global__ void strands_to_flags(const u8* __restrict__ in, u64 n, u8* __restrict__ out) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -273,32 +282,80 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
 
         Timer total(s), t(s);
         total.start();
-        t.start();
-        build_suffix_array(e->text.text.p, e->text.n, e->sa, s);
-        e->stats.ms_sa = t.stop();
-        t.start();
-        build_lcp(e->text.text.p, e->text.n, e->sa, e->lcp, s);
-        e->bwt.release();
-        e->stats.ms_lcp = t.stop();
-        e->sa.isa.release();
-
-        t.start();
         e->thresh_count = 0; e->thresh.release();
         if (merge) {
             e->thresh_count = 2 * (e->text.h_doc_len[0] + 1);       // candidate_thresh.resize(doc_lens[0] * 2), include/mem_finder.hpp:79-81
             e->thresh.alloc(e->thresh_count, s); e->thresh.zero();
         }
-        detect_intervals<u32>(e->lcp.p, e->sa.sa.p, (const u8*)nullptr, e->text.text.p, e->sa.m, e->prm, e->text.doc_start.p, merge ? e->thresh.p : nullptr, e->reports, s);
-        MMB_CUDA(cudaStreamSynchronize(s));
-        e->stats.ms_detect = t.stop();
-
-        t.start();
-        if (e->mum_mode) emit_mums<u32>(e->reports, e->sa.sa.p, e->prm, e->text.doc_start.p, e->text.doc_len.p, opts->want_text != 0, e->mums, s);
-        else emit_mems<u32>(e->reports, e->sa.sa.p, e->prm, e->text.doc_start.p, e->text.doc_len.p, opts->want_text != 0, e->mems, s);
-        e->stats.ms_emit = t.stop();
+        u16* thresh = merge ? e->thresh.p : nullptr;
+        bool want_text = opts->want_text != 0;
+        u64 n = e->text.n;
+        bool use_pfp = opts->route == 2 || (opts->route == 0 && n + 1 >= (1ull << 31));
+        e->route = use_pfp ? 2 : 1;
+        e->full_sa.release(); e->full_lcp.release(); e->bwt.release();
+        e->stats.pfp_phrases = e->stats.pfp_distinct_phrases = e->stats.pfp_dict_bytes = e->stats.pfp_tiles = 0;
+        if (!use_pfp) {
+            t.start();
+            build_suffix_array(e->text.text.p, n, e->sa, s);
+            e->stats.ms_sa = t.stop();
+            t.start();
+            build_lcp(e->text.text.p, n, e->sa, e->lcp, s);
+            e->stats.ms_lcp = t.stop();
+            e->sa.isa.release();
+            t.start();
+            detect_intervals<u32>(e->lcp.p, e->sa.sa.p, (const u8*)nullptr, e->text.text.p, e->sa.m, 0, e->prm, e->text.doc_start.p, thresh, e->reports, s);
+            MMB_CUDA(cudaStreamSynchronize(s));
+            e->stats.ms_detect = t.stop();
+            t.start();
+            if (e->mum_mode) emit_mums<u32>(e->reports, e->sa.sa.p, e->prm, e->text.doc_start.p, e->text.doc_len.p, want_text, e->mums, s);
+            else emit_mems<u32>(e->reports, e->sa.sa.p, e->prm, e->text.doc_start.p, e->text.doc_len.p, want_text, e->mems, s);
+            e->stats.ms_emit = t.stop();
+            e->stats.sa_rounds = e->sa.stats.rounds; e->stats.sa_sorted_elements = e->sa.stats.groups_sorted;
+        } else {
+            e->sa.sa.release(); e->sa.isa.release(); e->lcp.release();
+            t.start();
+            PfpIndex ix;
+            build_pfp_index(e->text.text.p, n, ix, s);
+            e->stats.ms_sa = t.stop();
+            e->stats.ms_lcp = 0;
+            e->stats.pfp_phrases = ix.np; e->stats.pfp_distinct_phrases = ix.nd; e->stats.pfp_dict_bytes = ix.dsize;
+            e->stats.sa_rounds = ix.stats_d.rounds + ix.stats_p.rounds; e->stats.sa_sorted_elements = ix.stats_d.groups_sorted + ix.stats_p.groups_sorted;
+            // how far back an interval can reach: the detector's halo
+            u64 hi = e->prm.max_freq;
+            if (e->prm.max_doc_freq) { u64 bound = (u64)e->prm.max_doc_freq * N; hi = hi ? std::min(hi, bound) : bound; }
+            if (hi == 0) throw Error(31, "unbounded total frequency (-f 0 with -F 0) is not supported by the windowed interval scan");
+            u32 halo = (u32)std::min<u64>((hi + 8) & ~3ull, 1u << 22);
+            u64 tile_ranks = opts->tile_ranks ? opts->tile_ranks : (1ull << 26);
+            struct Consumer : TileConsumer {
+                mmb_engine* e; cudaStream_t s; u16* thresh; bool keep; std::vector<MumTable> mparts; std::vector<MemTable> eparts; u32 tiles = 0;
+                void consume(const StreamTile& tile) override {
+                    ++tiles;
+                    Reports rep;
+                    detect_intervals<u64>(tile.lcp, tile.sa, (const u8*)nullptr, e->text.text.p, tile.count, tile.first, e->prm, e->text.doc_start.p, thresh, rep, s);
+                    if (e->mum_mode) { MumTable part; mum_rows<u64>(rep, tile.sa, e->prm, e->text.doc_start.p, e->text.doc_len.p, part, s); mparts.push_back(std::move(part)); }
+                    else { MemTable part; mem_rows<u64>(rep, tile.sa, e->prm, e->text.doc_start.p, e->text.doc_len.p, part, s); eparts.push_back(std::move(part)); }
+                    if (keep) {
+                        u64 fresh = tile.count - tile.first, at = tile.rank0 + tile.first;
+                        MMB_CUDA(cudaMemcpyAsync(e->full_sa.p + at, tile.sa + tile.first, fresh * 8, cudaMemcpyDeviceToDevice, s));
+                        MMB_CUDA(cudaMemcpyAsync(e->full_lcp.p + at, tile.lcp + tile.first, fresh * 4, cudaMemcpyDeviceToDevice, s));
+                    }
+                    MMB_CUDA(cudaStreamSynchronize(s));
+                }
+            } consumer;
+            consumer.e = e; consumer.s = s; consumer.thresh = thresh; consumer.keep = opts->keep_arrays != 0;
+            if (consumer.keep) { e->full_sa.alloc(n + 1, s); e->full_lcp.alloc(n + 1, s); }
+            t.start();
+            stream_suffixes(e->text.text.p, ix, tile_ranks, halo, consumer, s);
+            e->stats.ms_detect = t.stop();
+            e->stats.pfp_tiles = consumer.tiles;
+            t.start();
+            if (e->mum_mode) { concat_mums(consumer.mparts, N, e->mums, s); if (want_text) mum_text(e->mums, N, s); }
+            else { concat_mems(consumer.eparts, e->mems, s); if (want_text) mem_text(e->mems, s); }
+            e->stats.ms_emit = t.stop();
+        }
         e->stats.ms_total = total.stop();
         e->stats.num_matches = e->mum_mode ? e->mums.count : e->mems.count;
-        e->stats.sa_rounds = e->sa.stats.rounds; e->stats.sa_sorted_elements = e->sa.stats.groups_sorted;
+        e->stats.route = e->route;
         e->found = true;
     });
 }
@@ -400,7 +457,17 @@ int mmb_copy_thresholds(mmb_engine* e, uint16_t* dst) {
 int mmb_copy_arrays(mmb_engine* e, uint64_t* sa, uint64_t* lcp, uint8_t* bwt) {
     if (!e || !e->found) return fail(MMB_ERR_STATE, "no results: call mmb_find first");
     return guarded([&] {
-        cudaStream_t s = e->stream; u64 m = e->sa.m;
+        cudaStream_t s = e->stream;
+        if (e->route == 2) {
+            if (!e->full_sa.p) throw Error(1, "the suffix stream was not kept: run mmb_find with keep_arrays = 1");
+            u64 m = e->text.n + 1;
+            copy_out(e->full_sa.p, sa, m, s);
+            if (lcp) { DevBuf<u64> w; w.alloc(m, s); MMB_LAUNCH(widen_u32, ceil_div(m, 256), 256, 0, s, (const u32*)e->full_lcp.p, m, w.p); copy_out(w.p, lcp, m, s); MMB_CUDA(cudaStreamSynchronize(s)); }
+            if (bwt) { DevBuf<u8> b; b.alloc(m, s); MMB_LAUNCH(bwt_from_sa64, ceil_div(m, 256), 256, 0, s, (const u8*)e->text.text.p, (const u64*)e->full_sa.p, m, b.p); copy_out(b.p, bwt, m, s); MMB_CUDA(cudaStreamSynchronize(s)); }
+            MMB_CUDA(cudaStreamSynchronize(s));
+            return;
+        }
+        u64 m = e->sa.m;
         DevBuf<u64> wide; wide.alloc(m, s);
         if (sa) { MMB_LAUNCH(widen_u32, ceil_div(m, 256), 256, 0, s, e->sa.sa.p, m, wide.p); copy_out(wide.p, sa, m, s); MMB_CUDA(cudaStreamSynchronize(s)); }
         if (lcp) { MMB_LAUNCH(widen_u32, ceil_div(m, 256), 256, 0, s, e->lcp.p, m, wide.p); copy_out(wide.p, lcp, m, s); MMB_CUDA(cudaStreamSynchronize(s)); }

@@ -1,0 +1,411 @@
+// mumemto_b200/csrc/pfp.cu -- builds the prefix-free-parse index of the text on the device (see pfp.h for the construction).
+//
+// Stages (all kernels hand-written; the device-wide sorts and scans come from prims.h):
+//   1 trigger scan            2 passes over T (count, then write): every position hashes its own 10-byte window
+//   2 phrase identity         one 64-bit content hash per phrase, radix sort by hash, byte-wise verification against the group head
+//                             (a hash collision between different phrases is detected there and the stage is retried with a new seed)
+//   3 dictionary D'           distinct phrases + terminators; per-position `limit` (distance to the terminator) and phrase id
+//   4 suffix order of D'      shared doubling engine (sa.cu) in "limit" mode: equal dictionary suffixes stay tied on purpose
+//   5 phrase ranks -> parse   rank of the whole-phrase suffixes; parse = rank of every phrase occurrence
+//   6 suffix order of parse   same engine on the integer alphabet
+//   7 s_lcp                   text-level LCP of rank-adjacent parse suffixes: chunked Kasai over phrases + one byte comparison of the
+//                             two differing phrases
+//   8 range-minimum index over s_lcp (block minima + sparse table), occurrence lists of every phrase ordered by the rank of the parse
+//     suffix that follows, with the text LCP between consecutive occurrences
+#include "pfp.h"
+#include "pfp_device.cuh"
+#include "prims.h"
+
+namespace mmb {
+
+namespace {
+
+constexpr u32 TPB = 256;
+constexpr u32 FULL = 0xffffffffu;
+constexpr u32 SCAN_BLOCK = 4096;        // text positions per block in the trigger passes (16 per thread)
+
+__device__ __forceinline__ u64 load8(const u8* __restrict__ t, u64 i) {      // unaligned 8-byte little-endian load (reads <= 11 bytes past i)
+    const u32* w = reinterpret_cast<const u32*>(t + (i & ~3ull));
+    u32 sh = (u32)(i & 3) * 8;
+    u32 a = w[0], b = w[1], c = w[2];
+    u32 lo = sh ? __funnelshift_r(a, b, sh) : a;
+    u32 hi = sh ? __funnelshift_r(b, c, sh) : b;
+    return ((u64)hi << 32) | lo;
+}
+__host__ __device__ __forceinline__ u64 mix64(u64 x) {
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+    return x;
+}
+// trigger test for the window T[e-9 .. e]
+__device__ __forceinline__ bool is_trigger(const u8* __restrict__ text, u64 e) {
+    u64 x = load8(text, e - (PFP_W - 1));
+    u64 y = (u64)text[e - 1] | ((u64)text[e] << 8);
+    u64 h = mix64(x ^ (y * 0x9E3779B97F4A7C15ull));
+    return (u32)(h >> 33) % PFP_P == 0;
+}
+
+// exclusive block scan of one u32 per thread; *total = block sum
+__device__ __forceinline__ u32 block_scan(u32 mine, u32* total) {
+    __shared__ u32 warp_sums[TPB / 32];
+    u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, inc = mine;
+#pragma unroll
+    for (u32 d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    u32 before = 0, all = 0;
+    for (u32 w = 0; w < TPB / 32; ++w) { if (w < warp) before += warp_sums[w]; all += warp_sums[w]; }
+    *total = all;
+    __syncthreads();
+    return before + inc - mine;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(TPB) trigger_pass(const u8* __restrict__ text, u64 n, u32* __restrict__ block_count, const u32* __restrict__ block_base,
+                                                    u64* __restrict__ ends) {
+    u64 e0 = (u64)blockIdx.x * SCAN_BLOCK + (u64)threadIdx.x * 16;
+    u32 mask = 0;
+#pragma unroll
+    for (u32 k = 0; k < 16; ++k) { u64 e = e0 + k; if (e >= PFP_W && e < n && is_trigger(text, e)) mask |= 1u << k; }
+    u32 total, before = block_scan((u32)__popc(mask), &total);
+    if (!WRITE) { if (threadIdx.x == 0) block_count[blockIdx.x] = total; return; }
+    u32 at = block_base[blockIdx.x] + before;
+    while (mask) { u32 k = (u32)__ffs((int)mask) - 1; mask &= mask - 1; ends[at++] = e0 + k; }
+}
+
+__global__ void __launch_bounds__(TPB) phrase_starts(const u64* __restrict__ ends, u32 np, u64 n, u64* __restrict__ pstart) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > np) return;
+    pstart[j] = (j == 0) ? 0 : ((j == np) ? n : ends[j - 1] - PFP_W + 1);
+}
+
+// phrase j = T'[pstart[j] .. pstart[j+1] + w - 1], length pstart[j+1] - pstart[j] + w; bytes at or past n read as 0 (text has zero slack)
+__global__ void __launch_bounds__(TPB) phrase_hash(const u8* __restrict__ text, const u64* __restrict__ pstart, u32 np, u64 seed, u64* __restrict__ keys,
+                                                   u32* __restrict__ vals) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= np) return;
+    u64 s = pstart[j], len = pstart[j + 1] - s + PFP_W;
+    u64 h = seed ^ mix64(len);
+    u64 k = 0;
+    for (; (k + 1) * 8 <= len; ++k) h += mix64(load8(text, s + k * 8) + (k + 1) * 0x9E3779B97F4A7C15ull + seed);
+    u32 rem = (u32)(len - k * 8);
+    if (rem) { u64 wd = load8(text, s + k * 8) & ((1ull << (8 * rem)) - 1); h += mix64(wd + (k + 1) * 0x9E3779B97F4A7C15ull + seed); }
+    keys[j] = h; vals[j] = j;
+}
+
+__global__ void __launch_bounds__(TPB) hash_boundaries(const u64* __restrict__ keys, u32 np, u32* __restrict__ flag) {
+    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < np) flag[q] = (q == 0 || keys[q] != keys[q - 1]) ? 1u : 0u;
+}
+
+// after the inclusive numbering of groups: representative (first member) per group, provisional id per phrase, byte-wise verification
+__global__ void __launch_bounds__(TPB) assign_groups(const u32* __restrict__ flag, const u32* __restrict__ gnum_excl, const u32* __restrict__ order, u32 np,
+                                                     u32* __restrict__ pid, u32* __restrict__ rep) {
+    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= np) return;
+    u32 g = gnum_excl[q] + flag[q] - 1;
+    pid[order[q]] = g;
+    if (flag[q]) rep[g] = order[q];
+}
+__global__ void __launch_bounds__(TPB) verify_groups(const u8* __restrict__ text, const u64* __restrict__ pstart, const u32* __restrict__ pid,
+                                                     const u32* __restrict__ rep, u32 np, u32* __restrict__ mismatch) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= np) return;
+    u32 r = rep[pid[j]];
+    if (r == j) return;
+    u64 a = pstart[j], b = pstart[r], la = pstart[j + 1] - a + PFP_W, lb = pstart[r + 1] - b + PFP_W;
+    bool bad = la != lb;
+    u64 k = 0;
+    for (; !bad && (k + 1) * 8 <= la; ++k) bad = load8(text, a + k * 8) != load8(text, b + k * 8);
+    u32 rem = (u32)(la - k * 8);
+    if (!bad && rem) { u64 msk = (1ull << (8 * rem)) - 1; bad = (load8(text, a + k * 8) & msk) != (load8(text, b + k * 8) & msk); }
+    if (bad) *mismatch = 1;
+}
+
+__global__ void __launch_bounds__(TPB) dict_lengths(const u64* __restrict__ pstart, const u32* __restrict__ rep, u32 nd, u64* __restrict__ dlen) {
+    u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < nd) { u32 j = rep[g]; dlen[g] = pstart[j + 1] - pstart[j] + PFP_W + 1; }      // + terminator
+    if (g == nd) dlen[g] = 0;
+}
+__global__ void narrow_offsets(const u64* __restrict__ in, u32 n, u32* __restrict__ out) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (u32)in[i];
+}
+// one warp per distinct phrase: copy its bytes, append the terminator, fill limit[] and dphrase[]
+__global__ void __launch_bounds__(TPB) dict_fill(const u8* __restrict__ text, u64 n, const u64* __restrict__ pstart, const u32* __restrict__ rep,
+                                                 const u32* __restrict__ doff, u32 nd, u8* __restrict__ dict, u32* __restrict__ limit,
+                                                 u32* __restrict__ dphrase) {
+    u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= nd) return;
+    u64 s = pstart[rep[g]];
+    u32 o = doff[g], total = doff[g + 1] - o;       // phrase length + 1
+    for (u32 t = lane; t < total; t += 32) {
+        u64 p = s + t;
+        dict[o + t] = (t + 1 < total && p < n) ? text[p] : (u8)0;
+        limit[o + t] = total - t;
+        dphrase[o + t] = g;
+    }
+}
+
+__global__ void __launch_bounds__(TPB) dict_histogram(const u8* __restrict__ d, u32 n, u32* __restrict__ hist) {
+    __shared__ u32 h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    u32 stride = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) atomicAdd(&h[d[i]], 1u);
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(TPB) dict_keys(const u8* __restrict__ d, const u32* __restrict__ limit, u32 n, const u8* __restrict__ lut, u32 bits,
+                                                 u32 cpk, u64* __restrict__ keys, u32* __restrict__ vals) {
+    __shared__ u8 code[256];
+    code[threadIdx.x] = lut[threadIdx.x];
+    __syncthreads();
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 lim = limit[i];
+    u64 key = 0;
+    for (u32 t = 0; t < cpk; ++t) key = (key << bits) | (u64)(t < lim ? code[d[i + t]] : 0);
+    keys[i] = key; vals[i] = i;
+}
+
+__global__ void __launch_bounds__(TPB) phrase_rank_keys(const u32* __restrict__ isa_d, const u32* __restrict__ doff, u32 nd, u64* __restrict__ keys,
+                                                        u32* __restrict__ vals) {
+    u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < nd) { keys[g] = isa_d[doff[g]]; vals[g] = g; }
+}
+__global__ void __launch_bounds__(TPB) phrase_rank_scatter(const u32* __restrict__ order, u32 nd, u32* __restrict__ prank) {
+    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nd) prank[order[r]] = r + 1;
+}
+__global__ void __launch_bounds__(TPB) make_parse(const u32* __restrict__ pid, const u32* __restrict__ prank, u32 np, u32* __restrict__ parse) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < np) parse[j] = prank[pid[j]];
+    if (j == np) parse[j] = 0;
+}
+__global__ void __launch_bounds__(TPB) parse_keys(const u32* __restrict__ parse, u32 m, u32 b, u64* __restrict__ keys, u32* __restrict__ vals) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    u64 nxt = (j + 1 < m) ? parse[j + 1] : 0;
+    keys[j] = ((u64)parse[j] << b) | nxt; vals[j] = j;
+}
+
+// longest common prefix of T'[a..) and T'[b..) (symbols at or past n are 0), at most cap
+__device__ __forceinline__ u64 text_lcp(const u8* __restrict__ t, u64 a, u64 b, u64 cap) {
+    u64 l = 0;
+    while (l + 8 <= cap) {
+        u64 x = load8(t, a + l) ^ load8(t, b + l);
+        if (x) return l + (u64)((__ffsll((long long)x) - 1) >> 3);
+        l += 8;
+    }
+    while (l < cap && t[a + l] == t[b + l]) ++l;
+    return l;
+}
+
+constexpr u32 KASAI_CHUNK = 32;
+__global__ void __launch_bounds__(128) parse_lcp(const u8* __restrict__ text, u64 n, const u64* __restrict__ pstart, const u32* __restrict__ parse,
+                                                 const u32* __restrict__ sa_p, const u32* __restrict__ isa_p, u32 m, u32* __restrict__ s_lcp,
+                                                 u32* __restrict__ overflow) {
+    u64 first = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * KASAI_CHUNK;
+    u32 l = 0;
+    for (u32 k = 0; k < KASAI_CHUNK; ++k) {
+        u64 j = first + k;
+        if (j >= m) return;
+        u32 r = isa_p[j];
+        if (r == 0) { s_lcp[0] = 0; l = 0; continue; }
+        u64 j2 = sa_p[r - 1];
+        while (parse[j + l] == parse[j2 + l]) ++l;                   // the terminator 0 at m-1 is unique, so this stops inside the array
+        u64 common = pstart[j + l] - pstart[j];
+        if (parse[j + l] && parse[j2 + l]) {
+            u64 pa = pstart[j + l], pb = pstart[j2 + l];
+            u64 cap = min(pstart[j + l + 1] - pa, pstart[j2 + l + 1] - pb) + PFP_W;     // shorter of the two phrases
+            common += text_lcp(text, pa, pb, cap);
+        }
+        if (common > 0xfffffffeull) { *overflow = 1; common = 0xfffffffeull; }
+        s_lcp[r] = (u32)common;
+        if (l) --l;
+    }
+}
+
+// ---- range minimum over s_lcp
+__global__ void __launch_bounds__(TPB) rmq_block_minima(const u32* __restrict__ v, u32 m, u32 nblocks, u32* __restrict__ out) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    u32 lo = b * 32, hi = min(lo + 32, m), mn = 0xffffffffu;
+    for (u32 i = lo; i < hi; ++i) mn = min(mn, v[i]);
+    out[b] = mn;
+}
+__global__ void __launch_bounds__(TPB) rmq_level(const u32* __restrict__ prev, u32 nblocks, u32 half, u32* __restrict__ out) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    u32 o = b + half;
+    out[b] = o < nblocks ? min(prev[b], prev[o]) : prev[b];
+}
+
+__global__ void __launch_bounds__(TPB) occ_keys(const u32* __restrict__ parse, const u32* __restrict__ isa_p, u32 np, u64* __restrict__ keys,
+                                                u32* __restrict__ vals) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < np) { keys[j] = ((u64)parse[j] << 32) | isa_p[j + 1]; vals[j] = j; }
+}
+__global__ void __launch_bounds__(TPB) occ_fill(const u64* __restrict__ keys, const u32* __restrict__ order, const u64* __restrict__ pstart, u32 np, u32 nd,
+                                                const u32* __restrict__ s_lcp, const u32* __restrict__ rmq, u32 rmq_blocks, u32* __restrict__ occ_first,
+                                                u32* __restrict__ next_rank, u64* __restrict__ next_start, u32* __restrict__ occ_lcp) {
+    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q == 0) { occ_first[0] = 0; occ_first[nd + 1] = np; }
+    if (q >= np) return;
+    u64 key = keys[q];
+    u32 rank = (u32)(key >> 32), nr = (u32)key;
+    bool first = (q == 0) || (u32)(keys[q - 1] >> 32) != rank;
+    if (first) occ_first[rank] = q;
+    next_rank[q] = nr;
+    next_start[q] = pstart[order[q] + 1];
+    occ_lcp[q] = first ? 0u : range_min(s_lcp, rmq, rmq_blocks, (u32)keys[q - 1] + 1, nr);
+}
+
+}  // namespace
+
+void build_pfp_index(const u8* text, u64 n, PfpIndex& ix, cudaStream_t s) {
+    ix.n = n;
+    if (n < PFP_W + 2) throw Error(70, "text too short for the prefix-free parse route");
+    // ---- 1. triggers
+    u64 nblk64 = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    if (nblk64 > 0x7fffffffull) throw Error(71, "text too long");
+    u32 nblk = (u32)nblk64;
+    DevBuf<u32> bcount, bbase; bcount.alloc(nblk + 1, s); bbase.alloc(nblk + 1, s);
+    MMB_CUDA(cudaMemsetAsync(bcount.p + nblk, 0, 4, s));
+    auto tp0 = trigger_pass<false>; auto tp1 = trigger_pass<true>;
+    MMB_LAUNCH(tp0, nblk, TPB, 0, s, text, n, bcount.p, (const u32*)nullptr, (u64*)nullptr);
+    prim::exclusive_sum(bcount.p, bbase.p, nblk + 1, s);
+    u64 ntrig = to_host(bbase.p + nblk, 1, s)[0];
+    if (ntrig + 2 >= 0xfffffff0ull) throw Error(72, "too many phrases");
+    u32 np = (u32)ntrig + 1;
+    ix.np = np;
+    DevBuf<u64> ends; ends.alloc(np, s);
+    MMB_LAUNCH(tp1, nblk, TPB, 0, s, text, n, bcount.p, (const u32*)bbase.p, ends.p);
+    u64 last_end = n + PFP_W - 1;
+    MMB_CUDA(cudaMemcpyAsync(ends.p + np - 1, &last_end, 8, cudaMemcpyHostToDevice, s));
+    ix.pstart.alloc(np + 1, s);
+    MMB_LAUNCH(phrase_starts, ceil_div(np + 1, TPB), TPB, 0, s, (const u64*)ends.p, np, n, ix.pstart.p);
+    MMB_CUDA(cudaStreamSynchronize(s));           // last_end lives on this stack frame
+    ends.release(); bcount.release(); bbase.release();
+
+    // ---- 2. phrase identity
+    DevBuf<u32> pid, rep; pid.alloc(np, s); rep.alloc(np, s);
+    u32 nd = 0;
+    for (u64 attempt = 0;; ++attempt) {
+        if (attempt == 8) throw Error(73, "phrase hashing kept colliding");
+        DevBuf<u64> ka, kb; DevBuf<u32> va, vb, flag, gnum, mismatch;
+        ka.alloc(np, s); kb.alloc(np, s); va.alloc(np, s); vb.alloc(np, s); flag.alloc(np, s); gnum.alloc(np, s); mismatch.alloc(1, s); mismatch.zero();
+        MMB_LAUNCH(phrase_hash, ceil_div(np, TPB), TPB, 0, s, text, (const u64*)ix.pstart.p, np, mix64(attempt + 0x1234567ull), ka.p, va.p);
+        prim::sort_pairs(ka.p, kb.p, va.p, vb.p, np, 0, 64, s);
+        MMB_LAUNCH(hash_boundaries, ceil_div(np, TPB), TPB, 0, s, (const u64*)kb.p, np, flag.p);
+        prim::exclusive_sum(flag.p, gnum.p, np, s);
+        MMB_LAUNCH(assign_groups, ceil_div(np, TPB), TPB, 0, s, (const u32*)flag.p, (const u32*)gnum.p, (const u32*)vb.p, np, pid.p, rep.p);
+        MMB_LAUNCH(verify_groups, ceil_div(np, TPB), TPB, 0, s, text, (const u64*)ix.pstart.p, (const u32*)pid.p, (const u32*)rep.p, np, mismatch.p);
+        u32 tail[3];
+        MMB_CUDA(cudaMemcpyAsync(&tail[0], gnum.p + np - 1, 4, cudaMemcpyDeviceToHost, s));
+        MMB_CUDA(cudaMemcpyAsync(&tail[1], flag.p + np - 1, 4, cudaMemcpyDeviceToHost, s));
+        MMB_CUDA(cudaMemcpyAsync(&tail[2], mismatch.p, 4, cudaMemcpyDeviceToHost, s));
+        MMB_CUDA(cudaStreamSynchronize(s));
+        nd = tail[0] + tail[1];
+        if (!tail[2]) break;
+    }
+    ix.nd = nd;
+
+    // ---- 3. dictionary
+    {
+        DevBuf<u64> dlen, doff64; dlen.alloc(nd + 1, s); doff64.alloc(nd + 1, s);
+        MMB_LAUNCH(dict_lengths, ceil_div(nd + 1, TPB), TPB, 0, s, (const u64*)ix.pstart.p, (const u32*)rep.p, nd, dlen.p);
+        prim::exclusive_sum(dlen.p, doff64.p, nd + 1, s);
+        u64 dsize = to_host(doff64.p + nd, 1, s)[0];
+        if (dsize >= 0xffffff00ull) throw Error(74, "dictionary too large for 32-bit indices");
+        ix.dsize = (u32)dsize;
+        ix.doff.alloc(nd + 1, s);
+        MMB_LAUNCH(narrow_offsets, ceil_div(nd + 1, TPB), TPB, 0, s, (const u64*)doff64.p, nd + 1, ix.doff.p);
+    }
+    u32 dsize = ix.dsize;
+    ix.dict.alloc((u64)dsize + 64, s); ix.limit.alloc(dsize, s); ix.dphrase.alloc(dsize, s);
+    MMB_CUDA(cudaMemsetAsync(ix.dict.p + dsize, 0, 64, s));
+    MMB_LAUNCH(dict_fill, ceil_div((u64)nd * 32, TPB), TPB, 0, s, text, n, (const u64*)ix.pstart.p, (const u32*)rep.p, (const u32*)ix.doff.p, nd, ix.dict.p,
+               ix.limit.p, ix.dphrase.p);
+    rep.release();
+
+    // ---- 4. suffix order of the dictionary (ties allowed)
+    {
+        DevBuf<u32> hist; hist.alloc(256, s); hist.zero();
+        MMB_LAUNCH(dict_histogram, 148 * 8, TPB, 0, s, (const u8*)ix.dict.p, dsize, hist.p);
+        std::vector<u32> h = to_host(hist.p, 256, s);
+        std::vector<u8> lut(256, 0); u32 sigma = 0;
+        for (int c = 1; c < 256; ++c) if (h[c]) lut[c] = (u8)(++sigma);
+        u32 bits = 1; while ((1u << bits) <= sigma) ++bits;
+        u32 cpk = 64 / bits;
+        DevBuf<u8> d_lut; d_lut.alloc(256, s);
+        MMB_CUDA(cudaMemcpyAsync(d_lut.p, lut.data(), 256, cudaMemcpyHostToDevice, s));
+        ix.sa_d.alloc(dsize, s); ix.isa_d.alloc(dsize, s);
+        GroupStore groups;
+        {
+            DevBuf<u64> ka, kb; DevBuf<u32> va; ka.alloc(dsize, s); kb.alloc(dsize, s); va.alloc(dsize, s);
+            MMB_LAUNCH(dict_keys, ceil_div(dsize, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const u32*)ix.limit.p, dsize, (const u8*)d_lut.p, bits, cpk, ka.p, va.p);
+            order_by_initial_keys(ka.p, kb.p, va.p, dsize, (int)(bits * cpk), cpk, ix.limit.p, ix.sa_d.p, ix.isa_d.p, groups, s);
+        }
+        refine_by_doubling(ix.sa_d.p, ix.isa_d.p, dsize, cpk, ix.limit.p, groups, ix.stats_d, s);
+        MMB_CUDA(cudaStreamSynchronize(s));       // lut lives on this stack frame
+    }
+
+    // ---- 5. phrase ranks and the parse
+    ix.prank.alloc(nd, s);
+    {
+        DevBuf<u64> ka, kb; DevBuf<u32> va, vb; ka.alloc(nd, s); kb.alloc(nd, s); va.alloc(nd, s); vb.alloc(nd, s);
+        MMB_LAUNCH(phrase_rank_keys, ceil_div(nd, TPB), TPB, 0, s, (const u32*)ix.isa_d.p, (const u32*)ix.doff.p, nd, ka.p, va.p);
+        prim::sort_pairs(ka.p, kb.p, va.p, vb.p, nd, 0, 32, s);
+        MMB_LAUNCH(phrase_rank_scatter, ceil_div(nd, TPB), TPB, 0, s, (const u32*)vb.p, nd, ix.prank.p);
+    }
+    u32 m = np + 1;
+    ix.parse.alloc((u64)m + 1, s);
+    MMB_LAUNCH(make_parse, ceil_div(m, TPB), TPB, 0, s, (const u32*)pid.p, (const u32*)ix.prank.p, np, ix.parse.p);
+    MMB_CUDA(cudaMemsetAsync(ix.parse.p + m, 0, 4, s));
+    pid.release();
+
+    // ---- 6. suffix order of the parse
+    DevBuf<u32> sa_p; sa_p.alloc(m, s); ix.isa_p.alloc(m, s);
+    {
+        u32 b = 1; while ((1ull << b) <= nd) ++b;
+        GroupStore groups;
+        {
+            DevBuf<u64> ka, kb; DevBuf<u32> va; ka.alloc(m, s); kb.alloc(m, s); va.alloc(m, s);
+            MMB_LAUNCH(parse_keys, ceil_div(m, TPB), TPB, 0, s, (const u32*)ix.parse.p, m, b, ka.p, va.p);
+            order_by_initial_keys(ka.p, kb.p, va.p, m, (int)(2 * b), 2, nullptr, sa_p.p, ix.isa_p.p, groups, s);
+        }
+        refine_by_doubling(sa_p.p, ix.isa_p.p, m, 2, nullptr, groups, ix.stats_p, s);
+    }
+
+    // ---- 7. text-level LCP between rank-adjacent parse suffixes
+    ix.s_lcp.alloc(m, s);
+    {
+        DevBuf<u32> overflow; overflow.alloc(1, s); overflow.zero();
+        u64 threads = ((u64)m + KASAI_CHUNK - 1) / KASAI_CHUNK;
+        MMB_LAUNCH(parse_lcp, ceil_div(threads, 128), 128, 0, s, text, n, (const u64*)ix.pstart.p, (const u32*)ix.parse.p, (const u32*)sa_p.p,
+                   (const u32*)ix.isa_p.p, m, ix.s_lcp.p, overflow.p);
+        if (to_host(overflow.p, 1, s)[0]) throw Error(75, "a common prefix longer than 2^32 symbols: not supported");
+    }
+    sa_p.release();
+
+    // ---- 8. range-minimum index and occurrence lists
+    ix.rmq_blocks = (m + 31) / 32;
+    ix.rmq_levels = 1; while ((1u << ix.rmq_levels) <= ix.rmq_blocks) ++ix.rmq_levels;
+    ix.rmq.alloc((u64)ix.rmq_levels * ix.rmq_blocks, s);
+    MMB_LAUNCH(rmq_block_minima, ceil_div(ix.rmq_blocks, TPB), TPB, 0, s, (const u32*)ix.s_lcp.p, m, ix.rmq_blocks, ix.rmq.p);
+    for (u32 k = 1; k < ix.rmq_levels; ++k)
+        MMB_LAUNCH(rmq_level, ceil_div(ix.rmq_blocks, TPB), TPB, 0, s, (const u32*)(ix.rmq.p + (u64)(k - 1) * ix.rmq_blocks), ix.rmq_blocks, 1u << (k - 1),
+                   ix.rmq.p + (u64)k * ix.rmq_blocks);
+    ix.occ_first.alloc(nd + 2, s); ix.occ_next_rank.alloc(np, s); ix.occ_next_start.alloc(np, s); ix.occ_lcp.alloc(np, s);
+    {
+        DevBuf<u64> ka, kb; DevBuf<u32> va, vb; ka.alloc(np, s); kb.alloc(np, s); va.alloc(np, s); vb.alloc(np, s);
+        u32 b = 1; while ((1ull << b) <= nd) ++b;
+        MMB_LAUNCH(occ_keys, ceil_div(np, TPB), TPB, 0, s, (const u32*)ix.parse.p, (const u32*)ix.isa_p.p, np, ka.p, va.p);
+        prim::sort_pairs(ka.p, kb.p, va.p, vb.p, np, 0, (int)(32 + b), s);
+        MMB_LAUNCH(occ_fill, ceil_div(np, TPB), TPB, 0, s, (const u64*)kb.p, (const u32*)vb.p, (const u64*)ix.pstart.p, np, nd, (const u32*)ix.s_lcp.p,
+                   (const u32*)ix.rmq.p, ix.rmq_blocks, ix.occ_first.p, ix.occ_next_rank.p, ix.occ_next_start.p, ix.occ_lcp.p);
+    }
+}
+
+}  // namespace mmb

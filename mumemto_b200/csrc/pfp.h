@@ -1,0 +1,66 @@
+// mumemto_b200/csrc/pfp.h -- prefix-free parsing route (pfp.cu, stream.cu): suffix stream of T from the suffix arrays of a
+// dictionary and a parse that are ~|T|/25 and |T|/100 in size on pangenome-like input.
+//
+// Reference: pfparser (include/newscan.hpp:310-423), dictionary / parse / pf_parsing (include/dictionary.hpp:103-157,
+// include/parse.hpp:77-146, include/pfp.hpp:171-244) and the enumeration loop pfp_lcp::process (include/pfp_lcp_mum.hpp:115-231)
+// -- rows B, C, D of SURVEY.md section 8.  The outputs of that path do not depend on the hash, window or modulus, so
+// the device parse uses its own window hash; what is kept is the construction:
+//   T' = T . 0^w.  Trigger positions e (w <= e < n) are where hash(T[e-w+1..e]) % p == 0, plus the forced last one n+w-1.
+//   Phrase j = T'[s_j .. e_j], s_0 = 0, s_{j+1} = e_j - w + 1 (consecutive phrases overlap by w).  Text position i belongs to the
+//   phrase with s_j <= i <= e_j - w; its "dictionary suffix" is alpha(i) = T'[i .. e_j], longer than w.  The set of all alpha is
+//   prefix-free, so two text suffixes compare by (alpha, then the parse suffix that follows), and
+//   lcp = lcp(alpha, alpha') if they differ, else |alpha| - w + lcp of the following phrase-aligned suffixes.
+#pragma once
+#include "common.cuh"
+#include "sa.h"
+
+namespace mmb {
+
+constexpr u32 PFP_W = 10;           // window (reference default -w 10)
+constexpr u32 PFP_P = 100;          // modulus (reference default -m 100)
+
+struct PfpIndex {
+    u64 n = 0;                      // |T|
+    // parse
+    u32 np = 0;                     // phrases; the parse has np + 1 symbols (terminator 0)
+    DevBuf<u64> pstart;             // [np + 1] text position of each phrase start; pstart[np] = n
+    DevBuf<u32> parse;              // [np + 1] lexicographic rank of each phrase (1-based), parse[np] = 0
+    DevBuf<u32> isa_p;              // [np + 1] rank of each parse suffix
+    DevBuf<u32> s_lcp;              // [np + 1] lcp in TEXT symbols between parse suffixes of adjacent rank (s_lcp[0] = 0)
+    // range-minimum over s_lcp: minima of 32-entry blocks and a sparse table over the blocks
+    u32 rmq_blocks = 0, rmq_levels = 0;
+    DevBuf<u32> rmq;                // [rmq_levels][rmq_blocks]
+    // dictionary D' = distinct phrases, each followed by a terminator 0
+    u32 nd = 0;                     // distinct phrases
+    u32 dsize = 0;                  // |D'|
+    DevBuf<u8> dict;                // [dsize + 64]
+    DevBuf<u32> limit;              // [dsize] symbols from here up to and including the terminator
+    DevBuf<u32> sa_d, isa_d;        // suffix order of D' (equal strings share one head rank in isa_d)
+    DevBuf<u32> dphrase;            // [dsize] distinct-phrase id (in D' order) of every dictionary position
+    DevBuf<u32> doff;               // [nd + 1] start of each distinct phrase in D'
+    DevBuf<u32> prank;              // [nd] lexicographic rank (1-based) of each distinct phrase
+    // occurrences of every phrase rank, ordered by the rank of the parse suffix that follows them
+    DevBuf<u32> occ_first;          // [nd + 2] indexed by phrase rank
+    DevBuf<u32> occ_next_rank;      // [np] isa_p of the following parse suffix
+    DevBuf<u64> occ_next_start;     // [np] text position where the following phrase starts
+    DevBuf<u32> occ_lcp;            // [np] text lcp between the following suffixes of this and the previous occurrence of the phrase
+    SaStats stats_d, stats_p;
+};
+
+void build_pfp_index(const u8* text, u64 n, PfpIndex& out, cudaStream_t s);
+
+// One window of the suffix stream in rank order, with `halo` ranks of the previous window in front of it.
+struct StreamTile {
+    u64 rank0 = 0;                  // global rank of view index 0
+    u64 count = 0;                  // valid entries in the view (halo included)
+    u64 first = 0;                  // view index of the first rank that is new in this tile
+    const u64* sa = nullptr;        // [count]
+    const u32* lcp = nullptr;       // [count + 64], zero padded
+    bool last = false;
+};
+
+// Calls consume(tile) for consecutive tiles of about tile_ranks ranks, each carrying `halo` ranks of overlap.
+struct TileConsumer { virtual void consume(const StreamTile& t) = 0; virtual ~TileConsumer() {} };
+void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 halo, TileConsumer& consumer, cudaStream_t s);
+
+}  // namespace mmb

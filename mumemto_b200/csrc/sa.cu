@@ -125,7 +125,7 @@ __device__ __forceinline__ u32 round_key(u32 s, u32 h, u32 m, const u32* __restr
 template <int WIDTH, int K>
 __global__ void __launch_bounds__(TPB) sort_groups_warp(const Group* __restrict__ groups, u32 ngroups, u32 h, u32 m, u32* __restrict__ sa,
                                                         const u32* __restrict__ isa, const u32* __restrict__ limit, u32* __restrict__ nh,
-                                                        GroupLists next) {
+                                                        u8* __restrict__ changed, GroupLists next) {
     u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
     u32 gi = tid / WIDTH, lane = tid % WIDTH;
     bool have = gi < ngroups;
@@ -157,11 +157,14 @@ __global__ void __launch_bounds__(TPB) sort_groups_warp(const Group* __restrict_
             }
         }
     }
+    // A group whose keys are all equal did not split: nothing moves, no rank changes, and it is carried over as it is.
+    bool split = (size > 0) && (eq[0] != size);           // element 0 exists in every listed group; uniform over the group's lanes
+    if (lane == 0 && have) changed[gi] = split ? 1 : 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         u32 e = lane + (u32)WIDTH * k;
         bool valid = e < size;
-        if (valid) {
+        if (valid && split) {
             u32 slot = head + lt[k] + before[k];
             sa[slot] = s[k];
             nh[slot] = head + lt[k];
@@ -228,14 +231,17 @@ __global__ void __launch_bounds__(TPB) sort_groups_block(const Group* __restrict
 // ------------------------------------------------------------------------------------------------ applying new head ranks
 template <int WIDTH, int K>
 __global__ void __launch_bounds__(TPB) apply_groups_warp(const Group* __restrict__ groups, u32 ngroups, const u32* __restrict__ sa,
-                                                         const u32* __restrict__ nh, u32* __restrict__ isa) {
+                                                         const u32* __restrict__ nh, const u8* __restrict__ changed, u32* __restrict__ isa) {
     u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
     u32 gi = tid / WIDTH, lane = tid % WIDTH;
-    if (gi >= ngroups) return;
+    if (gi >= ngroups || !changed[gi]) return;
     Group g = groups[gi];
     u32 head = g_head(g), size = g_size(g);
 #pragma unroll
-    for (int k = 0; k < K; ++k) { u32 e = lane + (u32)WIDTH * k; if (e < size) isa[sa[head + e]] = nh[head + e]; }
+    for (int k = 0; k < K; ++k) {
+        u32 e = lane + (u32)WIDTH * k;
+        if (e < size) { u32 r = nh[head + e]; if (r != head) isa[sa[head + e]] = r; }      // the first run keeps the old head rank
+    }
 }
 __global__ void __launch_bounds__(TPB) apply_groups_block(const Group* __restrict__ groups, const u32* __restrict__ sa, const u32* __restrict__ nh,
                                                           u32* __restrict__ isa) {
@@ -290,16 +296,17 @@ __global__ void __launch_bounds__(TPB) large_apply(const u32* __restrict__ pos, 
 u32 bits_for(u64 x) { u32 b = 1; while ((1ull << b) <= x && b < 63) ++b; return b; }   // bits to represent values 0..x
 
 template <int WIDTH, int K>
-void launch_warp_class(const Group* groups, u32 n, u32 h, u32 m, u32* sa, u32* isa, const u32* limit, u32* nh, const GroupLists& next, cudaStream_t s) {
+void launch_warp_class(const Group* groups, u32 n, u32 h, u32 m, u32* sa, u32* isa, const u32* limit, u32* nh, u8* changed, const GroupLists& next,
+                       cudaStream_t s) {
     if (!n) return;
     auto k = sort_groups_warp<WIDTH, K>;
-    MMB_LAUNCH(k, ceil_div((u64)n * WIDTH, TPB), TPB, 0, s, groups, n, h, m, sa, (const u32*)isa, limit, nh, next);
+    MMB_LAUNCH(k, ceil_div((u64)n * WIDTH, TPB), TPB, 0, s, groups, n, h, m, sa, (const u32*)isa, limit, nh, changed, next);
 }
 template <int WIDTH, int K>
-void launch_apply_class(const Group* groups, u32 n, const u32* sa, const u32* nh, u32* isa, cudaStream_t s) {
+void launch_apply_class(const Group* groups, u32 n, const u32* sa, const u32* nh, const u8* changed, u32* isa, cudaStream_t s) {
     if (!n) return;
     auto k = apply_groups_warp<WIDTH, K>;
-    MMB_LAUNCH(k, ceil_div((u64)n * WIDTH, TPB), TPB, 0, s, groups, n, sa, nh, isa);
+    MMB_LAUNCH(k, ceil_div((u64)n * WIDTH, TPB), TPB, 0, s, groups, n, sa, nh, changed, isa);
 }
 
 const u32 kClassMinSize[NCLASS] = {2, 5, 9, 17, 33, 65, 129, 257, BLOCK_SORT_MAX + 1};
@@ -325,6 +332,7 @@ static GroupLists lists_of(GroupStore& g) {
 void refine_by_doubling(u32* sa, u32* isa, u32 m, u32 h0, const u32* limit, GroupStore& cur, SaStats& st, cudaStream_t s) {
     GroupStore nxt; nxt.alloc(m, s);
     DevBuf<u32> nh; nh.alloc(m, s);
+    DevBuf<u8> changed; changed.alloc(cur.first[NCLASS], s);      // one flag per listed group, laid out like the class lists
     int sort_bits = 32 + (int)bits_for(m);
     for (u64 h = h0;; h *= 2) {
         std::vector<u32> cnt = to_host(cur.counts.p, NCLASS, s);
@@ -345,13 +353,13 @@ void refine_by_doubling(u32* sa, u32* isa, u32 m, u32 h0, const u32* limit, Grou
         GroupLists next = lists_of(nxt);
         const Group* G[NCLASS];
         for (int c = 0; c < NCLASS; ++c) G[c] = cur.groups.p + cur.first[c];
-        launch_warp_class<4, 1>(G[0], cnt[0], hh, m, sa, isa, limit, nh.p, next, s);
-        launch_warp_class<8, 1>(G[1], cnt[1], hh, m, sa, isa, limit, nh.p, next, s);
-        launch_warp_class<16, 1>(G[2], cnt[2], hh, m, sa, isa, limit, nh.p, next, s);
-        launch_warp_class<32, 1>(G[3], cnt[3], hh, m, sa, isa, limit, nh.p, next, s);
-        launch_warp_class<32, 2>(G[4], cnt[4], hh, m, sa, isa, limit, nh.p, next, s);
-        launch_warp_class<32, 4>(G[5], cnt[5], hh, m, sa, isa, limit, nh.p, next, s);
-        launch_warp_class<32, 8>(G[6], cnt[6], hh, m, sa, isa, limit, nh.p, next, s);
+        launch_warp_class<4, 1>(G[0], cnt[0], hh, m, sa, isa, limit, nh.p, changed.p + cur.first[0], next, s);
+        launch_warp_class<8, 1>(G[1], cnt[1], hh, m, sa, isa, limit, nh.p, changed.p + cur.first[1], next, s);
+        launch_warp_class<16, 1>(G[2], cnt[2], hh, m, sa, isa, limit, nh.p, changed.p + cur.first[2], next, s);
+        launch_warp_class<32, 1>(G[3], cnt[3], hh, m, sa, isa, limit, nh.p, changed.p + cur.first[3], next, s);
+        launch_warp_class<32, 2>(G[4], cnt[4], hh, m, sa, isa, limit, nh.p, changed.p + cur.first[4], next, s);
+        launch_warp_class<32, 4>(G[5], cnt[5], hh, m, sa, isa, limit, nh.p, changed.p + cur.first[5], next, s);
+        launch_warp_class<32, 8>(G[6], cnt[6], hh, m, sa, isa, limit, nh.p, changed.p + cur.first[6], next, s);
         if (cnt[7]) MMB_LAUNCH(sort_groups_block, cnt[7], TPB, 0, s, G[7], hh, m, sa, (const u32*)isa, limit, nh.p, next);
         DevBuf<u32> lpos; u32 A = 0;
         if (cnt[8]) {
@@ -375,13 +383,13 @@ void refine_by_doubling(u32* sa, u32* isa, u32 m, u32 h0, const u32* limit, Grou
             prim::inclusive_max(cand.p, head.p, A, s);
             MMB_LAUNCH(large_finish, ceil_div(A, TPB), TPB, 0, s, (const u32*)lpos.p, (const u64*)lkey_b.p, (const u32*)head.p, A, nh.p, next);
         }
-        launch_apply_class<4, 1>(G[0], cnt[0], sa, nh.p, isa, s);
-        launch_apply_class<8, 1>(G[1], cnt[1], sa, nh.p, isa, s);
-        launch_apply_class<16, 1>(G[2], cnt[2], sa, nh.p, isa, s);
-        launch_apply_class<32, 1>(G[3], cnt[3], sa, nh.p, isa, s);
-        launch_apply_class<32, 2>(G[4], cnt[4], sa, nh.p, isa, s);
-        launch_apply_class<32, 4>(G[5], cnt[5], sa, nh.p, isa, s);
-        launch_apply_class<32, 8>(G[6], cnt[6], sa, nh.p, isa, s);
+        launch_apply_class<4, 1>(G[0], cnt[0], sa, nh.p, changed.p + cur.first[0], isa, s);
+        launch_apply_class<8, 1>(G[1], cnt[1], sa, nh.p, changed.p + cur.first[1], isa, s);
+        launch_apply_class<16, 1>(G[2], cnt[2], sa, nh.p, changed.p + cur.first[2], isa, s);
+        launch_apply_class<32, 1>(G[3], cnt[3], sa, nh.p, changed.p + cur.first[3], isa, s);
+        launch_apply_class<32, 2>(G[4], cnt[4], sa, nh.p, changed.p + cur.first[4], isa, s);
+        launch_apply_class<32, 4>(G[5], cnt[5], sa, nh.p, changed.p + cur.first[5], isa, s);
+        launch_apply_class<32, 8>(G[6], cnt[6], sa, nh.p, changed.p + cur.first[6], isa, s);
         if (cnt[7]) MMB_LAUNCH(apply_groups_block, cnt[7], TPB, 0, s, G[7], (const u32*)sa, (const u32*)nh.p, isa);
         if (A) MMB_LAUNCH(large_apply, ceil_div(A, TPB), TPB, 0, s, (const u32*)lpos.p, A, (const u32*)sa, (const u32*)nh.p, isa);
         cur.groups.swap(nxt.groups); cur.counts.swap(nxt.counts);

@@ -1,0 +1,276 @@
+// mumemto_b200/csrc/stream.cu -- enumerate the suffix stream of T (rank order: SA and LCP) from the prefix-free-parse index, tile by tile.
+//
+// Replaces the hot loop of the reference, pfp_lcp::process (include/pfp_lcp_mum.hpp:115-231): walk the dictionary suffix array, group
+// equal dictionary suffixes, merge the occurrence lists of their phrases by the rank of the parse suffix that follows (a priority
+// queue there), and for every text suffix derive SA (:337-341) and LCP (:145,179,284-321) -- row D of SURVEY.md section 8.
+//
+// Here a "member" is one owned dictionary suffix (longer than w) in dictionary-suffix order; it contributes one text suffix per
+// occurrence of its phrase.  Members with equal strings form a group.
+//   expand_members   one warp per member streams its phrase's occurrence list: SA = start of the following phrase - (|alpha| - w).
+//                    A group with a single member is already in final order and its LCPs are |alpha| - w + (precomputed LCP between
+//                    consecutive occurrences); the first suffix of a group gets lcp(alpha_prev, alpha) from a byte comparison.
+//   merge_small      one block per multi-member group (<= 2048 suffixes): bitonic sort by following-suffix rank in shared memory, LCP by
+//                    range-minimum queries over s_lcp.      merge_large: the same through a device-wide radix sort.
+// Tiles end on group boundaries and carry `halo` ranks of the previous tile so that the interval detector can look back.
+// Traffic per text suffix: occurrence list 16 B read, SA 8 B + LCP 4 B written (+ 4 B key for multi-member groups).
+#include "pfp.h"
+#include "pfp_device.cuh"
+#include "prims.h"
+
+namespace mmb {
+
+namespace {
+
+constexpr u32 TPB = 256;
+constexpr u32 MERGE_MAX = 2048;
+constexpr u32 NOT_START = 0xffffffffu;
+
+__device__ __forceinline__ u64 load8(const u8* __restrict__ t, u64 i) {
+    const u32* w = reinterpret_cast<const u32*>(t + (i & ~3ull));
+    u32 sh = (u32)(i & 3) * 8;
+    u32 a = w[0], b = w[1], c = w[2];
+    u32 lo = sh ? __funnelshift_r(a, b, sh) : a;
+    u32 hi = sh ? __funnelshift_r(b, c, sh) : b;
+    return ((u64)hi << 32) | lo;
+}
+
+__global__ void __launch_bounds__(TPB) owned_flags(const u32* __restrict__ sa_d, const u32* __restrict__ limit, u32 dsize, u32* __restrict__ flag) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < dsize) flag[p] = limit[sa_d[p]] >= PFP_W + 2 ? 1u : 0u;      // |alpha| = limit - 1 > w
+    if (p == dsize) flag[p] = 0;
+}
+
+__global__ void __launch_bounds__(TPB) members_fill(const u32* __restrict__ sa_d, const u32* __restrict__ isa_d, const u32* __restrict__ dphrase,
+                                                    const u32* __restrict__ prank, const u32* __restrict__ occ_first, const u32* __restrict__ flag,
+                                                    const u32* __restrict__ idx, u32 dsize, u32* __restrict__ mem_i, u32* __restrict__ mem_head,
+                                                    u32* __restrict__ mem_cnt) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= dsize || !flag[p]) return;
+    u32 k = idx[p], i = sa_d[p], r = prank[dphrase[i]];
+    mem_i[k] = i; mem_head[k] = isa_d[i]; mem_cnt[k] = occ_first[r + 1] - occ_first[r];
+}
+
+// lcp between the strings of consecutive members that start a new group (byte comparison inside the dictionary)
+__global__ void __launch_bounds__(TPB) group_lcp(const u8* __restrict__ dict, const u32* __restrict__ limit, const u32* __restrict__ mem_i,
+                                                 const u32* __restrict__ mem_head, u32 K, u32* __restrict__ glcp) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    if (k == 0) { glcp[0] = 0; return; }
+    if (mem_head[k] == mem_head[k - 1]) { glcp[k] = NOT_START; return; }
+    u32 a = mem_i[k - 1], b = mem_i[k];
+    u32 cap = min(limit[a], limit[b]) - 1, l = 0;                  // different strings of a prefix-free set differ before either ends
+    while (l + 8 <= cap) {
+        u64 x = load8(dict, (u64)a + l) ^ load8(dict, (u64)b + l);
+        if (x) { l += (u32)((__ffsll((long long)x) - 1) >> 3); glcp[k] = l; return; }
+        l += 8;
+    }
+    while (l < cap && dict[a + l] == dict[b + l]) ++l;
+    glcp[k] = l;
+}
+
+__global__ void tile_bounds(const u64* __restrict__ out_base, const u32* __restrict__ glcp, u32 K, u64 tile_ranks, u32 nt, u32* __restrict__ bounds) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > nt) return;
+    if (t == nt) { bounds[t] = K; return; }
+    u64 target = (u64)t * tile_ranks;
+    u32 lo = 0, hi = K;                                     // first k with out_base[k] >= target
+    while (lo < hi) { u32 mid = lo + ((hi - lo) >> 1); if (out_base[mid] >= target) hi = mid; else lo = mid + 1; }
+    while (lo > 0 && lo < K && glcp[lo] == NOT_START) --lo;   // back to the start of that member's group
+    bounds[t] = lo;
+}
+
+// one warp per member of the tile
+__global__ void __launch_bounds__(TPB) expand_members(u32 k0, u32 k1, u32 K, const u32* __restrict__ mem_i, const u32* __restrict__ mem_cnt,
+                                                      const u64* __restrict__ out_base, const u32* __restrict__ glcp, const u32* __restrict__ limit,
+                                                      const u32* __restrict__ dphrase, const u32* __restrict__ prank, const u32* __restrict__ occ_first,
+                                                      const u32* __restrict__ occ_next_rank, const u64* __restrict__ occ_next_start,
+                                                      const u32* __restrict__ occ_lcp, u64 lead, u64* __restrict__ sa, u32* __restrict__ lcp,
+                                                      u32* __restrict__ key) {
+    u32 k = k0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (k >= k1) return;
+    u32 i = mem_i[k], shift = limit[i] - 1 - PFP_W, c = mem_cnt[k], q0 = occ_first[prank[dphrase[i]]];
+    u64 dst = out_base[k] - out_base[k0] + lead;
+    bool single = glcp[k] != NOT_START && (k + 1 == K || glcp[k + 1] != NOT_START);
+    for (u32 t = lane; t < c; t += 32) {
+        sa[dst + t] = occ_next_start[q0 + t] - shift;
+        if (single) lcp[dst + t] = t ? shift + occ_lcp[q0 + t] : glcp[k];
+        else key[dst + t] = occ_next_rank[q0 + t];
+    }
+}
+
+// group starts that have more than one member -> (first member, end member) by size
+__global__ void __launch_bounds__(TPB) collect_multi(u32 k0, u32 k1, u32 K, const u32* __restrict__ glcp, const u64* __restrict__ out_base,
+                                                     u64* __restrict__ small, u64* __restrict__ large, u32* __restrict__ counts) {
+    u32 k = k0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k1 || glcp[k] == NOT_START || k + 1 >= K || glcp[k + 1] != NOT_START) return;
+    u32 e = k + 1;
+    while (e < K && glcp[e] == NOT_START) ++e;
+    u64 g = out_base[e] - out_base[k];
+    if (g <= MERGE_MAX) small[atomicAdd(&counts[0], 1u)] = ((u64)k << 32) | e;
+    else large[atomicAdd(&counts[1], 1u)] = ((u64)k << 32) | e;
+}
+
+__global__ void __launch_bounds__(TPB) merge_small(const u64* __restrict__ groups, u32 k0, const u64* __restrict__ out_base, const u32* __restrict__ glcp,
+                                                   const u32* __restrict__ mem_i, const u32* __restrict__ limit, const u32* __restrict__ s_lcp,
+                                                   const u32* __restrict__ rmq, u32 rmq_blocks, u64 lead, u64* __restrict__ sa, u32* __restrict__ lcp,
+                                                   const u32* __restrict__ key) {
+    __shared__ u64 item[MERGE_MAX];       // key << 32 | index
+    __shared__ u64 pos[MERGE_MAX];
+    u64 g = groups[blockIdx.x];
+    u32 ks = (u32)(g >> 32), ke = (u32)g;
+    u64 base = out_base[ks] - out_base[k0] + lead;
+    u32 G = (u32)(out_base[ke] - out_base[ks]);
+    u32 shift = limit[mem_i[ks]] - 1 - PFP_W;
+    u32 n2 = 1; while (n2 < G) n2 <<= 1;
+    for (u32 e = threadIdx.x; e < n2; e += blockDim.x) {
+        if (e < G) { item[e] = ((u64)key[base + e] << 32) | e; pos[e] = sa[base + e]; } else item[e] = ~0ull;
+    }
+    __syncthreads();
+    for (u32 k = 2; k <= n2; k <<= 1)
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            for (u32 e = threadIdx.x; e < n2; e += blockDim.x) {
+                u32 partner = e ^ j;
+                if (partner > e) {
+                    u64 a = item[e], b = item[partner];
+                    if ((a > b) == ((e & k) == 0)) { item[e] = b; item[partner] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (u32 e = threadIdx.x; e < G; e += blockDim.x) {
+        u64 it = item[e];
+        sa[base + e] = pos[(u32)it];
+        lcp[base + e] = e ? shift + range_min(s_lcp, rmq, rmq_blocks, (u32)(item[e - 1] >> 32) + 1, (u32)(it >> 32)) : glcp[ks];
+    }
+}
+
+__global__ void large_sizes(const u64* __restrict__ groups, u32 n, const u64* __restrict__ out_base, u64* __restrict__ sizes) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { u64 g = groups[i]; sizes[i] = out_base[(u32)g] - out_base[(u32)(g >> 32)]; }
+    if (i == n) sizes[i] = 0;
+}
+__global__ void __launch_bounds__(TPB) large_gather(const u64* __restrict__ groups, const u64* __restrict__ fbase, u32 k0, const u64* __restrict__ out_base,
+                                                    u64 lead, const u64* __restrict__ sa, const u32* __restrict__ key, u64* __restrict__ fkeys,
+                                                    u64* __restrict__ fvals) {
+    u64 g = groups[blockIdx.x];
+    u32 ks = (u32)(g >> 32), ke = (u32)g;
+    u64 base = out_base[ks] - out_base[k0] + lead, G = out_base[ke] - out_base[ks], fb = fbase[blockIdx.x];
+    for (u64 e = (u64)blockIdx.y * blockDim.x + threadIdx.x; e < G; e += (u64)gridDim.y * blockDim.x) {
+        fkeys[fb + e] = ((u64)blockIdx.x << 32) | key[base + e];
+        fvals[fb + e] = sa[base + e];
+    }
+}
+__global__ void __launch_bounds__(TPB) large_scatter(const u64* __restrict__ groups, const u64* __restrict__ fbase, u64 total, u32 k0,
+                                                     const u64* __restrict__ out_base, const u32* __restrict__ glcp, const u32* __restrict__ mem_i,
+                                                     const u32* __restrict__ limit, const u32* __restrict__ s_lcp, const u32* __restrict__ rmq,
+                                                     u32 rmq_blocks, u64 lead, const u64* __restrict__ fkeys, const u64* __restrict__ fvals,
+                                                     u64* __restrict__ sa, u32* __restrict__ lcp) {
+    u64 a = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= total) return;
+    u64 fk = fkeys[a];
+    u32 seq = (u32)(fk >> 32);
+    u64 g = groups[seq];
+    u32 ks = (u32)(g >> 32);
+    u64 t = a - fbase[seq], dst = out_base[ks] - out_base[k0] + lead + t;
+    u32 shift = limit[mem_i[ks]] - 1 - PFP_W;
+    sa[dst] = fvals[a];
+    lcp[dst] = t ? shift + range_min(s_lcp, rmq, rmq_blocks, (u32)fkeys[a - 1] + 1, (u32)fk) : glcp[ks];
+}
+
+__global__ void tile_edges(u64* __restrict__ sa, u32* __restrict__ lcp, u64 n, int first_tile, u64 count) {
+    u32 t = threadIdx.x;
+    if (t < 64) lcp[count + t] = 0;                              // zero slack for the detector's rounded tile loads
+    if (first_tile && t == 0) { sa[0] = n; lcp[0] = 0; }         // rank 0: the sentinel suffix
+}
+
+}  // namespace
+
+void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 halo, TileConsumer& consumer, cudaStream_t s) {
+    (void)text;
+    u32 dsize = ix.dsize;
+    // ---- members (owned dictionary suffixes in suffix order)
+    DevBuf<u32> flag, idx; flag.alloc((u64)dsize + 1, s); idx.alloc((u64)dsize + 1, s);
+    MMB_LAUNCH(owned_flags, ceil_div((u64)dsize + 1, TPB), TPB, 0, s, (const u32*)ix.sa_d.p, (const u32*)ix.limit.p, dsize, flag.p);
+    prim::exclusive_sum(flag.p, idx.p, (u64)dsize + 1, s);
+    u32 K = to_host(idx.p + dsize, 1, s)[0];
+    DevBuf<u32> mem_i, mem_head, mem_cnt, glcp; DevBuf<u64> out_base;
+    mem_i.alloc(K, s); mem_head.alloc(K, s); mem_cnt.alloc((u64)K + 1, s); glcp.alloc((u64)K + 1, s); out_base.alloc((u64)K + 1, s);
+    MMB_CUDA(cudaMemsetAsync(mem_cnt.p + K, 0, 4, s));
+    MMB_LAUNCH(members_fill, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.sa_d.p, (const u32*)ix.isa_d.p, (const u32*)ix.dphrase.p, (const u32*)ix.prank.p,
+               (const u32*)ix.occ_first.p, (const u32*)flag.p, (const u32*)idx.p, dsize, mem_i.p, mem_head.p, mem_cnt.p);
+    flag.release(); idx.release();
+    prim::exclusive_sum(mem_cnt.p, out_base.p, (u64)K + 1, s);
+    u64 total = to_host(out_base.p + K, 1, s)[0];
+    if (total != ix.n) throw Error(76, "internal: the parse does not cover the text (" + std::to_string(total) + " of " + std::to_string(ix.n) + ")");
+    MMB_LAUNCH(group_lcp, ceil_div(K, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const u32*)ix.limit.p, (const u32*)mem_i.p, (const u32*)mem_head.p, K, glcp.p);
+    mem_head.release();
+
+    // ---- tile boundaries on group starts
+    u32 nt = (u32)((ix.n + tile_ranks - 1) / tile_ranks);
+    DevBuf<u32> d_bounds; d_bounds.alloc(nt + 1, s);
+    MMB_LAUNCH(tile_bounds, ceil_div(nt + 1, 128), 128, 0, s, (const u64*)out_base.p, (const u32*)glcp.p, K, tile_ranks, nt, d_bounds.p);
+    std::vector<u32> raw_bounds = to_host(d_bounds.p, nt + 1, s);
+    std::vector<u32> bounds;
+    for (u32 b : raw_bounds) if (bounds.empty() || b > bounds.back()) bounds.push_back(b);
+    if (bounds.empty() || bounds[0] != 0) bounds.insert(bounds.begin(), 0);
+    std::vector<u64> h_base(bounds.size());
+    for (size_t t = 0; t < bounds.size(); ++t) MMB_CUDA(cudaMemcpyAsync(&h_base[t], out_base.p + bounds[t], 8, cudaMemcpyDeviceToHost, s));
+    MMB_CUDA(cudaStreamSynchronize(s));
+    u64 max_new = 0;
+    for (size_t t = 0; t + 1 < bounds.size(); ++t) max_new = std::max(max_new, h_base[t + 1] - h_base[t]);
+
+    // ---- tile buffers: [halo | new ranks | 64 slack]; the first tile starts with the sentinel rank instead of a halo
+    u64 cap = (u64)halo + max_new + 1;
+    DevBuf<u64> sa, halo_sa, small, large; DevBuf<u32> lcp, key, halo_lcp, counts;
+    sa.alloc(cap, s); lcp.alloc(cap + 64, s); key.alloc(cap, s); halo_sa.alloc(halo + 1, s); halo_lcp.alloc(halo + 1, s); counts.alloc(2, s);
+    u64 rank_next = 0;                  // global rank of the first new entry of the coming tile
+    u64 halo_have = 0;
+    for (size_t t = 0; t + 1 < bounds.size(); ++t) {
+        u32 k0 = bounds[t], k1 = bounds[t + 1];
+        bool first_tile = (t == 0), last_tile = (t + 2 == bounds.size());
+        u64 fresh = h_base[t + 1] - h_base[t];
+        u64 lead = first_tile ? 1 : halo_have;          // view index of the first member-generated entry
+        if (!first_tile && halo_have) {
+            MMB_CUDA(cudaMemcpyAsync(sa.p, halo_sa.p, halo_have * 8, cudaMemcpyDeviceToDevice, s));
+            MMB_CUDA(cudaMemcpyAsync(lcp.p, halo_lcp.p, halo_have * 4, cudaMemcpyDeviceToDevice, s));
+        }
+        u32 nm = k1 - k0;
+        small.alloc((u64)nm / 2 + 1, s); large.alloc((u64)nm / 2 + 1, s); counts.zero();
+        MMB_LAUNCH(expand_members, ceil_div((u64)nm * 32, TPB), TPB, 0, s, k0, k1, K, (const u32*)mem_i.p, (const u32*)mem_cnt.p, (const u64*)out_base.p,
+                   (const u32*)glcp.p, (const u32*)ix.limit.p, (const u32*)ix.dphrase.p, (const u32*)ix.prank.p, (const u32*)ix.occ_first.p,
+                   (const u32*)ix.occ_next_rank.p, (const u64*)ix.occ_next_start.p, (const u32*)ix.occ_lcp.p, lead, sa.p, lcp.p, key.p);
+        MMB_LAUNCH(collect_multi, ceil_div(nm, TPB), TPB, 0, s, k0, k1, K, (const u32*)glcp.p, (const u64*)out_base.p, small.p, large.p, counts.p);
+        std::vector<u32> c = to_host(counts.p, 2, s);
+        if (c[0]) MMB_LAUNCH(merge_small, c[0], TPB, 0, s, (const u64*)small.p, k0, (const u64*)out_base.p, (const u32*)glcp.p, (const u32*)mem_i.p,
+                             (const u32*)ix.limit.p, (const u32*)ix.s_lcp.p, (const u32*)ix.rmq.p, ix.rmq_blocks, lead, sa.p, lcp.p, (const u32*)key.p);
+        if (c[1]) {
+            u32 nl = c[1];
+            DevBuf<u64> sizes, fbase, fk_a, fk_b, fv_a, fv_b;
+            sizes.alloc(nl + 1, s); fbase.alloc(nl + 1, s);
+            MMB_LAUNCH(large_sizes, ceil_div(nl + 1, TPB), TPB, 0, s, (const u64*)large.p, nl, (const u64*)out_base.p, sizes.p);
+            prim::exclusive_sum(sizes.p, fbase.p, nl + 1, s);
+            u64 ftotal = to_host(fbase.p + nl, 1, s)[0];
+            fk_a.alloc(ftotal, s); fk_b.alloc(ftotal, s); fv_a.alloc(ftotal, s); fv_b.alloc(ftotal, s);
+            dim3 grid(nl, 32);
+            MMB_LAUNCH(large_gather, grid, TPB, 0, s, (const u64*)large.p, (const u64*)fbase.p, k0, (const u64*)out_base.p, lead, (const u64*)sa.p,
+                       (const u32*)key.p, fk_a.p, fv_a.p);
+            prim::sort_pairs64(fk_a.p, fk_b.p, fv_a.p, fv_b.p, ftotal, 0, 64, s);
+            MMB_LAUNCH(large_scatter, ceil_div(ftotal, TPB), TPB, 0, s, (const u64*)large.p, (const u64*)fbase.p, ftotal, k0, (const u64*)out_base.p,
+                       (const u32*)glcp.p, (const u32*)mem_i.p, (const u32*)ix.limit.p, (const u32*)ix.s_lcp.p, (const u32*)ix.rmq.p, ix.rmq_blocks, lead,
+                       (const u64*)fk_b.p, (const u64*)fv_b.p, sa.p, lcp.p);
+        }
+        u64 count = lead + fresh;
+        MMB_LAUNCH(tile_edges, 1, 64, 0, s, sa.p, lcp.p, ix.n, (int)first_tile, count);
+        StreamTile tile;
+        tile.rank0 = first_tile ? 0 : rank_next - halo_have;
+        tile.count = count; tile.first = first_tile ? 0 : halo_have; tile.sa = sa.p; tile.lcp = lcp.p; tile.last = last_tile;
+        consumer.consume(tile);
+        // stash the tail as the next tile's halo
+        halo_have = std::min<u64>(halo, count);
+        MMB_CUDA(cudaMemcpyAsync(halo_sa.p, sa.p + (count - halo_have), halo_have * 8, cudaMemcpyDeviceToDevice, s));
+        MMB_CUDA(cudaMemcpyAsync(halo_lcp.p, lcp.p + (count - halo_have), halo_have * 4, cudaMemcpyDeviceToDevice, s));
+        rank_next = (first_tile ? 1 : rank_next) + fresh;
+    }
+}
+
+}  // namespace mmb

@@ -166,3 +166,60 @@ def test_size_independent_properties(cuda_lib, tmp_path):
                 seg = comp[seg[::-1]]
             assert (seg == ref).all()
     e.close()
+
+
+# ------------------------------------------------------------------------------------------------ prefix-free-parse route
+@pytest.mark.parametrize("name", ["strict", "partial", "mem", "anchor"])
+def test_c1_golden_pfp_route(cuda_lib, c1, name):
+    """C1 through the dictionary/parse route with 64 stream tiles: same golden md5s."""
+    d, paths, table = c1
+    st = api.find_files(paths, os.path.join(d, "p_" + name), route="pfp", tile_ranks=160000, _lib=cuda_lib, **util.flags_to_kwargs(table["outputs"][name]["flags"]))
+    got = {ext: util.md5(b) for ext, b in util.outputs(os.path.join(d, "p_" + name)).items()}
+    assert got == table["outputs"][name]["md5"]
+    assert st["route"] == 2 and st["pfp_tiles"] >= 60
+
+
+@pytest.mark.parametrize("name", ["strict", "arrays", "memF", "bumbl", "norc"])
+def test_t2_golden_pfp_route(cuda_lib, t2, name):
+    d, paths, table = t2
+    api.find_files(paths, os.path.join(d, "p_" + name), route="pfp", tile_ranks=9000, _lib=cuda_lib, **util.flags_to_kwargs(T2_FLAGS[name]))
+    got = {ext: util.md5(b) for ext, b in util.outputs(os.path.join(d, "p_" + name)).items()}
+    assert got == table["outputs"][name]["md5"]
+
+
+def test_pfp_route_repeats_and_many_docs(cuda_lib, oracle_bin, tmp_path):
+    rng = np.random.default_rng(17)
+    unit = util.random_dna(rng, 37)
+    body = util.random_dna(rng, 30000)
+    docs = [
+        "A" * 9000 + body + unit * 300 + "ACGT" * 400 + body[:7000] + "G" * 4500,
+        "A" * 300 + util.mutate(rng, body, 0.01) + unit * 260 + "C" * 150 + body[2000:9000],
+        util.mutate(rng, body, 0.02) + "AC" * 2700 + unit * 120 + "A" * 1000,
+    ]
+    p = [util.write_fasta(str(tmp_path / f"d{i}.fa"), [(f"d{i}", s)], width=77) for i, s in enumerate(docs)]
+    for i, flags in enumerate(([], ["-f", "4", "-k", "2", "-l", "15", "-A"], ["-r", "-f", "2"])):
+        o, g = str(tmp_path / f"o{i}"), str(tmp_path / f"g{i}")
+        util.run_cli(oracle_bin, ["-o", o, *flags, *p])
+        api.find_files(p, g, route="pfp", tile_ranks=50000, _lib=cuda_lib, **util.flags_to_kwargs(flags))
+        assert util.outputs(g) == util.outputs(o), flags
+    paths = util.appendix_a(str(tmp_path / "many"), N=70, L=3000, seed=24, snp=0.02)
+    for i, flags in enumerate(([], ["-k", "-2"], ["-M", "-n"])):
+        o, g = str(tmp_path / f"mo{i}"), str(tmp_path / f"mg{i}")
+        util.run_cli(oracle_bin, ["-o", o, *flags, *paths])
+        api.find_files(paths, g, route="pfp", _lib=cuda_lib, **util.flags_to_kwargs(flags))
+        assert util.outputs(g) == util.outputs(o), flags
+
+
+def test_pfp_route_equals_direct_route_pangenome(cuda_lib, tmp_path):
+    """64 haplotype-like documents (shared variants): the two routes must produce the same bytes (sizes where the CPU oracle is slow)."""
+    import bench
+    imgs = bench.make_collection(dict(N=64, L=300000, kind="pangenome"), seed=3)
+    paths = []
+    for i, im in enumerate(imgs):
+        p = str(tmp_path / f"h{i}.fa"); im.tofile(p); paths.append(p)
+    for i, flags in enumerate(([], ["-k", "-1"], ["-f", "3", "-F", "100"])):
+        a, b = str(tmp_path / f"a{i}"), str(tmp_path / f"b{i}")
+        api.find_files(paths, a, route="direct", _lib=cuda_lib, **util.flags_to_kwargs(flags))
+        st = api.find_files(paths, b, route="pfp", tile_ranks=1 << 22, _lib=cuda_lib, **util.flags_to_kwargs(flags))
+        assert util.outputs(a) == util.outputs(b), flags
+        assert st["pfp_dict_bytes"] < 0.2 * st["text_symbols"]

@@ -169,3 +169,53 @@ def test_simt_walk_kernel_fallback(simt_lib, oracle_bin, small, tmp_path, flags,
     """The leftward-walk detector (used when more than 64 interval sizes can qualify) must agree with the windowed one."""
     monkeypatch.setenv("MMB_FORCE_WALK", "1")
     both(simt_lib, oracle_bin, str(tmp_path), small, flags)
+
+
+# ------------------------------------------------------------------------------------------------ prefix-free-parse route (tiled stream)
+def both_pfp(simt_lib, oracle_bin, tmp, paths, flags, tile_ranks):
+    o, g = os.path.join(tmp, "o"), os.path.join(tmp, "g")
+    util.run_cli(oracle_bin, ["-o", o, *flags, *paths])
+    st = api.find_files(paths, g, route="pfp", tile_ranks=tile_ranks, _lib=simt_lib, **util.flags_to_kwargs(flags))
+    assert st["route"] == 2
+    assert util.outputs(g) == util.outputs(o), flags
+    return st
+
+
+@pytest.mark.parametrize("name", ["strict", "partial", "mem", "anchor", "arrays", "norc", "mem2", "memF", "bumbl"])
+def test_simt_pfp_route_equals_oracle(simt_lib, oracle_bin, small, tmp_path, name):
+    """Dictionary + parse suffix arrays, tiled enumeration (SA/LCP per tile with halo), same detector: byte-identical outputs, including the
+    .sa/.lcp/.bwt arrays, with tiles so small that intervals straddle tile boundaries."""
+    st = both_pfp(simt_lib, oracle_bin, str(tmp_path), small, FLAGSETS[name], tile_ranks=700)
+    assert st["pfp_tiles"] > 10 and st["pfp_distinct_phrases"] < st["pfp_phrases"]
+
+
+@pytest.mark.parametrize("block_order", [0, 2])
+def test_simt_pfp_route_repeats(simt_lib, oracle_bin, tmp_path, block_order):
+    """Tandem repeats and low-complexity runs: dictionary suffixes shared by many phrases (multi-member groups beyond one block's
+    shared-memory sort), long phrases, phrases of minimum length."""
+    rng = np.random.default_rng(17)
+    unit = util.random_dna(rng, 37)
+    body = util.random_dna(rng, 1500)
+    docs = [
+        "A" * 5200 + body + unit * 90 + "ACGT" * 40 + body[:700],
+        "A" * 300 + util.mutate(rng, body, 0.01) + unit * 60 + "C" * 150 + body[200:900],
+        util.mutate(rng, body, 0.02) + "AC" * 700 + unit * 20 + "A" * 100,
+    ]
+    p = [util.write_fasta(str(tmp_path / f"d{i}.fa"), [(f"d{i}", s)], width=77) for i, s in enumerate(docs)]
+    simt_lib.simt_set_block_order(block_order)
+    try:
+        for flags in ([], ["-f", "4", "-k", "2", "-l", "15", "-A"], ["-r", "-f", "2"]):
+            both_pfp(simt_lib, oracle_bin, str(tmp_path), p, flags, tile_ranks=3000)
+    finally:
+        simt_lib.simt_set_block_order(0)
+
+
+def test_simt_pfp_route_edge_inputs(simt_lib, oracle_bin, tmp_path):
+    rng = np.random.default_rng(5)
+    core = util.random_dna(rng, 700)
+    p = []
+    p.append(util.write_fasta(str(tmp_path / "multi.fa"), [("c1 desc", core[:250]), ("c2", core[250:480]), ("c3", core[480:])], width=50))
+    p.append(util.write_fasta(str(tmp_path / "lower.fasta"), [("x", util.mutate(rng, core, 0.02).lower())], width=61))
+    p.append(util.write_fasta(str(tmp_path / "iupac.fna"), [("y", util.mutate(rng, core, 0.01)[:300] + "NNNNNRYKMSWBDHVNU" + core[317:])], width=50, newline="\r\n"))
+    for flags in ([], ["-f", "2"], ["-k", "-1", "-l", "10", "-A"]):
+        both_pfp(simt_lib, oracle_bin, str(tmp_path), p, flags, tile_ranks=0)
