@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -52,6 +53,14 @@ inline void check(cudaError_t e, const char* what, const char* file, int line) {
 #endif
 
 inline u32 ceil_div(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
+
+// MMB_DEBUG=1: wall-clock of a host-side phase (synchronises the stream at both ends; never active in measured runs)
+struct PhaseTimer {
+    const char* name; cudaStream_t s; bool on; double t0 = 0;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    PhaseTimer(const char* n, cudaStream_t st) : name(n), s(st), on(getenv("MMB_DEBUG") != nullptr) { if (on) { cudaStreamSynchronize(s); t0 = now(); } }
+    ~PhaseTimer() { if (on) { cudaStreamSynchronize(s); fprintf(stderr, "[phase] %-28s %9.3f ms\n", name, now() - t0); } }
+};
 
 // Stream-ordered device buffer.
 template <class T>

@@ -267,6 +267,7 @@ void build_pfp_index(const u8* text, u64 n, PfpIndex& ix, cudaStream_t s) {
     ix.n = n;
     if (n < PFP_W + 2) throw Error(70, "text too short for the prefix-free parse route");
     // ---- 1. triggers
+    PhaseTimer* pt = new PhaseTimer("pfp 1 triggers", s);
     u64 nblk64 = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     if (nblk64 > 0x7fffffffull) throw Error(71, "text too long");
     u32 nblk = (u32)nblk64;
@@ -289,6 +290,7 @@ void build_pfp_index(const u8* text, u64 n, PfpIndex& ix, cudaStream_t s) {
     ends.release(); bcount.release(); bbase.release();
 
     // ---- 2. phrase identity
+    delete pt; pt = new PhaseTimer("pfp 2 phrase identity", s);
     DevBuf<u32> pid, rep; pid.alloc(np, s); rep.alloc(np, s);
     u32 nd = 0;
     for (u64 attempt = 0;; ++attempt) {
@@ -312,6 +314,7 @@ void build_pfp_index(const u8* text, u64 n, PfpIndex& ix, cudaStream_t s) {
     ix.nd = nd;
 
     // ---- 3. dictionary
+    delete pt; pt = new PhaseTimer("pfp 3 dictionary", s);
     {
         DevBuf<u64> dlen, doff64; dlen.alloc(nd + 1, s); doff64.alloc(nd + 1, s);
         MMB_LAUNCH(dict_lengths, ceil_div(nd + 1, TPB), TPB, 0, s, (const u64*)ix.pstart.p, (const u32*)rep.p, nd, dlen.p);
@@ -330,6 +333,7 @@ void build_pfp_index(const u8* text, u64 n, PfpIndex& ix, cudaStream_t s) {
     rep.release();
 
     // ---- 4. suffix order of the dictionary (ties allowed)
+    delete pt; pt = new PhaseTimer("pfp 4 dictionary SA", s);
     {
         DevBuf<u32> hist; hist.alloc(256, s); hist.zero();
         MMB_LAUNCH(dict_histogram, 148 * 8, TPB, 0, s, (const u8*)ix.dict.p, dsize, hist.p);
@@ -352,6 +356,7 @@ void build_pfp_index(const u8* text, u64 n, PfpIndex& ix, cudaStream_t s) {
     }
 
     // ---- 5. phrase ranks and the parse
+    delete pt; pt = new PhaseTimer("pfp 5 phrase ranks", s);
     ix.prank.alloc(nd, s);
     {
         DevBuf<u64> ka, kb; DevBuf<u32> va, vb; ka.alloc(nd, s); kb.alloc(nd, s); va.alloc(nd, s); vb.alloc(nd, s);
@@ -366,6 +371,7 @@ void build_pfp_index(const u8* text, u64 n, PfpIndex& ix, cudaStream_t s) {
     pid.release();
 
     // ---- 6. suffix order of the parse
+    delete pt; pt = new PhaseTimer("pfp 6 parse SA", s);
     DevBuf<u32> sa_p; sa_p.alloc(m, s); ix.isa_p.alloc(m, s);
     {
         u32 b = 1; while ((1ull << b) <= nd) ++b;
@@ -379,6 +385,7 @@ void build_pfp_index(const u8* text, u64 n, PfpIndex& ix, cudaStream_t s) {
     }
 
     // ---- 7. text-level LCP between rank-adjacent parse suffixes
+    delete pt; pt = new PhaseTimer("pfp 7 s_lcp", s);
     ix.s_lcp.alloc(m, s);
     {
         DevBuf<u32> overflow; overflow.alloc(1, s); overflow.zero();
@@ -390,6 +397,7 @@ void build_pfp_index(const u8* text, u64 n, PfpIndex& ix, cudaStream_t s) {
     sa_p.release();
 
     // ---- 8. range-minimum index and occurrence lists
+    delete pt; pt = new PhaseTimer("pfp 8 rmq + occurrences", s);
     ix.rmq_blocks = (m + 31) / 32;
     ix.rmq_levels = 1; while ((1u << ix.rmq_levels) <= ix.rmq_blocks) ++ix.rmq_levels;
     ix.rmq.alloc((u64)ix.rmq_levels * ix.rmq_blocks, s);
@@ -406,6 +414,7 @@ void build_pfp_index(const u8* text, u64 n, PfpIndex& ix, cudaStream_t s) {
         MMB_LAUNCH(occ_fill, ceil_div(np, TPB), TPB, 0, s, (const u64*)kb.p, (const u32*)vb.p, (const u64*)ix.pstart.p, np, nd, (const u32*)ix.s_lcp.p,
                    (const u32*)ix.rmq.p, ix.rmq_blocks, ix.occ_first.p, ix.occ_next_rank.p, ix.occ_next_start.p, ix.occ_lcp.p);
     }
+    delete pt;
 }
 
 }  // namespace mmb

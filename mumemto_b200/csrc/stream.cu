@@ -9,8 +9,9 @@
 //   expand_members   one warp per member streams its phrase's occurrence list: SA = start of the following phrase - (|alpha| - w).
 //                    A group with a single member is already in final order and its LCPs are |alpha| - w + (precomputed LCP between
 //                    consecutive occurrences); the first suffix of a group gets lcp(alpha_prev, alpha) from a byte comparison.
-//   merge_small      one block per multi-member group (<= 2048 suffixes): bitonic sort by following-suffix rank in shared memory, LCP by
-//                    range-minimum queries over s_lcp.      merge_large: the same through a device-wide radix sort.
+//                    Groups of 2..8 members are merged in the same kernel by binary searches in the other members' (sorted) lists.
+//   merge_small      groups with more members (repeats), <= 2048 suffixes: one block, bitonic sort by following-suffix rank in shared
+//                    memory, LCP by range-minimum queries over s_lcp.      merge_large: the same through a device-wide radix sort.
 // Tiles end on group boundaries and carry `halo` ranks of the previous tile so that the interval detector can look back.
 // Traffic per text suffix: occurrence list 16 B read, SA 8 B + LCP 4 B written (+ 4 B key for multi-member groups).
 #include "pfp.h"
@@ -79,22 +80,69 @@ __global__ void tile_bounds(const u64* __restrict__ out_base, const u32* __restr
     bounds[t] = lo;
 }
 
-// one warp per member of the tile
+constexpr u32 FUSE_MAX_MEMBERS = 8;      // groups with at most this many members are merged inside expand_members
+
+// first index in the ascending list v[0..c) whose value is >= x
+__device__ __forceinline__ u32 lower_bound_u32(const u32* __restrict__ v, u32 c, u32 x) {
+    u32 lo = 0, hi = c;
+    while (lo < hi) { u32 mid = (lo + hi) >> 1; if (v[mid] < x) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// One warp per member of the tile.  The occurrence list of every member is already ordered by the rank of the following parse
+// suffix, so in a group of M members the final slot of an element is its own index plus, for each other member, the number of that
+// member's elements with a smaller rank (one binary search each); the same searches give the predecessor in merged order, hence the
+// LCP.  Groups with more than FUSE_MAX_MEMBERS members only get their (rank, SA) pairs written here and are sorted afterwards.
 __global__ void __launch_bounds__(TPB) expand_members(u32 k0, u32 k1, u32 K, const u32* __restrict__ mem_i, const u32* __restrict__ mem_cnt,
                                                       const u64* __restrict__ out_base, const u32* __restrict__ glcp, const u32* __restrict__ limit,
                                                       const u32* __restrict__ dphrase, const u32* __restrict__ prank, const u32* __restrict__ occ_first,
                                                       const u32* __restrict__ occ_next_rank, const u64* __restrict__ occ_next_start,
-                                                      const u32* __restrict__ occ_lcp, u64 lead, u64* __restrict__ sa, u32* __restrict__ lcp,
-                                                      u32* __restrict__ key) {
+                                                      const u32* __restrict__ occ_lcp, const u32* __restrict__ s_lcp, const u32* __restrict__ rmq,
+                                                      u32 rmq_blocks, u64 lead, u64* __restrict__ sa, u32* __restrict__ lcp, u32* __restrict__ key) {
     u32 k = k0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (k >= k1) return;
     u32 i = mem_i[k], shift = limit[i] - 1 - PFP_W, c = mem_cnt[k], q0 = occ_first[prank[dphrase[i]]];
+    // the group of this member: [ks, ke)
+    u32 ks = k, ke = k + 1;                                    // bounded scans: only "at most FUSE_MAX_MEMBERS members" matters
+    for (u32 b = 0; glcp[ks] == NOT_START && b <= FUSE_MAX_MEMBERS; ++b) --ks;      // tiles start on group starts: stays inside the tile
+    bool big = glcp[ks] == NOT_START;
+    while (!big && ke < K && glcp[ke] == NOT_START) { ++ke; if (ke - ks > FUSE_MAX_MEMBERS) big = true; }
+    u32 M = big ? FUSE_MAX_MEMBERS + 1 : ke - ks;
     u64 dst = out_base[k] - out_base[k0] + lead;
-    bool single = glcp[k] != NOT_START && (k + 1 == K || glcp[k + 1] != NOT_START);
+    if (M == 1) {
+        for (u32 t = lane; t < c; t += 32) {
+            sa[dst + t] = occ_next_start[q0 + t] - shift;
+            lcp[dst + t] = t ? shift + occ_lcp[q0 + t] : glcp[k];
+        }
+        return;
+    }
+    if (M > FUSE_MAX_MEMBERS) {
+        for (u32 t = lane; t < c; t += 32) { sa[dst + t] = occ_next_start[q0 + t] - shift; key[dst + t] = occ_next_rank[q0 + t]; }
+        return;
+    }
+    u64 gbase = out_base[ks] - out_base[k0] + lead;
+    u32 oq[FUSE_MAX_MEMBERS], oc[FUSE_MAX_MEMBERS];            // the other members' lists
+#pragma unroll
+    for (u32 j = 0; j < FUSE_MAX_MEMBERS; ++j) {
+        oq[j] = 0; oc[j] = 0;
+        u32 kk = ks + j;
+        if (j < M && kk != k) { oq[j] = occ_first[prank[dphrase[mem_i[kk]]]]; oc[j] = mem_cnt[kk]; }
+    }
     for (u32 t = lane; t < c; t += 32) {
-        sa[dst + t] = occ_next_start[q0 + t] - shift;
-        if (single) lcp[dst + t] = t ? shift + occ_lcp[q0 + t] : glcp[k];
-        else key[dst + t] = occ_next_rank[q0 + t];
+        u32 r = occ_next_rank[q0 + t];
+        u32 slot = t;
+        bool has_pred = t > 0;
+        u32 pred = has_pred ? occ_next_rank[q0 + t - 1] : 0u;
+#pragma unroll
+        for (u32 j = 0; j < FUSE_MAX_MEMBERS; ++j) {
+            if (oc[j]) {
+                u32 lb = lower_bound_u32(occ_next_rank + oq[j], oc[j], r);
+                slot += lb;
+                if (lb) { u32 v = occ_next_rank[oq[j] + lb - 1]; if (!has_pred || v > pred) pred = v; has_pred = true; }
+            }
+        }
+        sa[gbase + slot] = occ_next_start[q0 + t] - shift;
+        lcp[gbase + slot] = has_pred ? shift + range_min(s_lcp, rmq, rmq_blocks, pred + 1, r) : glcp[ks];
     }
 }
 
@@ -105,6 +153,7 @@ __global__ void __launch_bounds__(TPB) collect_multi(u32 k0, u32 k1, u32 K, cons
     if (k >= k1 || glcp[k] == NOT_START || k + 1 >= K || glcp[k + 1] != NOT_START) return;
     u32 e = k + 1;
     while (e < K && glcp[e] == NOT_START) ++e;
+    if (e - k <= FUSE_MAX_MEMBERS) return;                     // merged inside expand_members
     u64 g = out_base[e] - out_base[k];
     if (g <= MERGE_MAX) small[atomicAdd(&counts[0], 1u)] = ((u64)k << 32) | e;
     else large[atomicAdd(&counts[1], 1u)] = ((u64)k << 32) | e;
@@ -188,6 +237,7 @@ __global__ void tile_edges(u64* __restrict__ sa, u32* __restrict__ lcp, u64 n, i
 void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 halo, TileConsumer& consumer, cudaStream_t s) {
     (void)text;
     u32 dsize = ix.dsize;
+    PhaseTimer* pt = new PhaseTimer("stream members+bounds", s);
     // ---- members (owned dictionary suffixes in suffix order)
     DevBuf<u32> flag, idx; flag.alloc((u64)dsize + 1, s); idx.alloc((u64)dsize + 1, s);
     MMB_LAUNCH(owned_flags, ceil_div((u64)dsize + 1, TPB), TPB, 0, s, (const u32*)ix.sa_d.p, (const u32*)ix.limit.p, dsize, flag.p);
@@ -219,6 +269,7 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
     u64 max_new = 0;
     for (size_t t = 0; t + 1 < bounds.size(); ++t) max_new = std::max(max_new, h_base[t + 1] - h_base[t]);
 
+    delete pt;
     // ---- tile buffers: [halo | new ranks | 64 slack]; the first tile starts with the sentinel rank instead of a halo
     u64 cap = (u64)halo + max_new + 1;
     DevBuf<u64> sa, halo_sa, small, large; DevBuf<u32> lcp, key, halo_lcp, counts;
@@ -228,6 +279,7 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
     for (size_t t = 0; t + 1 < bounds.size(); ++t) {
         u32 k0 = bounds[t], k1 = bounds[t + 1];
         bool first_tile = (t == 0), last_tile = (t + 2 == bounds.size());
+        PhaseTimer* tt = new PhaseTimer("stream tile: enumerate", s);
         u64 fresh = h_base[t + 1] - h_base[t];
         u64 lead = first_tile ? 1 : halo_have;          // view index of the first member-generated entry
         if (!first_tile && halo_have) {
@@ -238,7 +290,8 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
         small.alloc((u64)nm / 2 + 1, s); large.alloc((u64)nm / 2 + 1, s); counts.zero();
         MMB_LAUNCH(expand_members, ceil_div((u64)nm * 32, TPB), TPB, 0, s, k0, k1, K, (const u32*)mem_i.p, (const u32*)mem_cnt.p, (const u64*)out_base.p,
                    (const u32*)glcp.p, (const u32*)ix.limit.p, (const u32*)ix.dphrase.p, (const u32*)ix.prank.p, (const u32*)ix.occ_first.p,
-                   (const u32*)ix.occ_next_rank.p, (const u64*)ix.occ_next_start.p, (const u32*)ix.occ_lcp.p, lead, sa.p, lcp.p, key.p);
+                   (const u32*)ix.occ_next_rank.p, (const u64*)ix.occ_next_start.p, (const u32*)ix.occ_lcp.p, (const u32*)ix.s_lcp.p, (const u32*)ix.rmq.p,
+                   ix.rmq_blocks, lead, sa.p, lcp.p, key.p);
         MMB_LAUNCH(collect_multi, ceil_div(nm, TPB), TPB, 0, s, k0, k1, K, (const u32*)glcp.p, (const u64*)out_base.p, small.p, large.p, counts.p);
         std::vector<u32> c = to_host(counts.p, 2, s);
         if (c[0]) MMB_LAUNCH(merge_small, c[0], TPB, 0, s, (const u64*)small.p, k0, (const u64*)out_base.p, (const u32*)glcp.p, (const u32*)mem_i.p,
@@ -264,7 +317,8 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
         StreamTile tile;
         tile.rank0 = first_tile ? 0 : rank_next - halo_have;
         tile.count = count; tile.first = first_tile ? 0 : halo_have; tile.sa = sa.p; tile.lcp = lcp.p; tile.last = last_tile;
-        consumer.consume(tile);
+        delete tt;
+        { PhaseTimer ct("stream tile: consume", s); consumer.consume(tile); }
         // stash the tail as the next tile's halo
         halo_have = std::min<u64>(halo, count);
         MMB_CUDA(cudaMemcpyAsync(halo_sa.p, sa.p + (count - halo_have), halo_have * 8, cudaMemcpyDeviceToDevice, s));
