@@ -94,6 +94,50 @@ def make_collection(spec, seed, anchor_seed=None, first_index=0):
     return imgs
 
 
+def verify_sample(imgs, text, how_many=400, width=80):
+    """Check sampled output lines against the generated sequences (outside the timed region): every occurrence of a multi-MUM must
+    spell the same string (reverse-complemented on '-'), and its length must be at least 20.  Returns the number of lines checked."""
+    if not text:
+        return 0
+    comp = np.zeros(256, dtype=np.uint8); comp[list(b"ACGT")] = list(b"TGCA")
+    hdr = [int(np.argmax(im == 10)) + 1 for im in imgs]
+
+    def fetch(d, o, l):
+        idx = o + np.arange(l, dtype=np.int64)
+        return imgs[d][hdr[d] + idx + idx // width]
+
+    # sample line starts without splitting a multi-hundred-MB buffer
+    buf = np.frombuffer(text, dtype=np.uint8)
+    rng = np.random.default_rng(0)
+    starts = [0]
+    for p in rng.integers(0, len(buf), how_many):
+        nl = np.flatnonzero(buf[p:p + 4096] == 10)
+        if len(nl):
+            starts.append(int(p + nl[0] + 1))
+    checked = 0
+    for st in starts:
+        if st >= len(buf):
+            continue
+        end = st + int(np.argmax(buf[st:st + 8192] == 10))
+        fields = bytes(buf[st:end]).decode().split("\t")
+        if len(fields) != 3:
+            continue
+        l, offs, strands = int(fields[0]), fields[1].split(","), fields[2].split(",")
+        assert l >= 20 and len(offs) == len(imgs)
+        ref = None
+        for d, (o, sg) in enumerate(zip(offs, strands)):
+            if o == "":
+                continue
+            seg = fetch(d, int(o), l)
+            if sg == "-":
+                seg = comp[seg[::-1]]
+            if ref is None:
+                ref = seg
+            assert np.array_equal(seg, ref), f"occurrence mismatch in line at byte {st}"
+        checked += 1
+    return checked
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -118,61 +162,63 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax or None, "reasons": sorted(self.reasons)}
 
 
-def reference_arm(args, spec, rank):
-    """The reference's own CPU implementation of the path, timed on the host cores (rank 0 only)."""
-    if rank != 0:
-        return
+def bounded_sample(spec, budget_bases=8_000_000):
+    """A collection of the same generator small enough for the single-threaded reference: ~5-10 s of CPU per run."""
+    sample = dict(spec)
+    note = "whole workload"
+    if spec["N"] * spec["L"] > budget_bases:
+        sample["L"] = max(10_000, budget_bases // spec["N"])
+        note = f"{spec['N']}x{sample['L']} bp collection from the same generator (the reference's time grows linearly with input size)"
+    return sample, note
+
+
+def reference_exe():
     exe = os.path.join(ROOT, "oracle", "_ref", "mumemto_exec")
-    kind = "reference"
+    if os.path.exists(exe):
+        return exe, "reference"
+    exe = os.path.join(ROOT, "oracle", "_build", "mumemto_oracle")
     if not os.path.exists(exe):
-        exe, kind = os.path.join(ROOT, "oracle", "_build", "mumemto_oracle"), "port"
-        if not os.path.exists(exe):
-            subprocess.run(["make", "port"], cwd=os.path.join(ROOT, "oracle"), check=True, capture_output=True)
-    sample = spec
+        subprocess.run(["make", "port"], cwd=os.path.join(ROOT, "oracle"), check=True, capture_output=True)
+    return exe, "port"
+
+
+def run_reference(exe, sample, repeats, warmup):
     imgs = make_collection(sample, seed=1)
-    bases = sample["N"] * sample["L"]
+    times = []
     with tempfile.TemporaryDirectory() as d:
         paths = []
         for i, im in enumerate(imgs):
             p = os.path.join(d, f"h{i}.fa"); im.tofile(p); paths.append(p)
-        times = []
-        for it in range(args.warmup + args.steps):
+        for it in range(warmup + repeats):
             t0 = time.perf_counter()
             subprocess.run([exe, "-o", os.path.join(d, "ref"), *paths], check=True, capture_output=True)
-            dt = time.perf_counter() - t0
-            if it >= args.warmup:
-                times.append(dt)
-    t = float(np.mean(times))
-    v = bases / t
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    return float(np.mean(times))
+
+
+def reference_arm(args, spec, rank):
+    """The reference's own CPU implementation of the path, timed on the host cores (rank 0 only; the other ranks exit)."""
+    if rank != 0:
+        return
+    exe, kind = reference_exe()
+    sample, note = bounded_sample(spec)
+    t = run_reference(exe, sample, args.steps, min(args.warmup, 1))
+    v = sample["N"] * sample["L"] / t
+    desc = "reference sources compiled unmodified with sdsl/gsacak stand-ins (oracle/ref_shims), 1 thread: the reference has no threads or OpenMP"
     line = {"impl": "reference", "metric": "input bases/sec end-to-end (FASTA->.mums)", "value": v, "unit": "bases/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic", "config": {"workload": sample["desc"]},
-            "cpu_baseline": {"value": v, "unit": "bases/s", "cores": 1, "kind": kind,
-                             "sample": "whole workload; reference sources compiled unmodified with sdsl/gsacak stand-ins (oracle/ref_shims), 1 thread: the reference has no threads"},
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": {"workload": spec["desc"], "name": args.workload},
+            "cpu_baseline": {"value": v, "unit": "bases/s", "cores": 1, "kind": kind, "sample": note + "; " + desc},
             "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def cpu_baseline_sample(spec):
     """Bounded CPU run beside the GPU number (rank 0, N = 1): the reference build on (a sample of) the workload."""
-    exe = os.path.join(ROOT, "oracle", "_ref", "mumemto_exec")
-    kind = "reference"
-    if not os.path.exists(exe):
-        exe, kind = os.path.join(ROOT, "oracle", "_build", "mumemto_oracle"), "port"
-    sample = dict(spec)
-    budget_bases = 8_000_000          # ~ 15 s at ~0.5 Mbases/s
-    note = "whole workload"
-    if spec["N"] * spec["L"] > budget_bases:
-        sample["L"] = max(10_000, budget_bases // spec["N"])
-        note = f"{spec['N']}x{sample['L']} bp prefix-sized sample of the same generator (CPU time grows linearly in input size)"
-    imgs = make_collection(sample, seed=1)
-    with tempfile.TemporaryDirectory() as d:
-        paths = []
-        for i, im in enumerate(imgs):
-            p = os.path.join(d, f"h{i}.fa"); im.tofile(p); paths.append(p)
-        t0 = time.perf_counter()
-        subprocess.run([exe, "-o", os.path.join(d, "ref"), *paths], check=True, capture_output=True)
-        dt = time.perf_counter() - t0
+    exe, kind = reference_exe()
+    sample, note = bounded_sample(spec)
+    dt = run_reference(exe, sample, 1, 0)
     return {"value": sample["N"] * sample["L"] / dt, "unit": "bases/s", "cores": 1, "kind": kind,
             "sample": note + "; 1 thread (the reference is single-threaded); sdsl/gsacak replaced by stand-ins", "seconds": dt}
 
@@ -183,7 +229,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("MMB_WORKLOAD", "c1"))
+    ap.add_argument("--workload", default=os.environ.get("MMB_WORKLOAD", "c2"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--route", default=os.environ.get("MMB_ROUTE", "auto"), choices=["auto", "direct", "pfp"])
     ap.add_argument("--no-e2e", action="store_true")
@@ -265,6 +311,7 @@ def main():
     stage = {k: 0.0 for k in ("ms_text", "ms_sa", "ms_lcp", "ms_detect", "ms_emit")}
     st = None
     t_wall0 = time.perf_counter()
+    per_step_stages = []
     for a, b in ev:
         flush.zero_()
         a.record(stream)
@@ -272,6 +319,7 @@ def main():
         b.record(stream)
         for k in stage:
             stage[k] += st[k]
+        per_step_stages.append({k: round(st[k], 2) for k in stage})
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = eng.stats()["kernel_launches"] - launches0
@@ -302,6 +350,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = total_bases / float(te.item())
     sampler.stop_flag = True; sampler.join(timeout=2)
+    verified = verify_sample(imgs, bytes(out_host.numpy()[:out_bytes]) if (out_host is not None and rank == 0 and not multi) else b"")
 
     # ---- partition merge (N > 1): one NCCL all-gather of the partition tables, then the merge kernels on every rank
     merge_info = None
@@ -326,8 +375,8 @@ def main():
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "whole hot path (text+SA+LCP+detect+emit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-                "stages_ms": {k: v / args.steps for k, v in stage.items()}, "step_ms": step_ms, "e2e_stages_ms": e2e_stage,
-                "matches": int(st["num_matches"]), "sa_rounds": int(st["sa_rounds"]), "sa_sorted_elements": int(st["sa_sorted_elements"]),
+                "stages_ms": {k: v / args.steps for k, v in stage.items()}, "step_ms": step_ms, "per_step_stages": per_step_stages, "e2e_stages_ms": e2e_stage,
+                "matches": int(st["num_matches"]), "verified_sample_lines": int(verified), "sa_rounds": int(st["sa_rounds"]), "sa_sorted_elements": int(st["sa_sorted_elements"]),
                 "text_symbols": int(st["text_symbols"]), "wall_s_timed_region": t_wall, "clocks": sampler.summary(),
                 "route": int(st["route"]), "pfp": {k: int(st[k]) for k in ("pfp_phrases", "pfp_distinct_phrases", "pfp_dict_bytes", "pfp_tiles")}}
         if merge_info:
@@ -340,35 +389,18 @@ def main():
 
 
 def partition_merge(eng, dist, world, rank, spec):
-    """All ranks exchange (lengths, offsets, strands, thresholds) with NCCL all-gathers and fold them with the merge kernels."""
+    """One all-gather of every rank's partition table (device buffers, NCCL) and the merge kernels on every rank."""
     import torch
-    lengths, offsets, strands = eng.mums()
-    thr = eng.thresholds()
-    anchor_len = len(thr) // 2
-    n = torch.tensor([len(lengths)], device="cuda", dtype=torch.int64)
-    counts = [torch.zeros(1, device="cuda", dtype=torch.int64) for _ in range(world)]
-    dist.all_gather(counts, n)
-    counts = [int(c.item()) for c in counts]
-    nmax, N = max(counts + [1]), spec["N"]
-    def gather(arr, shape, dtype):
-        t = torch.zeros(shape, dtype=dtype, device="cuda")
-        src = torch.from_numpy(arr).cuda()
-        t.view(-1)[: src.numel()] = src.view(-1)
-        out = [torch.empty_like(t) for _ in range(world)]
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        dist.all_gather(out, t)
-        torch.cuda.synchronize()
-        return out, time.perf_counter() - t0
-    gl, t1 = gather(lengths.view(np.int32), (nmax,), torch.int32)
-    go, t2 = gather(offsets, (nmax, N), torch.int64)
-    gs, t3 = gather(strands, (nmax, N), torch.uint8)
-    gt, t4 = gather(thr[:anchor_len].view(np.int16), (anchor_len,), torch.int16)
-    parts = [(gl[r].data_ptr(), go[r].data_ptr(), gs[r].data_ptr(), gt[r].data_ptr(), counts[r], N) for r in range(world)]
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    eng.anchor_merge(parts, anchor_len, on_device=True)
-    torch.cuda.synchronize(); tm = time.perf_counter() - t0
-    return {"allgather_s": t1 + t2 + t3 + t4, "merge_s": tm, "merged_mums": int(eng.lib.mmb_merge_num_mums(eng.h)),
-            "merged_columns": int(eng.lib.mmb_merge_num_docs(eng.h)), "partition_mums": counts}
+    from mumemto_b200 import partition
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    parts = partition.gather_partitions(partition.local_partition(eng, dev), dist, world)
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    partition.merge_gathered(eng, parts)
+    torch.cuda.synchronize(); t2 = time.perf_counter()
+    return {"allgather_s": t1 - t0, "merge_s": t2 - t1, "merged_mums": int(eng.lib.mmb_merge_num_mums(eng.h)),
+            "merged_columns": int(eng.lib.mmb_merge_num_docs(eng.h)), "partition_mums": [int(p[4]) for p in parts],
+            "gathered_bytes": int(sum(p[0].numel() * 4 + p[1].numel() * 8 + p[2].numel() + p[3].numel() * 2 for p in parts))}
 
 
 if __name__ == "__main__":

@@ -33,6 +33,9 @@ struct Error : std::runtime_error {
 };
 
 extern unsigned long long g_kernel_launches;   // every MMB_LAUNCH, for bench.py's "gpu_launches"
+extern double g_host_alloc_ms, g_host_free_ms, g_host_sync_ms;      // host time inside cudaMallocAsync / cudaFreeAsync / stream syncs
+extern unsigned long long g_host_allocs, g_host_syncs;
+inline double host_now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 
 inline void check(cudaError_t e, const char* what, const char* file, int line) {
     if (e != cudaSuccess)
@@ -62,6 +65,14 @@ struct PhaseTimer {
     ~PhaseTimer() { if (on) { cudaStreamSynchronize(s); fprintf(stderr, "[phase] %-28s %9.3f ms\n", name, now() - t0); } }
 };
 
+// Device memory for the pipeline's many short-lived arrays.  All work of an engine is ordered on one stream, so a block released by
+// one stage can be handed to the next stage at once; blocks are cached per process and only go back to the driver when an allocation
+// fails or the engine is destroyed.  (cudaMallocAsync's pool showed 15..540 ms of allocator time per call of mmb_find on the tiled
+// route -- see profiles/README.md -- which is why the engine keeps its own free lists.)
+void* pool_alloc(size_t bytes, cudaStream_t s);
+void pool_free(void* p, cudaStream_t s);
+void pool_trim();          // give every cached block back to the driver
+
 // Stream-ordered device buffer.
 template <class T>
 struct DevBuf {
@@ -77,12 +88,12 @@ struct DevBuf {
     void alloc(size_t count, cudaStream_t stream) {
         release();
         s = stream; n = count;
-        void* q = nullptr;
-        MMB_CUDA(cudaMallocAsync(&q, (count ? count : 1) * sizeof(T), stream));
-        p = (T*)q;
+        double t0 = host_now_ms();
+        p = (T*)pool_alloc((count ? count : 1) * sizeof(T), stream);
+        g_host_alloc_ms += host_now_ms() - t0; ++g_host_allocs;
     }
     void zero() { if (n) MMB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
-    void release() { if (p) { cudaFreeAsync(p, s); p = nullptr; n = 0; } }
+    void release() { if (p) { double t0 = host_now_ms(); pool_free(p, s); g_host_free_ms += host_now_ms() - t0; p = nullptr; n = 0; } }
     size_t bytes() const { return n * sizeof(T); }
     void swap(DevBuf& o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(s, o.s); }
 };
@@ -90,8 +101,10 @@ struct DevBuf {
 template <class T>
 inline std::vector<T> to_host(const T* d, size_t n, cudaStream_t s) {
     std::vector<T> h(n);
+    double t0 = host_now_ms();
     if (n) MMB_CUDA(cudaMemcpyAsync(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost, s));
     MMB_CUDA(cudaStreamSynchronize(s));
+    g_host_sync_ms += host_now_ms() - t0; ++g_host_syncs;
     return h;
 }
 

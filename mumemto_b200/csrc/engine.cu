@@ -13,10 +13,66 @@
 #include "text.h"
 
 #include <cctype>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 
 namespace mmb {
 unsigned long long g_kernel_launches = 0;
+double g_host_alloc_ms = 0, g_host_free_ms = 0, g_host_sync_ms = 0;
+unsigned long long g_host_allocs = 0, g_host_syncs = 0;
 }
+
+// ---------------------------------------------------------------------------------------------- cached device allocator
+namespace mmb {
+namespace poolimpl {
+struct BlockCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks;          // size -> block
+    std::unordered_map<void*, size_t> live;            // blocks handed out
+    size_t cached_bytes = 0;
+} g_cache;
+size_t round_block(size_t b) { return b <= (1u << 20) ? ((b + 511) & ~(size_t)511) : ((b + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1)); }
+}  // namespace poolimpl
+using poolimpl::g_cache;
+using poolimpl::round_block;
+
+void pool_trim() {
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    cudaDeviceSynchronize();
+    for (auto& kv : g_cache.free_blocks) cudaFree(kv.second);
+    g_cache.free_blocks.clear(); g_cache.cached_bytes = 0;
+}
+
+void* pool_alloc(size_t bytes, cudaStream_t) {
+    size_t want = round_block(bytes);
+    {
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        auto it = g_cache.free_blocks.lower_bound(want);
+        if (it != g_cache.free_blocks.end() && it->first <= want + want / 4 + 4096) {      // best fit, at most 25 % slack
+            void* p = it->second; size_t sz = it->first;
+            g_cache.free_blocks.erase(it); g_cache.cached_bytes -= sz; g_cache.live[p] = sz;
+            return p;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); pool_trim(); e = cudaMalloc(&p, want); }
+    check(e, "cudaMalloc", __FILE__, __LINE__);
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    g_cache.live[p] = want;
+    return p;
+}
+
+void pool_free(void* p, cudaStream_t) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    auto it = g_cache.live.find(p);
+    if (it == g_cache.live.end()) return;
+    g_cache.free_blocks.emplace(it->second, p); g_cache.cached_bytes += it->second;
+    g_cache.live.erase(it);
+}
+}  // namespace mmb
 
 using namespace mmb;
 
@@ -223,6 +279,7 @@ void mmb_destroy(mmb_engine* e) {
     cudaStream_t s = e->stream; bool own = e->own_stream;
     delete e;
     if (own) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    pool_trim();
 }
 
 int mmb_load_fasta(mmb_engine* e, const uint8_t* const* files, const uint64_t* sizes, size_t nfiles, int use_revcomp) {
@@ -281,6 +338,8 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
         e->prm.revcomp = e->text.revcomp ? 1 : 0;
 
         Timer total(s), t(s);
+        double host0 = host_now_ms(), a0 = g_host_alloc_ms, f0 = g_host_free_ms, y0 = g_host_sync_ms;
+        unsigned long long na0 = g_host_allocs, ns0 = g_host_syncs;
         total.start();
         e->thresh_count = 0; e->thresh.release();
         if (merge) {
@@ -354,6 +413,9 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
             e->stats.ms_emit = t.stop();
         }
         e->stats.ms_total = total.stop();
+        if (getenv("MMB_PROFILE_HOST"))
+            fprintf(stderr, "[host] find %.2f ms wall; cudaMallocAsync %.2f ms in %llu calls; cudaFreeAsync %.2f ms; readback syncs %.2f ms in %llu; device %.2f ms\n",
+                    host_now_ms() - host0, g_host_alloc_ms - a0, g_host_allocs - na0, g_host_free_ms - f0, g_host_sync_ms - y0, g_host_syncs - ns0, e->stats.ms_total);
         e->stats.num_matches = e->mum_mode ? e->mums.count : e->mems.count;
         e->stats.route = e->route;
         e->found = true;

@@ -31,9 +31,9 @@ struct Temp {
     void* p = nullptr; cudaStream_t s;
     Temp(size_t bytes, cudaStream_t st) : s(st) {
         if (getenv("MMB_DEBUG")) fprintf(stderr, "[prims] temp storage %zu bytes\n", bytes);
-        MMB_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, st));
+        p = pool_alloc(bytes ? bytes : 1, st);
     }
-    ~Temp() { cudaFreeAsync(p, s); }
+    ~Temp() { pool_free(p, s); }
 };
 struct MaxOp { template <class T> __device__ __forceinline__ T operator()(const T& a, const T& b) const { return a > b ? a : b; } };
 
