@@ -349,14 +349,26 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
         u16* thresh = merge ? e->thresh.p : nullptr;
         bool want_text = opts->want_text != 0;
         u64 n = e->text.n;
+        // route: forced, or by size, or -- for texts either route can hold -- by how repetitive the collection is: the parse and the
+        // dictionary (stages 1-3 of the PFP route) are cheap, and the route pays off when the dictionary is a small fraction of the text
+        PfpIndex ix; PfpParse pp;
+        bool parsed = false;
         bool use_pfp = opts->route == 2 || (opts->route == 0 && n + 1 >= (1ull << 31));
+        Timer tparse(s); float ms_parse = 0;
+        if (opts->route == 0 && !use_pfp && n >= (1u << 16)) {
+            tparse.start();
+            pfp_parse(e->text.text.p, n, ix, pp, s); parsed = true;
+            ms_parse = tparse.stop();
+            use_pfp = (u64)ix.dsize * 3 <= n;
+            if (!use_pfp) { ix = PfpIndex(); pp = PfpParse(); }
+        }
         e->route = use_pfp ? 2 : 1;
         e->full_sa.release(); e->full_lcp.release(); e->bwt.release();
         e->stats.pfp_phrases = e->stats.pfp_distinct_phrases = e->stats.pfp_dict_bytes = e->stats.pfp_tiles = 0;
         if (!use_pfp) {
             t.start();
             build_suffix_array(e->text.text.p, n, e->sa, s);
-            e->stats.ms_sa = t.stop();
+            e->stats.ms_sa = t.stop() + ms_parse;
             t.start();
             build_lcp(e->text.text.p, n, e->sa, e->lcp, s);
             e->stats.ms_lcp = t.stop();
@@ -373,9 +385,10 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
         } else {
             e->sa.sa.release(); e->sa.isa.release(); e->lcp.release();
             t.start();
-            PfpIndex ix;
-            build_pfp_index(e->text.text.p, n, ix, s);
-            e->stats.ms_sa = t.stop();
+            if (!parsed) pfp_parse(e->text.text.p, n, ix, pp, s);
+            pfp_finish(e->text.text.p, n, ix, pp, s);
+            pp = PfpParse();
+            e->stats.ms_sa = t.stop() + ms_parse;
             e->stats.ms_lcp = 0;
             e->stats.pfp_phrases = ix.np; e->stats.pfp_distinct_phrases = ix.nd; e->stats.pfp_dict_bytes = ix.dsize;
             e->stats.sa_rounds = ix.stats_d.rounds + ix.stats_p.rounds; e->stats.sa_sorted_elements = ix.stats_d.groups_sorted + ix.stats_p.groups_sorted;

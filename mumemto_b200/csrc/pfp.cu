@@ -264,6 +264,13 @@ __global__ void __launch_bounds__(TPB) occ_fill(const u64* __restrict__ keys, co
 }  // namespace
 
 void build_pfp_index(const u8* text, u64 n, PfpIndex& ix, cudaStream_t s) {
+    PfpParse pp;
+    pfp_parse(text, n, ix, pp, s);
+    pfp_finish(text, n, ix, pp, s);
+}
+
+// stages 1-3: triggers, phrase identity, dictionary (cheap; tells how repetitive the collection is)
+void pfp_parse(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s) {
     ix.n = n;
     if (n < PFP_W + 2) throw Error(70, "text too short for the prefix-free parse route");
     // ---- 1. triggers
@@ -291,7 +298,7 @@ void build_pfp_index(const u8* text, u64 n, PfpIndex& ix, cudaStream_t s) {
 
     // ---- 2. phrase identity
     delete pt; pt = new PhaseTimer("pfp 2 phrase identity", s);
-    DevBuf<u32> pid, rep; pid.alloc(np, s); rep.alloc(np, s);
+    DevBuf<u32>& pid = pp.pid; DevBuf<u32> rep; pid.alloc(np, s); rep.alloc(np, s);
     u32 nd = 0;
     for (u64 attempt = 0;; ++attempt) {
         if (attempt == 8) throw Error(73, "phrase hashing kept colliding");
@@ -331,9 +338,15 @@ void build_pfp_index(const u8* text, u64 n, PfpIndex& ix, cudaStream_t s) {
     MMB_LAUNCH(dict_fill, ceil_div((u64)nd * 32, TPB), TPB, 0, s, text, n, (const u64*)ix.pstart.p, (const u32*)rep.p, (const u32*)ix.doff.p, nd, ix.dict.p,
                ix.limit.p, ix.dphrase.p);
     rep.release();
+    delete pt;
+}
 
+// stages 4-8
+void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s) {
+    u32 np = ix.np, nd = ix.nd, dsize = ix.dsize;
+    DevBuf<u32>& pid = pp.pid;
     // ---- 4. suffix order of the dictionary (ties allowed)
-    delete pt; pt = new PhaseTimer("pfp 4 dictionary SA", s);
+    PhaseTimer* pt = new PhaseTimer("pfp 4 dictionary SA", s);
     {
         DevBuf<u32> hist; hist.alloc(256, s); hist.zero();
         MMB_LAUNCH(dict_histogram, 148 * 8, TPB, 0, s, (const u8*)ix.dict.p, dsize, hist.p);

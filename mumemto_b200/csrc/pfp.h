@@ -47,7 +47,12 @@ struct PfpIndex {
     SaStats stats_d, stats_p;
 };
 
+struct PfpParse { DevBuf<u32> pid; };      // provisional phrase id of every phrase occurrence, handed from pfp_parse to pfp_finish
+
 void build_pfp_index(const u8* text, u64 n, PfpIndex& out, cudaStream_t s);
+// The same in two steps: parse + dictionary (stages 1-3, cheap) and everything else; `auto` routing looks at ix.dsize in between.
+void pfp_parse(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s);
+void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s);
 
 // One window of the suffix stream in rank order, with `halo` ranks of the previous window in front of it.
 struct StreamTile {

@@ -168,6 +168,21 @@ __global__ void fasta_chunk_states(const u8* __restrict__ chunk_map, const u32* 
     for (u32 c = chunk_first[f]; c < chunk_first[f + 1]; ++c) { chunk_state[c] = (u8)st; st = (chunk_map[c] >> (2 * st)) & 3; }
 }
 
+// Write `total` staged symbols to text[dst0 ..): bytes up to the first 4-byte boundary, aligned words, trailing bytes.
+// REVERSE: the run is the reverse complement of the staged symbols.
+template <bool REVERSE>
+__device__ __forceinline__ void write_run(u8* __restrict__ text, u64 dst0, const u8* stage, u32 total) {
+    auto get = [&](u32 j) -> u32 { return REVERSE ? (u32)complement_upper(stage[total - 1 - j]) : (u32)stage[j]; };
+    u32 head = min(total, (u32)((4 - (dst0 & 3)) & 3));
+    for (u32 j = threadIdx.x; j < head; j += blockDim.x) text[dst0 + j] = (u8)get(j);
+    u32 nwords = (total - head) >> 2;
+    for (u32 w = threadIdx.x; w < nwords; w += blockDim.x) {
+        u32 j = head + 4 * w;
+        *reinterpret_cast<u32*>(text + dst0 + j) = get(j) | (get(j + 1) << 8) | (get(j + 2) << 16) | (get(j + 3) << 24);
+    }
+    for (u32 j = head + 4 * nwords + threadIdx.x; j < total; j += blockDim.x) text[dst0 + j] = (u8)get(j);
+}
+
 template <bool SCATTER>
 __global__ void __launch_bounds__(TPB) fasta_pass(const u8* __restrict__ raw, const u64* __restrict__ file_off, const u64* __restrict__ file_end,
                                                   const u32* __restrict__ chunk_first, u32 nfiles, const u8* __restrict__ chunk_state, int raw_mode,
@@ -208,11 +223,12 @@ __global__ void __launch_bounds__(TPB) fasta_pass(const u8* __restrict__ raw, co
         if (threadIdx.x == 0) { chunk_kept[blockIdx.x] = kept_total; chunk_hdr[blockIdx.x] = hdr_total; }
         return;
     }
-    // second walk: write forward and reverse-complement symbols, and record starts
+    // second walk: kept symbols go to shared memory first (a chunk's kept symbols form ONE contiguous run in the forward text and one
+    // in the reverse complement), then the block writes both runs with aligned 4-byte stores
+    __shared__ u8 stage[CHUNK];
     u64 kidx = chunk_kept_base[blockIdx.x] + kept_before;       // global index among kept bases
     u32 hidx = chunk_hdr_base[blockIdx.x] + hdr_before;
-    u64 first_kept = chunk_kept_base[chunk_first[file]];
-    u64 base = doc_start[file], L = doc_len[file];
+    u32 local = kept_before;
     u32 s2 = st;
 #pragma unroll
     for (u32 k = 0; k < 16; ++k) {
@@ -223,14 +239,15 @@ __global__ void __launch_bounds__(TPB) fasta_pass(const u8* __restrict__ raw, co
         if (raw_mode) { bc.keep = true; bc.header = false; }
         else { u32 dummy = 0; bc = classify(s2, c, eol, &dummy); s2 = fsm_next(s2, c); }
         if (bc.header) { rec_pos[hidx] = v.begin + k; rec_before[hidx] = kidx; ++hidx; }
-        if (bc.keep) {
-            u64 q = kidx - first_kept;
-            u8 u = upper(c);
-            text[base + q] = u;
-            if (revcomp) text[base + 2 * L - q] = complement_upper(u);
-            ++kidx;
-        }
+        if (bc.keep) { stage[local++] = upper(c); ++kidx; }
     }
+    __syncthreads();
+    u64 base = doc_start[file], L = doc_len[file];
+    u64 q0 = chunk_kept_base[blockIdx.x] - chunk_kept_base[chunk_first[file]];      // document-relative index of the chunk's first kept base
+    u32 total = kept_total;
+    if (total == 0) return;
+    write_run<false>(text, base + q0, stage, total);
+    if (revcomp) write_run<true>(text, base + 2 * L - (q0 + total - 1), stage, total);
 }
 
 __global__ void fasta_doc_layout(const u64* __restrict__ chunk_kept_base, const u32* __restrict__ chunk_first, u32 nfiles, u32 nchunks,
