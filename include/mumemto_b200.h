@@ -55,7 +55,7 @@ typedef struct mmb_options {
     uint8_t route;               /* 0 auto; 1 direct suffix sorting of the text (|T| < 2^31); 2 prefix-free parse (dictionary + parse), any |T| < 2^40 */
     uint8_t keep_arrays;         /* 1: keep SA/LCP of the whole stream for mmb_copy_arrays even on the tiled (route 2) path */
     uint8_t reserved[6];
-    uint64_t tile_ranks;         /* route 2: ranks per stream tile, 0 = default (2^26) */
+    uint64_t tile_ranks;         /* route 2: ranks per stream tile, 0 = default (2^28) */
 } mmb_options;
 
 typedef struct mmb_stats {
@@ -128,6 +128,11 @@ MMB_API uint64_t mmb_merge_num_docs(const mmb_engine* e);
 MMB_API int mmb_merge_copy(mmb_engine* e, uint32_t* lengths, int64_t* offsets, uint8_t* strands /* 1 = '+' */, uint16_t* thresholds);
 MMB_API uint64_t mmb_merge_text_size(const mmb_engine* e);          /* merged .mums bytes (include/mumsio.hpp:283-296,318-326) */
 MMB_API int mmb_merge_copy_text(mmb_engine* e, void* host_dst);
+
+/* Measurement aid for bench.py: bracket every launch of the kernels whose name contains `name_substring` with CUDA events on the
+ * launching stream (NULL or "" switches it off and clears the record); mmb_profile_result adds up the recorded launches. */
+MMB_API int mmb_profile_kernel(const char* name_substring);
+MMB_API int mmb_profile_result(double* total_ms, uint64_t* launches);
 
 /* The text T itself (|T| bytes), for tests. */
 MMB_API int mmb_copy_symbols(mmb_engine* e, uint8_t* dst);

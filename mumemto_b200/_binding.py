@@ -66,6 +66,8 @@ _SIGNATURES = {
     "mmb_copy_thresholds": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mmb_copy_arrays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmb_copy_symbols": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mmb_profile_kernel": (C.c_int, [C.c_char_p]),
+    "mmb_profile_result": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "mmb_mum_table_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "mmb_anchor_merge": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_uint64, C.c_int]),
@@ -249,6 +251,15 @@ class Engine:
         flags = np.uint16(0x8000 | (0x2000 if partial else 0))
         head = flags.tobytes() + np.uint64(self.num_docs).tobytes() + np.uint64(len(lengths)).tobytes()
         return head + lengths.tobytes() + offsets.tobytes() + self.mum_strand_bits().tobytes()
+
+    # ------------------------------------------------------------------ measurement aid
+    def profile_kernel(self, name_substring):
+        self.lib.mmb_profile_kernel(name_substring.encode() if name_substring else None)
+
+    def profile_result(self):
+        ms, n = C.c_double(), C.c_uint64()
+        self.lib.mmb_profile_result(C.byref(ms), C.byref(n))
+        return ms.value, n.value
 
     # ------------------------------------------------------------------ partition merge
     def mum_table_device(self):

@@ -43,11 +43,18 @@ inline void check(cudaError_t e, const char* what, const char* file, int line) {
 }
 #define MMB_CUDA(x) ::mmb::check((x), #x, __FILE__, __LINE__)
 
+// Optional per-kernel timing for bench.py's roofline: launches whose name contains the selected substring are bracketed by CUDA
+// events on their own stream (no synchronisation); mmb_profile_result() adds the pairs up afterwards.
+void profile_before(const char* kernel_name, cudaStream_t s);
+void profile_after(const char* kernel_name, cudaStream_t s);
+
 #ifndef MMB_SIMT
 #define MMB_LAUNCH(kernel, grid, block, smem, stream, ...)                       \
     do {                                                                         \
         ++::mmb::g_kernel_launches;                                              \
+        ::mmb::profile_before(#kernel, (stream));                                \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);              \
+        ::mmb::profile_after(#kernel, (stream));                                 \
         ::mmb::check(cudaPeekAtLastError(), #kernel, __FILE__, __LINE__);        \
     } while (0)
 #define MMB_DYN_SMEM(type, name)                                  \

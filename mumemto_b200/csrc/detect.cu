@@ -252,6 +252,13 @@ __global__ void __launch_bounds__(DW_TPB) detect_window_kernel(const u32* __rest
                     u32 cs = __shfl_sync(0xffffffffu, size, src), cv = __shfl_sync(0xffffffffu, v, src), ccur = __shfl_sync(0xffffffffu, cur, src);
                     u32 cbefore = __shfl_sync(0xffffffffu, lc[idx - (have ? size : 0)], src);
                     u64 s0 = cj - cs;
+                    if (bwt && !prm.merge) {
+                        // cheap rejection first: an interval whose suffixes are all preceded by the same symbol is not left-maximal
+                        // (the common case inside long shared regions); only the BWT bytes of the tile are read for this
+                        bool d0 = false;
+                        for (u32 t = 1 + lane; t < cs; t += 32) d0 |= bwt[s0 + t] != bwt[s0 + t - 1];
+                        if (!__any_sync(0xffffffffu, d0)) continue;
+                    }
                     u64 bits[W];
 #pragma unroll
                     for (int w = 0; w < W; ++w) bits[w] = 0;
@@ -327,16 +334,16 @@ struct DetectArgs {
 template <class SAT, int W, int P>
 void launch_detect(const SAT* sa, const DetectArgs& a, cudaStream_t s) {
     if (a.use_window) {
-        auto k = detect_window_kernel<SAT, W, P>;
+        auto detect_window_k = detect_window_kernel<SAT, W, P>;
         size_t smem = 16 + (size_t)((a.prm.ndocs + 2) & ~1u) * 8 + (size_t)a.plan.span * 4 * (2 + a.plan.nkept);
 #ifndef MMB_SIMT
-        if (smem > 48 * 1024) MMB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) MMB_CUDA(cudaFuncSetAttribute(detect_window_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
-        MMB_LAUNCH(k, ceil_div(a.m, DW_TILE), DW_TPB, smem, s, a.lcp, sa, a.bwt, a.text, a.m, a.j_first, a.prm, a.plan, a.d_doc_start, a.rep, a.cap, a.count, a.thresh);
+        MMB_LAUNCH(detect_window_k, ceil_div(a.m, DW_TILE), DW_TPB, smem, s, a.lcp, sa, a.bwt, a.text, a.m, a.j_first, a.prm, a.plan, a.d_doc_start, a.rep, a.cap, a.count, a.thresh);
     } else {
-        auto k = detect_walk_kernel<SAT, W, P>;
+        auto detect_walk_k = detect_walk_kernel<SAT, W, P>;
         size_t smem = (size_t)(a.prm.ndocs + 1) * sizeof(u64);
-        MMB_LAUNCH(k, ceil_div(a.m - 1, TPB), TPB, smem, s, a.lcp, sa, a.bwt, a.text, a.m, a.j_first, a.prm, a.d_doc_start, a.rep, a.cap, a.count, a.thresh);
+        MMB_LAUNCH(detect_walk_k, ceil_div(a.m - 1, TPB), TPB, smem, s, a.lcp, sa, a.bwt, a.text, a.m, a.j_first, a.prm, a.d_doc_start, a.rep, a.cap, a.count, a.thresh);
     }
 }
 

@@ -199,8 +199,8 @@ void mum_rows(const Reports& rep, const SAT* sa, const DetectParams& prm, const 
     out.count = 0; out.text_bytes = 0; out.text.alloc(0, s);
     if (n == 0) { out.len.alloc(0, s); out.off.alloc(0, s); out.strand.alloc(0, s); return; }
     DevBuf<u32> valid, idx; valid.alloc(n, s); idx.alloc(n, s);
-    auto kv = mum_validate<SAT>;
-    MMB_LAUNCH(kv, warps_grid(n), TPB, 0, s, rep.rep.p, n, sa, d_doc_start, d_doc_len, N, prm.revcomp, valid.p);
+    auto mum_validate_k = mum_validate<SAT>;
+    MMB_LAUNCH(mum_validate_k, warps_grid(n), TPB, 0, s, rep.rep.p, n, sa, d_doc_start, d_doc_len, N, prm.revcomp, valid.p);
     prim::exclusive_sum(valid.p, idx.p, n, s);
     u32 tail[2];
     MMB_CUDA(cudaMemcpyAsync(&tail[0], idx.p + n - 1, 4, cudaMemcpyDeviceToHost, s));
@@ -214,8 +214,8 @@ void mum_rows(const Reports& rep, const SAT* sa, const DetectParams& prm, const 
     MMB_LAUNCH(compact_reports, ceil_div(n, 256), 256, 0, s, rep.rep.p, valid.p, idx.p, n, kept.p);
     MMB_CUDA(cudaMemsetAsync(out.off.p, 0xff, out.off.bytes(), s));
     MMB_CUDA(cudaMemsetAsync(out.strand.p, 0, out.strand.bytes(), s));
-    auto kr = mum_rows_kernel<SAT>;
-    MMB_LAUNCH(kr, warps_grid(nv), TPB, 0, s, kept.p, nv, sa, d_doc_start, d_doc_len, N, prm.revcomp, out.len.p, out.off.p, out.strand.p);
+    auto mum_rows_k = mum_rows_kernel<SAT>;
+    MMB_LAUNCH(mum_rows_k, warps_grid(nv), TPB, 0, s, kept.p, nv, sa, d_doc_start, d_doc_len, N, prm.revcomp, out.len.p, out.off.p, out.strand.p);
 }
 
 void mum_text(MumTable& out, u32 N, cudaStream_t s) {
@@ -224,12 +224,12 @@ void mum_text(MumTable& out, u32 N, cudaStream_t s) {
     if (nv == 0) { out.text.alloc(0, s); return; }
     DevBuf<u32> ll; DevBuf<u64> lo; ll.alloc(nv + 1, s); lo.alloc(nv + 1, s);
     MMB_CUDA(cudaMemsetAsync(ll.p + nv, 0, 4, s));
-    auto k1 = mum_lines<false>; auto k2 = mum_lines<true>;
-    MMB_LAUNCH(k1, warps_grid(nv), TPB, 0, s, out.len.p, out.off.p, out.strand.p, nv, N, ll.p, (const u64*)nullptr, (u8*)nullptr);
+    auto mum_lines_len_k = mum_lines<false>; auto mum_lines_write_k = mum_lines<true>;
+    MMB_LAUNCH(mum_lines_len_k, warps_grid(nv), TPB, 0, s, out.len.p, out.off.p, out.strand.p, nv, N, ll.p, (const u64*)nullptr, (u8*)nullptr);
     prim::exclusive_sum(ll.p, lo.p, nv + 1, s);
     out.text_bytes = to_host(lo.p + nv, 1, s)[0];
     out.text.alloc(out.text_bytes, s);
-    MMB_LAUNCH(k2, warps_grid(nv), TPB, 0, s, out.len.p, out.off.p, out.strand.p, nv, N, ll.p, lo.p, out.text.p);
+    MMB_LAUNCH(mum_lines_write_k, warps_grid(nv), TPB, 0, s, out.len.p, out.off.p, out.strand.p, nv, N, ll.p, lo.p, out.text.p);
 }
 
 template <class SAT>
@@ -250,8 +250,8 @@ void mem_rows(const Reports& rep, const SAT* sa, const DetectParams& prm, const 
     prim::exclusive_sum(occ.p, out.first.p, (u64)n + 1, s);
     out.total_occ = to_host(out.first.p + n, 1, s)[0];
     out.off.alloc(out.total_occ, s); out.doc.alloc(out.total_occ, s); out.strand.alloc(out.total_occ, s);
-    auto kr = mem_rows_kernel<SAT>;
-    MMB_LAUNCH(kr, warps_grid(n), TPB, 0, s, rep.rep.p, n, sa, d_doc_start, d_doc_len, N, prm.revcomp, out.first.p, out.len.p, out.off.p, out.doc.p,
+    auto mem_rows_k = mem_rows_kernel<SAT>;
+    MMB_LAUNCH(mem_rows_k, warps_grid(n), TPB, 0, s, rep.rep.p, n, sa, d_doc_start, d_doc_len, N, prm.revcomp, out.first.p, out.len.p, out.off.p, out.doc.p,
                out.strand.p);
 }
 
@@ -261,12 +261,12 @@ void mem_text(MemTable& out, cudaStream_t s) {
     if (n == 0) { out.text.alloc(0, s); return; }
     DevBuf<u32> ll; DevBuf<u64> lo; ll.alloc(n + 1, s); lo.alloc(n + 1, s);
     MMB_CUDA(cudaMemsetAsync(ll.p + n, 0, 4, s));
-    auto k1 = mem_lines<false>; auto k2 = mem_lines<true>;
-    MMB_LAUNCH(k1, warps_grid(n), TPB, 0, s, out.len.p, out.first.p, out.off.p, out.doc.p, out.strand.p, n, ll.p, (const u64*)nullptr, (u8*)nullptr);
+    auto mem_lines_len_k = mem_lines<false>; auto mem_lines_write_k = mem_lines<true>;
+    MMB_LAUNCH(mem_lines_len_k, warps_grid(n), TPB, 0, s, out.len.p, out.first.p, out.off.p, out.doc.p, out.strand.p, n, ll.p, (const u64*)nullptr, (u8*)nullptr);
     prim::exclusive_sum(ll.p, lo.p, n + 1, s);
     out.text_bytes = to_host(lo.p + n, 1, s)[0];
     out.text.alloc(out.text_bytes, s);
-    MMB_LAUNCH(k2, warps_grid(n), TPB, 0, s, out.len.p, out.first.p, out.off.p, out.doc.p, out.strand.p, n, ll.p, lo.p, out.text.p);
+    MMB_LAUNCH(mem_lines_write_k, warps_grid(n), TPB, 0, s, out.len.p, out.first.p, out.off.p, out.doc.p, out.strand.p, n, ll.p, lo.p, out.text.p);
 }
 
 template <class SAT>

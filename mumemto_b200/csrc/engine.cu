@@ -74,6 +74,29 @@ void pool_free(void* p, cudaStream_t) {
 }
 }  // namespace mmb
 
+// ---------------------------------------------------------------------------------------------- per-kernel event timing
+namespace mmb {
+namespace profimpl {
+std::string filter;                                    // empty = off
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pairs;
+bool open_pair = false;
+}  // namespace profimpl
+void profile_before(const char* name, cudaStream_t s) {
+    using namespace profimpl;
+    if (filter.empty() || !strstr(name, filter.c_str())) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, s);
+    pairs.emplace_back(a, b); open_pair = true;
+}
+void profile_after(const char* name, cudaStream_t s) {
+    using namespace profimpl;
+    if (!open_pair) return;
+    (void)name;
+    cudaEventRecord(pairs.back().second, s); open_pair = false;
+}
+}  // namespace mmb
+
 using namespace mmb;
 
 namespace {
@@ -397,13 +420,13 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
             if (e->prm.max_doc_freq) { u64 bound = (u64)e->prm.max_doc_freq * N; hi = hi ? std::min(hi, bound) : bound; }
             if (hi == 0) throw Error(31, "unbounded total frequency (-f 0 with -F 0) is not supported by the windowed interval scan");
             u32 halo = (u32)std::min<u64>((hi + 8) & ~3ull, 1u << 22);
-            u64 tile_ranks = opts->tile_ranks ? opts->tile_ranks : (1ull << 26);
+            u64 tile_ranks = opts->tile_ranks ? opts->tile_ranks : (1ull << 28);
             struct Consumer : TileConsumer {
                 mmb_engine* e; cudaStream_t s; u16* thresh; bool keep; std::vector<MumTable> mparts; std::vector<MemTable> eparts; u32 tiles = 0;
                 void consume(const StreamTile& tile) override {
                     ++tiles;
                     Reports rep;
-                    detect_intervals<u64>(tile.lcp, tile.sa, (const u8*)nullptr, e->text.text.p, tile.count, tile.first, e->prm, e->text.doc_start.p, thresh, rep, s);
+                    detect_intervals<u64>(tile.lcp, tile.sa, tile.bwt, e->text.text.p, tile.count, tile.first, e->prm, e->text.doc_start.p, thresh, rep, s);
                     if (e->mum_mode) { MumTable part; mum_rows<u64>(rep, tile.sa, e->prm, e->text.doc_start.p, e->text.doc_len.p, part, s); mparts.push_back(std::move(part)); }
                     else { MemTable part; mem_rows<u64>(rep, tile.sa, e->prm, e->text.doc_start.p, e->text.doc_len.p, part, s); eparts.push_back(std::move(part)); }
                     if (keep) {
@@ -620,6 +643,22 @@ int mmb_merge_copy(mmb_engine* e, uint32_t* lengths, int64_t* offsets, uint8_t* 
 int mmb_merge_copy_text(mmb_engine* e, void* host_dst) {
     if (!e || !e->has_merged) return fail(MMB_ERR_STATE, "no merge result");
     return guarded([&] { copy_out(e->merged_text.p, (u8*)host_dst, e->merged_text_bytes, e->stream); MMB_CUDA(cudaStreamSynchronize(e->stream)); });
+}
+
+int mmb_profile_kernel(const char* name_substring) {
+    for (auto& p : profimpl::pairs) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    profimpl::pairs.clear(); profimpl::open_pair = false;
+    profimpl::filter = name_substring ? name_substring : "";
+    return MMB_OK;
+}
+
+int mmb_profile_result(double* total_ms, uint64_t* launches) {
+    cudaDeviceSynchronize();
+    double t = 0;
+    for (auto& p : profimpl::pairs) { float ms = 0; if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) t += ms; }
+    if (total_ms) *total_ms = t;
+    if (launches) *launches = profimpl::pairs.size();
+    return MMB_OK;
 }
 
 int mmb_copy_symbols(mmb_engine* e, uint8_t* dst) {

@@ -203,12 +203,12 @@ void merge_text(const MergePartition& P, DevBuf<u8>& text, u64& bytes, cudaStrea
     if (!P.n) { text.alloc(0, s); return; }
     DevBuf<u32> ll; DevBuf<u64> lo; ll.alloc(P.n + 1, s); lo.alloc(P.n + 1, s);
     MMB_CUDA(cudaMemsetAsync(ll.p + P.n, 0, 4, s));
-    auto k1 = merged_lines<false>; auto k2 = merged_lines<true>;
-    MMB_LAUNCH(k1, ceil_div(P.n, TPB), TPB, 0, s, P.len.p, P.off.p, P.plus.p, P.n, P.ndocs, ll.p, (const u64*)nullptr, (u8*)nullptr);
+    auto merged_lines_len_k = merged_lines<false>; auto merged_lines_write_k = merged_lines<true>;
+    MMB_LAUNCH(merged_lines_len_k, ceil_div(P.n, TPB), TPB, 0, s, P.len.p, P.off.p, P.plus.p, P.n, P.ndocs, ll.p, (const u64*)nullptr, (u8*)nullptr);
     prim::exclusive_sum(ll.p, lo.p, P.n + 1, s);
     bytes = to_host(lo.p + P.n, 1, s)[0];
     text.alloc(bytes, s);
-    MMB_LAUNCH(k2, ceil_div(P.n, TPB), TPB, 0, s, P.len.p, P.off.p, P.plus.p, P.n, P.ndocs, ll.p, lo.p, text.p);
+    MMB_LAUNCH(merged_lines_write_k, ceil_div(P.n, TPB), TPB, 0, s, P.len.p, P.off.p, P.plus.p, P.n, P.ndocs, ll.p, lo.p, text.p);
 }
 
 }  // namespace mmb

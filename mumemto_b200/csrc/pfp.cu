@@ -280,15 +280,15 @@ void pfp_parse(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s
     u32 nblk = (u32)nblk64;
     DevBuf<u32> bcount, bbase; bcount.alloc(nblk + 1, s); bbase.alloc(nblk + 1, s);
     MMB_CUDA(cudaMemsetAsync(bcount.p + nblk, 0, 4, s));
-    auto tp0 = trigger_pass<false>; auto tp1 = trigger_pass<true>;
-    MMB_LAUNCH(tp0, nblk, TPB, 0, s, text, n, bcount.p, (const u32*)nullptr, (u64*)nullptr);
+    auto trigger_count_pass = trigger_pass<false>; auto trigger_write_pass = trigger_pass<true>;
+    MMB_LAUNCH(trigger_count_pass, nblk, TPB, 0, s, text, n, bcount.p, (const u32*)nullptr, (u64*)nullptr);
     prim::exclusive_sum(bcount.p, bbase.p, nblk + 1, s);
     u64 ntrig = to_host(bbase.p + nblk, 1, s)[0];
     if (ntrig + 2 >= 0xfffffff0ull) throw Error(72, "too many phrases");
     u32 np = (u32)ntrig + 1;
     ix.np = np;
     DevBuf<u64> ends; ends.alloc(np, s);
-    MMB_LAUNCH(tp1, nblk, TPB, 0, s, text, n, bcount.p, (const u32*)bbase.p, ends.p);
+    MMB_LAUNCH(trigger_write_pass, nblk, TPB, 0, s, text, n, bcount.p, (const u32*)bbase.p, ends.p);
     u64 last_end = n + PFP_W - 1;
     MMB_CUDA(cudaMemcpyAsync(ends.p + np - 1, &last_end, 8, cudaMemcpyHostToDevice, s));
     ix.pstart.alloc(np + 1, s);

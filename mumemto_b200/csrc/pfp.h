@@ -61,6 +61,7 @@ struct StreamTile {
     u64 first = 0;                  // view index of the first rank that is new in this tile
     const u64* sa = nullptr;        // [count]
     const u32* lcp = nullptr;       // [count + 64], zero padded
+    const u8* bwt = nullptr;        // [count] symbol preceding each suffix (0 for text position 0)
     bool last = false;
 };
 

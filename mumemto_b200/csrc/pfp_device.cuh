@@ -7,7 +7,7 @@ namespace mmb {
 // min of v[l..r] (inclusive, l <= r) with the two-level index of PfpIndex: rmq[k][b] = min of blocks [b, b + 2^k), 32 entries per block
 __device__ __forceinline__ u32 range_min(const u32* __restrict__ v, const u32* __restrict__ rmq, u32 nblocks, u32 l, u32 r) {
     u32 bl = l >> 5, br = r >> 5, mn = 0xffffffffu;
-    if (bl == br) { for (u32 i = l; i <= r; ++i) mn = min(mn, v[i]); return mn; }
+    if (r - l < 48) { for (u32 i = l; i <= r; ++i) mn = min(mn, v[i]); return mn; }      // short ranges (the common case): plain scan
     for (u32 i = l; i < (bl + 1) * 32; ++i) mn = min(mn, v[i]);
     for (u32 i = br * 32; i <= r; ++i) mn = min(mn, v[i]);
     if (bl + 1 < br) {

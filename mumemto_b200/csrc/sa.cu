@@ -299,14 +299,14 @@ template <int WIDTH, int K>
 void launch_warp_class(const Group* groups, u32 n, u32 h, u32 m, u32* sa, u32* isa, const u32* limit, u32* nh, u8* changed, const GroupLists& next,
                        cudaStream_t s) {
     if (!n) return;
-    auto k = sort_groups_warp<WIDTH, K>;
-    MMB_LAUNCH(k, ceil_div((u64)n * WIDTH, TPB), TPB, 0, s, groups, n, h, m, sa, (const u32*)isa, limit, nh, changed, next);
+    auto sort_groups_warp_k = sort_groups_warp<WIDTH, K>;
+    MMB_LAUNCH(sort_groups_warp_k, ceil_div((u64)n * WIDTH, TPB), TPB, 0, s, groups, n, h, m, sa, (const u32*)isa, limit, nh, changed, next);
 }
 template <int WIDTH, int K>
 void launch_apply_class(const Group* groups, u32 n, const u32* sa, const u32* nh, const u8* changed, u32* isa, cudaStream_t s) {
     if (!n) return;
-    auto k = apply_groups_warp<WIDTH, K>;
-    MMB_LAUNCH(k, ceil_div((u64)n * WIDTH, TPB), TPB, 0, s, groups, n, sa, nh, changed, isa);
+    auto apply_groups_warp_k = apply_groups_warp<WIDTH, K>;
+    MMB_LAUNCH(apply_groups_warp_k, ceil_div((u64)n * WIDTH, TPB), TPB, 0, s, groups, n, sa, nh, changed, isa);
 }
 
 const u32 kClassMinSize[NCLASS] = {2, 5, 9, 17, 33, 65, 129, 257, BLOCK_SORT_MAX + 1};

@@ -41,14 +41,31 @@ __global__ void __launch_bounds__(TPB) owned_flags(const u32* __restrict__ sa_d,
     if (p == dsize) flag[p] = 0;
 }
 
+// Everything expand_members needs to know about a member, gathered once (16 bytes, read coalesced there).
+struct MemberMeta {
+    u32 q0;         // first entry of the phrase's occurrence list
+    u32 cnt;        // occurrences of the phrase
+    u32 shift;      // |alpha| - w
+    u8 before;      // symbol preceding the suffix inside the phrase (valid if inside)
+    u8 inside;      // 0: the suffix starts its phrase, the preceding symbol comes from the text
+    u8 back;        // distance to the first member of the group (FUSE_MAX_MEMBERS + 1 = group too large to merge in place)
+    u8 members;     // members in the group (same cap)
+};
+
 __global__ void __launch_bounds__(TPB) members_fill(const u32* __restrict__ sa_d, const u32* __restrict__ isa_d, const u32* __restrict__ dphrase,
-                                                    const u32* __restrict__ prank, const u32* __restrict__ occ_first, const u32* __restrict__ flag,
+                                                    const u32* __restrict__ prank, const u32* __restrict__ occ_first, const u32* __restrict__ limit,
+                                                    const u32* __restrict__ doff, const u8* __restrict__ dict, const u32* __restrict__ flag,
                                                     const u32* __restrict__ idx, u32 dsize, u32* __restrict__ mem_i, u32* __restrict__ mem_head,
-                                                    u32* __restrict__ mem_cnt) {
+                                                    u32* __restrict__ mem_cnt, MemberMeta* __restrict__ meta) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= dsize || !flag[p]) return;
-    u32 k = idx[p], i = sa_d[p], r = prank[dphrase[i]];
-    mem_i[k] = i; mem_head[k] = isa_d[i]; mem_cnt[k] = occ_first[r + 1] - occ_first[r];
+    u32 k = idx[p], i = sa_d[p], g = dphrase[i], r = prank[g];
+    u32 q0 = occ_first[r], cnt = occ_first[r + 1] - q0;
+    mem_i[k] = i; mem_head[k] = isa_d[i]; mem_cnt[k] = cnt;
+    MemberMeta m;
+    m.q0 = q0; m.cnt = cnt; m.shift = limit[i] - 1 - PFP_W;
+    m.inside = i > doff[g] ? 1 : 0; m.before = m.inside ? dict[i - 1] : (u8)0; m.back = 0; m.members = 1;
+    meta[k] = m;
 }
 
 // lcp between the strings of consecutive members that start a new group (byte comparison inside the dictionary)
@@ -69,6 +86,20 @@ __global__ void __launch_bounds__(TPB) group_lcp(const u8* __restrict__ dict, co
     glcp[k] = l;
 }
 
+constexpr u32 FUSE_MAX_MEMBERS = 8;      // groups with at most this many members are merged inside expand_members
+
+// distance to the group start and group size for every member, capped at FUSE_MAX_MEMBERS + 1
+__global__ void __launch_bounds__(TPB) group_shape(const u32* __restrict__ glcp, u32 K, MemberMeta* __restrict__ meta) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    u32 ks = k, ke = k + 1;
+    for (u32 b = 0; glcp[ks] == NOT_START && b <= FUSE_MAX_MEMBERS; ++b) --ks;
+    bool big = glcp[ks] == NOT_START;
+    while (!big && ke < K && glcp[ke] == NOT_START) { ++ke; if (ke - ks > FUSE_MAX_MEMBERS) big = true; }
+    meta[k].back = (u8)(big ? FUSE_MAX_MEMBERS + 1 : k - ks);
+    meta[k].members = (u8)(big ? FUSE_MAX_MEMBERS + 1 : ke - ks);
+}
+
 __global__ void tile_bounds(const u64* __restrict__ out_base, const u32* __restrict__ glcp, u32 K, u64 tile_ranks, u32 nt, u32* __restrict__ bounds) {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > nt) return;
@@ -79,8 +110,6 @@ __global__ void tile_bounds(const u64* __restrict__ out_base, const u32* __restr
     while (lo > 0 && lo < K && glcp[lo] == NOT_START) --lo;   // back to the start of that member's group
     bounds[t] = lo;
 }
-
-constexpr u32 FUSE_MAX_MEMBERS = 8;      // groups with at most this many members are merged inside expand_members
 
 // first index in the ascending list v[0..c) whose value is >= x
 __device__ __forceinline__ u32 lower_bound_u32(const u32* __restrict__ v, u32 c, u32 x) {
@@ -93,40 +122,43 @@ __device__ __forceinline__ u32 lower_bound_u32(const u32* __restrict__ v, u32 c,
 // suffix, so in a group of M members the final slot of an element is its own index plus, for each other member, the number of that
 // member's elements with a smaller rank (one binary search each); the same searches give the predecessor in merged order, hence the
 // LCP.  Groups with more than FUSE_MAX_MEMBERS members only get their (rank, SA) pairs written here and are sorted afterwards.
-__global__ void __launch_bounds__(TPB) expand_members(u32 k0, u32 k1, u32 K, const u32* __restrict__ mem_i, const u32* __restrict__ mem_cnt,
-                                                      const u64* __restrict__ out_base, const u32* __restrict__ glcp, const u32* __restrict__ limit,
-                                                      const u32* __restrict__ dphrase, const u32* __restrict__ prank, const u32* __restrict__ occ_first,
-                                                      const u32* __restrict__ occ_next_rank, const u64* __restrict__ occ_next_start,
-                                                      const u32* __restrict__ occ_lcp, const u32* __restrict__ s_lcp, const u32* __restrict__ rmq,
-                                                      u32 rmq_blocks, u64 lead, u64* __restrict__ sa, u32* __restrict__ lcp, u32* __restrict__ key) {
+__global__ void __launch_bounds__(TPB) expand_members(u32 k0, u32 k1, const MemberMeta* __restrict__ meta, const u64* __restrict__ out_base,
+                                                      const u32* __restrict__ glcp, const u32* __restrict__ occ_next_rank,
+                                                      const u64* __restrict__ occ_next_start, const u32* __restrict__ occ_lcp,
+                                                      const u32* __restrict__ s_lcp, const u32* __restrict__ rmq, u32 rmq_blocks,
+                                                      const u8* __restrict__ text, u64 lead, u64* __restrict__ sa, u32* __restrict__ lcp,
+                                                      u32* __restrict__ key, u8* __restrict__ bwt) {
     u32 k = k0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (k >= k1) return;
-    u32 i = mem_i[k], shift = limit[i] - 1 - PFP_W, c = mem_cnt[k], q0 = occ_first[prank[dphrase[i]]];
-    // the group of this member: [ks, ke)
-    u32 ks = k, ke = k + 1;                                    // bounded scans: only "at most FUSE_MAX_MEMBERS members" matters
-    for (u32 b = 0; glcp[ks] == NOT_START && b <= FUSE_MAX_MEMBERS; ++b) --ks;      // tiles start on group starts: stays inside the tile
-    bool big = glcp[ks] == NOT_START;
-    while (!big && ke < K && glcp[ke] == NOT_START) { ++ke; if (ke - ks > FUSE_MAX_MEMBERS) big = true; }
-    u32 M = big ? FUSE_MAX_MEMBERS + 1 : ke - ks;
-    u64 dst = out_base[k] - out_base[k0] + lead;
-    if (M == 1) {
+    MemberMeta me = meta[k];
+    u32 shift = me.shift, c = me.cnt, q0 = me.q0;
+    u64 tile_base = out_base[k0];
+    u64 dst = out_base[k] - tile_base + lead;
+    // the symbol before the suffix: inside the phrase it is one dictionary byte for every occurrence; at a phrase start it is the text
+    // symbol before that occurrence
+    bool inside = me.inside != 0; u8 before = me.before;
+    if (me.members == 1) {
+        u32 first_lcp = glcp[k];
         for (u32 t = lane; t < c; t += 32) {
-            sa[dst + t] = occ_next_start[q0 + t] - shift;
-            lcp[dst + t] = t ? shift + occ_lcp[q0 + t] : glcp[k];
+            u64 pos = occ_next_start[q0 + t] - shift;
+            sa[dst + t] = pos;
+            bwt[dst + t] = inside ? before : (pos ? text[pos - 1] : (u8)0);
+            lcp[dst + t] = t ? shift + occ_lcp[q0 + t] : first_lcp;
         }
         return;
     }
-    if (M > FUSE_MAX_MEMBERS) {
+    if (me.members > FUSE_MAX_MEMBERS) {
         for (u32 t = lane; t < c; t += 32) { sa[dst + t] = occ_next_start[q0 + t] - shift; key[dst + t] = occ_next_rank[q0 + t]; }
-        return;
+        return;                                                // bwt of these is filled after the sort (bwt_of_groups)
     }
-    u64 gbase = out_base[ks] - out_base[k0] + lead;
+    u32 ks = k - me.back, M = me.members;
+    u64 gbase = out_base[ks] - tile_base + lead;
+    u32 first_lcp = glcp[ks];
     u32 oq[FUSE_MAX_MEMBERS], oc[FUSE_MAX_MEMBERS];            // the other members' lists
 #pragma unroll
     for (u32 j = 0; j < FUSE_MAX_MEMBERS; ++j) {
         oq[j] = 0; oc[j] = 0;
-        u32 kk = ks + j;
-        if (j < M && kk != k) { oq[j] = occ_first[prank[dphrase[mem_i[kk]]]]; oc[j] = mem_cnt[kk]; }
+        if (j < M && ks + j != k) { MemberMeta o = meta[ks + j]; oq[j] = o.q0; oc[j] = o.cnt; }
     }
     for (u32 t = lane; t < c; t += 32) {
         u32 r = occ_next_rank[q0 + t];
@@ -141,8 +173,10 @@ __global__ void __launch_bounds__(TPB) expand_members(u32 k0, u32 k1, u32 K, con
                 if (lb) { u32 v = occ_next_rank[oq[j] + lb - 1]; if (!has_pred || v > pred) pred = v; has_pred = true; }
             }
         }
-        sa[gbase + slot] = occ_next_start[q0 + t] - shift;
-        lcp[gbase + slot] = has_pred ? shift + range_min(s_lcp, rmq, rmq_blocks, pred + 1, r) : glcp[ks];
+        u64 pos = occ_next_start[q0 + t] - shift;
+        sa[gbase + slot] = pos;
+        bwt[gbase + slot] = inside ? before : (pos ? text[pos - 1] : (u8)0);
+        lcp[gbase + slot] = has_pred ? shift + range_min(s_lcp, rmq, rmq_blocks, pred + 1, r) : first_lcp;
     }
 }
 
@@ -226,16 +260,23 @@ __global__ void __launch_bounds__(TPB) large_scatter(const u64* __restrict__ gro
     lcp[dst] = t ? shift + range_min(s_lcp, rmq, rmq_blocks, (u32)fkeys[a - 1] + 1, (u32)fk) : glcp[ks];
 }
 
-__global__ void tile_edges(u64* __restrict__ sa, u32* __restrict__ lcp, u64 n, int first_tile, u64 count) {
+__global__ void tile_edges(u64* __restrict__ sa, u32* __restrict__ lcp, u8* __restrict__ bwt, const u8* __restrict__ text, u64 n, int first_tile,
+                           u64 count) {
     u32 t = threadIdx.x;
     if (t < 64) lcp[count + t] = 0;                              // zero slack for the detector's rounded tile loads
-    if (first_tile && t == 0) { sa[0] = n; lcp[0] = 0; }         // rank 0: the sentinel suffix
+    if (first_tile && t == 0) { sa[0] = n; lcp[0] = 0; bwt[0] = n ? text[n - 1] : (u8)0; }      // rank 0: the sentinel suffix
+}
+// suffixes of groups that went through the sort kernels: the symbol before them from the text
+__global__ void bwt_of_groups(const u64* __restrict__ groups, u32 k0, const u64* __restrict__ out_base, u64 lead, const u8* __restrict__ text,
+                              const u64* __restrict__ sa, u8* __restrict__ bwt) {
+    u64 g = groups[blockIdx.x];
+    u64 base = out_base[(u32)(g >> 32)] - out_base[k0] + lead, G = out_base[(u32)g] - out_base[(u32)(g >> 32)];
+    for (u64 e = (u64)blockIdx.y * blockDim.x + threadIdx.x; e < G; e += (u64)gridDim.y * blockDim.x) { u64 p = sa[base + e]; bwt[base + e] = p ? text[p - 1] : (u8)0; }
 }
 
 }  // namespace
 
 void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 halo, TileConsumer& consumer, cudaStream_t s) {
-    (void)text;
     u32 dsize = ix.dsize;
     PhaseTimer* pt = new PhaseTimer("stream members+bounds", s);
     // ---- members (owned dictionary suffixes in suffix order)
@@ -243,17 +284,19 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
     MMB_LAUNCH(owned_flags, ceil_div((u64)dsize + 1, TPB), TPB, 0, s, (const u32*)ix.sa_d.p, (const u32*)ix.limit.p, dsize, flag.p);
     prim::exclusive_sum(flag.p, idx.p, (u64)dsize + 1, s);
     u32 K = to_host(idx.p + dsize, 1, s)[0];
-    DevBuf<u32> mem_i, mem_head, mem_cnt, glcp; DevBuf<u64> out_base;
-    mem_i.alloc(K, s); mem_head.alloc(K, s); mem_cnt.alloc((u64)K + 1, s); glcp.alloc((u64)K + 1, s); out_base.alloc((u64)K + 1, s);
+    DevBuf<u32> mem_i, mem_head, mem_cnt, glcp; DevBuf<u64> out_base; DevBuf<MemberMeta> meta;
+    meta.alloc(K, s); mem_i.alloc(K, s); mem_head.alloc(K, s); mem_cnt.alloc((u64)K + 1, s); glcp.alloc((u64)K + 1, s); out_base.alloc((u64)K + 1, s);
     MMB_CUDA(cudaMemsetAsync(mem_cnt.p + K, 0, 4, s));
     MMB_LAUNCH(members_fill, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.sa_d.p, (const u32*)ix.isa_d.p, (const u32*)ix.dphrase.p, (const u32*)ix.prank.p,
-               (const u32*)ix.occ_first.p, (const u32*)flag.p, (const u32*)idx.p, dsize, mem_i.p, mem_head.p, mem_cnt.p);
+               (const u32*)ix.occ_first.p, (const u32*)ix.limit.p, (const u32*)ix.doff.p, (const u8*)ix.dict.p, (const u32*)flag.p, (const u32*)idx.p, dsize,
+               mem_i.p, mem_head.p, mem_cnt.p, meta.p);
     flag.release(); idx.release();
     prim::exclusive_sum(mem_cnt.p, out_base.p, (u64)K + 1, s);
     u64 total = to_host(out_base.p + K, 1, s)[0];
     if (total != ix.n) throw Error(76, "internal: the parse does not cover the text (" + std::to_string(total) + " of " + std::to_string(ix.n) + ")");
     MMB_LAUNCH(group_lcp, ceil_div(K, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const u32*)ix.limit.p, (const u32*)mem_i.p, (const u32*)mem_head.p, K, glcp.p);
     mem_head.release();
+    MMB_LAUNCH(group_shape, ceil_div(K, TPB), TPB, 0, s, (const u32*)glcp.p, K, meta.p);
 
     // ---- tile boundaries on group starts
     u32 nt = (u32)((ix.n + tile_ranks - 1) / tile_ranks);
@@ -272,8 +315,9 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
     delete pt;
     // ---- tile buffers: [halo | new ranks | 64 slack]; the first tile starts with the sentinel rank instead of a halo
     u64 cap = (u64)halo + max_new + 1;
-    DevBuf<u64> sa, halo_sa, small, large; DevBuf<u32> lcp, key, halo_lcp, counts;
-    sa.alloc(cap, s); lcp.alloc(cap + 64, s); key.alloc(cap, s); halo_sa.alloc(halo + 1, s); halo_lcp.alloc(halo + 1, s); counts.alloc(2, s);
+    DevBuf<u64> sa, halo_sa, small, large; DevBuf<u32> lcp, key, halo_lcp, counts; DevBuf<u8> bwt, halo_bwt;
+    sa.alloc(cap, s); lcp.alloc(cap + 64, s); key.alloc(cap, s); bwt.alloc(cap, s); halo_sa.alloc(halo + 1, s); halo_lcp.alloc(halo + 1, s);
+    halo_bwt.alloc(halo + 1, s); counts.alloc(2, s);
     u64 rank_next = 0;                  // global rank of the first new entry of the coming tile
     u64 halo_have = 0;
     for (size_t t = 0; t + 1 < bounds.size(); ++t) {
@@ -285,17 +329,21 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
         if (!first_tile && halo_have) {
             MMB_CUDA(cudaMemcpyAsync(sa.p, halo_sa.p, halo_have * 8, cudaMemcpyDeviceToDevice, s));
             MMB_CUDA(cudaMemcpyAsync(lcp.p, halo_lcp.p, halo_have * 4, cudaMemcpyDeviceToDevice, s));
+            MMB_CUDA(cudaMemcpyAsync(bwt.p, halo_bwt.p, halo_have, cudaMemcpyDeviceToDevice, s));
         }
         u32 nm = k1 - k0;
         small.alloc((u64)nm / 2 + 1, s); large.alloc((u64)nm / 2 + 1, s); counts.zero();
-        MMB_LAUNCH(expand_members, ceil_div((u64)nm * 32, TPB), TPB, 0, s, k0, k1, K, (const u32*)mem_i.p, (const u32*)mem_cnt.p, (const u64*)out_base.p,
-                   (const u32*)glcp.p, (const u32*)ix.limit.p, (const u32*)ix.dphrase.p, (const u32*)ix.prank.p, (const u32*)ix.occ_first.p,
+        MMB_LAUNCH(expand_members, ceil_div((u64)nm * 32, TPB), TPB, 0, s, k0, k1, (const MemberMeta*)meta.p, (const u64*)out_base.p, (const u32*)glcp.p,
                    (const u32*)ix.occ_next_rank.p, (const u64*)ix.occ_next_start.p, (const u32*)ix.occ_lcp.p, (const u32*)ix.s_lcp.p, (const u32*)ix.rmq.p,
-                   ix.rmq_blocks, lead, sa.p, lcp.p, key.p);
+                   ix.rmq_blocks, text, lead, sa.p, lcp.p, key.p, bwt.p);
         MMB_LAUNCH(collect_multi, ceil_div(nm, TPB), TPB, 0, s, k0, k1, K, (const u32*)glcp.p, (const u64*)out_base.p, small.p, large.p, counts.p);
         std::vector<u32> c = to_host(counts.p, 2, s);
-        if (c[0]) MMB_LAUNCH(merge_small, c[0], TPB, 0, s, (const u64*)small.p, k0, (const u64*)out_base.p, (const u32*)glcp.p, (const u32*)mem_i.p,
-                             (const u32*)ix.limit.p, (const u32*)ix.s_lcp.p, (const u32*)ix.rmq.p, ix.rmq_blocks, lead, sa.p, lcp.p, (const u32*)key.p);
+        if (c[0]) {
+            MMB_LAUNCH(merge_small, c[0], TPB, 0, s, (const u64*)small.p, k0, (const u64*)out_base.p, (const u32*)glcp.p, (const u32*)mem_i.p,
+                       (const u32*)ix.limit.p, (const u32*)ix.s_lcp.p, (const u32*)ix.rmq.p, ix.rmq_blocks, lead, sa.p, lcp.p, (const u32*)key.p);
+            dim3 gb(c[0], 1);
+            MMB_LAUNCH(bwt_of_groups, gb, TPB, 0, s, (const u64*)small.p, k0, (const u64*)out_base.p, lead, text, (const u64*)sa.p, bwt.p);
+        }
         if (c[1]) {
             u32 nl = c[1];
             DevBuf<u64> sizes, fbase, fk_a, fk_b, fv_a, fv_b;
@@ -311,18 +359,21 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
             MMB_LAUNCH(large_scatter, ceil_div(ftotal, TPB), TPB, 0, s, (const u64*)large.p, (const u64*)fbase.p, ftotal, k0, (const u64*)out_base.p,
                        (const u32*)glcp.p, (const u32*)mem_i.p, (const u32*)ix.limit.p, (const u32*)ix.s_lcp.p, (const u32*)ix.rmq.p, ix.rmq_blocks, lead,
                        (const u64*)fk_b.p, (const u64*)fv_b.p, sa.p, lcp.p);
+            dim3 gb(nl, 32);
+            MMB_LAUNCH(bwt_of_groups, gb, TPB, 0, s, (const u64*)large.p, k0, (const u64*)out_base.p, lead, text, (const u64*)sa.p, bwt.p);
         }
         u64 count = lead + fresh;
-        MMB_LAUNCH(tile_edges, 1, 64, 0, s, sa.p, lcp.p, ix.n, (int)first_tile, count);
+        MMB_LAUNCH(tile_edges, 1, 64, 0, s, sa.p, lcp.p, bwt.p, text, ix.n, (int)first_tile, count);
         StreamTile tile;
         tile.rank0 = first_tile ? 0 : rank_next - halo_have;
-        tile.count = count; tile.first = first_tile ? 0 : halo_have; tile.sa = sa.p; tile.lcp = lcp.p; tile.last = last_tile;
+        tile.count = count; tile.first = first_tile ? 0 : halo_have; tile.sa = sa.p; tile.lcp = lcp.p; tile.bwt = bwt.p; tile.last = last_tile;
         delete tt;
         { PhaseTimer ct("stream tile: consume", s); consumer.consume(tile); }
         // stash the tail as the next tile's halo
         halo_have = std::min<u64>(halo, count);
         MMB_CUDA(cudaMemcpyAsync(halo_sa.p, sa.p + (count - halo_have), halo_have * 8, cudaMemcpyDeviceToDevice, s));
         MMB_CUDA(cudaMemcpyAsync(halo_lcp.p, lcp.p + (count - halo_have), halo_have * 4, cudaMemcpyDeviceToDevice, s));
+        MMB_CUDA(cudaMemcpyAsync(halo_bwt.p, bwt.p + (count - halo_have), halo_have, cudaMemcpyDeviceToDevice, s));
         rank_next = (first_tile ? 1 : rank_next) + fresh;
     }
 }

@@ -303,8 +303,8 @@ void build_text(const u8* d_raw, const std::vector<u64>& file_off, const std::ve
             MMB_LAUNCH(fasta_chunk_maps, nchunks, TPB, 0, s, d_raw, d_off.p, d_end.p, d_first.p, nfiles, d_map.p);
             MMB_LAUNCH(fasta_chunk_states, ceil_div(nfiles, 128), 128, 0, s, d_map.p, d_first.p, nfiles, d_state.p);
         }
-        auto count_pass = fasta_pass<false>;
-        MMB_LAUNCH(count_pass, nchunks, TPB, 0, s, d_raw, d_off.p, d_end.p, d_first.p, nfiles, d_state.p, (int)raw_mode, d_kept.p, d_hdr.p, d_flag.p,
+        auto fasta_count_pass = fasta_pass<false>;
+        MMB_LAUNCH(fasta_count_pass, nchunks, TPB, 0, s, d_raw, d_off.p, d_end.p, d_first.p, nfiles, d_state.p, (int)raw_mode, d_kept.p, d_hdr.p, d_flag.p,
                    (const u64*)nullptr, (const u32*)nullptr, (const u64*)nullptr, (const u64*)nullptr, (int)revcomp, (u8*)nullptr, (u64*)nullptr, (u64*)nullptr);
     }
     prim::exclusive_sum(d_kept.p, d_kept_base.p, nchunks + 1, s);     // entry [nchunks] = total
@@ -324,8 +324,8 @@ void build_text(const u8* d_raw, const std::vector<u64>& file_off, const std::ve
     d_rec_pos.alloc(total_hdr, s); d_rec_before.alloc(total_hdr, s);
     MMB_LAUNCH(fasta_terminators, ceil_div(nfiles, 128), 128, 0, s, out.doc_start.p, out.doc_len.p, nfiles, (int)revcomp, out.text.p);
     if (nchunks) {
-        auto scatter_pass = fasta_pass<true>;
-        MMB_LAUNCH(scatter_pass, nchunks, TPB, 0, s, d_raw, d_off.p, d_end.p, d_first.p, nfiles, d_state.p, (int)raw_mode, d_kept.p, d_hdr.p, d_flag.p,
+        auto fasta_scatter_pass = fasta_pass<true>;
+        MMB_LAUNCH(fasta_scatter_pass, nchunks, TPB, 0, s, d_raw, d_off.p, d_end.p, d_first.p, nfiles, d_state.p, (int)raw_mode, d_kept.p, d_hdr.p, d_flag.p,
                    d_kept_base.p, d_hdr_base.p, out.doc_start.p, out.doc_len.p, (int)revcomp, out.text.p, d_rec_pos.p, d_rec_before.p);
     }
     out.h_doc_start = to_host(out.doc_start.p, nfiles + 1, s);

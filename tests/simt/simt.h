@@ -195,6 +195,7 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *
 #define MMB_LAUNCH(kernel, grid, block, smem, stream, ...)                                                          \
     do {                                                                                                            \
         ++::mmb::g_kernel_launches;                                                                                 \
+        ::mmb::profile_before(#kernel, (stream)); ::mmb::profile_after(#kernel, (stream));                          \
         auto mmb_args_ = std::make_tuple(__VA_ARGS__); /* evaluate the arguments once, like a real launch does */   \
         auto mmb_kernel_ = kernel;                                                                                  \
         simt::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { std::apply(mmb_kernel_, mmb_args_); });       \

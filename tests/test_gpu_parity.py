@@ -223,3 +223,79 @@ def test_pfp_route_equals_direct_route_pangenome(cuda_lib, tmp_path):
         st = api.find_files(paths, b, route="pfp", tile_ranks=1 << 22, _lib=cuda_lib, **util.flags_to_kwargs(flags))
         assert util.outputs(a) == util.outputs(b), flags
         assert st["pfp_dict_bytes"] < 0.2 * st["text_symbols"]
+
+
+# ------------------------------------------------------------------------------------------------ the drop-in executables
+BIN = os.path.join(util.ROOT, "mumemto_b200", "bin")
+
+
+@pytest.mark.parametrize("name", ["strict", "partial", "mem", "bumbl", "partial_bumbl", "anchor", "string_merge", "arrays", "norc"])
+def test_cli_mumemto_exec_t2_golden(t2, name):
+    """bin/mumemto_exec with the reference's flags writes byte-identical files (PREFIX.lengths compared after path normalisation)."""
+    d, paths, table = t2
+    flags = {**T2_FLAGS, "string_merge": ["-M"]}[name]
+    util.run_cli(os.path.join(BIN, "mumemto_exec"), ["-o", os.path.join(d, "c_" + name), *flags, *paths])
+    got = {ext: util.md5(b) for ext, b in util.outputs(os.path.join(d, "c_" + name)).items()}
+    assert got == table["outputs"][name]["md5"]
+    lines = open(os.path.join(d, "c_" + name + ".lengths")).read().splitlines()
+    assert lines[0] == f"{os.path.realpath(paths[0])} * 20000" and lines[1] == f"{os.path.realpath(paths[0])} h0 20000" and len(lines) == 10
+
+
+@pytest.mark.parametrize("tag", ["merge2", "merge3"])
+def test_cli_anchor_merge_t2_golden(t2, tag):
+    d, paths, table = t2
+    names = []
+    for i, idx in enumerate(table["outputs"][tag]["partitions"]):
+        pre = os.path.join(d, f"cm_{tag}_{i}")
+        util.run_cli(os.path.join(BIN, "mumemto_exec"), ["-o", pre, "-M", "-n", *[paths[j] for j in idx]])
+        names.append(pre + ".mums")
+    util.run_cli(os.path.join(BIN, "anchor_merge"), [*names, "-o", os.path.join(d, "cm_" + tag)])
+    got = {ext: util.md5(b) for ext, b in util.outputs(os.path.join(d, "cm_" + tag)).items()}
+    assert got == table["outputs"][tag]["md5"]
+    # .bumbl partitions and .bumbl output go through the same fold
+    names_b = []
+    for i, idx in enumerate(table["outputs"][tag]["partitions"]):
+        pre = os.path.join(d, f"cb_{tag}_{i}")
+        util.run_cli(os.path.join(BIN, "mumemto_exec"), ["-o", pre, "-M", "-n", "-b", *[paths[j] for j in idx]])
+        names_b.append(pre + ".bumbl")
+    util.run_cli(os.path.join(BIN, "anchor_merge"), [*names_b, "-o", os.path.join(d, "cb_" + tag + ".bumbl")])
+    assert util.md5_file(os.path.join(d, "cb_" + tag + ".athresh")) == table["outputs"][tag]["md5"][".athresh"]
+    import numpy as np
+    raw = open(os.path.join(d, "cb_" + tag + ".bumbl"), "rb").read()
+    n_seqs, n_mums = np.frombuffer(raw[2:18], dtype=np.uint64)
+    assert (int(n_seqs), int(n_mums)) == (5, 368)
+
+
+def test_library_abi_from_c(tmp_path):
+    """A C program written against the reference's header (include/mumemto.h = mumemto_library/mumemto.h) links and runs."""
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "mumemto.h"
+int main(void) {
+    const char* a[] = {"ACGTACGT"}; const char* b[] = {"TACGTAAA"};
+    mumemto_doc_view docs[2] = {{a, 1}, {b, 1}};
+    mumemto_mem_result* r = NULL;
+    int rc = mumemto_mem(docs, 2, 3, 1, 0, 0, 2, 0, &r);
+    if (rc) { printf("rc %d %s\n", rc, mumemto_last_error()); return 1; }
+    printf("%zu %zu\n", num_docs_mem(r), num_mems(r));
+    for (size_t i = 0; i < num_mems(r); ++i) {
+        mumemto_mem_match_view v = mem_at(r, i);
+        printf("%u", v.length);
+        for (size_t k = 0; k < v.occurrences; ++k) printf(" %lld/%zu/%c", (long long)v.offsets[k], v.seq_ids[k], v.strands[k] ? '+' : '-');
+        printf("\n");
+    }
+    mem_free(r);
+    mumemto_mum_result* m = NULL;
+    rc = mumemto_mum(docs, 2, 3, 1, 0, 0, &m);
+    printf("%d %zu %zu\n", rc, num_mums(m), doc_record_offsets(m)[2]);
+    mum_free(m);
+    return 0;
+}
+''')
+    exe = tmp_path / "t"
+    lib = os.path.join(util.ROOT, "mumemto_b200", "lib")
+    import subprocess
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(util.ROOT, "include"), str(src), "-L", lib, f"-Wl,-rpath,{lib}", "-lmumemto_b200", "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out == ["2 2", "5 0/1/- 1/1/+ 0/0/+ 4/0/-", "5 3/0/+ 0/0/- 1/1/- 0/1/+", "0 0 2"]
