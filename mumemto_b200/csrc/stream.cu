@@ -118,65 +118,68 @@ __device__ __forceinline__ u32 lower_bound_u32(const u32* __restrict__ v, u32 c,
     return lo;
 }
 
-// One warp per member of the tile.  The occurrence list of every member is already ordered by the rank of the following parse
-// suffix, so in a group of M members the final slot of an element is its own index plus, for each other member, the number of that
-// member's elements with a smaller rank (one binary search each); the same searches give the predecessor in merged order, hence the
-// LCP.  Groups with more than FUSE_MAX_MEMBERS members only get their (rank, SA) pairs written here and are sorted afterwards.
-__global__ void __launch_bounds__(TPB) expand_members(u32 k0, u32 k1, const MemberMeta* __restrict__ meta, const u64* __restrict__ out_base,
-                                                      const u32* __restrict__ glcp, const u32* __restrict__ occ_next_rank,
-                                                      const u64* __restrict__ occ_next_start, const u32* __restrict__ occ_lcp,
-                                                      const u32* __restrict__ s_lcp, const u32* __restrict__ rmq, u32 rmq_blocks,
-                                                      const u8* __restrict__ text, u64 lead, u64* __restrict__ sa, u32* __restrict__ lcp,
-                                                      u32* __restrict__ key, u8* __restrict__ bwt) {
-    u32 k = k0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (k >= k1) return;
-    MemberMeta me = meta[k];
-    u32 shift = me.shift, c = me.cnt, q0 = me.q0;
-    u64 tile_base = out_base[k0];
-    u64 dst = out_base[k] - tile_base + lead;
-    // the symbol before the suffix: inside the phrase it is one dictionary byte for every occurrence; at a phrase start it is the text
-    // symbol before that occurrence
-    bool inside = me.inside != 0; u8 before = me.before;
-    if (me.members == 1) {
-        u32 first_lcp = glcp[k];
-        for (u32 t = lane; t < c; t += 32) {
-            u64 pos = occ_next_start[q0 + t] - shift;
-            sa[dst + t] = pos;
-            bwt[dst + t] = inside ? before : (pos ? text[pos - 1] : (u8)0);
-            lcp[dst + t] = t ? shift + occ_lcp[q0 + t] : first_lcp;
-        }
-        return;
-    }
-    if (me.members > FUSE_MAX_MEMBERS) {
-        for (u32 t = lane; t < c; t += 32) { sa[dst + t] = occ_next_start[q0 + t] - shift; key[dst + t] = occ_next_rank[q0 + t]; }
-        return;                                                // bwt of these is filled after the sort (bwt_of_groups)
-    }
-    u32 ks = k - me.back, M = me.members;
-    u64 gbase = out_base[ks] - tile_base + lead;
-    u32 first_lcp = glcp[ks];
-    u32 oq[FUSE_MAX_MEMBERS], oc[FUSE_MAX_MEMBERS];            // the other members' lists
+// Load-balanced expansion: each warp owns 32 consecutive members, scans their occurrence counts, and then walks the warp's output
+// range 32 suffixes at a time, so every lane produces one text suffix per step no matter how the occurrences are spread over the
+// members (phrases occur 1 .. 2N times).  The occurrence list of every member is already ordered by the rank of the following parse
+// suffix, so in a group of M <= 8 members the final slot of an element is its own index plus, for each other member, the number of
+// that member's elements with a smaller rank (one binary search each); the same searches give the predecessor in merged order, hence
+// the LCP.  Groups with more members only get their (rank, SA) pairs written here and are sorted afterwards.
+constexpr u32 EXP_TPB = 256;
+__global__ void __launch_bounds__(EXP_TPB) expand_members(u32 k0, u32 k1, const MemberMeta* __restrict__ meta, const u64* __restrict__ out_base,
+                                                          const u32* __restrict__ glcp, const u32* __restrict__ occ_next_rank,
+                                                          const u64* __restrict__ occ_next_start, const u32* __restrict__ occ_lcp,
+                                                          const u32* __restrict__ s_lcp, const u32* __restrict__ rmq, u32 rmq_blocks,
+                                                          const u8* __restrict__ text, u64 lead, u64* __restrict__ sa, u32* __restrict__ lcp,
+                                                          u32* __restrict__ key, u8* __restrict__ bwt) {
+    __shared__ MemberMeta smeta[EXP_TPB / 32][32];
+    __shared__ u32 soff[EXP_TPB / 32][33];
+    u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u64 kw64 = (u64)k0 + ((u64)blockIdx.x * (EXP_TPB / 32) + w) * 32;          // first member of this warp
+    if (kw64 >= k1) return;                                                    // whole warp
+    u32 kw = (u32)kw64, k = kw + lane;
+    MemberMeta me; me.q0 = 0; me.cnt = 0; me.shift = 0; me.before = 0; me.inside = 0; me.back = 0; me.members = 1;
+    if (k < k1) me = meta[k];
+    u32 incl = me.cnt;
 #pragma unroll
-    for (u32 j = 0; j < FUSE_MAX_MEMBERS; ++j) {
-        oq[j] = 0; oc[j] = 0;
-        if (j < M && ks + j != k) { MemberMeta o = meta[ks + j]; oq[j] = o.q0; oc[j] = o.cnt; }
-    }
-    for (u32 t = lane; t < c; t += 32) {
-        u32 r = occ_next_rank[q0 + t];
-        u32 slot = t;
-        bool has_pred = t > 0;
-        u32 pred = has_pred ? occ_next_rank[q0 + t - 1] : 0u;
+    for (u32 d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    u32 T = __shfl_sync(0xffffffffu, incl, 31);
+    smeta[w][lane] = me; soff[w][lane] = incl - me.cnt;
+    if (lane == 31) soff[w][32] = T;
+    __syncwarp();
+    const u64 tile_base = out_base[k0];
+    const u64 wbase = out_base[kw] - tile_base + lead;
+    for (u32 e = lane; e < T; e += 32) {
+        u32 mi = 0;                                        // largest index with soff[mi] <= e (every member has at least one occurrence)
 #pragma unroll
-        for (u32 j = 0; j < FUSE_MAX_MEMBERS; ++j) {
-            if (oc[j]) {
-                u32 lb = lower_bound_u32(occ_next_rank + oq[j], oc[j], r);
+        for (u32 step = 16; step > 0; step >>= 1) if (mi + step < 32 && soff[w][mi + step] <= e) mi += step;
+        const MemberMeta m = smeta[w][mi];
+        u32 t = e - soff[w][mi], kk = kw + mi, q = m.q0 + t;
+        u64 pos = occ_next_start[q] - m.shift;
+        u8 sym = m.inside ? m.before : (pos ? text[pos - 1] : (u8)0);
+        if (m.members == 1) {
+            sa[wbase + e] = pos; bwt[wbase + e] = sym;
+            lcp[wbase + e] = t ? m.shift + occ_lcp[q] : glcp[kk];
+        } else if (m.members > FUSE_MAX_MEMBERS) {
+            sa[wbase + e] = pos; key[wbase + e] = occ_next_rank[q];            // bwt of these is filled after the sort (bwt_of_groups)
+        } else {
+            u32 ks = kk - m.back;
+            u64 gbase = (ks >= kw) ? wbase + soff[w][ks - kw] : out_base[ks] - tile_base + lead;
+            u32 r = occ_next_rank[q], slot = t;
+            bool has_pred = t > 0;
+            u32 pred = has_pred ? occ_next_rank[q - 1] : 0u;
+            for (u32 j = 0; j < m.members; ++j) {
+                u32 kj = ks + j;
+                if (kj == kk) continue;
+                u32 oq, oc;
+                if (kj >= kw && kj < kw + 32) { oq = smeta[w][kj - kw].q0; oc = smeta[w][kj - kw].cnt; }
+                else { MemberMeta o = meta[kj]; oq = o.q0; oc = o.cnt; }
+                u32 lb = lower_bound_u32(occ_next_rank + oq, oc, r);
                 slot += lb;
-                if (lb) { u32 v = occ_next_rank[oq[j] + lb - 1]; if (!has_pred || v > pred) pred = v; has_pred = true; }
+                if (lb) { u32 v = occ_next_rank[oq + lb - 1]; if (!has_pred || v > pred) pred = v; has_pred = true; }
             }
+            sa[gbase + slot] = pos; bwt[gbase + slot] = sym;
+            lcp[gbase + slot] = has_pred ? m.shift + range_min(s_lcp, rmq, rmq_blocks, pred + 1, r) : glcp[ks];
         }
-        u64 pos = occ_next_start[q0 + t] - shift;
-        sa[gbase + slot] = pos;
-        bwt[gbase + slot] = inside ? before : (pos ? text[pos - 1] : (u8)0);
-        lcp[gbase + slot] = has_pred ? shift + range_min(s_lcp, rmq, rmq_blocks, pred + 1, r) : first_lcp;
     }
 }
 
@@ -333,7 +336,7 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
         }
         u32 nm = k1 - k0;
         small.alloc((u64)nm / 2 + 1, s); large.alloc((u64)nm / 2 + 1, s); counts.zero();
-        MMB_LAUNCH(expand_members, ceil_div((u64)nm * 32, TPB), TPB, 0, s, k0, k1, (const MemberMeta*)meta.p, (const u64*)out_base.p, (const u32*)glcp.p,
+        MMB_LAUNCH(expand_members, ceil_div(nm, EXP_TPB), EXP_TPB, 0, s, k0, k1, (const MemberMeta*)meta.p, (const u64*)out_base.p, (const u32*)glcp.p,
                    (const u32*)ix.occ_next_rank.p, (const u64*)ix.occ_next_start.p, (const u32*)ix.occ_lcp.p, (const u32*)ix.s_lcp.p, (const u32*)ix.rmq.p,
                    ix.rmq_blocks, text, lead, sa.p, lcp.p, key.p, bwt.p);
         MMB_LAUNCH(collect_multi, ceil_div(nm, TPB), TPB, 0, s, k0, k1, K, (const u32*)glcp.p, (const u64*)out_base.p, small.p, large.p, counts.p);

@@ -28,13 +28,6 @@ constexpr u32 MAP_ID = 0xE4;    // 2 bits per input state: 3->3, 2->2, 1->1, 0->
 
 __device__ __forceinline__ bool is_marker(u8 c) { return c == '>' || c == '@'; }
 
-__device__ __forceinline__ u32 fsm_next(u32 st, u8 c) {
-    if (st == ST_PRE) return is_marker(c) ? ST_HDR : ST_PRE;
-    if (c == '\n') return ST_BOL;
-    if (st == ST_BOL) return is_marker(c) ? ST_HDR : ST_SEQ;
-    return st;
-}
-
 __device__ __forceinline__ u32 map_compose(u32 a, u32 b) {   // apply a, then b
     u32 r = 0;
 #pragma unroll
@@ -60,7 +53,8 @@ struct ChunkView {
     u64 fend;       // absolute end of the file
     u32 nbytes;     // 0..16 valid bytes for this thread
     u8 b[16];
-    u8 after;       // byte following b[nbytes-1] inside the file, or '\n' at end of file
+    u32 nl, mk, cr, pl;     // 16-bit masks over b[]: '\n', header marker ('>' '@'), '\r', '+'
+    bool eof_or_nl_after;   // the byte after b[nbytes-1] is '\n' or the file ends there
 };
 
 // chunk index -> (file, chunk start).  chunk_first[f] = index of the first chunk of file f (N+1 entries).
@@ -72,8 +66,11 @@ __device__ __forceinline__ u32 find_file(const u32* __restrict__ chunk_first, u3
 
 __device__ __forceinline__ void load_view(const u8* __restrict__ raw, const u64* __restrict__ file_off, const u64* __restrict__ file_end,
                                           const u32* __restrict__ chunk_first, u32 nfiles, ChunkView& v, u32& file) {
+    __shared__ u32 s_file;
     u32 chunk = blockIdx.x;
-    file = find_file(chunk_first, nfiles, chunk);
+    if (threadIdx.x == 0) s_file = find_file(chunk_first, nfiles, chunk);
+    __syncthreads();
+    file = s_file;
     u64 fbeg = file_off[file];
     v.fend = file_end[file];
     v.begin = fbeg + (u64)(chunk - chunk_first[file]) * CHUNK + (u64)threadIdx.x * 16;
@@ -87,8 +84,16 @@ __device__ __forceinline__ void load_view(const u8* __restrict__ raw, const u64*
 #pragma unroll
         for (int k = 0; k < 16; ++k) v.b[k] = (k < (int)v.nbytes) ? raw[v.begin + k] : (u8)0;
     }
-    v.after = '\n';
-    if (v.nbytes && v.b[v.nbytes - 1] == '\r' && v.begin + v.nbytes < v.fend) v.after = raw[v.begin + v.nbytes];
+    v.nl = v.mk = v.cr = v.pl = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        u8 c = v.b[k];
+        v.nl |= (u32)(c == '\n') << k; v.mk |= (u32)is_marker(c) << k; v.cr |= (u32)(c == '\r') << k; v.pl |= (u32)(c == '+') << k;
+    }
+    u32 valid = (1u << v.nbytes) - 1;
+    v.nl &= valid; v.mk &= valid; v.cr &= valid; v.pl &= valid;
+    v.eof_or_nl_after = true;
+    if (v.nbytes && ((v.cr >> (v.nbytes - 1)) & 1) && v.begin + v.nbytes < v.fend) v.eof_or_nl_after = raw[v.begin + v.nbytes] == '\n';
 }
 
 // Exclusive composition scan of per-thread maps over the block; *total = map of the whole block.
@@ -112,16 +117,48 @@ __device__ __forceinline__ u32 block_map_scan(u32 mine, u32* total) {
     return map_compose(before, excl);
 }
 
+// state after the thread's bytes for each of the four start states, from the masks alone
 __device__ __forceinline__ u32 thread_map(const ChunkView& v) {
-    u32 m = 0;
-#pragma unroll
-    for (u32 s = 0; s < 4; ++s) {
-        u32 st = s;
-#pragma unroll
-        for (u32 k = 0; k < 16; ++k) if (k < v.nbytes) st = fsm_next(st, v.b[k]);
-        m |= st << (2 * s);
+    if (v.nbytes == 0) return MAP_ID;
+    bool has_nl = v.nl != 0;
+    u32 tail = ST_BOL;                                      // state after the last newline of these bytes
+    if (has_nl) {
+        u32 last = 31 - (u32)__clz((int)v.nl);
+        if (last + 1 < v.nbytes) tail = ((v.mk >> (last + 1)) & 1) ? ST_HDR : ST_SEQ;
     }
-    return m;
+    u32 from_bol = has_nl ? tail : ((v.mk & 1) ? ST_HDR : ST_SEQ);
+    u32 from_hdr = has_nl ? tail : ST_HDR;
+    u32 from_seq = has_nl ? tail : ST_SEQ;
+    u32 from_pre = ST_PRE;
+    if (v.mk) {
+        u32 fm = (u32)__ffs((int)v.mk) - 1;
+        from_pre = (v.nl >> fm) >> 1 ? tail : ST_HDR;        // a newline after the first marker ends that header
+    }
+    return (from_pre << (2 * ST_PRE)) | (from_bol << (2 * ST_BOL)) | (from_hdr << (2 * ST_HDR)) | (from_seq << (2 * ST_SEQ));
+}
+
+// Which of the thread's bytes are sequence symbols (keep) and which start a header, given the state before its first byte.
+struct ByteMasks { u32 keep, header, fastq; };
+__device__ __forceinline__ ByteMasks classify_bytes(const ChunkView& v, u32 st) {
+    ByteMasks r; r.keep = r.header = r.fastq = 0;
+    if (v.nbytes == 0) return r;
+    u32 valid = (1u << v.nbytes) - 1;
+    u32 cut = 0;                                            // bytes below this index are still before the first header of the file
+    u32 pre_marker = 0;
+    if (st == ST_PRE) {
+        if (!v.mk) return r;
+        cut = (u32)__ffs((int)v.mk) - 1; pre_marker = 1u << cut;
+    }
+    u32 from_cut = valid & ~((1u << cut) - 1);
+    u32 line_start = ((v.nl << 1) | (st == ST_BOL ? 1u : 0u)) & valid;
+    r.header = ((v.mk & line_start) | pre_marker) & from_cut;
+    u32 run = ~v.nl & valid;                                // header text runs up to (not including) the next newline
+    u32 start = r.header | ((st == ST_HDR ? 1u : 0u) & run);
+    u32 in_header = ((start + run) ^ run) & run;            // carry trick: fill from each start bit to the end of its run of non-newlines
+    u32 eol_next = (v.nl >> 1) | (v.eof_or_nl_after ? 1u << (v.nbytes - 1) : 0u);
+    r.keep = from_cut & ~v.nl & ~in_header & ~(v.cr & eol_next);
+    r.fastq = v.pl & line_start & from_cut & ~in_header;
+    return r;
 }
 
 // Exclusive sum of one u32 per thread over the block; *total = block sum.
@@ -138,18 +175,6 @@ __device__ __forceinline__ u32 block_sum_scan(u32 mine, u32* total) {
     *total = all;
     __syncthreads();
     return before + inc - mine;
-}
-
-// Per-byte decision shared by the counting and the scattering pass.
-struct ByteClass { bool keep, header; };
-__device__ __forceinline__ ByteClass classify(u32 st, u8 c, bool eol_follows, u32* fastq_flag) {
-    ByteClass r;
-    bool in_seq = (st == ST_BOL || st == ST_SEQ);
-    bool marker = is_marker(c);
-    r.header = marker && (st == ST_PRE || st == ST_BOL);
-    if (st == ST_BOL && c == '+') *fastq_flag = 1;
-    r.keep = in_seq && c != '\n' && !(marker && st == ST_BOL) && !(c == '\r' && eol_follows);
-    return r;
 }
 
 __global__ void __launch_bounds__(TPB) fasta_chunk_maps(const u8* __restrict__ raw, const u64* __restrict__ file_off, const u64* __restrict__ file_end,
@@ -200,22 +225,11 @@ __global__ void __launch_bounds__(TPB) fasta_pass(const u8* __restrict__ raw, co
         u32 prefix = block_map_scan(thread_map(v), &total);
         st = (prefix >> (2 * (u32)chunk_state[blockIdx.x])) & 3;
     }
-    // first walk: counts
-    u32 kept = 0, hdr = 0, fq = 0;
-    {
-        u32 s2 = st;
-#pragma unroll
-        for (u32 k = 0; k < 16; ++k) {
-            if (k >= v.nbytes) break;
-            u8 c = v.b[k];
-            bool eol = (k + 1 < v.nbytes) ? (v.b[(k + 1) & 15] == '\n') : (v.after == '\n');
-            if (raw_mode) { ++kept; continue; }
-            ByteClass bc = classify(s2, c, eol, &fq);
-            kept += bc.keep; hdr += bc.header;
-            s2 = fsm_next(s2, c);
-        }
-    }
-    if (fq) *fastq_flag = 1;
+    ByteMasks bm;
+    if (raw_mode) { bm.keep = (1u << v.nbytes) - 1; bm.header = 0; bm.fastq = 0; }
+    else bm = classify_bytes(v, st);
+    u32 kept = (u32)__popc(bm.keep), hdr = (u32)__popc(bm.header);
+    if (bm.fastq) *fastq_flag = 1;
     u32 kept_total, hdr_total;
     u32 kept_before = block_sum_scan(kept, &kept_total);
     u32 hdr_before = block_sum_scan(hdr, &hdr_total);
@@ -223,23 +237,16 @@ __global__ void __launch_bounds__(TPB) fasta_pass(const u8* __restrict__ raw, co
         if (threadIdx.x == 0) { chunk_kept[blockIdx.x] = kept_total; chunk_hdr[blockIdx.x] = hdr_total; }
         return;
     }
-    // second walk: kept symbols go to shared memory first (a chunk's kept symbols form ONE contiguous run in the forward text and one
-    // in the reverse complement), then the block writes both runs with aligned 4-byte stores
+    // kept symbols go to shared memory first (a chunk's kept symbols form ONE contiguous run in the forward text and one in the
+    // reverse complement), then the block writes both runs with aligned 4-byte stores
     __shared__ u8 stage[CHUNK];
-    u64 kidx = chunk_kept_base[blockIdx.x] + kept_before;       // global index among kept bases
+    u64 kbase = chunk_kept_base[blockIdx.x] + kept_before;      // global index among kept bases of this thread's first kept byte
     u32 hidx = chunk_hdr_base[blockIdx.x] + hdr_before;
     u32 local = kept_before;
-    u32 s2 = st;
 #pragma unroll
     for (u32 k = 0; k < 16; ++k) {
-        if (k >= v.nbytes) break;
-        u8 c = v.b[k];
-        bool eol = (k + 1 < v.nbytes) ? (v.b[(k + 1) & 15] == '\n') : (v.after == '\n');
-        ByteClass bc;
-        if (raw_mode) { bc.keep = true; bc.header = false; }
-        else { u32 dummy = 0; bc = classify(s2, c, eol, &dummy); s2 = fsm_next(s2, c); }
-        if (bc.header) { rec_pos[hidx] = v.begin + k; rec_before[hidx] = kidx; ++hidx; }
-        if (bc.keep) { stage[local++] = upper(c); ++kidx; }
+        if ((bm.header >> k) & 1) { rec_pos[hidx] = v.begin + k; rec_before[hidx] = kbase + (u32)__popc(bm.keep & ((1u << k) - 1)); ++hidx; }
+        if ((bm.keep >> k) & 1) stage[local++] = upper(v.b[k]);
     }
     __syncthreads();
     u64 base = doc_start[file], L = doc_len[file];

@@ -10,10 +10,5 @@ echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()"
 echo "=== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -q -x --durations=8 2>&1 | tail -20
 echo "=== bench c1"; timeout 900 python bench.py --workload c1 --steps 10 --warmup 3 | tee gpurun_out/bench_c1.json | cut -c1-400
 echo "=== bench c2 (default)"; timeout 2400 python bench.py | tee gpurun_out/bench_c2.json | cut -c1-3000
-echo "=== ncu launch list (c1, 1 step)"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_c1.csv python bench.py --workload c1 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_bench.log 2>&1
-wc -l gpurun_out/launches_c1.csv
-echo "=== ncu launch list (h64_16m pfp, 1 step)"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_h64_16m_pfp.csv python bench.py --workload h64_16m --route pfp --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_bench2.log 2>&1
-wc -l gpurun_out/launches_h64_16m_pfp.csv
+echo "=== bench h64_16m pfp"; timeout 900 python bench.py --workload h64_16m --route pfp --steps 3 --warmup 3 --no-cpu-baseline --no-e2e | cut -c1-1500
 echo "=== done"
