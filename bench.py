@@ -35,6 +35,8 @@ WORKLOADS = {
     "h64_4m": dict(N=64, L=4_000_000, kind="pangenome", desc="64x4 Mbp human-chr-like haplotypes, strict multi-MUMs"),
     "h64_16m": dict(N=64, L=16_000_000, kind="pangenome", desc="64x16 Mbp human-chr-like haplotypes, strict multi-MUMs"),
     "c2": dict(N=64, L=100_000_000, kind="pangenome", desc="64x100 Mbp synthetic human-chr-like haplotypes, strict multi-MUMs [BASELINE configs[1]]"),
+    # one partition of BASELINE configs[4] (256x100 Mbp = 8 partitions of 32 genomes, 1 per GPU): anchor + 31 haplotypes, -M -n
+    "c5": dict(N=32, L=100_000_000, kind="pangenome", desc="partition of 32x100 Mbp haplotypes sharing anchor h0, strict multi-MUMs -M -n [BASELINE configs[4]: 1 partition per GPU, NCCL all-gather + merge]"),
 }
 ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 
@@ -238,8 +240,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--roofline-kernel", default=None, help="kernel (name substring) whose launches are timed with CUDA events for the roofline line")
     args = ap.parse_args()
-    spec = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and args.workload == "c2":
+        args.workload = "c5"            # several GPUs: the partition-merge configuration, one 32-genome partition per GPU
+    spec = WORKLOADS[args.workload]
 
     if args.impl == "reference":
         reference_arm(args, spec, rank)

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 exec > >(tee gpurun_out/gpu_multi.log) 2>&1
 nvidia-smi --query-gpu=index,name,memory.total --format=csv
 timeout 600 python -c "import __graft_entry__ as g; g.build()" || echo BUILD_FAILED
-for w in h64_4m c2; do
+for w in h64_4m; do
   echo "=== bench $w N=$N"
   timeout 1800 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --workload $w --steps 3 --warmup 3 2> gpurun_out/multi_${w}_err.log | tee gpurun_out/bench_${w}_n${N}.json | cut -c1-2500
   tail -5 gpurun_out/multi_${w}_err.log
