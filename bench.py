@@ -8,7 +8,7 @@ A step = one pass of the hot path over one synthetic collection:
           (left on the device); timed per step with CUDA events on the stream the kernels are launched on, L2 flushed between steps.
   e2e   : the same through the reference-facing call with HOST buffers: pinned FASTA images -> H2D -> hot path -> D2H of the .mums bytes.
 N > 1 (torchrun): every rank owns one partition (shared anchor h0 + its own haplotypes, -M -n), no collective on the data path
-(scaling "weak"); the partition tables are then exchanged with one NCCL all-gather and folded by the merge kernels (reported aside).
+(scaling "weak") until the exchange step inside every timed step: one NCCL all-gather of the partition tables, then the merge kernels.
 --impl reference times the reference's own CPU implementation (oracle/_ref/mumemto_exec = reference sources compiled unmodified,
 single-threaded because the reference has no threads) on the same workload.
 """
@@ -261,7 +261,15 @@ def main():
 
     # ---- synthetic input: N = 1 -> the named collection; N > 1 -> one partition per rank sharing the anchor document
     multi = world > 1
-    imgs = make_collection(spec, seed=1 + 1000 * rank, anchor_seed=(12345 if (multi and spec["kind"] == "pangenome") else None),
+    cache = os.environ.get("MMB_CACHE_DIR")      # optional: keep the generated FASTA images between runs on the same box
+    cache_file = os.path.join(cache, f"{args.workload}_r{rank}_w{world}.npy") if cache else None
+    imgs = None
+    if cache_file and os.path.exists(cache_file):
+        data = np.load(cache_file, mmap_mode="r")
+        sz = np.load(cache_file + ".sizes.npy")
+        at0 = np.concatenate([[0], np.cumsum(sz)[:-1]])
+        imgs = [data[o:o + n] for o, n in zip(at0, sz)]
+    imgs = imgs or make_collection(spec, seed=1 + 1000 * rank, anchor_seed=(12345 if (multi and spec["kind"] == "pangenome") else None),
                            first_index=0) if not (multi and spec["kind"] == "independent") else make_collection(spec, seed=1)
     if multi and spec["kind"] == "independent":
         # partitions of the Appendix-A collection cannot share an anchor unless it is the same h0: rank r keeps h0 + its own variants
@@ -272,6 +280,10 @@ def main():
             s[m] = (s[m] + r2.integers(1, 4, m.sum())) % 4
             return s.astype(np.uint8)
         imgs = [fasta_image("h0", variant(7))] + [fasta_image(f"h{rank * 100 + i}", variant(1000 * rank + i + 11)) for i in range(1, spec["N"])]
+    if cache_file and not os.path.exists(cache_file):
+        os.makedirs(cache, exist_ok=True)
+        np.save(cache_file + ".sizes.npy", np.array([im.size for im in imgs], dtype=np.int64))
+        np.save(cache_file, np.concatenate(imgs))
     bases_rank = spec["N"] * spec["L"]
     new_bases_rank = bases_rank if not multi else (spec["N"] - 1) * spec["L"]      # the anchor is counted once
     total_bases = bases_rank if not multi else spec["L"] + world * new_bases_rank
@@ -289,9 +301,15 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
     opts = dict(merge=multi, anchor_merge=multi, route=args.route)
 
+    from mumemto_b200 import partition
+    tdev = torch.device("cuda", local)
+
     def step_device():
         eng.load_fasta_device(dev.data_ptr(), offsets, sizes)
-        return eng.find(want_text=True, **opts)
+        st = eng.find(want_text=True, **opts)
+        if multi:       # the exchange step of the path: one all-gather of the partition tables, then the merge kernels on every rank
+            partition.partition_merge(eng, dist, world, tdev, fetch=False)
+        return st
 
     out_host = None
 
@@ -303,6 +321,10 @@ def main():
         if out_host is None or out_host.numel() < n:
             out_host = torch.empty(max(n, 1), dtype=torch.uint8).pin_memory()
         eng.copy_text_into(out_host.numpy())
+        if multi:       # partition .mums above, then exchange + merge and the merged .mums back to the host
+            partition.partition_merge(eng, dist, world, tdev, fetch=False)
+            merged = eng.merge_text()
+            n += len(merged)
         return n
 
     def barrier():
@@ -310,7 +332,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    min_warm = int(os.environ.get("MMB_MIN_WARMUP", "3"))      # profiling runs only; a bench line always has >= 3 warm-up steps
+    for _ in range(max(args.warmup, min_warm, 1)):
         flush.zero_(); st_warm = step_device()
     # dominant kernel per route (profiles/README.md): algorithmic bytes per suffix it must move
     ROOF = {"expand_members": 29.0,      # occurrence list 16 B read; SA 8 + LCP 4 + BWT 1 B written
@@ -424,7 +447,7 @@ def partition_merge(eng, dist, world, rank, spec):
     torch.cuda.synchronize(); t1 = time.perf_counter()
     partition.merge_gathered(eng, parts)
     torch.cuda.synchronize(); t2 = time.perf_counter()
-    return {"allgather_s": t1 - t0, "merge_s": t2 - t1, "merged_mums": int(eng.lib.mmb_merge_num_mums(eng.h)),
+    return {"in_timed_step": True, "allgather_s": t1 - t0, "merge_s": t2 - t1, "merged_mums": int(eng.lib.mmb_merge_num_mums(eng.h)),
             "merged_columns": int(eng.lib.mmb_merge_num_docs(eng.h)), "partition_mums": [int(p[4]) for p in parts],
             "gathered_bytes": int(sum(p[0].numel() * 4 + p[1].numel() * 8 + p[2].numel() + p[3].numel() * 2 for p in parts))}
 

@@ -317,6 +317,151 @@ __global__ void __launch_bounds__(DW_TPB) detect_window_kernel(const u32* __rest
     }
 }
 
+// ------------------------------------------------------------------------------------------------ chunked window-minimum detector
+// Same test as detect_window_kernel, but the minimum of the smallest window (size_lo - 1 entries ending at j-1) costs O(1) per rank
+// instead of one shared-memory pass per power of two: the staged tile is cut into chunks of C = (size_lo - 1) | 1 ranks (C >= the
+// window, C odd), one thread walks one chunk.  Pass 1 writes the suffix minima of every chunk; in pass 2 the window of rank j is the
+// tail of the previous chunk (one suffix minimum) joined with the head of its own chunk (a running minimum in a register).  Lanes
+// are C words apart and C is odd, so every shared-memory access is conflict-free.  Larger sizes extend the window one entry at a
+// time.  Candidates are verified exactly as in detect_window_kernel.
+constexpr u32 DC_TPB = 128;
+struct ChunkPlan {
+    u32 size_lo, size_hi;
+    u32 w0;                     // size_lo - 1: entries in the smallest window
+    u32 chunk;                  // C
+    u32 halo_chunks;            // H: chunks staged in front of the first closing rank (H * C >= size_hi)
+    u32 rounds;                 // R: chunks per thread; a block stages R * DC_TPB chunks and closes (R * DC_TPB - H) * C ranks
+    u32 span;                   // staged entries: R * DC_TPB * C + 4, rounded up to a multiple of 4
+};
+
+template <class SAT, int W, int P>
+__global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restrict__ lcp, const SAT* __restrict__ sa, const u8* __restrict__ bwt,
+                                                             const u8* __restrict__ text, u64 m, u64 j_first, DetectParams prm, ChunkPlan plan,
+                                                             const u64* __restrict__ doc_start_g, Report* __restrict__ reports, u32 cap,
+                                                             u32* __restrict__ count, u16* __restrict__ thresh) {
+    MMB_DYN_SMEM(u64, smem64);
+    u64* bar = smem64;                                  // 16 bytes reserved
+    u64* doc_start = smem64 + 2;                        // ndocs + 1 (+1 pad to keep 16-byte alignment)
+    u32* lc = reinterpret_cast<u32*>(doc_start + ((prm.ndocs + 2) & ~1u));      // the lcp tile
+    u32* suf = lc + plan.span;                          // suffix minima inside every chunk
+    const u32 C = plan.chunk, H = plan.halo_chunks, G = plan.rounds * DC_TPB, W0 = plan.w0, span = plan.span;
+    const i64 origin = (i64)blockIdx.x * (i64)(G - H) * C - (i64)H * C;         // rank of the first entry of chunk 0
+    const i64 origin_al = origin - (((origin % 4) + 4) % 4);                    // staging starts on a 16-byte boundary of lcp
+    const u32 d = (u32)(origin - origin_al);                                    // chunk g occupies lc[d + g*C .. d + (g+1)*C)
+
+    for (u32 i = threadIdx.x; i <= prm.ndocs; i += blockDim.x) doc_start[i] = doc_start_g[i];
+    {   // stage lcp[origin_al .. origin_al + span): ranks below 0 or at/after m read as 0 (an lcp of 0 closes everything)
+        u64 lo = origin_al < 0 ? 0 : (u64)origin_al, hi = min((u64)(origin_al + (i64)span), m);
+        u32 skip = (u32)((i64)lo - origin_al);
+        for (u32 i = threadIdx.x; i < skip; i += blockDim.x) lc[i] = 0;
+        u32 have = hi > lo ? (u32)(hi - lo) : 0u, padded = min((have + 3) & ~3u, span - skip);      // lcp is allocated with slack past m
+        if (padded) tma_load_tile(lc + skip, lcp + lo, padded * 4, bar); else __syncthreads();
+        for (u32 i = skip + have + threadIdx.x; i < span; i += blockDim.x) lc[i] = 0;
+    }
+    __syncthreads();
+    for (u32 g = threadIdx.x; g < G; g += DC_TPB) {     // pass 1
+        u32 base = d + g * C, mn = 0xffffffffu;
+#pragma unroll 4
+        for (u32 k = C; k-- > 0;) { mn = min(mn, lc[base + k]); suf[base + k] = mn; }
+    }
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31;
+    for (u32 r = 0; r < plan.rounds; ++r) {             // pass 2 (warp-uniform loops: the verification below is warp-cooperative)
+        const u32 g = r * DC_TPB + threadIdx.x;
+        const u32 base = d + g * C;
+        const u64 j0 = (u64)(origin + (i64)g * C);      // only used when g >= H, where it is non-negative
+        u32 run = 0xffffffffu;                          // min(lc[base .. base + k - 1])
+        for (u32 k = 0; k < C; ++k) {
+            const u32 idx = base + k;
+            const u64 j = j0 + k;
+            const u32 cur = lc[idx];
+            u32 v = 0;
+            if (g >= H) v = (k >= W0) ? run : min(suf[idx - W0], run);      // k = W0 only when C = W0 + 1: the window is the chunk's head
+            run = min(run, cur);
+            bool active = g >= H && j >= j_first && j >= 1 && j < m && v > cur && v >= prm.min_len;
+            if (!__any_sync(0xffffffffu, active)) continue;
+            u32 size = plan.size_lo;
+            for (;;) {                                  // one candidate per lane per turn
+                bool have = false;
+                while (active && size <= plan.size_hi) {
+                    if (j < size || v <= cur || v < prm.min_len) { active = false; break; }
+                    u32 before = lc[idx - size];
+                    if (before < v) { have = true; break; }
+                    ++size; v = min(v, before);
+                }
+                if (!have) active = false;
+                unsigned cand = __ballot_sync(0xffffffffu, have);
+                if (!cand) break;
+                if (P == 1 && prm.max_doc_freq == 1) {
+                    while (cand) {
+                        int src = __ffs((int)cand) - 1; cand &= cand - 1;
+                        u64 cj = __shfl_sync(0xffffffffu, j, src);
+                        u32 cs = __shfl_sync(0xffffffffu, size, src), cv = __shfl_sync(0xffffffffu, v, src), ccur = __shfl_sync(0xffffffffu, cur, src);
+                        u32 cbefore = __shfl_sync(0xffffffffu, lc[idx - (have ? size : 0)], src);
+                        u64 s0 = cj - cs;
+                        if (bwt && !prm.merge) {
+                            bool d0 = false;
+                            for (u32 t = 1 + lane; t < cs; t += 32) d0 |= bwt[s0 + t] != bwt[s0 + t - 1];
+                            if (!__any_sync(0xffffffffu, d0)) continue;
+                        }
+                        u64 bits[W];
+#pragma unroll
+                        for (int w = 0; w < W; ++w) bits[w] = 0;
+                        u64 anchor = ~0ull; bool differs = false; u32 carry = 0;
+                        for (u32 t0 = 0; t0 < cs; t0 += 32) {
+                            u32 t = t0 + lane;
+                            u32 sym = 0;
+                            if (t < cs) {
+                                u64 rk = s0 + t; u64 p = (u64)sa[rk];
+                                u32 dd = find_doc(doc_start, prm.ndocs, p);
+                                bits[(W == 1) ? 0 : (dd >> 6)] |= 1ull << (dd & 63);
+                                if (dd == 0) anchor = p;
+                                sym = bwt ? bwt[rk] : (p ? text[p - 1] : (u8)0);
+                            }
+                            u32 left = __shfl_up_sync(0xffffffffu, sym, 1);
+                            if (lane == 0) left = carry;
+                            if (t < cs && t > 0 && left != sym) differs = true;
+                            carry = __shfl_sync(0xffffffffu, sym, 31);
+                        }
+                        u32 distinct = 0;
+#pragma unroll
+                        for (int w = 0; w < W; ++w) {
+                            u64 b = bits[w];
+#pragma unroll
+                            for (u32 dd = 16; dd > 0; dd >>= 1) b |= __shfl_xor_sync(0xffffffffu, b, dd);
+                            distinct += (u32)__popcll(b);
+                        }
+                        differs = __any_sync(0xffffffffu, differs);
+                        if (distinct == cs && distinct >= prm.num_distinct) {          // every document at most once
+                            if (prm.merge && anchor != ~0ull) thresh[anchor] = (u16)min(max(cbefore, ccur), 65535u);
+                            if (differs && lane == 0) {
+                                u32 slot = atomicAdd(count, 1u);
+                                if (slot < cap) { Report rp; rp.key = (cj << 20) | cs; rp.s = s0; rp.len = cv; rp.pad = 0; reports[slot] = rp; }
+                            }
+                        }
+                    }
+                } else if (have) {
+                    DocCounter<W, P> docs; docs.clear();
+                    u64 s0 = j - size; bool ok = true, differs = false;
+                    u8 prev_sym = 0;
+                    for (u32 t = 0; t < size && ok; ++t) {
+                        u64 rk = s0 + t; u64 p = (u64)sa[rk];
+                        ok = docs.add(find_doc(doc_start, prm.ndocs, p), prm.max_doc_freq);
+                        u8 sym = bwt ? bwt[rk] : (p ? text[p - 1] : (u8)0);
+                        if (t > 0 && sym != prev_sym) differs = true;
+                        prev_sym = sym;
+                    }
+                    if (ok && docs.distinct >= prm.num_distinct && differs) {
+                        u32 slot = atomicAdd(count, 1u);
+                        if (slot < cap) { Report rp; rp.key = (j << 20) | size; rp.s = s0; rp.len = v; rp.pad = 0; reports[slot] = rp; }
+                    }
+                }
+                if (have) { v = min(v, lc[idx - size]); ++size; }
+            }
+        }
+    }
+}
+
 __global__ void report_keys(const Report* __restrict__ rep, u32 n, u64* __restrict__ keys, u32* __restrict__ idx) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { keys[i] = rep[i].key; idx[i] = i; }
@@ -329,11 +474,20 @@ __global__ void report_gather(const Report* __restrict__ rep, const u32* __restr
 struct DetectArgs {
     const u32* lcp; const u8* bwt; const u8* text; u64 m; u64 j_first; DetectParams prm; const u64* d_doc_start; Report* rep; u32 cap; u32* count; u16* thresh;
     bool use_window; WindowPlan plan;
+    bool use_chunk = false; ChunkPlan cplan;
 };
 
 template <class SAT, int W, int P>
 void launch_detect(const SAT* sa, const DetectArgs& a, cudaStream_t s) {
-    if (a.use_window) {
+    if (a.use_chunk) {
+        auto detect_chunk_k = detect_chunk_kernel<SAT, W, P>;
+        size_t smem = 16 + (size_t)((a.prm.ndocs + 2) & ~1u) * 8 + (size_t)a.cplan.span * 4 * 2;
+#ifndef MMB_SIMT
+        if (smem > 48 * 1024) MMB_CUDA(cudaFuncSetAttribute(detect_chunk_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+        u64 per_block = (u64)(a.cplan.rounds * DC_TPB - a.cplan.halo_chunks) * a.cplan.chunk;
+        MMB_LAUNCH(detect_chunk_k, ceil_div(a.m, per_block), DC_TPB, smem, s, a.lcp, sa, a.bwt, a.text, a.m, a.j_first, a.prm, a.cplan, a.d_doc_start, a.rep, a.cap, a.count, a.thresh);
+    } else if (a.use_window) {
         auto detect_window_k = detect_window_kernel<SAT, W, P>;
         size_t smem = 16 + (size_t)((a.prm.ndocs + 2) & ~1u) * 8 + (size_t)a.plan.span * 4 * (2 + a.plan.nkept);
 #ifndef MMB_SIMT
@@ -359,6 +513,21 @@ void dispatch_planes(const SAT* sa, const DetectArgs& a, cudaStream_t s) {
 u32 floor_log2(u32 x) { u32 t = 0; while ((2u << t) <= x) ++t; return t; }
 
 // Which interval sizes can qualify, and whether the windowed kernel covers them.  Returns false if nothing can qualify at all.
+// The chunked kernel: any size range whose smallest window fits a chunk of <= 127 ranks (two staged arrays of DC_TPB chunks).
+bool make_chunk_plan(u64 lo, u64 hi, ChunkPlan& cp) {
+    const char* force = getenv("MMB_DETECT");
+    if (force && strcmp(force, "chunk") != 0) return false;
+    if (hi - lo + 1 > DW_MAX_SIZES || lo - 1 > 127) return false;
+    cp.size_lo = (u32)lo; cp.size_hi = (u32)hi; cp.w0 = (u32)lo - 1;
+    cp.chunk = cp.w0 | 1u;
+    cp.halo_chunks = ((u32)hi + cp.chunk - 1) / cp.chunk;
+    u32 want = 8192 / (DC_TPB * cp.chunk);
+    cp.rounds = std::min(32u, std::max(1u, want));
+    while (cp.rounds * DC_TPB < 2 * cp.halo_chunks + 1) ++cp.rounds;           // at least half of the staged chunks close ranks
+    cp.span = (cp.rounds * DC_TPB * cp.chunk + 4 + 3) & ~3u;
+    return true;
+}
+
 bool make_plan(const DetectParams& prm, bool& use_window, WindowPlan& pl) {
     u64 hi = prm.max_freq;
     if (prm.max_doc_freq) { u64 bound = (u64)prm.max_doc_freq * prm.ndocs; hi = hi ? std::min(hi, bound) : bound; }
@@ -371,7 +540,8 @@ bool make_plan(const DetectParams& prm, bool& use_window, WindowPlan& pl) {
     if (pl.span > DW_TPB * 6) return true;
     pl.lev_lo = floor_log2(pl.size_lo - 1); pl.lev_hi = floor_log2(pl.size_hi - 1);
     pl.nkept = pl.lev_hi >= 1 ? pl.lev_hi - std::max(pl.lev_lo, 1u) + 1 : 0;
-    use_window = !getenv("MMB_FORCE_WALK");
+    const char* force = getenv("MMB_DETECT");
+    use_window = !getenv("MMB_FORCE_WALK") && !(force && strcmp(force, "walk") == 0);
     return true;
 }
 
@@ -389,6 +559,11 @@ void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, const u8* te
     DetectArgs a;
     a.lcp = lcp; a.bwt = bwt; a.text = text; a.m = m; a.j_first = j_first; a.prm = prm; a.d_doc_start = d_doc_start; a.thresh = thresh;
     if (m < 2 || !make_plan(prm, a.use_window, a.plan)) { out.rep.alloc(0, s); return; }
+    {
+        u64 hi = prm.max_freq;
+        if (prm.max_doc_freq) { u64 bound = (u64)prm.max_doc_freq * prm.ndocs; hi = hi ? std::min(hi, bound) : bound; }
+        a.use_chunk = !getenv("MMB_FORCE_WALK") && make_chunk_plan(std::max<u64>(2, prm.num_distinct), hi, a.cplan);
+    }
     DevBuf<u32> d_count; d_count.alloc(1, s);
     u64 cap = std::max<u64>(1u << 16, (m - std::min(m, j_first)) / 64);
     DevBuf<Report> raw;

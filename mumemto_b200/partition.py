@@ -3,7 +3,7 @@
 Mirrors what `mumemto merge p1.mums p2.mums ...` does through files (reference mumemto/merge_mums.py:171-192 -> anchor_merge,
 src/merge_candidates.cpp:170-255): every partition was run with -M -n and shares its first sequence (the anchor); partitions are folded
 in rank order, which fixes the column order of the merged table.  The exchange is a `torch.distributed.all_gather` (NCCL between GPUs;
-gloo in the CPU tests) of {lengths, offsets, strands, thresholds[0..L0]}, padded to the largest partition.
+gloo in the CPU tests) of {lengths, offsets, strands, thresholds[0..L0]} packed into one byte payload per rank.
 """
 import numpy as np
 import torch
@@ -31,43 +31,53 @@ def local_partition(engine, device):
             torch.from_numpy(thr[: len(thr) // 2].view(np.int16).copy()))
 
 
+def _layout(n, nd, L):
+    """Byte offsets of (lengths u32[n], offsets i64[n][nd], strands u8[n][nd], thresholds u16[L]) inside one rank's payload."""
+    a8 = lambda x: (x + 7) & ~7
+    o_off = a8(4 * n)
+    o_str = o_off + 8 * n * nd
+    o_thr = a8(o_str + n * nd)
+    return 0, o_off, o_str, o_thr, (o_thr + 2 * L + 15) & ~15
+
+
 def gather_partitions(part, dist, world):
-    """all_gather of one partition per rank -> list of (lengths, offsets, strands, thresholds, n_mums, ndocs) in rank order."""
+    """ONE payload all-gather (plus a 3-integer size exchange that shapes it): every rank packs its partition table into a byte buffer
+    (NCCL and gloo have no 16-bit integer type), padded to the largest partition; the gathered buffer is then viewed in place.
+    Returns a list of (lengths, offsets, strands, thresholds, n_mums, ndocs) in rank order."""
     lengths, offsets, strands, thr = part
     dev = lengths.device
-    meta = torch.tensor([lengths.shape[0], offsets.shape[1] if offsets.dim() == 2 else 0, thr.shape[0]], dtype=torch.int64, device=dev)
-    metas = [torch.zeros_like(meta) for _ in range(world)]
-    dist.all_gather(metas, meta)
-    metas = [m.tolist() for m in metas]
+    n, nd, L = int(lengths.shape[0]), int(offsets.shape[1]) if offsets.dim() == 2 else 0, int(thr.shape[0])
+    meta = torch.tensor([n, nd, L], dtype=torch.int64, device=dev)
+    metas = torch.zeros(world * 3, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(metas, meta)
+    metas = metas.view(world, 3).tolist()
     if len({m[2] for m in metas}) != 1:
         raise ValueError("partitions do not share their first sequence (threshold lengths differ)")
-    nmax, dmax = max(m[0] for m in metas), max(m[1] for m in metas)
-
-    def padded(t, shape):
-        buf = torch.zeros(shape, dtype=t.dtype, device=dev)
-        if t.numel():
-            if len(shape) == 1:
-                buf[: t.shape[0]] = t
-            else:
-                buf[: t.shape[0], : t.shape[1]] = t
-        return buf
-
-    out = []
-    for t, shape in ((lengths, (max(nmax, 1),)), (offsets, (max(nmax, 1), max(dmax, 1))), (strands, (max(nmax, 1), max(dmax, 1))), (thr, (thr.shape[0],))):
-        mine = padded(t, shape)
-        raw = mine.view(torch.uint8).reshape(-1)                 # NCCL and gloo have no 16-bit integer type: exchange bytes
-        bufs = [torch.empty_like(raw) for _ in range(world)]
-        dist.all_gather(bufs, raw)
-        out.append([b.view(mine.dtype).reshape(shape) for b in bufs])
+    stride = max(_layout(*m)[4] for m in metas)
+    mine = torch.zeros(stride, dtype=torch.uint8, device=dev)
+    o_len, o_off, o_str, o_thr, _ = _layout(n, nd, L)
+    if n:
+        mine[o_len:o_len + 4 * n].view(torch.int32).copy_(lengths)
+        mine[o_off:o_off + 8 * n * nd].view(torch.int64).copy_(offsets.reshape(-1))
+        mine[o_str:o_str + n * nd].copy_(strands.reshape(-1))
+    if L:
+        mine[o_thr:o_thr + 2 * L].view(torch.int16).copy_(thr)
+    everything = torch.empty(world * stride, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(everything, mine)
     parts = []
-    for r, (n, nd, _) in enumerate(metas):
-        # un-pad the column dimension so that rows are contiguous [n][nd]
-        parts.append((out[0][r][:n].contiguous(), out[1][r][:n, :nd].contiguous(), out[2][r][:n, :nd].contiguous(), out[3][r].contiguous(), n, nd))
+    for r, (rn, rnd, rL) in enumerate(metas):
+        base = r * stride
+        q_len, q_off, q_str, q_thr, _ = _layout(rn, rnd, rL)
+        parts.append((everything[base + q_len: base + q_len + 4 * rn].view(torch.int32),
+                      everything[base + q_off: base + q_off + 8 * rn * rnd].view(torch.int64).view(rn, rnd),
+                      everything[base + q_str: base + q_str + rn * rnd].view(rn, rnd),
+                      everything[base + q_thr: base + q_thr + 2 * rL].view(torch.int16), rn, rnd))
     return parts
 
 
-def merge_gathered(engine, parts):
-    """Fold the gathered partitions with the engine's merge kernels; returns (lengths, offsets, strands, thresholds) as numpy."""
+def merge_gathered(engine, parts, fetch=True):
+    """Fold the gathered partitions with the engine's merge kernels; returns (lengths, offsets, strands, thresholds) as numpy, or
+    nothing with fetch=False (the merged table and its .mums text stay on the device)."""
     anchor_len = parts[0][3].shape[0]
     on_device = parts[0][0].is_cuda
     if on_device:
@@ -76,10 +86,10 @@ def merge_gathered(engine, parts):
         host = [(p[0].numpy().view(np.uint32), p[1].numpy(), p[2].numpy(), p[3].numpy().view(np.uint16), p[4], p[5]) for p in parts]
         args = [(np.ascontiguousarray(a), np.ascontiguousarray(b), np.ascontiguousarray(c), np.ascontiguousarray(d), n, nd) for a, b, c, d, n, nd in host]
     engine.anchor_merge(args, anchor_len, on_device=on_device)
-    return engine.merge_result()
+    return engine.merge_result() if fetch else None
 
 
-def partition_merge(engine, dist, world, device):
+def partition_merge(engine, dist, world, device, fetch=True):
     """Everything after the per-rank find(): exchange + merge.  Every rank ends up with the merged result."""
     parts = gather_partitions(local_partition(engine, device), dist, world)
-    return merge_gathered(engine, parts)
+    return merge_gathered(engine, parts, fetch=fetch)
