@@ -161,6 +161,43 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const void* src, u32 by
 #endif
 }
 
+
+// Two bulk copies on two mbarriers (second optional: bytes2 = 0); everybody waits for both.  Leaves the block synchronised.
+__device__ __forceinline__ void tma_load_two(void* dst1, const void* src1, u32 bytes1, void* dst2, const void* src2, u32 bytes2, u64* bar) {
+#ifdef MMB_SIMT
+    if (threadIdx.x == 0) { if (bytes1) memcpy(dst1, src1, bytes1); if (bytes2) memcpy(dst2, src2, bytes2); }
+    (void)bar;
+    __syncthreads();
+#else
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    u32 total = bytes1 + bytes2;
+    if (total == 0) return;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(total) : "memory");
+        if (bytes1)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst1)), "l"(src1),
+                         "r"(bytes1), "r"(smem_u32(bar))
+                         : "memory");
+        if (bytes2)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst2)), "l"(src2),
+                         "r"(bytes2), "r"(smem_u32(bar))
+                         : "memory");
+    }
+    u32 done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar))
+            : "memory");
+    }
+#endif
+}
+
 template <class SAT, int W, int P>
 __global__ void __launch_bounds__(DW_TPB) detect_window_kernel(const u32* __restrict__ lcp, const SAT* __restrict__ sa, const u8* __restrict__ bwt,
                                                               const u8* __restrict__ text, u64 m, u64 j_first, DetectParams prm, WindowPlan plan,
@@ -323,7 +360,12 @@ __global__ void __launch_bounds__(DW_TPB) detect_window_kernel(const u32* __rest
 // window, C odd), one thread walks one chunk.  Pass 1 writes the suffix minima of every chunk; in pass 2 the window of rank j is the
 // tail of the previous chunk (one suffix minimum) joined with the head of its own chunk (a running minimum in a register).  Lanes
 // are C words apart and C is odd, so every shared-memory access is conflict-free.  Larger sizes extend the window one entry at a
-// time.  Candidates are verified exactly as in detect_window_kernel.
+// time.
+// FAST (MUM modes over a stream tile that carries BWT symbols, no -M): the BWT bytes of the tile are staged too, pass 1 notes the
+// last rank of every chunk whose symbol differs from its predecessor's, and pass 2 carries "last change at or before j-1" in a
+// register -- the reference's own left-maximality test (last_bwt_change > start, include/mem_finder.hpp:165-166,189-192) -- so that
+// intervals that are not left-maximal (the common case inside shared regions) are dropped by the lane that found them and only the
+// survivors reach the warp-cooperative document check.
 constexpr u32 DC_TPB = 128;
 struct ChunkPlan {
     u32 size_lo, size_hi;
@@ -331,62 +373,109 @@ struct ChunkPlan {
     u32 chunk;                  // C
     u32 halo_chunks;            // H: chunks staged in front of the first closing rank (H * C >= size_hi)
     u32 rounds;                 // R: chunks per thread; a block stages R * DC_TPB chunks and closes (R * DC_TPB - H) * C ranks
-    u32 span;                   // staged entries: R * DC_TPB * C + 4, rounded up to a multiple of 4
+    u32 span;                   // staged lcp entries: R * DC_TPB * C + 4, rounded up to a multiple of 4
+    u32 span_b;                 // staged bwt bytes (FAST): R * DC_TPB * C + 32, rounded up to a multiple of 16
 };
 
-template <class SAT, int W, int P>
+template <class SAT, int W, int P, bool FAST>
 __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restrict__ lcp, const SAT* __restrict__ sa, const u8* __restrict__ bwt,
                                                              const u8* __restrict__ text, u64 m, u64 j_first, DetectParams prm, ChunkPlan plan,
                                                              const u64* __restrict__ doc_start_g, Report* __restrict__ reports, u32 cap,
                                                              u32* __restrict__ count, u16* __restrict__ thresh) {
     MMB_DYN_SMEM(u64, smem64);
-    u64* bar = smem64;                                  // 16 bytes reserved
+    u64* bar = smem64;                                  // 2 mbarriers (16 bytes)
     u64* doc_start = smem64 + 2;                        // ndocs + 1 (+1 pad to keep 16-byte alignment)
     u32* lc = reinterpret_cast<u32*>(doc_start + ((prm.ndocs + 2) & ~1u));      // the lcp tile
     u32* suf = lc + plan.span;                          // suffix minima inside every chunk
+    u8* bt = reinterpret_cast<u8*>(suf + plan.span);    // FAST: the bwt tile
+    int* lastin = reinterpret_cast<int*>(bt + plan.span_b);                     // FAST: per chunk, tile index of its last symbol change (-1: none)
     const u32 C = plan.chunk, H = plan.halo_chunks, G = plan.rounds * DC_TPB, W0 = plan.w0, span = plan.span;
-    const i64 origin = (i64)blockIdx.x * (i64)(G - H) * C - (i64)H * C;         // rank of the first entry of chunk 0
+    const i64 origin = (i64)blockIdx.x * (i64)(G - H) * C - (i64)H * C;         // rank of tile index 0 (first entry of chunk 0)
     const i64 origin_al = origin - (((origin % 4) + 4) % 4);                    // staging starts on a 16-byte boundary of lcp
-    const u32 d = (u32)(origin - origin_al);                                    // chunk g occupies lc[d + g*C .. d + (g+1)*C)
+    const u32 d = (u32)(origin - origin_al);                                    // tile index x lives at lc[d + x]
+    const i64 origin_b = (origin - 1) - ((((origin - 1) % 16) + 16) % 16);      // same for the bytes, one rank earlier
+    const u32 db = (u32)(origin - origin_b);                                    // tile index x lives at bt[db + x], db >= 1
 
     for (u32 i = threadIdx.x; i <= prm.ndocs; i += blockDim.x) doc_start[i] = doc_start_g[i];
     {   // stage lcp[origin_al .. origin_al + span): ranks below 0 or at/after m read as 0 (an lcp of 0 closes everything)
         u64 lo = origin_al < 0 ? 0 : (u64)origin_al, hi = min((u64)(origin_al + (i64)span), m);
         u32 skip = (u32)((i64)lo - origin_al);
-        for (u32 i = threadIdx.x; i < skip; i += blockDim.x) lc[i] = 0;
         u32 have = hi > lo ? (u32)(hi - lo) : 0u, padded = min((have + 3) & ~3u, span - skip);      // lcp is allocated with slack past m
-        if (padded) tma_load_tile(lc + skip, lcp + lo, padded * 4, bar); else __syncthreads();
+        u32 skip_b = 0, have_b = 0, padded_b = 0; u64 lo_b = 0;
+        if (FAST) {
+            lo_b = origin_b < 0 ? 0 : (u64)origin_b;
+            u64 hi_b = min((u64)(origin_b + (i64)plan.span_b), m);
+            skip_b = (u32)((i64)lo_b - origin_b);
+            have_b = hi_b > lo_b ? (u32)(hi_b - lo_b) : 0u; padded_b = min((have_b + 15) & ~15u, plan.span_b - skip_b);   // bwt has slack too
+        }
+        tma_load_two(lc + skip, lcp + lo, padded * 4, bt + skip_b, FAST ? bwt + lo_b : nullptr, padded_b, bar);
+        for (u32 i = threadIdx.x; i < skip; i += blockDim.x) lc[i] = 0;
         for (u32 i = skip + have + threadIdx.x; i < span; i += blockDim.x) lc[i] = 0;
+        if (FAST) {
+            for (u32 i = threadIdx.x; i < skip_b; i += blockDim.x) bt[i] = 0;
+            for (u32 i = skip_b + have_b + threadIdx.x; i < plan.span_b; i += blockDim.x) bt[i] = 0;
+        }
     }
     __syncthreads();
     for (u32 g = threadIdx.x; g < G; g += DC_TPB) {     // pass 1
         u32 base = d + g * C, mn = 0xffffffffu;
+        if (FAST) {
+            const u8* b = bt + db + g * C;
+            int last = -1; u32 right = b[C - 1];
 #pragma unroll 4
-        for (u32 k = C; k-- > 0;) { mn = min(mn, lc[base + k]); suf[base + k] = mn; }
+            for (u32 k = C; k-- > 0;) {
+                mn = min(mn, lc[base + k]); suf[base + k] = mn;
+                u32 left = b[(int)k - 1];
+                if (left != right && last < 0) last = (int)(g * C + k);
+                right = left;
+            }
+            lastin[g] = last;
+        } else {
+#pragma unroll 4
+            for (u32 k = C; k-- > 0;) { mn = min(mn, lc[base + k]); suf[base + k] = mn; }
+        }
     }
     __syncthreads();
     const u32 lane = threadIdx.x & 31;
     for (u32 r = 0; r < plan.rounds; ++r) {             // pass 2 (warp-uniform loops: the verification below is warp-cooperative)
         const u32 g = r * DC_TPB + threadIdx.x;
         const u32 base = d + g * C;
-        const u64 j0 = (u64)(origin + (i64)g * C);      // only used when g >= H, where it is non-negative
+        const i64 j0 = origin + (i64)g * C;             // rank of the chunk's first entry
+        // closing ranks of this chunk that are examined: k in [k_lo, k_hi)
+        u32 k_lo = C, k_hi = 0;
+        if (g >= H) {
+            i64 first = max((i64)max(j_first, (u64)1), j0), end = min((i64)m, j0 + (i64)C);
+            if (first < end) { k_lo = (u32)(first - j0); k_hi = (u32)(end - j0); }
+        }
         u32 run = 0xffffffffu;                          // min(lc[base .. base + k - 1])
+        int last = -0x40000000;                         // FAST: tile index of the last symbol change at or before the previous rank
+        u32 prev_sym = 0;
+        const u8* b = bt + db + g * C;
+        if (FAST && g >= H) {
+            for (u32 back = 1; back <= H; ++back) { int l = lastin[g - back]; if (l >= 0) { last = l; break; } }
+            prev_sym = b[-1];
+        }
         for (u32 k = 0; k < C; ++k) {
             const u32 idx = base + k;
-            const u64 j = j0 + k;
             const u32 cur = lc[idx];
             u32 v = 0;
             if (g >= H) v = (k >= W0) ? run : min(suf[idx - W0], run);      // k = W0 only when C = W0 + 1: the window is the chunk's head
             run = min(run, cur);
-            bool active = g >= H && j >= j_first && j >= 1 && j < m && v > cur && v >= prm.min_len;
+            const int x = (int)(g * C + k);
+            const int last_before = last;
+            if (FAST && g >= H) { u32 sym = b[k]; if (sym != prev_sym) last = x; prev_sym = sym; }
+            bool active = k >= k_lo && k < k_hi && v > cur && v >= prm.min_len;
+            if (FAST && plan.size_lo == plan.size_hi)   // one size: decide here, so that the warp only converges for real candidates
+                active = active && lc[idx - plan.size_lo] < v && last_before > x - (int)plan.size_lo;
             if (!__any_sync(0xffffffffu, active)) continue;
+            const u64 j = (u64)(j0 + k);
             u32 size = plan.size_lo;
             for (;;) {                                  // one candidate per lane per turn
                 bool have = false;
                 while (active && size <= plan.size_hi) {
                     if (j < size || v <= cur || v < prm.min_len) { active = false; break; }
                     u32 before = lc[idx - size];
-                    if (before < v) { have = true; break; }
+                    if (before < v && (!FAST || last_before > x - (int)size)) { have = true; break; }
                     ++size; v = min(v, before);
                 }
                 if (!have) active = false;
@@ -399,7 +488,7 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
                         u32 cs = __shfl_sync(0xffffffffu, size, src), cv = __shfl_sync(0xffffffffu, v, src), ccur = __shfl_sync(0xffffffffu, cur, src);
                         u32 cbefore = __shfl_sync(0xffffffffu, lc[idx - (have ? size : 0)], src);
                         u64 s0 = cj - cs;
-                        if (bwt && !prm.merge) {
+                        if (!FAST && bwt && !prm.merge) {
                             bool d0 = false;
                             for (u32 t = 1 + lane; t < cs; t += 32) d0 |= bwt[s0 + t] != bwt[s0 + t - 1];
                             if (!__any_sync(0xffffffffu, d0)) continue;
@@ -426,10 +515,10 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
                         u32 distinct = 0;
 #pragma unroll
                         for (int w = 0; w < W; ++w) {
-                            u64 b = bits[w];
+                            u64 bb = bits[w];
 #pragma unroll
-                            for (u32 dd = 16; dd > 0; dd >>= 1) b |= __shfl_xor_sync(0xffffffffu, b, dd);
-                            distinct += (u32)__popcll(b);
+                            for (u32 dd = 16; dd > 0; dd >>= 1) bb |= __shfl_xor_sync(0xffffffffu, bb, dd);
+                            distinct += (u32)__popcll(bb);
                         }
                         differs = __any_sync(0xffffffffu, differs);
                         if (distinct == cs && distinct >= prm.num_distinct) {          // every document at most once
@@ -443,13 +532,13 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
                 } else if (have) {
                     DocCounter<W, P> docs; docs.clear();
                     u64 s0 = j - size; bool ok = true, differs = false;
-                    u8 prev_sym = 0;
+                    u8 psym = 0;
                     for (u32 t = 0; t < size && ok; ++t) {
                         u64 rk = s0 + t; u64 p = (u64)sa[rk];
                         ok = docs.add(find_doc(doc_start, prm.ndocs, p), prm.max_doc_freq);
                         u8 sym = bwt ? bwt[rk] : (p ? text[p - 1] : (u8)0);
-                        if (t > 0 && sym != prev_sym) differs = true;
-                        prev_sym = sym;
+                        if (t > 0 && sym != psym) differs = true;
+                        psym = sym;
                     }
                     if (ok && docs.distinct >= prm.num_distinct && differs) {
                         u32 slot = atomicAdd(count, 1u);
@@ -480,8 +569,9 @@ struct DetectArgs {
 template <class SAT, int W, int P>
 void launch_detect(const SAT* sa, const DetectArgs& a, cudaStream_t s) {
     if (a.use_chunk) {
-        auto detect_chunk_k = detect_chunk_kernel<SAT, W, P>;
-        size_t smem = 16 + (size_t)((a.prm.ndocs + 2) & ~1u) * 8 + (size_t)a.cplan.span * 4 * 2;
+        bool fast = a.bwt && !a.prm.merge && P == 1 && a.prm.max_doc_freq == 1;
+        auto detect_chunk_k = fast ? detect_chunk_kernel<SAT, W, P, true> : detect_chunk_kernel<SAT, W, P, false>;
+        size_t smem = 16 + (size_t)((a.prm.ndocs + 2) & ~1u) * 8 + (size_t)a.cplan.span * 4 * 2 + (fast ? a.cplan.span_b + (size_t)a.cplan.rounds * DC_TPB * 4 : 0);
 #ifndef MMB_SIMT
         if (smem > 48 * 1024) MMB_CUDA(cudaFuncSetAttribute(detect_chunk_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
@@ -525,6 +615,7 @@ bool make_chunk_plan(u64 lo, u64 hi, ChunkPlan& cp) {
     cp.rounds = std::min(32u, std::max(1u, want));
     while (cp.rounds * DC_TPB < 2 * cp.halo_chunks + 1) ++cp.rounds;           // at least half of the staged chunks close ranks
     cp.span = (cp.rounds * DC_TPB * cp.chunk + 4 + 3) & ~3u;
+    cp.span_b = (cp.rounds * DC_TPB * cp.chunk + 32 + 15) & ~15u;
     return true;
 }
 

@@ -36,12 +36,13 @@ __host__ __device__ __forceinline__ u64 mix64(u64 x) {
     x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
     return x;
 }
-// trigger test for the window T[e-9 .. e]
-__device__ __forceinline__ bool is_trigger(const u8* __restrict__ text, u64 e) {
-    u64 x = load8(text, e - (PFP_W - 1));
-    u64 y = (u64)text[e - 1] | ((u64)text[e] << 8);
-    u64 h = mix64(x ^ (y * 0x9E3779B97F4A7C15ull));
-    return (u32)(h >> 33) % PFP_P == 0;
+// Trigger test for the window T[e-9 .. e], given as its last eight bytes (x, little-endian: T[e] in the top byte) and the two bytes
+// before them (y).  Any deterministic function of the ten bytes is a valid rule (the outputs of the path do not depend on it,
+// SURVEY 8a row B); this one costs three 32-bit multiply-adds and a finaliser.
+__device__ __forceinline__ bool window_triggers(u32 x_lo, u32 x_hi, u32 y) {
+    u32 h = x_lo * 0x9E3779B1u ^ x_hi * 0x85EBCA77u ^ y * 0xC2B2AE3Du;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return (h >> 8) % PFP_P == 0;
 }
 
 // exclusive block scan of one u32 per thread; *total = block sum
@@ -59,15 +60,40 @@ __device__ __forceinline__ u32 block_scan(u32 mine, u32* total) {
     return before + inc - mine;
 }
 
-template <bool WRITE>
-__global__ void __launch_bounds__(TPB) trigger_pass(const u8* __restrict__ text, u64 n, u32* __restrict__ block_count, const u32* __restrict__ block_base,
-                                                    u64* __restrict__ ends) {
+// Pass 1: every thread reads the 28 bytes around its 16 positions once (one 128-bit load + three words), tests the 16 windows from
+// registers and keeps the result as a 16-bit mask; the block's trigger count goes to block_count.
+__global__ void __launch_bounds__(TPB) trigger_masks(const u8* __restrict__ text, u64 n, u16* __restrict__ masks, u32* __restrict__ block_count) {
     u64 e0 = (u64)blockIdx.x * SCAN_BLOCK + (u64)threadIdx.x * 16;
     u32 mask = 0;
+    if (e0 < n) {
+        u32 w[7];                                       // bytes e0-12 .. e0+15 (the text allocation is 16-byte aligned with 64 bytes of slack)
+        if (e0) { const u32* q = reinterpret_cast<const u32*>(text + e0 - 12); w[0] = q[0]; w[1] = q[1]; w[2] = q[2]; }
+        else { w[0] = w[1] = w[2] = 0; }
+        uint4 c = *reinterpret_cast<const uint4*>(text + e0);
+        w[3] = c.x; w[4] = c.y; w[5] = c.z; w[6] = c.w;
 #pragma unroll
-    for (u32 k = 0; k < 16; ++k) { u64 e = e0 + k; if (e >= PFP_W && e < n && is_trigger(text, e)) mask |= 1u << k; }
+        for (u32 k = 0; k < 16; ++k) {
+            // T[e0+k] is byte 12+k of w[]; the window starts at byte 3+k
+            const u32 first = 3 + k, wi = first >> 2, sh = (first & 3) * 8;
+            u32 y = sh ? __funnelshift_r(w[wi], w[wi + 1], sh) : w[wi];
+            y &= 0xffffu;
+            const u32 f2 = first + 2, wj = f2 >> 2, sj = (f2 & 3) * 8;
+            u32 x_lo = sj ? __funnelshift_r(w[wj], w[wj + 1], sj) : w[wj];
+            u32 x_hi = sj ? __funnelshift_r(w[wj + 1], wj + 2 < 7 ? w[wj + 2] : 0u, sj) : w[wj + 1];
+            u64 e = e0 + k;
+            if (e >= PFP_W && e < n && window_triggers(x_lo, x_hi, y)) mask |= 1u << k;
+        }
+    }
+    masks[(u64)blockIdx.x * TPB + threadIdx.x] = (u16)mask;
+    u32 total; block_scan((u32)__popc(mask), &total);
+    if (threadIdx.x == 0) block_count[blockIdx.x] = total;
+}
+
+// Pass 2: positions of the set bits, in text order.
+__global__ void __launch_bounds__(TPB) trigger_positions(const u16* __restrict__ masks, const u32* __restrict__ block_base, u64* __restrict__ ends) {
+    u64 e0 = (u64)blockIdx.x * SCAN_BLOCK + (u64)threadIdx.x * 16;
+    u32 mask = masks[(u64)blockIdx.x * TPB + threadIdx.x];
     u32 total, before = block_scan((u32)__popc(mask), &total);
-    if (!WRITE) { if (threadIdx.x == 0) block_count[blockIdx.x] = total; return; }
     u32 at = block_base[blockIdx.x] + before;
     while (mask) { u32 k = (u32)__ffs((int)mask) - 1; mask &= mask - 1; ends[at++] = e0 + k; }
 }
@@ -166,6 +192,26 @@ __global__ void __launch_bounds__(TPB) dict_keys(const u8* __restrict__ d, const
     u64 key = 0;
     for (u32 t = 0; t < cpk; ++t) key = (key << bits) | (u64)(t < lim ? code[d[i + t]] : 0);
     keys[i] = key; vals[i] = i;
+}
+
+// A dictionary suffix is "owned" (longer than w) iff symbol w of its initial sort key is a real symbol (codes are >= 1, the
+// terminator and everything after it is 0).  All suffixes that share a key agree on this, and later rounds only reorder suffixes
+// inside groups of equal keys, so the flag of a RANK is final right after the initial sort -- no random access needed.
+__global__ void __launch_bounds__(TPB) owned_from_keys(const u64* __restrict__ sorted_keys, u32 dsize, u32 shift, u32 symbol_mask, u32* __restrict__ flag) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < dsize) flag[p] = ((u32)(sorted_keys[p] >> shift) & symbol_mask) ? 1u : 0u;
+    if (p == dsize) flag[p] = 0;
+}
+
+// The one exception: the last phrase ends with w padding zeros that ARE symbols of its string, so its last w owned suffixes show a
+// zero at symbol w.  They contain padding, hence are unique strings, and isa_d gives their exact final rank.
+__global__ void owned_fix_last_phrase(const u32* __restrict__ pid, u32 np, const u32* __restrict__ doff, const u32* __restrict__ limit,
+                                      const u32* __restrict__ isa_d, u32* __restrict__ flag) {
+    u32 g = pid[np - 1];
+    for (u32 i = doff[g] + threadIdx.x; i < doff[g + 1]; i += blockDim.x) {
+        u32 lim = limit[i];
+        if (lim >= PFP_W + 2 && lim <= 2 * PFP_W + 1) flag[isa_d[i]] = 1;
+    }
 }
 
 __global__ void __launch_bounds__(TPB) phrase_rank_keys(const u32* __restrict__ isa_d, const u32* __restrict__ doff, u32 nd, u64* __restrict__ keys,
@@ -280,15 +326,16 @@ void pfp_parse(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s
     u32 nblk = (u32)nblk64;
     DevBuf<u32> bcount, bbase; bcount.alloc(nblk + 1, s); bbase.alloc(nblk + 1, s);
     MMB_CUDA(cudaMemsetAsync(bcount.p + nblk, 0, 4, s));
-    auto trigger_count_pass = trigger_pass<false>; auto trigger_write_pass = trigger_pass<true>;
-    MMB_LAUNCH(trigger_count_pass, nblk, TPB, 0, s, text, n, bcount.p, (const u32*)nullptr, (u64*)nullptr);
+    DevBuf<u16> masks; masks.alloc((u64)nblk * TPB, s);
+    MMB_LAUNCH(trigger_masks, nblk, TPB, 0, s, text, n, masks.p, bcount.p);
     prim::exclusive_sum(bcount.p, bbase.p, nblk + 1, s);
     u64 ntrig = to_host(bbase.p + nblk, 1, s)[0];
     if (ntrig + 2 >= 0xfffffff0ull) throw Error(72, "too many phrases");
     u32 np = (u32)ntrig + 1;
     ix.np = np;
     DevBuf<u64> ends; ends.alloc(np, s);
-    MMB_LAUNCH(trigger_write_pass, nblk, TPB, 0, s, text, n, bcount.p, (const u32*)bbase.p, ends.p);
+    MMB_LAUNCH(trigger_positions, nblk, TPB, 0, s, (const u16*)masks.p, (const u32*)bbase.p, ends.p);
+    masks.release();
     u64 last_end = n + PFP_W - 1;
     MMB_CUDA(cudaMemcpyAsync(ends.p + np - 1, &last_end, 8, cudaMemcpyHostToDevice, s));
     ix.pstart.alloc(np + 1, s);
@@ -363,8 +410,13 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
             DevBuf<u64> ka, kb; DevBuf<u32> va; ka.alloc(dsize, s); kb.alloc(dsize, s); va.alloc(dsize, s);
             MMB_LAUNCH(dict_keys, ceil_div(dsize, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const u32*)ix.limit.p, dsize, (const u8*)d_lut.p, bits, cpk, ka.p, va.p);
             order_by_initial_keys(ka.p, kb.p, va.p, dsize, (int)(bits * cpk), cpk, ix.limit.p, ix.sa_d.p, ix.isa_d.p, groups, s);
+            if (cpk > PFP_W) {
+                ix.owned.alloc((u64)dsize + 1, s);
+                MMB_LAUNCH(owned_from_keys, ceil_div((u64)dsize + 1, TPB), TPB, 0, s, (const u64*)kb.p, dsize, bits * (cpk - 1 - PFP_W), (1u << bits) - 1, ix.owned.p);
+            }
         }
         refine_by_doubling(ix.sa_d.p, ix.isa_d.p, dsize, cpk, ix.limit.p, groups, ix.stats_d, s);
+        if (ix.owned.p) MMB_LAUNCH(owned_fix_last_phrase, 1, 256, 0, s, (const u32*)pid.p, np, (const u32*)ix.doff.p, (const u32*)ix.limit.p, (const u32*)ix.isa_d.p, ix.owned.p);
         MMB_CUDA(cudaStreamSynchronize(s));       // lut lives on this stack frame
     }
 

@@ -52,31 +52,44 @@ struct MemberMeta {
     u8 members;     // members in the group (same cap)
 };
 
-__global__ void __launch_bounds__(TPB) members_fill(const u32* __restrict__ sa_d, const u32* __restrict__ isa_d, const u32* __restrict__ dphrase,
-                                                    const u32* __restrict__ prank, const u32* __restrict__ occ_first, const u32* __restrict__ limit,
-                                                    const u32* __restrict__ doff, const u8* __restrict__ dict, const u32* __restrict__ flag,
-                                                    const u32* __restrict__ idx, u32 dsize, u32* __restrict__ mem_i, u32* __restrict__ mem_head,
-                                                    u32* __restrict__ mem_cnt, MemberMeta* __restrict__ meta) {
+// Everything members_fill needs to know about a dictionary position, gathered once in dictionary order (coalesced) so that the
+// member pass does one 16-byte random read per member instead of four.
+struct __align__(16) DictRecord { u32 limit, phrase, head, before; };      // before: symbol preceding the position, 0x100 = it starts its phrase
+__global__ void __launch_bounds__(TPB) dict_records(const u32* __restrict__ limit, const u32* __restrict__ dphrase, const u32* __restrict__ isa_d,
+                                                    const u32* __restrict__ doff, const u8* __restrict__ dict, u32 dsize, DictRecord* __restrict__ rec) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dsize) return;
+    DictRecord r; r.limit = limit[i]; r.phrase = dphrase[i]; r.head = isa_d[i];
+    r.before = i > doff[r.phrase] ? (u32)dict[i - 1] : 0x100u;
+    rec[i] = r;
+}
+
+__global__ void __launch_bounds__(TPB) members_fill(const u32* __restrict__ sa_d, const DictRecord* __restrict__ rec, const u32* __restrict__ prank,
+                                                    const u32* __restrict__ occ_first, const u32* __restrict__ flag, const u32* __restrict__ idx, u32 dsize,
+                                                    u32* __restrict__ mem_i, u32* __restrict__ mem_head, u32* __restrict__ mem_cnt,
+                                                    MemberMeta* __restrict__ meta) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= dsize || !flag[p]) return;
-    u32 k = idx[p], i = sa_d[p], g = dphrase[i], r = prank[g];
+    u32 k = idx[p], i = sa_d[p];
+    DictRecord d = rec[i];
+    u32 r = prank[d.phrase];
     u32 q0 = occ_first[r], cnt = occ_first[r + 1] - q0;
-    mem_i[k] = i; mem_head[k] = isa_d[i]; mem_cnt[k] = cnt;
+    mem_i[k] = i; mem_head[k] = d.head; mem_cnt[k] = cnt;
     MemberMeta m;
-    m.q0 = q0; m.cnt = cnt; m.shift = limit[i] - 1 - PFP_W;
-    m.inside = i > doff[g] ? 1 : 0; m.before = m.inside ? dict[i - 1] : (u8)0; m.back = 0; m.members = 1;
+    m.q0 = q0; m.cnt = cnt; m.shift = d.limit - 1 - PFP_W;
+    m.inside = d.before < 0x100u ? 1 : 0; m.before = (u8)d.before; m.back = 0; m.members = 1;
     meta[k] = m;
 }
 
 // lcp between the strings of consecutive members that start a new group (byte comparison inside the dictionary)
-__global__ void __launch_bounds__(TPB) group_lcp(const u8* __restrict__ dict, const u32* __restrict__ limit, const u32* __restrict__ mem_i,
+__global__ void __launch_bounds__(TPB) group_lcp(const u8* __restrict__ dict, const MemberMeta* __restrict__ meta, const u32* __restrict__ mem_i,
                                                  const u32* __restrict__ mem_head, u32 K, u32* __restrict__ glcp) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
     if (k == 0) { glcp[0] = 0; return; }
     if (mem_head[k] == mem_head[k - 1]) { glcp[k] = NOT_START; return; }
     u32 a = mem_i[k - 1], b = mem_i[k];
-    u32 cap = min(limit[a], limit[b]) - 1, l = 0;                  // different strings of a prefix-free set differ before either ends
+    u32 cap = min(meta[k - 1].shift, meta[k].shift) + PFP_W, l = 0;      // |alpha| of the shorter; different strings of a prefix-free set differ before either ends
     while (l + 8 <= cap) {
         u64 x = load8(dict, (u64)a + l) ^ load8(dict, (u64)b + l);
         if (x) { l += (u32)((__ffsll((long long)x) - 1) >> 3); glcp[k] = l; return; }
@@ -283,21 +296,30 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
     u32 dsize = ix.dsize;
     PhaseTimer* pt = new PhaseTimer("stream members+bounds", s);
     // ---- members (owned dictionary suffixes in suffix order)
-    DevBuf<u32> flag, idx; flag.alloc((u64)dsize + 1, s); idx.alloc((u64)dsize + 1, s);
-    MMB_LAUNCH(owned_flags, ceil_div((u64)dsize + 1, TPB), TPB, 0, s, (const u32*)ix.sa_d.p, (const u32*)ix.limit.p, dsize, flag.p);
-    prim::exclusive_sum(flag.p, idx.p, (u64)dsize + 1, s);
+    DevBuf<u32> flag_own, idx; idx.alloc((u64)dsize + 1, s);
+    const u32* flag = ix.owned.p;
+    if (!flag) {        // alphabets too large for the key-based flag (pfp.cu)
+        flag_own.alloc((u64)dsize + 1, s);
+        MMB_LAUNCH(owned_flags, ceil_div((u64)dsize + 1, TPB), TPB, 0, s, (const u32*)ix.sa_d.p, (const u32*)ix.limit.p, dsize, flag_own.p);
+        flag = flag_own.p;
+    }
+    prim::exclusive_sum(flag, idx.p, (u64)dsize + 1, s);
     u32 K = to_host(idx.p + dsize, 1, s)[0];
     DevBuf<u32> mem_i, mem_head, mem_cnt, glcp; DevBuf<u64> out_base; DevBuf<MemberMeta> meta;
     meta.alloc(K, s); mem_i.alloc(K, s); mem_head.alloc(K, s); mem_cnt.alloc((u64)K + 1, s); glcp.alloc((u64)K + 1, s); out_base.alloc((u64)K + 1, s);
     MMB_CUDA(cudaMemsetAsync(mem_cnt.p + K, 0, 4, s));
-    MMB_LAUNCH(members_fill, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.sa_d.p, (const u32*)ix.isa_d.p, (const u32*)ix.dphrase.p, (const u32*)ix.prank.p,
-               (const u32*)ix.occ_first.p, (const u32*)ix.limit.p, (const u32*)ix.doff.p, (const u8*)ix.dict.p, (const u32*)flag.p, (const u32*)idx.p, dsize,
-               mem_i.p, mem_head.p, mem_cnt.p, meta.p);
-    flag.release(); idx.release();
+    {
+        DevBuf<DictRecord> rec; rec.alloc(dsize, s);
+        MMB_LAUNCH(dict_records, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.limit.p, (const u32*)ix.dphrase.p, (const u32*)ix.isa_d.p, (const u32*)ix.doff.p,
+                   (const u8*)ix.dict.p, dsize, rec.p);
+        MMB_LAUNCH(members_fill, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.sa_d.p, (const DictRecord*)rec.p, (const u32*)ix.prank.p,
+                   (const u32*)ix.occ_first.p, flag, (const u32*)idx.p, dsize, mem_i.p, mem_head.p, mem_cnt.p, meta.p);
+    }
+    flag_own.release(); idx.release();
     prim::exclusive_sum(mem_cnt.p, out_base.p, (u64)K + 1, s);
     u64 total = to_host(out_base.p + K, 1, s)[0];
     if (total != ix.n) throw Error(76, "internal: the parse does not cover the text (" + std::to_string(total) + " of " + std::to_string(ix.n) + ")");
-    MMB_LAUNCH(group_lcp, ceil_div(K, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const u32*)ix.limit.p, (const u32*)mem_i.p, (const u32*)mem_head.p, K, glcp.p);
+    MMB_LAUNCH(group_lcp, ceil_div(K, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const MemberMeta*)meta.p, (const u32*)mem_i.p, (const u32*)mem_head.p, K, glcp.p);
     mem_head.release();
     MMB_LAUNCH(group_shape, ceil_div(K, TPB), TPB, 0, s, (const u32*)glcp.p, K, meta.p);
 
@@ -319,7 +341,7 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
     // ---- tile buffers: [halo | new ranks | 64 slack]; the first tile starts with the sentinel rank instead of a halo
     u64 cap = (u64)halo + max_new + 1;
     DevBuf<u64> sa, halo_sa, small, large; DevBuf<u32> lcp, key, halo_lcp, counts; DevBuf<u8> bwt, halo_bwt;
-    sa.alloc(cap, s); lcp.alloc(cap + 64, s); key.alloc(cap, s); bwt.alloc(cap, s); halo_sa.alloc(halo + 1, s); halo_lcp.alloc(halo + 1, s);
+    sa.alloc(cap, s); lcp.alloc(cap + 64, s); key.alloc(cap, s); bwt.alloc(cap + 64, s); halo_sa.alloc(halo + 1, s); halo_lcp.alloc(halo + 1, s);
     halo_bwt.alloc(halo + 1, s); counts.alloc(2, s);
     u64 rank_next = 0;                  // global rank of the first new entry of the coming tile
     u64 halo_have = 0;
