@@ -354,6 +354,51 @@ __global__ void __launch_bounds__(DW_TPB) detect_window_kernel(const u32* __rest
     }
 }
 
+// Warp-cooperative check of one MUM-mode candidate (all lanes hold the same arguments): the interval [s0, s0 + cs) qualifies iff its
+// suffixes come from cs distinct documents and cs >= num_distinct; it is reported iff it is also left-maximal.
+template <class SAT, int W>
+__device__ __forceinline__ void verify_mum_candidate(u64 cj, u32 cs, u32 cv, u32 ccur, u32 cbefore, const SAT* __restrict__ sa,
+                                                     const u8* __restrict__ bwt, const u8* __restrict__ text, const u64* doc_start,
+                                                     const DetectParams& prm, Report* __restrict__ reports, u32 cap, u32* __restrict__ count,
+                                                     u16* __restrict__ thresh, u32 lane) {
+    const u64 s0 = cj - cs;
+    u64 bits[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) bits[w] = 0;
+    u64 anchor = ~0ull; bool differs = false; u32 carry = 0;
+    for (u32 t0 = 0; t0 < cs; t0 += 32) {
+        u32 t = t0 + lane;
+        u32 sym = 0;
+        if (t < cs) {
+            u64 rk = s0 + t; u64 p = (u64)sa[rk];
+            u32 dd = find_doc(doc_start, prm.ndocs, p);
+            bits[(W == 1) ? 0 : (dd >> 6)] |= 1ull << (dd & 63);
+            if (dd == 0) anchor = p;
+            sym = bwt ? bwt[rk] : (p ? text[p - 1] : (u8)0);
+        }
+        u32 left = __shfl_up_sync(0xffffffffu, sym, 1);
+        if (lane == 0) left = carry;
+        if (t < cs && t > 0 && left != sym) differs = true;
+        carry = __shfl_sync(0xffffffffu, sym, 31);
+    }
+    u32 distinct = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        u64 bb = bits[w];
+#pragma unroll
+        for (u32 dd = 16; dd > 0; dd >>= 1) bb |= __shfl_xor_sync(0xffffffffu, bb, dd);
+        distinct += (u32)__popcll(bb);
+    }
+    differs = __any_sync(0xffffffffu, differs);
+    if (distinct == cs && distinct >= prm.num_distinct) {          // every document at most once
+        if (prm.merge && anchor != ~0ull) thresh[anchor] = (u16)min(max(cbefore, ccur), 65535u);
+        if (differs && lane == 0) {
+            u32 slot = atomicAdd(count, 1u);
+            if (slot < cap) { Report rp; rp.key = (cj << 20) | cs; rp.s = s0; rp.len = cv; rp.pad = 0; reports[slot] = rp; }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ chunked window-minimum detector
 // Same test as detect_window_kernel, but the minimum of the smallest window (size_lo - 1 entries ending at j-1) costs O(1) per rank
 // instead of one shared-memory pass per power of two: the staged tile is cut into chunks of C = (size_lo - 1) | 1 ranks (C >= the
@@ -454,6 +499,55 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
         if (FAST && g >= H) {
             for (u32 back = 1; back <= H; ++back) { int l = lastin[g - back]; if (l >= 0) { last = l; break; } }
             prev_sym = b[-1];
+        }
+        if (FAST && plan.size_lo == plan.size_hi) {
+            // One interval size (strict multi-MUMs): the lane decides alone whether rank j closes a left-maximal interval of that size
+            // and only notes it in a bit mask; the warp converges once per eight ranks, and the rare survivors recompute their window
+            // minimum (= the match length) by brute force before the cooperative document check.
+            const u32 S = plan.size_lo;
+            const u32* plc = lc + base;
+            const u32* psuf = suf + base - (g >= H ? W0 : 0u);      // chunks in the halo are walked for nothing: keep their reads in bounds
+            const u32* pbef = lc + base - (g >= H ? S : 0u);
+            const int x0 = (int)(g * C);
+            for (u32 k0 = 0; k0 < C; k0 += 8) {
+                u32 cmask = 0;
+#pragma unroll
+                for (u32 u = 0; u < 8; ++u) {
+                    const u32 k = k0 + u;
+                    if (k < C) {
+                        const u32 cur = plc[k];
+                        const u32 v = (k >= W0) ? run : min(psuf[k], run);
+                        run = min(run, cur);
+                        const int last_before = last;
+                        const u32 sym = b[k];
+                        if (sym != prev_sym) last = x0 + (int)k;
+                        prev_sym = sym;
+                        bool c = k >= k_lo && k < k_hi && v > cur && v >= prm.min_len;
+                        if (c) c = pbef[k] < v && last_before > x0 + (int)k - (int)S;
+                        cmask |= (u32)c << u;
+                    }
+                }
+                if (!__any_sync(0xffffffffu, cmask != 0)) continue;
+                for (;;) {
+                    const bool have = cmask != 0;
+                    unsigned cand = __ballot_sync(0xffffffffu, have);
+                    if (!cand) break;
+                    u32 kc = 0, vv = 0xffffffffu;
+                    if (have) {
+                        kc = k0 + (u32)__ffs((int)cmask) - 1; cmask &= cmask - 1;
+                        for (u32 t = 1; t <= W0; ++t) vv = min(vv, lc[base + kc - t]);
+                    }
+                    const u64 jc = (u64)(j0 + (i64)kc);
+                    const u32 curc = lc[base + kc];
+                    while (cand) {
+                        int src = __ffs((int)cand) - 1; cand &= cand - 1;
+                        u64 cj = __shfl_sync(0xffffffffu, jc, src);
+                        u32 cv = __shfl_sync(0xffffffffu, vv, src), ccur = __shfl_sync(0xffffffffu, curc, src);
+                        verify_mum_candidate<SAT, W>(cj, S, cv, ccur, 0u, sa, bwt, text, doc_start, prm, reports, cap, count, thresh, lane);
+                    }
+                }
+            }
+            continue;
         }
         for (u32 k = 0; k < C; ++k) {
             const u32 idx = base + k;

@@ -44,18 +44,27 @@ struct GroupLists {
     u32* count;                 // NCLASS counters
 };
 
-// Append groups from a converged warp: lanes that want to append are matched by class and one lane per class reserves the slots.
+// Append groups from converged code: EVERY thread of the block must call this (want = false when it has nothing).  Lanes are matched
+// by class inside the warp, one lane per (warp, class) reserves in a shared-memory counter and one thread per (block, class) in the
+// global one -- thousands of warps adding to the same global counter serialise in L2 otherwise (the lists hold ~1e8 groups per round).
 __device__ __forceinline__ void append_group_warp(bool want, u32 head, u32 size, const GroupLists& L) {
+    __shared__ u32 s_cnt[NCLASS], s_base[NCLASS];
+    if (threadIdx.x < NCLASS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
     unsigned wanting = __ballot_sync(FULL, want);
-    if (!want) return;
-    int cls = size_class(size);
-    unsigned peers = __match_any_sync(wanting, cls);
     u32 lane = threadIdx.x & 31;
-    int leader = __ffs((int)peers) - 1;
-    u32 base = 0;
-    if ((int)lane == leader) base = atomicAdd(&L.count[cls], (u32)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    L.list[cls][base + __popc(peers & ((1u << lane) - 1))] = ((u64)head << 32) | size;
+    int cls = 0; unsigned peers = 0; u32 wbase = 0;
+    if (want) {
+        cls = size_class(size);
+        peers = __match_any_sync(wanting, cls);
+        int leader = __ffs((int)peers) - 1;
+        if ((int)lane == leader) wbase = atomicAdd(&s_cnt[cls], (u32)__popc(peers));
+        wbase = __shfl_sync(peers, wbase, leader);
+    }
+    __syncthreads();
+    if (threadIdx.x < NCLASS && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&L.count[threadIdx.x], s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (want) L.list[cls][s_base[cls] + wbase + __popc(peers & ((1u << lane) - 1))] = ((u64)head << 32) | size;
 }
 // Same from divergent code (few callers per block).
 __device__ __forceinline__ void append_group_single(u32 head, u32 size, const GroupLists& L) {
