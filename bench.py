@@ -238,6 +238,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--route", default=os.environ.get("MMB_ROUTE", "auto"), choices=["auto", "direct", "pfp"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tile-ranks", type=int, default=0, help="ranks per stream tile on the PFP route (0 = engine default)")
     ap.add_argument("--roofline-kernel", default=None, help="kernel (name substring) whose launches are timed with CUDA events for the roofline line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -299,7 +300,7 @@ def main():
     dev = host.cuda(non_blocking=False)
     pinned_imgs = [hv[o:o + s] for o, s in zip(offsets, sizes)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
-    opts = dict(merge=multi, anchor_merge=multi, route=args.route)
+    opts = dict(merge=multi, anchor_merge=multi, route=args.route, tile_ranks=args.tile_ranks)
 
     from mumemto_b200 import partition
     tdev = torch.device("cuda", local)

@@ -420,7 +420,8 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
             if (e->prm.max_doc_freq) { u64 bound = (u64)e->prm.max_doc_freq * N; hi = hi ? std::min(hi, bound) : bound; }
             if (hi == 0) throw Error(31, "unbounded total frequency (-f 0 with -F 0) is not supported by the windowed interval scan");
             u32 halo = (u32)std::min<u64>((hi + 8) & ~3ull, 1u << 22);
-            u64 tile_ranks = opts->tile_ranks ? opts->tile_ranks : (1ull << 28);
+            // ranks per stream tile: 17 B per rank of tile buffers; C2 measured 745 / 731 / 722 ms per step at 2^28 / 2^29 / 2^30
+            u64 tile_ranks = opts->tile_ranks ? opts->tile_ranks : (1ull << 30);
             struct Consumer : TileConsumer {
                 mmb_engine* e; cudaStream_t s; u16* thresh; bool keep; std::vector<MumTable> mparts; std::vector<MemTable> eparts; u32 tiles = 0;
                 void consume(const StreamTile& tile) override {

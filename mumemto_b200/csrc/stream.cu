@@ -138,17 +138,18 @@ __device__ __forceinline__ u32 lower_bound_u32(const u32* __restrict__ v, u32 c,
 // that member's elements with a smaller rank (one binary search each); the same searches give the predecessor in merged order, hence
 // the LCP.  Groups with more members only get their (rank, SA) pairs written here and are sorted afterwards.
 constexpr u32 EXP_TPB = 256;
-constexpr u32 EXP_CACHE = 1024;          // following-suffix ranks staged per warp for the in-kernel merges
-__global__ void __launch_bounds__(EXP_TPB, 5) expand_members(int cache_keys, u32 k0, u32 k1, const MemberMeta* __restrict__ meta, const u64* __restrict__ out_base,
-                                                          const u32* __restrict__ glcp, const u32* __restrict__ occ_next_rank,
-                                                          const u64* __restrict__ occ_next_start, const u32* __restrict__ occ_lcp,
-                                                          const u32* __restrict__ s_lcp, const u32* __restrict__ rmq, u32 rmq_blocks,
-                                                          const u8* __restrict__ text, u64 lead, u64* __restrict__ sa, u32* __restrict__ lcp,
-                                                          u32* __restrict__ key, u8* __restrict__ bwt) {
+// The kernel waits on memory (ncu: long-scoreboard stalls dominate), so what matters is how many loads are in flight: MINB = resident
+// blocks per SM the register allocation is tuned for, PREFETCH = how many iterations ahead the list entries are touched.  Measured on
+// C2 (profiles/README.md): <6,0> 170 ms, <8,0> 144 ms, <6,1> 159 ms, <8,1> 138 ms per step.
+template <int MINB, int PREFETCH>
+__global__ void __launch_bounds__(EXP_TPB, MINB) expand_members(u32 k0, u32 k1, const MemberMeta* __restrict__ meta, const u64* __restrict__ out_base,
+                                                                const u32* __restrict__ glcp, const u32* __restrict__ occ_next_rank,
+                                                                const u64* __restrict__ occ_next_start, const u32* __restrict__ occ_lcp,
+                                                                const u32* __restrict__ s_lcp, const u32* __restrict__ rmq, u32 rmq_blocks,
+                                                                const u8* __restrict__ text, u64 lead, u64* __restrict__ sa, u32* __restrict__ lcp,
+                                                                u32* __restrict__ key, u8* __restrict__ bwt) {
     __shared__ MemberMeta smeta[EXP_TPB / 32][32];
     __shared__ u32 soff[EXP_TPB / 32][33];
-    MMB_DYN_SMEM(u32, skeys_all);                                          // [EXP_TPB / 32][EXP_CACHE] when cache_keys, else nothing
-    u32* const skeys_w = skeys_all + (threadIdx.x >> 5) * EXP_CACHE;
     u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     u64 kw64 = (u64)k0 + ((u64)blockIdx.x * (EXP_TPB / 32) + w) * 32;          // first member of this warp
     if (kw64 >= k1) return;                                                    // whole warp
@@ -170,22 +171,21 @@ __global__ void __launch_bounds__(EXP_TPB, 5) expand_members(int cache_keys, u32
         for (u32 step = 16; step > 0; step >>= 1) if (mi + step < 32 && soff[w][mi + step] <= e) mi += step;
         return mi;
     };
-    // Groups of 2..8 members are merged by binary searches in the other members' lists.  When the warp's lists fit, their keys (rank
-    // of the following parse suffix) are staged in shared memory first, so that the searches do not chase global memory.
-    const bool fusing = me.members > 1 && me.members <= FUSE_MAX_MEMBERS;
-    const bool cached = cache_keys && __any_sync(0xffffffffu, fusing) && T <= EXP_CACHE;
-    if (cached) {
-        for (u32 e = lane; e < T; e += 32) {
-            u32 mi = member_of(e);
-            const u32 mm = smeta[w][mi].members;
-            if (mm > 1 && mm <= FUSE_MAX_MEMBERS) skeys_w[e] = occ_next_rank[smeta[w][mi].q0 + (e - soff[w][mi])];
-        }
-        __syncwarp();
-    }
+    u32 mi_next = lane < T ? member_of(lane) : 0u;
     for (u32 e = lane; e < T; e += 32) {
-        u32 mi = member_of(e);
+        const u32 mi = mi_next;
         const MemberMeta m = smeta[w][mi];
         u32 t = e - soff[w][mi], kk = kw + mi, q = m.q0 + t;
+        if (e + 32 < T) mi_next = member_of(e + 32);
+        if (PREFETCH > 0 && e + 32 * PREFETCH < T) {
+#ifndef MMB_SIMT
+            const u32 ep = e + 32 * PREFETCH;
+            const u32 mp = PREFETCH == 1 ? mi_next : member_of(ep);
+            const u32 qn = smeta[w][mp].q0 + (ep - soff[w][mp]);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(occ_next_start + qn));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(occ_lcp + qn));
+#endif
+        }
         u64 pos = occ_next_start[q] - m.shift;
         u8 sym = m.inside ? m.before : (pos ? text[pos - 1] : (u8)0);
         if (m.members == 1) {
@@ -196,31 +196,18 @@ __global__ void __launch_bounds__(EXP_TPB, 5) expand_members(int cache_keys, u32
         } else {
             u32 ks = kk - m.back;
             u64 gbase = (ks >= kw) ? wbase + soff[w][ks - kw] : out_base[ks] - tile_base + lead;
-            u32 r = cached ? skeys_w[e] : occ_next_rank[q], slot = t;
+            u32 r = occ_next_rank[q], slot = t;
             bool has_pred = t > 0;
-            u32 pred = has_pred ? (cached ? skeys_w[e - 1] : occ_next_rank[q - 1]) : 0u;
+            u32 pred = has_pred ? occ_next_rank[q - 1] : 0u;
             for (u32 j = 0; j < m.members; ++j) {
                 u32 kj = ks + j;
                 if (kj == kk) continue;
-                u32 lb, v = 0;
-                if (kj >= kw && kj < kw + 32) {
-                    const u32 oc = smeta[w][kj - kw].cnt;
-                    if (cached) {
-                        const u32* list = &skeys_w[soff[w][kj - kw]];
-                        lb = lower_bound_u32(list, oc, r);
-                        if (lb) v = list[lb - 1];
-                    } else {
-                        const u32* list = occ_next_rank + smeta[w][kj - kw].q0;
-                        lb = lower_bound_u32(list, oc, r);
-                        if (lb) v = list[lb - 1];
-                    }
-                } else {
-                    MemberMeta o = meta[kj];
-                    lb = lower_bound_u32(occ_next_rank + o.q0, o.cnt, r);
-                    if (lb) v = occ_next_rank[o.q0 + lb - 1];
-                }
+                u32 oq, oc;
+                if (kj >= kw && kj < kw + 32) { oq = smeta[w][kj - kw].q0; oc = smeta[w][kj - kw].cnt; }
+                else { MemberMeta o = meta[kj]; oq = o.q0; oc = o.cnt; }
+                u32 lb = lower_bound_u32(occ_next_rank + oq, oc, r);
                 slot += lb;
-                if (lb) { if (!has_pred || v > pred) pred = v; has_pred = true; }
+                if (lb) { u32 v = occ_next_rank[oq + lb - 1]; if (!has_pred || v > pred) pred = v; has_pred = true; }
             }
             sa[gbase + slot] = pos; bwt[gbase + slot] = sym;
             lcp[gbase + slot] = has_pred ? m.shift + range_min(s_lcp, rmq, rmq_blocks, pred + 1, r) : glcp[ks];
@@ -375,7 +362,7 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
     DevBuf<u64> sa, halo_sa, small, large; DevBuf<u32> lcp, key, halo_lcp, counts; DevBuf<u8> bwt, halo_bwt;
     sa.alloc(cap, s); lcp.alloc(cap + 64, s); key.alloc(cap, s); bwt.alloc(cap + 64, s); halo_sa.alloc(halo + 1, s); halo_lcp.alloc(halo + 1, s);
     halo_bwt.alloc(halo + 1, s); counts.alloc(2, s);
-    const int cache_keys = getenv("MMB_EXPAND_CACHE") ? atoi(getenv("MMB_EXPAND_CACHE")) : 1;
+    const int expand_variant = getenv("MMB_EXPAND_VARIANT") ? atoi(getenv("MMB_EXPAND_VARIANT")) : 0;
     u64 rank_next = 0;                  // global rank of the first new entry of the coming tile
     u64 halo_have = 0;
     for (size_t t = 0; t + 1 < bounds.size(); ++t) {
@@ -391,9 +378,20 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
         }
         u32 nm = k1 - k0;
         small.alloc((u64)nm / 2 + 1, s); large.alloc((u64)nm / 2 + 1, s); counts.zero();
-        MMB_LAUNCH(expand_members, ceil_div(nm, EXP_TPB), EXP_TPB, cache_keys ? (size_t)(EXP_TPB / 32) * EXP_CACHE * 4 : 0, s, cache_keys, k0, k1, (const MemberMeta*)meta.p, (const u64*)out_base.p, (const u32*)glcp.p,
-                   (const u32*)ix.occ_next_rank.p, (const u64*)ix.occ_next_start.p, (const u32*)ix.occ_lcp.p, (const u32*)ix.s_lcp.p, (const u32*)ix.rmq.p,
-                   ix.rmq_blocks, text, lead, sa.p, lcp.p, key.p, bwt.p);
+        {
+            auto launch_expand = [&](auto expand_members_k) {
+                MMB_LAUNCH(expand_members_k, ceil_div(nm, EXP_TPB), EXP_TPB, 0, s, k0, k1, (const MemberMeta*)meta.p, (const u64*)out_base.p, (const u32*)glcp.p,
+                           (const u32*)ix.occ_next_rank.p, (const u64*)ix.occ_next_start.p, (const u32*)ix.occ_lcp.p, (const u32*)ix.s_lcp.p,
+                           (const u32*)ix.rmq.p, ix.rmq_blocks, text, lead, sa.p, lcp.p, key.p, bwt.p);
+            };
+            switch (expand_variant) {
+                case 1: launch_expand(expand_members<8, 0>); break;
+                case 2: launch_expand(expand_members<6, 1>); break;
+                case 4: launch_expand(expand_members<8, 2>); break;
+                case 5: launch_expand(expand_members<6, 0>); break;
+                default: launch_expand(expand_members<8, 1>); break;
+            }
+        }
         MMB_LAUNCH(collect_multi, ceil_div(nm, TPB), TPB, 0, s, k0, k1, K, (const u32*)glcp.p, (const u64*)out_base.p, small.p, large.p, counts.p);
         std::vector<u32> c = to_host(counts.p, 2, s);
         if (c[0]) {
