@@ -406,11 +406,12 @@ __device__ __forceinline__ void verify_mum_candidate(u64 cj, u32 cs, u32 cv, u32
 // tail of the previous chunk (one suffix minimum) joined with the head of its own chunk (a running minimum in a register).  Lanes
 // are C words apart and C is odd, so every shared-memory access is conflict-free.  Larger sizes extend the window one entry at a
 // time.
-// FAST (MUM modes over a stream tile that carries BWT symbols, no -M): the BWT bytes of the tile are staged too, pass 1 notes the
+// FAST (MUM modes over a stream tile that carries BWT symbols): the BWT bytes of the tile are staged too, pass 1 notes the
 // last rank of every chunk whose symbol differs from its predecessor's, and pass 2 carries "last change at or before j-1" in a
 // register -- the reference's own left-maximality test (last_bwt_change > start, include/mem_finder.hpp:165-166,189-192) -- so that
 // intervals that are not left-maximal (the common case inside shared regions) are dropped by the lane that found them and only the
-// survivors reach the warp-cooperative document check.
+// survivors reach the warp-cooperative document check.  With -M every interval of the right size reaches that check (its threshold is
+// recorded whether or not it is left-maximal), still from the once-per-eight-ranks convergence point of the single-size loop.
 constexpr u32 DC_TPB = 128;
 struct ChunkPlan {
     u32 size_lo, size_hi;
@@ -523,7 +524,8 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
                         if (sym != prev_sym) last = x0 + (int)k;
                         prev_sym = sym;
                         bool c = k >= k_lo && k < k_hi && v > cur && v >= prm.min_len;
-                        if (c) c = pbef[k] < v && last_before > x0 + (int)k - (int)S;
+                        // -M needs the threshold of every interval that passes the size / document test, left-maximal or not
+                        if (c) c = pbef[k] < v && (prm.merge || last_before > x0 + (int)k - (int)S);
                         cmask |= (u32)c << u;
                     }
                 }
@@ -538,12 +540,12 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
                         for (u32 t = 1; t <= W0; ++t) vv = min(vv, lc[base + kc - t]);
                     }
                     const u64 jc = (u64)(j0 + (i64)kc);
-                    const u32 curc = lc[base + kc];
+                    const u32 curc = lc[base + kc], befc = have ? pbef[kc] : 0u;
                     while (cand) {
                         int src = __ffs((int)cand) - 1; cand &= cand - 1;
                         u64 cj = __shfl_sync(0xffffffffu, jc, src);
-                        u32 cv = __shfl_sync(0xffffffffu, vv, src), ccur = __shfl_sync(0xffffffffu, curc, src);
-                        verify_mum_candidate<SAT, W>(cj, S, cv, ccur, 0u, sa, bwt, text, doc_start, prm, reports, cap, count, thresh, lane);
+                        u32 cv = __shfl_sync(0xffffffffu, vv, src), ccur = __shfl_sync(0xffffffffu, curc, src), cbef = __shfl_sync(0xffffffffu, befc, src);
+                        verify_mum_candidate<SAT, W>(cj, S, cv, ccur, cbef, sa, bwt, text, doc_start, prm, reports, cap, count, thresh, lane);
                     }
                 }
             }
@@ -559,8 +561,6 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
             const int last_before = last;
             if (FAST && g >= H) { u32 sym = b[k]; if (sym != prev_sym) last = x; prev_sym = sym; }
             bool active = k >= k_lo && k < k_hi && v > cur && v >= prm.min_len;
-            if (FAST && plan.size_lo == plan.size_hi)   // one size: decide here, so that the warp only converges for real candidates
-                active = active && lc[idx - plan.size_lo] < v && last_before > x - (int)plan.size_lo;
             if (!__any_sync(0xffffffffu, active)) continue;
             const u64 j = (u64)(j0 + k);
             u32 size = plan.size_lo;
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
                 while (active && size <= plan.size_hi) {
                     if (j < size || v <= cur || v < prm.min_len) { active = false; break; }
                     u32 before = lc[idx - size];
-                    if (before < v && (!FAST || last_before > x - (int)size)) { have = true; break; }
+                    if (before < v && (!FAST || prm.merge || last_before > x - (int)size)) { have = true; break; }
                     ++size; v = min(v, before);
                 }
                 if (!have) active = false;
@@ -663,7 +663,7 @@ struct DetectArgs {
 template <class SAT, int W, int P>
 void launch_detect(const SAT* sa, const DetectArgs& a, cudaStream_t s) {
     if (a.use_chunk) {
-        bool fast = a.bwt && !a.prm.merge && P == 1 && a.prm.max_doc_freq == 1;
+        bool fast = a.bwt && P == 1 && a.prm.max_doc_freq == 1 && (!a.prm.merge || a.cplan.size_lo == a.cplan.size_hi);
         auto detect_chunk_k = fast ? detect_chunk_kernel<SAT, W, P, true> : detect_chunk_kernel<SAT, W, P, false>;
         size_t smem = 16 + (size_t)((a.prm.ndocs + 2) & ~1u) * 8 + (size_t)a.cplan.span * 4 * 2 + (fast ? a.cplan.span_b + (size_t)a.cplan.rounds * DC_TPB * 4 : 0);
 #ifndef MMB_SIMT

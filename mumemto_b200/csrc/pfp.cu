@@ -197,9 +197,17 @@ __global__ void __launch_bounds__(TPB) dict_keys(const u8* __restrict__ d, const
 // A dictionary suffix is "owned" (longer than w) iff symbol w of its initial sort key is a real symbol (codes are >= 1, the
 // terminator and everything after it is 0).  All suffixes that share a key agree on this, and later rounds only reorder suffixes
 // inside groups of equal keys, so the flag of a RANK is final right after the initial sort -- no random access needed.
-__global__ void __launch_bounds__(TPB) owned_from_keys(const u64* __restrict__ sorted_keys, u32 dsize, u32 shift, u32 symbol_mask, u32* __restrict__ flag) {
+__global__ void __launch_bounds__(TPB) owned_from_keys(const u64* __restrict__ sorted_keys, u32 dsize, u32 bits, u32 cpk, u32* __restrict__ flag,
+                                                       u8* __restrict__ klcp) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < dsize) flag[p] = ((u32)(sorted_keys[p] >> shift) & symbol_mask) ? 1u : 0u;
+    if (p < dsize) {
+        u64 key = sorted_keys[p];
+        flag[p] = ((u32)(key >> (bits * (cpk - 1 - PFP_W))) & ((1u << bits) - 1)) ? 1u : 0u;
+        // symbols this key shares with the previous rank's (the same for every later order of the ranks inside a group of equal keys)
+        u32 shared = 0;
+        if (p) { u64 x = key ^ sorted_keys[p - 1]; shared = x ? cpk - 1 - (u32)(63 - __clzll((long long)x)) / bits : cpk; }
+        klcp[p] = (u8)shared;
+    }
     if (p == dsize) flag[p] = 0;
 }
 
@@ -411,8 +419,8 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
             MMB_LAUNCH(dict_keys, ceil_div(dsize, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const u32*)ix.limit.p, dsize, (const u8*)d_lut.p, bits, cpk, ka.p, va.p);
             order_by_initial_keys(ka.p, kb.p, va.p, dsize, (int)(bits * cpk), cpk, ix.limit.p, ix.sa_d.p, ix.isa_d.p, groups, s);
             if (cpk > PFP_W) {
-                ix.owned.alloc((u64)dsize + 1, s);
-                MMB_LAUNCH(owned_from_keys, ceil_div((u64)dsize + 1, TPB), TPB, 0, s, (const u64*)kb.p, dsize, bits * (cpk - 1 - PFP_W), (1u << bits) - 1, ix.owned.p);
+                ix.owned.alloc((u64)dsize + 1, s); ix.klcp.alloc(dsize, s); ix.key_symbols = cpk;
+                MMB_LAUNCH(owned_from_keys, ceil_div((u64)dsize + 1, TPB), TPB, 0, s, (const u64*)kb.p, dsize, bits, cpk, ix.owned.p, ix.klcp.p);
             }
         }
         refine_by_doubling(ix.sa_d.p, ix.isa_d.p, dsize, cpk, ix.limit.p, groups, ix.stats_d, s);

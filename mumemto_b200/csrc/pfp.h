@@ -37,6 +37,8 @@ struct PfpIndex {
     DevBuf<u32> limit;              // [dsize] symbols from here up to and including the terminator
     DevBuf<u32> sa_d, isa_d;        // suffix order of D' (equal strings share one head rank in isa_d)
     DevBuf<u32> owned;              // [dsize + 1] by rank in sa_d: 1 = the suffix is longer than w (may be empty: stream.cu then derives it)
+    DevBuf<u8> klcp;                // [dsize] by rank in sa_d: symbols shared with the previous rank inside the initial sort key, capped at
+    u32 key_symbols = 0;            //   key_symbols (both from the sorted keys; empty when `owned` is)
     DevBuf<u32> dphrase;            // [dsize] distinct-phrase id (in D' order) of every dictionary position
     DevBuf<u32> doff;               // [nd + 1] start of each distinct phrase in D'
     DevBuf<u32> prank;              // [nd] lexicographic rank (1-based) of each distinct phrase

@@ -66,11 +66,16 @@ __global__ void __launch_bounds__(TPB) dict_records(const u32* __restrict__ limi
 
 __global__ void __launch_bounds__(TPB) members_fill(const u32* __restrict__ sa_d, const DictRecord* __restrict__ rec, const u32* __restrict__ prank,
                                                     const u32* __restrict__ occ_first, const u32* __restrict__ flag, const u32* __restrict__ idx, u32 dsize,
-                                                    u32* __restrict__ mem_i, u32* __restrict__ mem_head, u32* __restrict__ mem_cnt,
-                                                    MemberMeta* __restrict__ meta) {
+                                                    const u8* __restrict__ klcp, u32* __restrict__ mem_i, u32* __restrict__ mem_head,
+                                                    u32* __restrict__ mem_cnt, MemberMeta* __restrict__ meta, u8* __restrict__ mem_klcp) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= dsize || !flag[p]) return;
     u32 k = idx[p], i = sa_d[p];
+    if (klcp) {         // key symbols shared with the previous MEMBER: minimum over the ranks skipped in between (suffixes of <= w symbols)
+        u32 mn = klcp[p];
+        for (u32 q = p; q-- > 0 && !flag[q];) mn = min(mn, (u32)klcp[q]);
+        mem_klcp[k] = (u8)mn;
+    }
     DictRecord d = rec[i];
     u32 r = prank[d.phrase];
     u32 q0 = occ_first[r], cnt = occ_first[r + 1] - q0;
@@ -81,15 +86,22 @@ __global__ void __launch_bounds__(TPB) members_fill(const u32* __restrict__ sa_d
     meta[k] = m;
 }
 
-// lcp between the strings of consecutive members that start a new group (byte comparison inside the dictionary)
+// lcp between the strings of consecutive members that start a new group: read off the initial sort keys when the two differ inside
+// them (mem_klcp < key_symbols), else a byte comparison inside the dictionary that starts after the key
 __global__ void __launch_bounds__(TPB) group_lcp(const u8* __restrict__ dict, const MemberMeta* __restrict__ meta, const u32* __restrict__ mem_i,
-                                                 const u32* __restrict__ mem_head, u32 K, u32* __restrict__ glcp) {
+                                                 const u32* __restrict__ mem_head, const u8* __restrict__ mem_klcp, u32 key_symbols, u32 K,
+                                                 u32* __restrict__ glcp) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
     if (k == 0) { glcp[0] = 0; return; }
     if (mem_head[k] == mem_head[k - 1]) { glcp[k] = NOT_START; return; }
-    u32 a = mem_i[k - 1], b = mem_i[k];
     u32 cap = min(meta[k - 1].shift, meta[k].shift) + PFP_W, l = 0;      // |alpha| of the shorter; different strings of a prefix-free set differ before either ends
+    if (mem_klcp) {
+        u32 shared = mem_klcp[k];
+        if (shared < key_symbols) { glcp[k] = min(shared, cap); return; }
+        l = min(key_symbols, cap);
+    }
+    u32 a = mem_i[k - 1], b = mem_i[k];
     while (l + 8 <= cap) {
         u64 x = load8(dict, (u64)a + l) ^ load8(dict, (u64)b + l);
         if (x) { l += (u32)((__ffsll((long long)x) - 1) >> 3); glcp[k] = l; return; }
@@ -324,7 +336,8 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
     }
     prim::exclusive_sum(flag, idx.p, (u64)dsize + 1, s);
     u32 K = to_host(idx.p + dsize, 1, s)[0];
-    DevBuf<u32> mem_i, mem_head, mem_cnt, glcp; DevBuf<u64> out_base; DevBuf<MemberMeta> meta;
+    DevBuf<u32> mem_i, mem_head, mem_cnt, glcp; DevBuf<u64> out_base; DevBuf<MemberMeta> meta; DevBuf<u8> mem_klcp;
+    if (ix.klcp.p) mem_klcp.alloc(K, s);
     meta.alloc(K, s); mem_i.alloc(K, s); mem_head.alloc(K, s); mem_cnt.alloc((u64)K + 1, s); glcp.alloc((u64)K + 1, s); out_base.alloc((u64)K + 1, s);
     MMB_CUDA(cudaMemsetAsync(mem_cnt.p + K, 0, 4, s));
     {
@@ -332,13 +345,14 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
         MMB_LAUNCH(dict_records, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.limit.p, (const u32*)ix.dphrase.p, (const u32*)ix.isa_d.p, (const u32*)ix.doff.p,
                    (const u8*)ix.dict.p, dsize, rec.p);
         MMB_LAUNCH(members_fill, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.sa_d.p, (const DictRecord*)rec.p, (const u32*)ix.prank.p,
-                   (const u32*)ix.occ_first.p, flag, (const u32*)idx.p, dsize, mem_i.p, mem_head.p, mem_cnt.p, meta.p);
+                   (const u32*)ix.occ_first.p, flag, (const u32*)idx.p, dsize, (const u8*)ix.klcp.p, mem_i.p, mem_head.p, mem_cnt.p, meta.p, mem_klcp.p);
     }
     flag_own.release(); idx.release();
     prim::exclusive_sum(mem_cnt.p, out_base.p, (u64)K + 1, s);
     u64 total = to_host(out_base.p + K, 1, s)[0];
     if (total != ix.n) throw Error(76, "internal: the parse does not cover the text (" + std::to_string(total) + " of " + std::to_string(ix.n) + ")");
-    MMB_LAUNCH(group_lcp, ceil_div(K, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const MemberMeta*)meta.p, (const u32*)mem_i.p, (const u32*)mem_head.p, K, glcp.p);
+    MMB_LAUNCH(group_lcp, ceil_div(K, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const MemberMeta*)meta.p, (const u32*)mem_i.p, (const u32*)mem_head.p, (const u8*)mem_klcp.p, ix.key_symbols, K, glcp.p);
+    mem_klcp.release();
     mem_head.release();
     MMB_LAUNCH(group_shape, ceil_div(K, TPB), TPB, 0, s, (const u32*)glcp.p, K, meta.p);
 
