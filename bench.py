@@ -238,6 +238,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--route", default=os.environ.get("MMB_ROUTE", "auto"), choices=["auto", "direct", "pfp"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--merge-mode", action="store_true", help="N = 1 only: run the partition flags (-M -n) without an exchange, to time that mode")
     ap.add_argument("--tile-ranks", type=int, default=0, help="ranks per stream tile on the PFP route (0 = engine default)")
     ap.add_argument("--roofline-kernel", default=None, help="kernel (name substring) whose launches are timed with CUDA events for the roofline line")
     args = ap.parse_args()
@@ -300,7 +301,7 @@ def main():
     dev = host.cuda(non_blocking=False)
     pinned_imgs = [hv[o:o + s] for o, s in zip(offsets, sizes)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
-    opts = dict(merge=multi, anchor_merge=multi, route=args.route, tile_ranks=args.tile_ranks)
+    opts = dict(merge=multi or args.merge_mode, anchor_merge=multi or args.merge_mode, route=args.route, tile_ranks=args.tile_ranks)
 
     from mumemto_b200 import partition
     tdev = torch.device("cuda", local)

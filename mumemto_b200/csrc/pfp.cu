@@ -194,6 +194,19 @@ __global__ void __launch_bounds__(TPB) dict_keys(const u8* __restrict__ d, const
     keys[i] = key; vals[i] = i;
 }
 
+// Pair layout of the dictionary's rank array for the doubling rounds (sa.cu, Isa): word 2i+1 = offset of position i inside its phrase.
+__global__ void __launch_bounds__(TPB) phrase_offsets(const u32* __restrict__ limit, const u32* __restrict__ dphrase, const u32* __restrict__ doff, u32 dsize,
+                                                      u32* __restrict__ isa2) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dsize) return;
+    u32 g = dphrase[i];
+    isa2[2 * (u64)i + 1] = (doff[g + 1] - doff[g]) - limit[i];
+}
+__global__ void __launch_bounds__(TPB) unpair_ranks(const u32* __restrict__ isa2, u32 dsize, u32* __restrict__ isa) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < dsize) isa[i] = isa2[2 * (u64)i];
+}
+
 // A dictionary suffix is "owned" (longer than w) iff symbol w of its initial sort key is a real symbol (codes are >= 1, the
 // terminator and everything after it is 0).  All suffixes that share a key agree on this, and later rounds only reorder suffixes
 // inside groups of equal keys, so the flag of a RANK is final right after the initial sort -- no random access needed.
@@ -413,17 +426,21 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
         DevBuf<u8> d_lut; d_lut.alloc(256, s);
         MMB_CUDA(cudaMemcpyAsync(d_lut.p, lut.data(), 256, cudaMemcpyHostToDevice, s));
         ix.sa_d.alloc(dsize, s); ix.isa_d.alloc(dsize, s);
+        DevBuf<u32> isa2; isa2.alloc(2 * (u64)dsize, s);
+        MMB_LAUNCH(phrase_offsets, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.limit.p, (const u32*)ix.dphrase.p, (const u32*)ix.doff.p, dsize, isa2.p);
         GroupStore groups;
         {
             DevBuf<u64> ka, kb; DevBuf<u32> va; ka.alloc(dsize, s); kb.alloc(dsize, s); va.alloc(dsize, s);
             MMB_LAUNCH(dict_keys, ceil_div(dsize, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const u32*)ix.limit.p, dsize, (const u8*)d_lut.p, bits, cpk, ka.p, va.p);
-            order_by_initial_keys(ka.p, kb.p, va.p, dsize, (int)(bits * cpk), cpk, ix.limit.p, ix.sa_d.p, ix.isa_d.p, groups, s);
+            order_by_initial_keys(ka.p, kb.p, va.p, dsize, (int)(bits * cpk), cpk, ix.limit.p, ix.sa_d.p, isa2.p, groups, s, 2);
             if (cpk > PFP_W) {
                 ix.owned.alloc((u64)dsize + 1, s); ix.klcp.alloc(dsize, s); ix.key_symbols = cpk;
                 MMB_LAUNCH(owned_from_keys, ceil_div((u64)dsize + 1, TPB), TPB, 0, s, (const u64*)kb.p, dsize, bits, cpk, ix.owned.p, ix.klcp.p);
             }
         }
-        refine_by_doubling(ix.sa_d.p, ix.isa_d.p, dsize, cpk, ix.limit.p, groups, ix.stats_d, s);
+        refine_by_doubling(ix.sa_d.p, isa2.p, dsize, cpk, ix.limit.p, groups, ix.stats_d, s, 2);
+        MMB_LAUNCH(unpair_ranks, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)isa2.p, dsize, ix.isa_d.p);
+        isa2.release();
         if (ix.owned.p) MMB_LAUNCH(owned_fix_last_phrase, 1, 256, 0, s, (const u32*)pid.p, np, (const u32*)ix.doff.p, (const u32*)ix.limit.p, (const u32*)ix.isa_d.p, ix.owned.p);
         MMB_CUDA(cudaStreamSynchronize(s));       // lut lives on this stack frame
     }

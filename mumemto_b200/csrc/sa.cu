@@ -38,6 +38,14 @@ __device__ __forceinline__ int size_class(u32 size) {
     return size <= BLOCK_SORT_MAX ? 7 : 8;
 }
 
+// Head ranks by suffix.  stride 1: plain array.  stride 2 (dictionary mode): pairs (head rank, offset of the position inside its
+// phrase) -- the doubling key of suffix s at offset h then needs ONE random read, at s + h: the suffix is exhausted (nothing left to
+// compare, key 0) exactly when that position lies less than h symbols into its phrase, i.e. the phrase started after s.
+struct Isa {
+    u32* p; u32 stride;
+    __device__ __forceinline__ void set(u32 s, u32 rank) const { p[(u64)s * stride] = rank; }
+};
+
 // Next round's groups, one list per size class (so that no binning pass is needed).
 struct GroupLists {
     Group* list[NCLASS];
@@ -109,12 +117,12 @@ __global__ void __launch_bounds__(TPB) first_flags(const u64* __restrict__ keys,
 
 // isa from head ranks; the last member of every multi-member group appends the group (limit: see refine_by_doubling)
 __global__ void __launch_bounds__(TPB) first_ranks(const u64* __restrict__ keys, const u32* __restrict__ sa, const u32* __restrict__ head, u32 m, u32 h0,
-                                                   const u32* __restrict__ limit, u32* __restrict__ isa, GroupLists L) {
+                                                   const u32* __restrict__ limit, Isa isa, GroupLists L) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     bool want = false; u32 hd = 0;
     if (p < m) {
         hd = head[p];
-        isa[sa[p]] = hd;
+        isa.set(sa[p], hd);
         bool last = (p + 1 == m) || keys[p + 1] != keys[p];
         want = last && hd != p;
         if (want && limit && limit[sa[hd]] <= h0) want = false;   // the whole (terminated) suffix is inside the key: equal strings, final tie
@@ -123,17 +131,22 @@ __global__ void __launch_bounds__(TPB) first_ranks(const u64* __restrict__ keys,
 }
 
 // key of suffix s for the round with offset h: rank of the suffix h symbols further on (+1), 0 when there is nothing further
-__device__ __forceinline__ u32 round_key(u32 s, u32 h, u32 m, const u32* __restrict__ isa, const u32* __restrict__ limit) {
-    if (limit && limit[s] <= h) return 0u;
+__device__ __forceinline__ u32 round_key(u32 s, u32 h, u32 m, const Isa& isa, const u32* __restrict__ limit) {
     u64 t = (u64)s + h;
-    return t < m ? isa[t] + 1u : 0u;
+    if (isa.stride == 2) {
+        if (t >= m) return 0u;                              // past the last terminator
+        uint2 v = *reinterpret_cast<const uint2*>(isa.p + 2 * t);
+        return v.y < h ? 0u : v.x + 1u;
+    }
+    if (limit && limit[s] <= h) return 0u;
+    return t < m ? isa.p[t] + 1u : 0u;
 }
 
 // ------------------------------------------------------------------------------------------------ (sub-)warp rank sort
 // WIDTH lanes per group, K elements per lane (K > 1 only with WIDTH = 32).
 template <int WIDTH, int K>
 __global__ void __launch_bounds__(TPB) sort_groups_warp(const Group* __restrict__ groups, u32 ngroups, u32 h, u32 m, u32* __restrict__ sa,
-                                                        const u32* __restrict__ isa, const u32* __restrict__ limit, u32* __restrict__ nh,
+                                                        Isa isa, const u32* __restrict__ limit, u32* __restrict__ nh,
                                                         u8* __restrict__ changed, GroupLists next) {
     u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
     u32 gi = tid / WIDTH, lane = tid % WIDTH;
@@ -183,7 +196,7 @@ __global__ void __launch_bounds__(TPB) sort_groups_warp(const Group* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------ block bitonic sort
-__global__ void __launch_bounds__(TPB) sort_groups_block(const Group* __restrict__ groups, u32 h, u32 m, u32* __restrict__ sa, const u32* __restrict__ isa,
+__global__ void __launch_bounds__(TPB) sort_groups_block(const Group* __restrict__ groups, u32 h, u32 m, u32* __restrict__ sa, Isa isa,
                                                          const u32* __restrict__ limit, u32* __restrict__ nh, GroupLists next) {
     __shared__ u64 item[BLOCK_SORT_MAX];          // key << 32 | suffix
     __shared__ u16 start_of[BLOCK_SORT_MAX];      // 1 + index of the first element of the run each element belongs to (<= 4096)
@@ -240,7 +253,7 @@ __global__ void __launch_bounds__(TPB) sort_groups_block(const Group* __restrict
 // ------------------------------------------------------------------------------------------------ applying new head ranks
 template <int WIDTH, int K>
 __global__ void __launch_bounds__(TPB) apply_groups_warp(const Group* __restrict__ groups, u32 ngroups, const u32* __restrict__ sa,
-                                                         const u32* __restrict__ nh, const u8* __restrict__ changed, u32* __restrict__ isa) {
+                                                         const u32* __restrict__ nh, const u8* __restrict__ changed, Isa isa) {
     u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
     u32 gi = tid / WIDTH, lane = tid % WIDTH;
     if (gi >= ngroups || !changed[gi]) return;
@@ -249,14 +262,14 @@ __global__ void __launch_bounds__(TPB) apply_groups_warp(const Group* __restrict
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         u32 e = lane + (u32)WIDTH * k;
-        if (e < size) { u32 r = nh[head + e]; if (r != head) isa[sa[head + e]] = r; }      // the first run keeps the old head rank
+        if (e < size) { u32 r = nh[head + e]; if (r != head) isa.set(sa[head + e], r); }      // the first run keeps the old head rank
     }
 }
 __global__ void __launch_bounds__(TPB) apply_groups_block(const Group* __restrict__ groups, const u32* __restrict__ sa, const u32* __restrict__ nh,
-                                                          u32* __restrict__ isa) {
+                                                          Isa isa) {
     Group g = groups[blockIdx.x];
     u32 head = g_head(g), size = g_size(g);
-    for (u32 e = threadIdx.x; e < size; e += blockDim.x) isa[sa[head + e]] = nh[head + e];
+    for (u32 e = threadIdx.x; e < size; e += blockDim.x) isa.set(sa[head + e], nh[head + e]);
 }
 
 // ------------------------------------------------------------------------------------------------ large groups: flat list + radix sort
@@ -266,7 +279,7 @@ __global__ void large_sizes(const Group* __restrict__ groups, u32 n, u32* __rest
     if (i == n) sizes[i] = 0;
 }
 __global__ void __launch_bounds__(TPB) large_gather(const Group* __restrict__ groups, const u32* __restrict__ base, u32 h, u32 m,
-                                                    const u32* __restrict__ sa, const u32* __restrict__ isa, const u32* __restrict__ limit,
+                                                    const u32* __restrict__ sa, Isa isa, const u32* __restrict__ limit,
                                                     u64* __restrict__ keys, u32* __restrict__ vals, u32* __restrict__ pos) {
     Group g = groups[blockIdx.x];
     u32 head = g_head(g), size = g_size(g), b = base[blockIdx.x];
@@ -297,22 +310,22 @@ __global__ void __launch_bounds__(TPB) large_finish(const u32* __restrict__ pos,
     append_group_warp(want, hd, p - hd + 1, next);
 }
 __global__ void __launch_bounds__(TPB) large_apply(const u32* __restrict__ pos, u32 A, const u32* __restrict__ sa, const u32* __restrict__ nh,
-                                                   u32* __restrict__ isa) {
+                                                   Isa isa) {
     u32 a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a < A) isa[sa[pos[a]]] = nh[pos[a]];
+    if (a < A) isa.set(sa[pos[a]], nh[pos[a]]);
 }
 
 u32 bits_for(u64 x) { u32 b = 1; while ((1ull << b) <= x && b < 63) ++b; return b; }   // bits to represent values 0..x
 
 template <int WIDTH, int K>
-void launch_warp_class(const Group* groups, u32 n, u32 h, u32 m, u32* sa, u32* isa, const u32* limit, u32* nh, u8* changed, const GroupLists& next,
+void launch_warp_class(const Group* groups, u32 n, u32 h, u32 m, u32* sa, Isa isa, const u32* limit, u32* nh, u8* changed, const GroupLists& next,
                        cudaStream_t s) {
     if (!n) return;
     auto sort_groups_warp_k = sort_groups_warp<WIDTH, K>;
-    MMB_LAUNCH(sort_groups_warp_k, ceil_div((u64)n * WIDTH, TPB), TPB, 0, s, groups, n, h, m, sa, (const u32*)isa, limit, nh, changed, next);
+    MMB_LAUNCH(sort_groups_warp_k, ceil_div((u64)n * WIDTH, TPB), TPB, 0, s, groups, n, h, m, sa, isa, limit, nh, changed, next);
 }
 template <int WIDTH, int K>
-void launch_apply_class(const Group* groups, u32 n, const u32* sa, const u32* nh, const u8* changed, u32* isa, cudaStream_t s) {
+void launch_apply_class(const Group* groups, u32 n, const u32* sa, const u32* nh, const u8* changed, Isa isa, cudaStream_t s) {
     if (!n) return;
     auto apply_groups_warp_k = apply_groups_warp<WIDTH, K>;
     MMB_LAUNCH(apply_groups_warp_k, ceil_div((u64)n * WIDTH, TPB), TPB, 0, s, groups, n, sa, nh, changed, isa);
@@ -338,7 +351,8 @@ static GroupLists lists_of(GroupStore& g) {
 
 // Refine an order that is already sorted by the first h0 symbols (sa, isa = head ranks, cur = multi-member groups by size class,
 // all on the device) until every group is a single suffix or a set of suffixes that are equal up to their `limit` (dictionary mode).
-void refine_by_doubling(u32* sa, u32* isa, u32 m, u32 h0, const u32* limit, GroupStore& cur, SaStats& st, cudaStream_t s) {
+void refine_by_doubling(u32* sa, u32* isa_p, u32 m, u32 h0, const u32* limit, GroupStore& cur, SaStats& st, cudaStream_t s, u32 isa_stride) {
+    Isa isa{isa_p, isa_stride};
     GroupStore nxt; nxt.alloc(m, s);
     DevBuf<u32> nh; nh.alloc(m, s);
     DevBuf<u8> changed; changed.alloc(cur.first[NCLASS], s);      // one flag per listed group, laid out like the class lists
@@ -369,7 +383,7 @@ void refine_by_doubling(u32* sa, u32* isa, u32 m, u32 h0, const u32* limit, Grou
         launch_warp_class<32, 2>(G[4], cnt[4], hh, m, sa, isa, limit, nh.p, changed.p + cur.first[4], next, s);
         launch_warp_class<32, 4>(G[5], cnt[5], hh, m, sa, isa, limit, nh.p, changed.p + cur.first[5], next, s);
         launch_warp_class<32, 8>(G[6], cnt[6], hh, m, sa, isa, limit, nh.p, changed.p + cur.first[6], next, s);
-        if (cnt[7]) MMB_LAUNCH(sort_groups_block, cnt[7], TPB, 0, s, G[7], hh, m, sa, (const u32*)isa, limit, nh.p, next);
+        if (cnt[7]) MMB_LAUNCH(sort_groups_block, cnt[7], TPB, 0, s, G[7], hh, m, sa, isa, limit, nh.p, next);
         DevBuf<u32> lpos; u32 A = 0;
         if (cnt[8]) {
             u32 nl = cnt[8];
@@ -386,7 +400,7 @@ void refine_by_doubling(u32* sa, u32* isa, u32 m, u32 h0, const u32* limit, Grou
             A = to_host(base.p + nl, 1, s)[0];
             lpos.alloc(A, s); lkey_a.alloc(A, s); lkey_b.alloc(A, s); lval_a.alloc(A, s); lval_b.alloc(A, s); cand.alloc(A, s); head.alloc(A, s);
             dim3 grid(nl, 32);
-            MMB_LAUNCH(large_gather, grid, TPB, 0, s, G[8], (const u32*)base.p, hh, m, (const u32*)sa, (const u32*)isa, limit, lkey_a.p, lval_a.p, lpos.p);
+            MMB_LAUNCH(large_gather, grid, TPB, 0, s, G[8], (const u32*)base.p, hh, m, (const u32*)sa, isa, limit, lkey_a.p, lval_a.p, lpos.p);
             prim::sort_pairs(lkey_a.p, lkey_b.p, lval_a.p, lval_b.p, A, 0, sort_bits, s);
             MMB_LAUNCH(large_scatter, ceil_div(A, TPB), TPB, 0, s, (const u32*)lpos.p, (const u64*)lkey_b.p, (const u32*)lval_b.p, A, sa, cand.p);
             prim::inclusive_max(cand.p, head.p, A, s);
@@ -407,8 +421,9 @@ void refine_by_doubling(u32* sa, u32* isa, u32 m, u32 h0, const u32* limit, Grou
 }
 
 // Sort (key, suffix) pairs, derive head ranks and the first group lists.  keys are consumed.
-void order_by_initial_keys(u64* keys_in, u64* keys_tmp, u32* vals_in, u32 m, int key_bits, u32 h0, const u32* limit, u32* sa, u32* isa,
-                           GroupStore& groups, cudaStream_t s) {
+void order_by_initial_keys(u64* keys_in, u64* keys_tmp, u32* vals_in, u32 m, int key_bits, u32 h0, const u32* limit, u32* sa, u32* isa_p,
+                           GroupStore& groups, cudaStream_t s, u32 isa_stride) {
+    Isa isa{isa_p, isa_stride};
     DevBuf<u32> cand, head;
     cand.alloc(m, s); head.alloc(m, s);
     groups.alloc(m, s);

@@ -32,9 +32,11 @@ struct GroupStore {
 // Shared refinement engine (also used by pfp.cu).  sa is ordered by the first h0 symbols, isa holds head ranks, groups holds the
 // multi-member groups.  limit (optional): per suffix, the number of symbols after which nothing is left to compare (dictionary
 // suffixes end at their terminator and may tie).
+// isa_stride 2 (with limit): isa holds 2 m words, pairs (head rank, offset of the position inside its phrase); the caller fills the
+// offsets beforehand and the rounds then never read limit[].
 void order_by_initial_keys(u64* keys_in, u64* keys_tmp, u32* vals_in, u32 m, int key_bits, u32 h0, const u32* limit, u32* sa, u32* isa,
-                           GroupStore& groups, cudaStream_t s);
-void refine_by_doubling(u32* sa, u32* isa, u32 m, u32 h0, const u32* limit, GroupStore& groups, SaStats& st, cudaStream_t s);
+                           GroupStore& groups, cudaStream_t s, u32 isa_stride = 1);
+void refine_by_doubling(u32* sa, u32* isa, u32 m, u32 h0, const u32* limit, GroupStore& groups, SaStats& st, cudaStream_t s, u32 isa_stride = 1);
 
 // lcp[r] = longest common prefix of suffixes sa[r-1] and sa[r] (lcp[0] = 0), followed by 64 zero entries.
 void build_lcp(const u8* text, u64 n, const SuffixArray& sa, DevBuf<u32>& lcp, cudaStream_t s);
