@@ -412,6 +412,16 @@ def main():
         units = float(st["text_symbols"]) * args.steps       # suffixes the kernel processed over the timed region
         if roof_kernel == "sort_groups_warp":
             units = float(st["text_symbols"]) * max(1, int(st["sa_rounds"])) * args.steps      # upper bound: every suffix listed in every round
+        # DRAM bytes per suffix of that kernel from its ncu --set full capture (dram__bytes_read.sum + dram__bytes_write.sum of one launch
+        # divided by the suffixes that launch produced); the capture and its summary are under profiles/ncu/
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu", "traffic.json")) as f:
+                tr = json.load(f).get(roof_kernel)
+            if tr and roof_launches:
+                traffic = tr["dram_bytes_per_suffix"] * float(st["text_symbols"]) * args.steps / roof_launches
+        except Exception:
+            pass
         k_bytes = ROOF.get(roof_kernel, 0.0) * units
         k_achieved = (k_bytes / (roof_ms * 1e-3) / 1e9) if roof_ms > 0 else None
         line = {"metric": "input bases/sec end-to-end (FASTA->.mums)", "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
@@ -421,7 +431,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(sum(sizes)), "d2h_bytes_per_step": int(out_bytes)},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": k_achieved, "peak": peak, "unit": "GB/s",
-                             "frac": (k_achieved / peak) if k_achieved else None, "traffic": None,
+                             "frac": (k_achieved / peak) if k_achieved else None, "traffic": traffic, "achieved_per_launch_bytes": (k_bytes / roof_launches) if roof_launches else None,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "kernel_ms_per_step": roof_ms / args.steps,
                              "kernel_launches_per_step": roof_launches / args.steps, "kernel_share_of_step": (roof_ms / args.steps) / ms if ms else None,
                              "algorithmic_bytes_per_suffix": ROOF.get(roof_kernel),

@@ -25,6 +25,7 @@ namespace {
 constexpr u32 TPB = 256;
 constexpr u32 MERGE_MAX = 2048;
 constexpr u32 NOT_START = 0xffffffffu;
+constexpr u32 KLCP_UNKNOWN = 255;        // mem_klcp: the key-level lcp with the previous member was not derived (more symbols than any key holds)
 
 __device__ __forceinline__ u64 load8(const u8* __restrict__ t, u64 i) {
     const u32* w = reinterpret_cast<const u32*>(t + (i & ~3ull));
@@ -72,8 +73,11 @@ __global__ void __launch_bounds__(TPB) members_fill(const u32* __restrict__ sa_d
     if (p >= dsize || !flag[p]) return;
     u32 k = idx[p], i = sa_d[p];
     if (klcp) {         // key symbols shared with the previous MEMBER: minimum over the ranks skipped in between (suffixes of <= w symbols)
-        u32 mn = klcp[p];
-        for (u32 q = p; q-- > 0 && !flag[q];) mn = min(mn, (u32)klcp[q]);
+        // Runs of skipped ranks are usually a few entries, but equal short strings (phrase ends) form runs of millions: give up after
+        // 64 steps and let group_lcp compare the bytes from the start (KLCP_UNKNOWN).
+        u32 mn = klcp[p], q = p, steps = 0;
+        while (q > 0 && !flag[q - 1] && steps < 64) { --q; ++steps; mn = min(mn, (u32)klcp[q]); }
+        if (q > 0 && !flag[q - 1]) mn = KLCP_UNKNOWN;
         mem_klcp[k] = (u8)mn;
     }
     DictRecord d = rec[i];
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(TPB) group_lcp(const u8* __restrict__ dict, co
     if (mem_klcp) {
         u32 shared = mem_klcp[k];
         if (shared < key_symbols) { glcp[k] = min(shared, cap); return; }
-        l = min(key_symbols, cap);
+        if (shared != KLCP_UNKNOWN) l = min(key_symbols, cap);
     }
     u32 a = mem_i[k - 1], b = mem_i[k];
     while (l + 8 <= cap) {
