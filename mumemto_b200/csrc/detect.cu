@@ -503,8 +503,8 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
         }
         if (FAST && plan.size_lo == plan.size_hi) {
             // One interval size (strict multi-MUMs): the lane decides alone whether rank j closes a left-maximal interval of that size
-            // and only notes it in a bit mask; the warp converges once per eight ranks, and the rare survivors recompute their window
-            // minimum (= the match length) by brute force before the cooperative document check.
+            // and only notes it in a bit mask; the warp converges once per eight ranks for the cooperative document check of the survivors
+            // (rare, except with -M where every interval of that size needs its threshold recorded).
             const u32 S = plan.size_lo;
             const u32* plc = lc + base;
             const u32* psuf = suf + base - (g >= H ? W0 : 0u);      // chunks in the halo are walked for nothing: keep their reads in bounds
@@ -512,12 +512,15 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
             const int x0 = (int)(g * C);
             for (u32 k0 = 0; k0 < C; k0 += 8) {
                 u32 cmask = 0;
+                u32 v8[8];                              // window minima of the eight ranks (statically indexed: registers)
 #pragma unroll
                 for (u32 u = 0; u < 8; ++u) {
                     const u32 k = k0 + u;
+                    v8[u] = 0;
                     if (k < C) {
                         const u32 cur = plc[k];
                         const u32 v = (k >= W0) ? run : min(psuf[k], run);
+                        v8[u] = v;
                         run = min(run, cur);
                         const int last_before = last;
                         const u32 sym = b[k];
@@ -534,10 +537,12 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
                     const bool have = cmask != 0;
                     unsigned cand = __ballot_sync(0xffffffffu, have);
                     if (!cand) break;
-                    u32 kc = 0, vv = 0xffffffffu;
+                    u32 kc = 0, vv = 0;
                     if (have) {
-                        kc = k0 + (u32)__ffs((int)cmask) - 1; cmask &= cmask - 1;
-                        for (u32 t = 1; t <= W0; ++t) vv = min(vv, lc[base + kc - t]);
+                        const u32 bit = (u32)__ffs((int)cmask) - 1;
+                        kc = k0 + bit; cmask &= cmask - 1;
+#pragma unroll
+                        for (u32 u = 0; u < 8; ++u) if (bit == u) vv = v8[u];
                     }
                     const u64 jc = (u64)(j0 + (i64)kc);
                     const u32 curc = lc[base + kc], befc = have ? pbef[kc] : 0u;
