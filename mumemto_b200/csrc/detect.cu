@@ -355,9 +355,10 @@ __global__ void __launch_bounds__(DW_TPB) detect_window_kernel(const u32* __rest
 }
 
 // Warp-cooperative check of one MUM-mode candidate (all lanes hold the same arguments): the interval [s0, s0 + cs) qualifies iff its
-// suffixes come from cs distinct documents and cs >= num_distinct; it is reported iff it is also left-maximal.
+// suffixes come from cs distinct documents and cs >= num_distinct; it is reported iff it is also left-maximal (leftmax: 1 / 0 when the
+// caller already knows, -1 = derive it from the symbols that precede the suffixes).
 template <class SAT, int W>
-__device__ __forceinline__ void verify_mum_candidate(u64 cj, u32 cs, u32 cv, u32 ccur, u32 cbefore, const SAT* __restrict__ sa,
+__device__ __forceinline__ void verify_mum_candidate(u64 cj, u32 cs, u32 cv, u32 ccur, u32 cbefore, int leftmax, const SAT* __restrict__ sa,
                                                      const u8* __restrict__ bwt, const u8* __restrict__ text, const u64* doc_start,
                                                      const DetectParams& prm, Report* __restrict__ reports, u32 cap, u32* __restrict__ count,
                                                      u16* __restrict__ thresh, u32 lane) {
@@ -371,25 +372,32 @@ __device__ __forceinline__ void verify_mum_candidate(u64 cj, u32 cs, u32 cv, u32
         u32 sym = 0;
         if (t < cs) {
             u64 rk = s0 + t; u64 p = (u64)sa[rk];
-            u32 dd = find_doc(doc_start, prm.ndocs, p);
+            u32 dd;
+            if (prm.doc_coarse) { dd = prm.doc_coarse[p >> prm.coarse_shift]; while (doc_start[dd + 1] <= p) ++dd; }
+            else dd = find_doc(doc_start, prm.ndocs, p);
             bits[(W == 1) ? 0 : (dd >> 6)] |= 1ull << (dd & 63);
             if (dd == 0) anchor = p;
-            sym = bwt ? bwt[rk] : (p ? text[p - 1] : (u8)0);
+            if (leftmax < 0) sym = bwt ? bwt[rk] : (p ? text[p - 1] : (u8)0);
         }
-        u32 left = __shfl_up_sync(0xffffffffu, sym, 1);
-        if (lane == 0) left = carry;
-        if (t < cs && t > 0 && left != sym) differs = true;
-        carry = __shfl_sync(0xffffffffu, sym, 31);
+        if (leftmax < 0) {
+            u32 left = __shfl_up_sync(0xffffffffu, sym, 1);
+            if (lane == 0) left = carry;
+            if (t < cs && t > 0 && left != sym) differs = true;
+            carry = __shfl_sync(0xffffffffu, sym, 31);
+        }
     }
     u32 distinct = 0;
 #pragma unroll
     for (int w = 0; w < W; ++w) {
+#ifdef MMB_SIMT
         u64 bb = bits[w];
-#pragma unroll
         for (u32 dd = 16; dd > 0; dd >>= 1) bb |= __shfl_xor_sync(0xffffffffu, bb, dd);
         distinct += (u32)__popcll(bb);
+#else
+        distinct += (u32)__popc(__reduce_or_sync(0xffffffffu, (u32)bits[w])) + (u32)__popc(__reduce_or_sync(0xffffffffu, (u32)(bits[w] >> 32)));
+#endif
     }
-    differs = __any_sync(0xffffffffu, differs);
+    differs = leftmax < 0 ? __any_sync(0xffffffffu, differs) : leftmax != 0;
     if (distinct == cs && distinct >= prm.num_distinct) {          // every document at most once
         if (prm.merge && anchor != ~0ull) thresh[anchor] = (u16)min(max(cbefore, ccur), 65535u);
         if (differs && lane == 0) {
@@ -511,7 +519,7 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
             const u32* pbef = lc + base - (g >= H ? S : 0u);
             const int x0 = (int)(g * C);
             for (u32 k0 = 0; k0 < C; k0 += 8) {
-                u32 cmask = 0;
+                u32 cmask = 0, lmask = 0;               // candidates among the eight ranks, and which of them are left-maximal
                 u32 v8[8];                              // window minima of the eight ranks (statically indexed: registers)
 #pragma unroll
                 for (u32 u = 0; u < 8; ++u) {
@@ -528,8 +536,9 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
                         prev_sym = sym;
                         bool c = k >= k_lo && k < k_hi && v > cur && v >= prm.min_len;
                         // -M needs the threshold of every interval that passes the size / document test, left-maximal or not
-                        if (c) c = pbef[k] < v && (prm.merge || last_before > x0 + (int)k - (int)S);
-                        cmask |= (u32)c << u;
+                        const bool lm = last_before > x0 + (int)k - (int)S;
+                        if (c) c = pbef[k] < v && (prm.merge || lm);
+                        cmask |= (u32)c << u; lmask |= (u32)(c && lm) << u;
                     }
                 }
                 if (!__any_sync(0xffffffffu, cmask != 0)) continue;
@@ -537,10 +546,10 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
                     const bool have = cmask != 0;
                     unsigned cand = __ballot_sync(0xffffffffu, have);
                     if (!cand) break;
-                    u32 kc = 0, vv = 0;
+                    u32 kc = 0, vv = 0; int lmc = 0;
                     if (have) {
                         const u32 bit = (u32)__ffs((int)cmask) - 1;
-                        kc = k0 + bit; cmask &= cmask - 1;
+                        kc = k0 + bit; cmask &= cmask - 1; lmc = (int)((lmask >> bit) & 1);
 #pragma unroll
                         for (u32 u = 0; u < 8; ++u) if (bit == u) vv = v8[u];
                     }
@@ -550,7 +559,8 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
                         int src = __ffs((int)cand) - 1; cand &= cand - 1;
                         u64 cj = __shfl_sync(0xffffffffu, jc, src);
                         u32 cv = __shfl_sync(0xffffffffu, vv, src), ccur = __shfl_sync(0xffffffffu, curc, src), cbef = __shfl_sync(0xffffffffu, befc, src);
-                        verify_mum_candidate<SAT, W>(cj, S, cv, ccur, cbef, sa, bwt, text, doc_start, prm, reports, cap, count, thresh, lane);
+                        int clm = __shfl_sync(0xffffffffu, lmc, src);
+                        verify_mum_candidate<SAT, W>(cj, S, cv, ccur, cbef, clm, sa, bwt, text, doc_start, prm, reports, cap, count, thresh, lane);
                     }
                 }
             }

@@ -12,6 +12,10 @@ struct DetectParams {
     u32 ndocs;
     int revcomp;
     int merge;          // -M: record next-best thresholds
+    // optional: document of text position p = doc_coarse[p >> coarse_shift], then forward while doc_start[d + 1] <= p (at most 4096
+    // entries, built by the engine when the text is loaded); nullptr = binary search over doc_start
+    const u16* doc_coarse;
+    u32 coarse_shift;
 };
 
 // One reported interval [s, e] of ranks, all suffixes sharing a prefix of length len.  key = (e + 1) << 20 | order within the

@@ -135,6 +135,8 @@ struct mmb_engine {
     TextLayout text;
     std::vector<std::vector<RecordInfo>> records;
     DevBuf<u8> raw;                     // device copy of the input images (host-load path)
+    DevBuf<u16> doc_coarse;             // document of every 2^coarse_shift-th text position (DetectParams::doc_coarse)
+    u32 coarse_shift = 0;
 
     SuffixArray sa;
     DevBuf<u32> lcp;
@@ -215,6 +217,21 @@ void load_common(mmb_engine* e, const u8* d_raw, const u8* const* host_imgs, con
     Timer t(e->stream); t.start();
     build_text(d_raw, off, size, revcomp, raw_mode, e->text, e->stream);
     e->stats.ms_text = t.stop();
+    {   // coarse position -> document table for the detector's candidate checks
+        const std::vector<u64>& ds = e->text.h_doc_start;
+        u32 shift = 0;
+        while (((e->text.n >> shift) + 1) > 4096) ++shift;
+        std::vector<u16> tab((e->text.n >> shift) + 1);
+        u32 d = 0;
+        for (size_t i = 0; i < tab.size(); ++i) {
+            u64 pos = (u64)i << shift;
+            while (d + 1 < ds.size() - 1 && ds[d + 1] <= pos) ++d;
+            tab[i] = (u16)d;
+        }
+        e->doc_coarse.alloc(tab.size(), e->stream); e->coarse_shift = shift;
+        MMB_CUDA(cudaMemcpyAsync(e->doc_coarse.p, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice, e->stream));
+        MMB_CUDA(cudaStreamSynchronize(e->stream));       // tab lives on this stack frame
+    }
     finish_load(e, host_imgs, off, size, raw_mode);
     e->stats.text_symbols = e->text.n; e->stats.input_bases = e->text.total_bases;
     e->loaded = true;
@@ -359,6 +376,7 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
         bool merge = false;
         normalise(*opts, N, e->prm, e->mum_mode, merge);
         e->prm.revcomp = e->text.revcomp ? 1 : 0;
+        e->prm.doc_coarse = e->doc_coarse.p; e->prm.coarse_shift = e->coarse_shift;
 
         Timer total(s), t(s);
         double host0 = host_now_ms(), a0 = g_host_alloc_ms, f0 = g_host_free_ms, y0 = g_host_sync_ms;

@@ -117,6 +117,14 @@ template <class T> inline unsigned __match_any_sync(unsigned mask, T v) {
     simt::warp_barrier(mask);
     return r;
 }
+inline unsigned __reduce_or_sync(unsigned mask, unsigned v) {
+    *simt::warp_slot(simt::lane_id()) = v;
+    simt::warp_barrier(mask);
+    unsigned r = 0;
+    for (unsigned l = 0; l < 32; ++l) if (mask >> l & 1) r |= (unsigned)*simt::warp_slot(l);
+    simt::warp_barrier(mask);
+    return r;
+}
 inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
 
