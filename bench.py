@@ -314,19 +314,23 @@ def main():
         return st
 
     out_host = None
+    merged_host = None
 
     def step_e2e():
-        nonlocal out_host
+        nonlocal out_host, merged_host
         eng.load_fasta_bytes(pinned_imgs)
         eng.find(want_text=True, **opts)
         n = eng.lib.mmb_text_size(eng.h)
         if out_host is None or out_host.numel() < n:
             out_host = torch.empty(max(n, 1), dtype=torch.uint8).pin_memory()
         eng.copy_text_into(out_host.numpy())
-        if multi:       # partition .mums above, then exchange + merge and the merged .mums back to the host
+        if multi:       # partition .mums above, then exchange + merge; rank 0 brings the merged .mums back to the host (pinned buffer)
             partition.partition_merge(eng, dist, world, tdev, fetch=False)
-            merged = eng.merge_text()
-            n += len(merged)
+            if rank == 0:
+                mn = eng.merge_text_size()
+                if merged_host is None or merged_host.numel() < mn:
+                    merged_host = torch.empty(max(mn + mn // 8, 1), dtype=torch.uint8).pin_memory()
+                n += eng.merge_text_into(merged_host.numpy())
         return n
 
     def barrier():

@@ -291,3 +291,14 @@ class Engine:
         buf = np.empty(self.lib.mmb_merge_text_size(self.h), dtype=np.uint8)
         self._check(self.lib.mmb_merge_copy_text(self.h, _ptr(buf)))
         return buf.tobytes()
+
+    def merge_text_size(self):
+        return int(self.lib.mmb_merge_text_size(self.h))
+
+    def merge_text_into(self, host_array):
+        """Merged .mums bytes into a caller-owned (ideally pinned) uint8 array of at least merge_text_size() bytes; returns the size."""
+        n = self.merge_text_size()
+        if host_array.nbytes < n:
+            raise ValueError("destination too small for the merged text")
+        self._check(self.lib.mmb_merge_copy_text(self.h, _ptr(host_array)))
+        return n

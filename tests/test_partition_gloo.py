@@ -26,6 +26,8 @@ e.load_fasta_files(paths)
 e.find(merge=True, anchor_merge=True)
 lengths, offsets, strands, thr = partition.partition_merge(e, dist, world, torch.device("cpu"))
 text = e.merge_text()
+buf = np.zeros(e.merge_text_size() + 7, dtype=np.uint8)
+assert e.merge_text_into(buf) == len(text) and buf[:len(text)].tobytes() == text
 open(os.path.join({out!r}, "merged_rank%d.mums" % rank), "wb").write(text)
 thr.tofile(os.path.join({out!r}, "merged_rank%d.athresh" % rank))
 dist.destroy_process_group()

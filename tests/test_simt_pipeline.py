@@ -171,6 +171,17 @@ def test_simt_walk_kernel_fallback(simt_lib, oracle_bin, small, tmp_path, flags,
     both(simt_lib, oracle_bin, str(tmp_path), small, flags)
 
 
+@pytest.mark.parametrize("flags", [[], ["-k", "-1"], ["-f", "3", "-F", "100"], ["-M", "-n"]])
+def test_simt_window_kernel(simt_lib, oracle_bin, small, tmp_path, flags, monkeypatch):
+    """The power-of-two window-minimum detector (the default when the smallest interval size exceeds 128) must agree with the chunked
+    one on both routes."""
+    monkeypatch.setenv("MMB_DETECT", "window")
+    for sub in ("direct", "pfp"):
+        os.makedirs(str(tmp_path / sub), exist_ok=True)
+    both(simt_lib, oracle_bin, str(tmp_path / "direct"), small, flags)
+    both_pfp(simt_lib, oracle_bin, str(tmp_path / "pfp"), small, flags, tile_ranks=900)
+
+
 # ------------------------------------------------------------------------------------------------ prefix-free-parse route (tiled stream)
 def both_pfp(simt_lib, oracle_bin, tmp, paths, flags, tile_ranks):
     o, g = os.path.join(tmp, "o"), os.path.join(tmp, "g")
