@@ -6,6 +6,8 @@
  *   mmb_load_fasta / _device   RefBuilder::build_input_file            src/ref_builder.cpp:211-314
  *   mmb_load_records           RefBuilder::build_input_file_lib        src/ref_builder.cpp:330-384
  *   mmb_find                   the body of build_main after parsing    src/pfp_mum.cpp:76-94,116-145
+ *   mmb_find_from_arrays       the -a branch: RefBuilder(prefix) +     src/ref_builder.cpp:140-168, src/pfp_mum.cpp:96-110,
+ *                              file_lcp::process                       include/read_arrays.hpp:66-84
  *                              = gsacak_lcp / pf_parsing + pfp_lcp::process feeding mem_finder::update
  *                              (include/direct_gsacak.hpp:50-116, include/pfp_lcp_mum.hpp:115-231, include/mem_finder.hpp:161-170)
  *   mmb_options                BuildOptions + validate/set_parameters  include/pfp_mum.hpp:56-198
@@ -66,7 +68,7 @@ typedef struct mmb_stats {
     uint32_t sa_rounds;
     uint64_t sa_sorted_elements;
     float ms_text, ms_sa, ms_lcp, ms_detect, ms_emit, ms_total;   /* CUDA-event times of the last mmb_find (ms_text: last load) */
-    uint32_t route;              /* route taken by the last mmb_find (1 direct, 2 prefix-free parse) */
+    uint32_t route;              /* route taken by the last mmb_find (1 direct, 2 prefix-free parse, 3 arrays given by the caller) */
     uint32_t pfp_phrases, pfp_distinct_phrases, pfp_dict_bytes, pfp_tiles;
 } mmb_stats;
 
@@ -86,6 +88,12 @@ MMB_API int mmb_load_records(mmb_engine* e, const char* const* records, const si
 
 /* The hot path.  Everything stays on the device until one of the copy functions below is called. */
 MMB_API int mmb_find(mmb_engine* e, const mmb_options* opts);
+/* Detection over PRE-COMPUTED arrays in the reference's on-disk format (-A output: 5-byte little-endian SA and LCP entries, one BWT
+ * byte per rank), host memory.  doc_lengths = forward bases per document (PREFIX.lengths); `entries` ranks are processed, starting at
+ * rank 0 -- the reference's reader stops after |T| of the |T|+1 entries of the files, and so does its CLI twin here.  Replaces any
+ * loaded text; results are read with the same accessors as after mmb_find (mmb_copy_arrays is not available afterwards). */
+MMB_API int mmb_find_from_arrays(mmb_engine* e, const uint64_t* doc_lengths, size_t ndocs, int use_revcomp, const uint8_t* sa5,
+                                 const uint8_t* lcp5, const uint8_t* bwt, uint64_t entries, const mmb_options* opts);
 MMB_API int mmb_get_stats(const mmb_engine* e, mmb_stats* out);
 
 /* Documents and FASTA records (for PREFIX.lengths, src/ref_builder.cpp:193-209). */

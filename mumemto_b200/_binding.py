@@ -67,6 +67,8 @@ _SIGNATURES = {
     "mmb_copy_arrays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmb_copy_symbols": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mmb_profile_kernel": (C.c_int, [C.c_char_p]),
+    "mmb_find_from_arrays": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                       C.POINTER(Options)]),
     "mmb_profile_result": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "mmb_mum_table_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "mmb_anchor_merge": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
@@ -168,6 +170,17 @@ class Engine:
         o = Options(min_match_len, num_distinct_docs, rare_freq, max_mem_freq, int(merge), int(anchor_merge), int(cli_normalise), int(want_text),
                     self.ROUTES[route], int(keep_arrays), (C.c_uint8 * 6)(), int(tile_ranks))
         self._check(self.lib.mmb_find(self.h, C.byref(o)))
+        return self.stats()
+
+    def find_from_arrays(self, doc_lengths, sa5, lcp5, bwt, entries, revcomp=True, min_match_len=20, num_distinct_docs=0, rare_freq=1,
+                         max_mem_freq=0, merge=False, anchor_merge=False, cli_normalise=True, want_text=True, tile_ranks=0):
+        """Detection over pre-computed arrays in the reference's file format (uint8 arrays: 5-byte LE SA / LCP entries, BWT bytes)."""
+        o = Options(min_match_len, num_distinct_docs, rare_freq, max_mem_freq, int(merge), int(anchor_merge), int(cli_normalise), int(want_text),
+                    0, 0, (C.c_uint8 * 6)(), int(tile_ranks))
+        dl = np.ascontiguousarray(doc_lengths, dtype=np.uint64)
+        self._keep_arrays = (dl, sa5, lcp5, bwt)
+        self._check(self.lib.mmb_find_from_arrays(self.h, dl.ctypes.data_as(C.POINTER(C.c_uint64)), len(dl), int(revcomp), _ptr(sa5), _ptr(lcp5),
+                                                  _ptr(bwt), int(entries), C.byref(o)))
         return self.stats()
 
     def stats(self):

@@ -135,6 +135,47 @@ def find_files(paths, prefix, min_match_len=20, num_distinct_docs=0, rare_freq=1
         e.close()
 
 
+def read_lengths(path, revcomp=True):
+    """PREFIX.lengths -> forward bases per document, the way RefBuilder(prefix) reads it (src/ref_builder.cpp:140-168): lines
+    `path * total` (or the two-word form `path total`) count, per-record lines are skipped."""
+    out = []
+    with open(path) as f:
+        for line in f:
+            w = line.rstrip("\n").split(" ")
+            if len(w) == 2:
+                out.append(int(w[1]))
+            elif len(w) == 3 and w[1] == "*":
+                out.append(int(w[2]))
+    return out
+
+
+def find_arrays(arrays_prefix, prefix, min_match_len=20, num_distinct_docs=0, rare_freq=1, max_mem_freq=0, revcomp=True, binary=False, merge=False,
+                anchor_merge=False, device=0, tile_ranks=0, _lib=None):
+    """`mumemto_exec -a arrays_prefix [flags] -o prefix`: detection over arrays_prefix.{lengths,sa,lcp,bwt} (reference src/pfp_mum.cpp:96-110,
+    include/read_arrays.hpp:66-84 -- which stops after |T| of the |T|+1 entries)."""
+    lengths = read_lengths(arrays_prefix + ".lengths", revcomp)
+    sa5 = np.fromfile(arrays_prefix + ".sa", dtype=np.uint8); lcp5 = np.fromfile(arrays_prefix + ".lcp", dtype=np.uint8)
+    bwt = np.fromfile(arrays_prefix + ".bwt", dtype=np.uint8)
+    total = sum((2 if revcomp else 1) * (l + 1) for l in lengths)
+    if len(sa5) < 5 * total or len(lcp5) < 5 * total or len(bwt) < total:
+        raise ValueError("array files are shorter than the sequence lengths imply")
+    e = Engine(device, _lib=_lib)
+    try:
+        if binary and rare_freq != 1:
+            binary = False
+        st = e.find_from_arrays(lengths, sa5, lcp5, bwt, total, revcomp=revcomp, min_match_len=min_match_len, num_distinct_docs=num_distinct_docs,
+                                rare_freq=rare_freq, max_mem_freq=max_mem_freq, merge=merge, anchor_merge=anchor_merge, want_text=not binary,
+                                tile_ranks=tile_ranks)
+        N = e.num_docs
+        k = num_distinct_docs
+        k = 2 if k < -N else (N + k if k <= 0 else (2 if k == 1 else min(k, N)))
+        e._partial = k < N
+        write_outputs(e, prefix, None, binary=binary, anchor_merge=anchor_merge)
+        return st
+    finally:
+        e.close()
+
+
 def read_mums(path):
     """Strict .mums text -> (lengths u32[n], offsets i64[n][N], strands u8[n][N] with 1 = '+'); include/mumsio.hpp:40-103."""
     lengths, offsets, strands = [], [], []

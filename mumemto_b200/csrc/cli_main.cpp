@@ -4,7 +4,8 @@
 // (include/pfp_mum.hpp:80-147), the RefBuilder input checks (src/ref_builder.cpp:52-138: file-list, extensions, de-duplication,
 // at least two inputs), the output files of mem_finder (include/mem_finder.hpp:91-158,451-503) and PREFIX.lengths
 // (src/ref_builder.cpp:193-209).  Everything between reading the files and writing the results runs on the GPU through
-// include/mumemto_b200.h.  Stage files of the CPU algorithm (-p/-P/-K .dict/.parse, -a array input) have no counterpart here.
+// include/mumemto_b200.h.  -a PREFIX (detection over PREFIX.sa/.lcp/.bwt + PREFIX.lengths, src/pfp_mum.cpp:96-110) is supported; the
+// .dict/.parse stage files of the CPU algorithm (-p/-P/-K) have no counterpart here.
 #include <getopt.h>
 #include <zlib.h>
 
@@ -33,7 +34,8 @@ namespace fs = std::filesystem;
 static void status(const char* what) { std::fprintf(stderr, "\033[32m[build_main] \033[m%s", what); }
 
 struct Options {
-    std::string input_list, output_prefix = "output";
+    std::string input_list, output_prefix = "output", arrays_in;
+    bool use_gsacak = false;
     std::vector<std::string> files;
     bool use_rcomp = true, arrays_out = false, binary = false, merge = false, anchor_merge = false;
     int num_distinct_docs = 0, max_mem_freq = 0, rare_freq = 1;
@@ -58,6 +60,7 @@ static int usage() {
         "\t-r, --no-revcomp                do not include the reverse complement of the sequences\n"
         "\t-b, --binary                    output binary format (multi-MUMs only)\n"
         "\t-A, --arrays-out                write LCP, BWT, and SA to file\n"
+        "\t-a, --arrays-in       [PREFIX]  compute matches from precomputed LCP, BWT, SA (with shared PREFIX)\n"
         "\t-M, --merge                     output extra metadata to enable merging multi-MUMs\n"
         "\t-n, --anchor                    use anchor-based merging (uses first sequence as anchor)\n"
         "Exact match parameters:\n"
@@ -66,7 +69,7 @@ static int usage() {
         "\t-f, --per-seq-freq    [INT]     maximum number of occurences per sequence (default: 1)\n"
         "\t-F, --max-total-freq  [INT]     maximum number of total occurences of match\n"
         "Accepted for compatibility, no effect on results: -w, -m, -g, -s\n"
-        "Not available (stage files of the CPU algorithm): -p, -P, -K, -a\n"
+        "Not available (stage files of the CPU algorithm): -p, -P, -K\n"
         "Engine: -d, --device [INT]\n\n");
     return 0;
 }
@@ -78,6 +81,14 @@ static std::string slurp(const std::string& path) {          // gzopen reads pla
     std::string out; std::vector<char> buf(1 << 22); int k;
     while ((k = gzread(f, buf.data(), (unsigned)buf.size())) > 0) out.append(buf.data(), k);
     gzclose(f);
+    return out;
+}
+
+static std::string slurp_plain(const std::string& path) {    // binary array files: no transparent gzip detection
+    std::ifstream in(path, std::ios::binary | std::ios::ate);
+    if (!in) fatal("cannot open " + path);
+    std::string out((size_t)in.tellg(), '\0');
+    in.seekg(0); in.read(out.data(), (std::streamsize)out.size());
     return out;
 }
 
@@ -108,7 +119,9 @@ int main(int argc, char** argv) {
             case 'h': usage(); return 0;
             case 'i': o.input_list = optarg; break;
             case 'o': o.output_prefix = optarg; break;
-            case 'w': case 'm': case 's': case 'g': break;          // PFP window / modulus / overlap / gsacak: results do not depend on them
+            case 'w': case 'm': case 's': break;                    // PFP window / modulus / overlap: results do not depend on them
+            case 'g': o.use_gsacak = true; break;                   // no effect on results either; only checked against -a like the reference
+            case 'a': o.arrays_in = optarg; break;
             case 'r': o.use_rcomp = false; break;
             case 'k': o.num_distinct_docs = std::atoi(optarg); break;
             case 'l': o.min_match_len = (size_t)std::atoi(optarg); break;
@@ -119,8 +132,8 @@ int main(int argc, char** argv) {
             case 'M': o.merge = true; break;
             case 'n': o.anchor_merge = true; break;
             case 'd': o.device = std::atoi(optarg); break;
-            case 'a': case 'p': case 'P': case 'K':
-                fatal("-p/-P/-K/-a use stage files of the CPU algorithm (.dict/.parse/.sa/.lcp/.bwt input); the GPU engine has no such stages");
+            case 'p': case 'P': case 'K':
+                fatal("-p/-P/-K use stage files of the CPU algorithm (.dict/.parse); the GPU engine has no such stages");
             default: usage(); return 1;
         }
     }
@@ -129,14 +142,40 @@ int main(int argc, char** argv) {
     // BuildOptions::validate
     if (!o.input_list.empty() && !fs::is_regular_file(o.input_list)) fatal("The provided file-list is not valid.");
     if (!o.input_list.empty() && !o.files.empty()) { status("Using filelist, ignoring positional args\n"); o.files.clear(); }
-    if (o.input_list.empty() && o.files.empty()) fatal("Need to provide a file-list or files as positional args for processing.");
+    if (o.input_list.empty() && o.files.empty() && o.arrays_in.empty()) fatal("Need to provide a file-list or files as positional args for processing.");
     fs::path pp(o.output_prefix);
     if (pp.parent_path().string().empty() && !pp.string().empty()) o.output_prefix = "./" + o.output_prefix;
     else if (!fs::exists(pp.parent_path())) fs::create_directories(pp.parent_path());
+    if (o.use_gsacak && !o.arrays_in.empty()) fatal("--use-gsacak flag is incompatible with --arrays-in flag");
     if (o.anchor_merge) o.merge = true;
+    if (!o.arrays_in.empty()) {
+        if (!fs::is_regular_file(o.arrays_in + ".sa")) fatal("Missing *.sa file. Expected file: " + o.arrays_in + ".sa");
+        else if (!fs::is_regular_file(o.arrays_in + ".lcp")) fatal("Missing *.lcp file. Expected file: " + o.arrays_in + ".lcp");
+        else if (!fs::is_regular_file(o.arrays_in + ".bwt")) fatal("Missing *.bwt file. Expected file: " + o.arrays_in + ".bwt");
+    }
     if (o.rare_freq < 0) fatal("Per-sequence MEM frequency must be > 0 (or 0 for no limit).");
     if (o.binary && o.rare_freq != 1) { status("binary output is not supported for multi-MEMs, ignoring flag\n"); o.binary = false; }
 
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&]() { auto t = std::chrono::steady_clock::now(); double s = std::chrono::duration<double>(t - t0).count(); t0 = t; return s; };
+    mmb_engine* e = nullptr;
+    std::vector<uint64_t> arr_lengths; std::string arr_sa, arr_lcp, arr_bwt;         // -a: inputs of mmb_find_from_arrays
+    if (!o.arrays_in.empty()) {
+        // RefBuilder(prefix) (src/ref_builder.cpp:140-168): document lengths from PREFIX.lengths, no sequence data at all
+        std::string lf = o.arrays_in + ".lengths";
+        if (!fs::is_regular_file(lf)) fatal("Lengths file required for using intermediate files. File should match output prefix: " + lf);
+        std::ifstream in(lf); std::string line;
+        while (std::getline(in, line)) {
+            std::vector<std::string> w; std::string cur; std::istringstream ss(line);
+            while (std::getline(ss, cur, ' ')) w.push_back(cur);
+            if (w.size() == 2) arr_lengths.push_back(std::stoull(w[1]));
+            else if (w.size() == 3 && w[1] == "*") arr_lengths.push_back(std::stoull(w[2]));
+        }
+        status("reading the suffix array, LCP and BWT files");
+        arr_sa = slurp_plain(o.arrays_in + ".sa"); arr_lcp = slurp_plain(o.arrays_in + ".lcp"); arr_bwt = slurp_plain(o.arrays_in + ".bwt");
+        std::fprintf(stderr, " done.  (%.3f sec)\n", lap());
+        CHECK(mmb_create(o.device, nullptr, &e));
+    } else {
     // RefBuilder constructors: collect, check, de-duplicate
     std::vector<std::string> inputs;
     if (!o.input_list.empty()) {
@@ -162,13 +201,10 @@ int main(int argc, char** argv) {
     }
     if (inputs.size() <= 1) fatal("Multiple FASTA inputs required. Perhaps split a multi-FASTA into multiple files?");
 
-    auto t0 = std::chrono::steady_clock::now();
-    auto lap = [&]() { auto t = std::chrono::steady_clock::now(); double s = std::chrono::duration<double>(t - t0).count(); t0 = t; return s; };
 
     status("parsing input files");
     std::vector<std::string> images;
     for (auto& f : inputs) images.push_back(slurp(f));
-    mmb_engine* e = nullptr;
     CHECK(mmb_create(o.device, nullptr, &e));
     std::vector<const uint8_t*> ptrs; std::vector<uint64_t> sizes;
     for (auto& im : images) { ptrs.push_back((const uint8_t*)im.data()); sizes.push_back(im.size()); }
@@ -186,11 +222,21 @@ int main(int argc, char** argv) {
         }
     }
 
+    }
+
     mmb_options mo; mmb_default_options(&mo);
     mo.min_match_len = (uint32_t)o.min_match_len; mo.num_distinct_docs = o.num_distinct_docs; mo.rare_freq = o.rare_freq; mo.max_mem_freq = o.max_mem_freq;
     mo.merge = o.merge; mo.anchor_merge = o.anchor_merge; mo.cli_normalise = 1; mo.want_text = o.binary ? 0 : 1;
     bool mum_mode = (o.rare_freq == 1);
     status(mum_mode ? "finding multi-MUMs on the GPU" : "finding multi-MEMs on the GPU");
+    if (!o.arrays_in.empty()) {
+        uint64_t total = 0;                 // file_lcp::process walks total_length = |T| ranks (include/read_arrays.hpp:66-84), one less than the files hold
+        for (uint64_t l : arr_lengths) total += (o.use_rcomp ? 2 : 1) * (l + 1);
+        if (arr_sa.size() < 5 * total || arr_lcp.size() < 5 * total || arr_bwt.size() < total) fatal("array files are shorter than the sequence lengths imply");
+        CHECK(mmb_find_from_arrays(e, arr_lengths.data(), arr_lengths.size(), o.use_rcomp, (const uint8_t*)arr_sa.data(), (const uint8_t*)arr_lcp.data(),
+                                   (const uint8_t*)arr_bwt.data(), total, &mo));
+        o.arrays_out = false;               // -A only applies to the array producers (pfp_lcp / gsacak_lcp)
+    } else
     CHECK(mmb_find(e, &mo));
     std::fprintf(stderr, " done.  (%.3f sec)\n", lap());
 

@@ -108,7 +108,7 @@ int fail(int code, const std::string& msg) { g_error = msg; return code; }
 int map_error(const Error& e) {
     int c = e.code;
     if (c == 10) return MMB_ERR_CUDA;
-    if (c == 13 || c == 21 || c == 40 || c == 41) return MMB_ERR_INPUT;
+    if (c == 13 || c == 21 || c == 40 || c == 41 || c == 42) return MMB_ERR_INPUT;
     if (c == 12 || c == 20 || (c >= 30 && c <= 39) || (c >= 50 && c <= 59)) return MMB_ERR_PARAM;
     return MMB_ERR_INTERNAL;
 }
@@ -210,6 +210,23 @@ void finish_load(mmb_engine* e, const u8* const* host_imgs, const std::vector<u6
     }
 }
 
+// coarse position -> document table for the detector's candidate checks (DetectParams::doc_coarse)
+void build_doc_coarse(mmb_engine* e) {
+    const std::vector<u64>& ds = e->text.h_doc_start;
+    u32 shift = 0;
+    while (((e->text.n >> shift) + 1) > 4096) ++shift;
+    std::vector<u16> tab((e->text.n >> shift) + 1);
+    u32 d = 0;
+    for (size_t i = 0; i < tab.size(); ++i) {
+        u64 pos = (u64)i << shift;
+        while (d + 1 < ds.size() - 1 && ds[d + 1] <= pos) ++d;
+        tab[i] = (u16)d;
+    }
+    e->doc_coarse.alloc(tab.size(), e->stream); e->coarse_shift = shift;
+    MMB_CUDA(cudaMemcpyAsync(e->doc_coarse.p, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice, e->stream));
+    MMB_CUDA(cudaStreamSynchronize(e->stream));       // tab lives on this stack frame
+}
+
 void load_common(mmb_engine* e, const u8* d_raw, const u8* const* host_imgs, const std::vector<u64>& off, const std::vector<u64>& size,
                  bool revcomp, bool raw_mode) {
     if (off.size() < 2) throw Error(41, "Multiple FASTA inputs required. Perhaps split a multi-FASTA into multiple files?");
@@ -217,21 +234,7 @@ void load_common(mmb_engine* e, const u8* d_raw, const u8* const* host_imgs, con
     Timer t(e->stream); t.start();
     build_text(d_raw, off, size, revcomp, raw_mode, e->text, e->stream);
     e->stats.ms_text = t.stop();
-    {   // coarse position -> document table for the detector's candidate checks
-        const std::vector<u64>& ds = e->text.h_doc_start;
-        u32 shift = 0;
-        while (((e->text.n >> shift) + 1) > 4096) ++shift;
-        std::vector<u16> tab((e->text.n >> shift) + 1);
-        u32 d = 0;
-        for (size_t i = 0; i < tab.size(); ++i) {
-            u64 pos = (u64)i << shift;
-            while (d + 1 < ds.size() - 1 && ds[d + 1] <= pos) ++d;
-            tab[i] = (u16)d;
-        }
-        e->doc_coarse.alloc(tab.size(), e->stream); e->coarse_shift = shift;
-        MMB_CUDA(cudaMemcpyAsync(e->doc_coarse.p, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice, e->stream));
-        MMB_CUDA(cudaStreamSynchronize(e->stream));       // tab lives on this stack frame
-    }
+    build_doc_coarse(e);
     finish_load(e, host_imgs, off, size, raw_mode);
     e->stats.text_symbols = e->text.n; e->stats.input_bases = e->text.total_bases;
     e->loaded = true;
@@ -261,6 +264,15 @@ void copy_out(const T* d, T* h, u64 n, cudaStream_t s) {
 __global__ void widen_u32(const u32* __restrict__ in, u64 n, u64* __restrict__ out) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i];
+}
+// 5-byte little-endian entries (the reference's .sa / .lcp files) -> u64 / u32; *overflow is set when an lcp does not fit 32 bits
+__global__ void unpack5(const u8* __restrict__ raw, u64 n, u64* __restrict__ out64, u32* __restrict__ out32, u32* __restrict__ overflow) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u8* q = raw + 5 * i;
+    u64 v = (u64)q[0] | ((u64)q[1] << 8) | ((u64)q[2] << 16) | ((u64)q[3] << 24) | ((u64)q[4] << 32);
+    if (out64) out64[i] = v;
+    if (out32) { if (v > 0xfffffffeull) { *overflow = 1; v = 0xfffffffeull; } out32[i] = (u32)v; }
 }
 __global__ void bwt_from_sa64(const u8* __restrict__ text, const u64* __restrict__ sa, u64 m, u8* __restrict__ bwt) {
     u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -367,7 +379,7 @@ int mmb_load_records(mmb_engine* e, const char* const* records, const size_t* n_
 
 int mmb_find(mmb_engine* e, const mmb_options* opts) {
     if (!e || !opts) return fail(MMB_ERR_ARG, "null argument");
-    if (!e->loaded) return fail(MMB_ERR_STATE, "mmb_find before a successful mmb_load_*");
+    if (!e->loaded || !e->text.text.p) return fail(MMB_ERR_STATE, "mmb_find before a successful mmb_load_*");
     return guarded([&] {
         MMB_CUDA(cudaSetDevice(e->device));
         cudaStream_t s = e->stream;
@@ -477,6 +489,86 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
     });
 }
 
+int mmb_find_from_arrays(mmb_engine* e, const uint64_t* doc_lengths, size_t ndocs, int use_revcomp, const uint8_t* sa5, const uint8_t* lcp5,
+                         const uint8_t* bwt, uint64_t entries, const mmb_options* opts) {
+    if (!e || !doc_lengths || !sa5 || !lcp5 || !bwt || !opts) return fail(MMB_ERR_ARG, "null argument");
+    return guarded([&] {
+        MMB_CUDA(cudaSetDevice(e->device));
+        cudaStream_t s = e->stream;
+        e->found = false; e->loaded = false;
+        if (ndocs < 2) throw Error(41, "Multiple FASTA inputs required. Perhaps split a multi-FASTA into multiple files?");
+        u32 N = (u32)ndocs;
+        // document layout from the lengths alone (RefBuilder(prefix), src/ref_builder.cpp:140-168 + build_bv :171-191); no text
+        TextLayout& tl = e->text;
+        tl.text.release(); tl.revcomp = use_revcomp != 0; tl.h_rec_pos.clear(); tl.h_rec_before.clear();
+        tl.h_doc_len.assign(doc_lengths, doc_lengths + ndocs); tl.h_doc_start.assign(ndocs + 1, 0); tl.total_bases = 0;
+        for (u32 d = 0; d < N; ++d) {
+            tl.h_doc_start[d + 1] = tl.h_doc_start[d] + (tl.revcomp ? 2 : 1) * (tl.h_doc_len[d] + 1);
+            tl.total_bases += tl.h_doc_len[d];
+        }
+        tl.n = tl.h_doc_start[N];
+        if (entries == 0 || entries > tl.n + 1) throw Error(42, "array length does not match the sequence lengths");
+        tl.doc_start.alloc(N + 1, s); tl.doc_len.alloc(N, s);
+        MMB_CUDA(cudaMemcpyAsync(tl.doc_start.p, tl.h_doc_start.data(), (N + 1) * 8, cudaMemcpyHostToDevice, s));
+        MMB_CUDA(cudaMemcpyAsync(tl.doc_len.p, tl.h_doc_len.data(), N * 8, cudaMemcpyHostToDevice, s));
+        MMB_CUDA(cudaStreamSynchronize(s));
+        e->records.assign(N, {});
+        build_doc_coarse(e);
+        e->stats = mmb_stats{}; e->stats.text_symbols = tl.n; e->stats.input_bases = tl.total_bases;
+
+        bool merge = false;
+        normalise(*opts, N, e->prm, e->mum_mode, merge);
+        e->prm.revcomp = tl.revcomp ? 1 : 0;
+        e->prm.doc_coarse = e->doc_coarse.p; e->prm.coarse_shift = e->coarse_shift;
+        Timer total(s), t(s);
+        total.start();
+        e->thresh_count = 0; e->thresh.release();
+        if (merge) { e->thresh_count = 2 * (tl.h_doc_len[0] + 1); e->thresh.alloc(e->thresh_count, s); e->thresh.zero(); }
+        u16* thresh = merge ? e->thresh.p : nullptr;
+        e->sa.sa.release(); e->sa.isa.release(); e->lcp.release(); e->bwt.release(); e->full_sa.release(); e->full_lcp.release();
+        e->route = 3;
+
+        u64 hi = e->prm.max_freq;
+        if (e->prm.max_doc_freq) { u64 bound = (u64)e->prm.max_doc_freq * N; hi = hi ? std::min(hi, bound) : bound; }
+        if (hi == 0) throw Error(31, "unbounded total frequency (-f 0 with -F 0) is not supported by the windowed interval scan");
+        u64 halo = std::min<u64>((hi + 8) & ~3ull, 1u << 22);
+        u64 tile = opts->tile_ranks ? opts->tile_ranks : (1ull << 26);
+        u64 cap = halo + std::min(tile, entries);
+        DevBuf<u8> raw_sa, raw_lcp, d_bwt; DevBuf<u64> d_sa; DevBuf<u32> d_lcp, overflow;
+        raw_sa.alloc(cap * 5, s); raw_lcp.alloc(cap * 5, s); d_bwt.alloc(cap + 64, s); d_sa.alloc(cap, s); d_lcp.alloc(cap + 64, s);
+        overflow.alloc(1, s); overflow.zero();
+        std::vector<MumTable> mparts; std::vector<MemTable> eparts;
+        t.start();
+        for (u64 start = 0; start < entries; start += tile) {
+            u64 first = std::min(halo, start), view0 = start - first, count = first + std::min(tile, entries - start);
+            MMB_CUDA(cudaMemcpyAsync(raw_sa.p, sa5 + view0 * 5, count * 5, cudaMemcpyHostToDevice, s));
+            MMB_CUDA(cudaMemcpyAsync(raw_lcp.p, lcp5 + view0 * 5, count * 5, cudaMemcpyHostToDevice, s));
+            MMB_CUDA(cudaMemcpyAsync(d_bwt.p, bwt + view0, count, cudaMemcpyHostToDevice, s));
+            MMB_CUDA(cudaMemsetAsync(d_bwt.p + count, 0, 64, s));
+            MMB_CUDA(cudaMemsetAsync(d_lcp.p + count, 0, 64 * 4, s));
+            MMB_LAUNCH(unpack5, ceil_div(count, 256), 256, 0, s, (const u8*)raw_sa.p, count, d_sa.p, (u32*)nullptr, overflow.p);
+            MMB_LAUNCH(unpack5, ceil_div(count, 256), 256, 0, s, (const u8*)raw_lcp.p, count, (u64*)nullptr, d_lcp.p, overflow.p);
+            Reports rep;
+            detect_intervals<u64>(d_lcp.p, d_sa.p, d_bwt.p, (const u8*)nullptr, count, first, e->prm, tl.doc_start.p, thresh, rep, s);
+            if (e->mum_mode) { MumTable part; mum_rows<u64>(rep, d_sa.p, e->prm, tl.doc_start.p, tl.doc_len.p, part, s); mparts.push_back(std::move(part)); }
+            else { MemTable part; mem_rows<u64>(rep, d_sa.p, e->prm, tl.doc_start.p, tl.doc_len.p, part, s); eparts.push_back(std::move(part)); }
+            MMB_CUDA(cudaStreamSynchronize(s));
+            ++e->stats.pfp_tiles;
+        }
+        if (to_host(overflow.p, 1, s)[0]) throw Error(75, "a common prefix longer than 2^32 symbols: not supported");
+        e->stats.ms_detect = t.stop();
+        t.start();
+        bool want_text = opts->want_text != 0;
+        if (e->mum_mode) { concat_mums(mparts, N, e->mums, s); if (want_text) mum_text(e->mums, N, s); }
+        else { concat_mems(eparts, e->mems, s); if (want_text) mem_text(e->mems, s); }
+        e->stats.ms_emit = t.stop();
+        e->stats.ms_total = total.stop();
+        e->stats.num_matches = e->mum_mode ? e->mums.count : e->mems.count;
+        e->stats.route = e->route;
+        e->loaded = true; e->found = true;
+    });
+}
+
 int mmb_get_stats(const mmb_engine* e, mmb_stats* out) {
     if (!e || !out) return fail(MMB_ERR_ARG, "null argument");
     *out = e->stats;
@@ -575,6 +667,7 @@ int mmb_copy_arrays(mmb_engine* e, uint64_t* sa, uint64_t* lcp, uint8_t* bwt) {
     if (!e || !e->found) return fail(MMB_ERR_STATE, "no results: call mmb_find first");
     return guarded([&] {
         cudaStream_t s = e->stream;
+        if (e->route == 3) throw Error(1, "the arrays were supplied by the caller (mmb_find_from_arrays)");
         if (e->route == 2) {
             if (!e->full_sa.p) throw Error(1, "the suffix stream was not kept: run mmb_find with keep_arrays = 1");
             u64 m = e->text.n + 1;
@@ -681,7 +774,7 @@ int mmb_profile_result(double* total_ms, uint64_t* launches) {
 }
 
 int mmb_copy_symbols(mmb_engine* e, uint8_t* dst) {
-    if (!e || !e->loaded) return fail(MMB_ERR_STATE, "no input loaded");
+    if (!e || !e->loaded || !e->text.text.p) return fail(MMB_ERR_STATE, "no input loaded");
     return guarded([&] { copy_out(e->text.text.p, dst, e->text.n, e->stream); MMB_CUDA(cudaStreamSynchronize(e->stream)); });
 }
 

@@ -1,0 +1,33 @@
+"""GPU twin of tests/test_arrays_in.py: `-a PREFIX` through the CUDA library and the drop-in executable (runs last: the file name sorts
+after the other GPU tests)."""
+import os
+import subprocess
+
+import pytest
+
+import util
+from mumemto_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+REF = os.path.join(util.ROOT, "oracle", "_ref", "mumemto_exec")
+EXE = os.path.join(util.ROOT, "mumemto_b200", "bin", "mumemto_exec")
+
+
+def test_arrays_in_gpu(cuda_lib, oracle_bin, tmp_path):
+    paths = util.appendix_a(str(tmp_path / "data"), N=5, L=20000, seed=42, identical_ends=True)
+    full = str(tmp_path / "full")
+    api.find_files(paths, full, arrays_out=True, _lib=cuda_lib)             # our own -A dump (byte-identical to the reference's, test_t2_golden[arrays])
+    for i, flags in enumerate(([], ["-k", "-1"], ["-f", "3", "-F", "100"], ["-M", "-n"], ["-b"])):
+        want = str(tmp_path / f"w{i}")
+        if os.path.exists(REF):
+            subprocess.run([REF, "-o", want, "-a", full, *flags], check=True, capture_output=True)
+        else:                                                               # t2's last rank closes nothing: the normal run is the same
+            util.run_cli(oracle_bin, ["-o", want, *flags, *paths])
+        g, c = str(tmp_path / f"g{i}"), str(tmp_path / f"c{i}")
+        st = api.find_arrays(full, g, tile_ranks=(0 if i % 2 else 50000), _lib=cuda_lib, **util.flags_to_kwargs(flags))
+        assert st["route"] == 3
+        assert util.outputs(g) == util.outputs(want), flags
+        r = subprocess.run([EXE, "-o", c, "-a", full, *flags], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert util.outputs(c) == util.outputs(want), flags
