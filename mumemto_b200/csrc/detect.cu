@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(TPB) detect_walk_kernel(const u32* __restrict_
             if (prm.merge && anchor_sa != ~0ull) thresh[anchor_sa] = (u16)min(max(before, cur), 65535u);
             if (left_differs) {
                 u32 slot = atomicAdd(count, 1u);
-                if (slot < cap) { Report r; r.key = (j << 20) | size; r.s = k; r.len = v; r.pad = 0; reports[slot] = r; }
+                if (slot < cap) { Report r; r.key = (j << 20) | min(size, 0xfffffu); r.s = k; r.len = v; r.pad = 0; reports[slot] = r; }
             }
         }
         v = before;
@@ -664,6 +664,14 @@ __global__ void report_keys(const Report* __restrict__ rep, u32 n, u64* __restri
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { keys[i] = rep[i].key; idx[i] = i; }
 }
+__global__ void report_size_keys(const Report* __restrict__ rep, u32 n, u64* __restrict__ keys, u32* __restrict__ idx) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { keys[i] = (rep[i].key >> 20) - rep[i].s; idx[i] = i; }
+}
+__global__ void report_rank_keys(const Report* __restrict__ rep, const u32* __restrict__ idx, u32 n, u64* __restrict__ keys) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = rep[idx[i]].key >> 20;
+}
 __global__ void report_gather(const Report* __restrict__ rep, const u32* __restrict__ idx, u32 n, Report* __restrict__ out) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = rep[idx[i]];
@@ -732,8 +740,9 @@ bool make_plan(const DetectParams& prm, bool& use_window, WindowPlan& pl) {
     u64 hi = prm.max_freq;
     if (prm.max_doc_freq) { u64 bound = (u64)prm.max_doc_freq * prm.ndocs; hi = hi ? std::min(hi, bound) : bound; }
     u64 lo = std::max<u64>(2, prm.num_distinct);
-    if (hi < lo) return false;
     use_window = false;
+    if (hi == 0) return true;                       // no limit at all: the leftward walk
+    if (hi < lo) return false;
     if (hi - lo + 1 > DW_MAX_SIZES) return true;
     pl.size_lo = (u32)lo; pl.size_hi = (u32)hi;
     pl.halo = ((u32)hi + 3) & ~3u; pl.span = pl.halo + DW_TILE;
@@ -751,8 +760,9 @@ template <class SAT>
 void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, const u8* text, u64 m, u64 j_first, const DetectParams& prm,
                       const u64* d_doc_start, u16* thresh, Reports& out, cudaStream_t s) {
     // the leftward walk is bounded by max_freq, or else by max_doc_freq * ndocs (a document overflows); with neither it is unbounded
-    if (prm.max_freq == 0 && prm.max_doc_freq == 0)
-        throw Error(31, "unbounded total frequency (-f 0 with -F 0) is not supported by the windowed interval scan");
+    const bool unbounded = prm.max_freq == 0 && prm.max_doc_freq == 0;
+    if (unbounded && !(prm.whole_stream && j_first == 0))
+        throw Error(31, "unbounded total frequency (-f 0 with -F 0) needs the whole suffix stream in one view (direct route, or one tile)");
     if (prm.max_freq >= (1u << 20)) throw Error(32, "maximum total frequency must be below 2^20");
     if (prm.ndocs > 1024) throw Error(33, "more than 1024 input sequences are not supported");
     out.count = 0;
@@ -762,7 +772,7 @@ void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, const u8* te
     {
         u64 hi = prm.max_freq;
         if (prm.max_doc_freq) { u64 bound = (u64)prm.max_doc_freq * prm.ndocs; hi = hi ? std::min(hi, bound) : bound; }
-        a.use_chunk = !getenv("MMB_FORCE_WALK") && make_chunk_plan(std::max<u64>(2, prm.num_distinct), hi, a.cplan);
+        a.use_chunk = hi != 0 && !getenv("MMB_FORCE_WALK") && make_chunk_plan(std::max<u64>(2, prm.num_distinct), hi, a.cplan);
     }
     DevBuf<u32> d_count; d_count.alloc(1, s);
     u64 cap = std::max<u64>(1u << 16, (m - std::min(m, j_first)) / 64);
@@ -783,8 +793,17 @@ void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, const u8* te
     if (n == 0) return;
     DevBuf<u64> ka, kb; DevBuf<u32> ia, ib;
     ka.alloc(n, s); kb.alloc(n, s); ia.alloc(n, s); ib.alloc(n, s);
-    MMB_LAUNCH(report_keys, ceil_div(n, 256), 256, 0, s, raw.p, n, ka.p, ia.p);
-    prim::sort_pairs(ka.p, kb.p, ia.p, ib.p, n, 0, 64, s);
+    if (!unbounded) {
+        MMB_LAUNCH(report_keys, ceil_div(n, 256), 256, 0, s, raw.p, n, ka.p, ia.p);
+        prim::sort_pairs(ka.p, kb.p, ia.p, ib.p, n, 0, 64, s);
+    } else {
+        // interval sizes may exceed the 20 bits the key has for them: stable sort by size first, then by closing rank
+        MMB_LAUNCH(report_size_keys, ceil_div(n, 256), 256, 0, s, raw.p, n, ka.p, ia.p);
+        prim::sort_pairs(ka.p, kb.p, ia.p, ib.p, n, 0, 64, s);
+        MMB_LAUNCH(report_rank_keys, ceil_div(n, 256), 256, 0, s, raw.p, (const u32*)ib.p, n, ka.p);
+        prim::sort_pairs(ka.p, kb.p, ib.p, ia.p, n, 0, 44, s);
+        ia.swap(ib);
+    }
     MMB_LAUNCH(report_gather, ceil_div(n, 256), 256, 0, s, raw.p, ib.p, n, out.rep.p);
 }
 

@@ -16,6 +16,9 @@ struct DetectParams {
     // entries, built by the engine when the text is loaded); nullptr = binary search over doc_start
     const u16* doc_coarse;
     u32 coarse_shift;
+    // the arrays handed to detect_intervals are the WHOLE suffix stream (not a tile): required for max_freq == 0 && max_doc_freq == 0,
+    // where an interval may be of any size
+    int whole_stream;
 };
 
 // One reported interval [s, e] of ranks, all suffixes sharing a prefix of length len.  key = (e + 1) << 20 | order within the

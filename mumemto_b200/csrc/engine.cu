@@ -406,9 +406,13 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
         // dictionary (stages 1-3 of the PFP route) are cheap, and the route pays off when the dictionary is a small fraction of the text
         PfpIndex ix; PfpParse pp;
         bool parsed = false;
-        bool use_pfp = opts->route == 2 || (opts->route == 0 && n + 1 >= (1ull << 31));
+        const bool unbounded = e->prm.max_freq == 0 && e->prm.max_doc_freq == 0;      // -f 0 without -F: intervals of any size
+        if (unbounded && (opts->route == 2 || n + 1 >= (1ull << 31)))
+            throw Error(31, "unbounded total frequency (-f 0 with -F 0) needs the whole suffix stream on the device: direct route only (text below 2^31 symbols)");
+        e->prm.whole_stream = 0;
+        bool use_pfp = !unbounded && (opts->route == 2 || (opts->route == 0 && n + 1 >= (1ull << 31)));
         Timer tparse(s); float ms_parse = 0;
-        if (opts->route == 0 && !use_pfp && n >= (1u << 16)) {
+        if (opts->route == 0 && !use_pfp && !unbounded && n >= (1u << 16)) {
             tparse.start();
             pfp_parse(e->text.text.p, n, ix, pp, s); parsed = true;
             ms_parse = tparse.stop();
@@ -427,6 +431,7 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
             e->stats.ms_lcp = t.stop();
             e->sa.isa.release();
             t.start();
+            e->prm.whole_stream = 1;
             detect_intervals<u32>(e->lcp.p, e->sa.sa.p, (const u8*)nullptr, e->text.text.p, e->sa.m, 0, e->prm, e->text.doc_start.p, thresh, e->reports, s);
             MMB_CUDA(cudaStreamSynchronize(s));
             e->stats.ms_detect = t.stop();
@@ -530,9 +535,13 @@ int mmb_find_from_arrays(mmb_engine* e, const uint64_t* doc_lengths, size_t ndoc
 
         u64 hi = e->prm.max_freq;
         if (e->prm.max_doc_freq) { u64 bound = (u64)e->prm.max_doc_freq * N; hi = hi ? std::min(hi, bound) : bound; }
-        if (hi == 0) throw Error(31, "unbounded total frequency (-f 0 with -F 0) is not supported by the windowed interval scan");
         u64 halo = std::min<u64>((hi + 8) & ~3ull, 1u << 22);
         u64 tile = opts->tile_ranks ? opts->tile_ranks : (1ull << 26);
+        if (hi == 0) {                                  // no frequency limit: only with the whole stream in one view
+            if (entries >= (1ull << 31)) throw Error(31, "unbounded total frequency (-f 0 with -F 0) needs the whole suffix stream in one view (below 2^31 ranks)");
+            tile = entries; halo = 0;
+        }
+        e->prm.whole_stream = tile >= entries ? 1 : 0;
         u64 cap = halo + std::min(tile, entries);
         DevBuf<u8> raw_sa, raw_lcp, d_bwt; DevBuf<u64> d_sa; DevBuf<u32> d_lcp, overflow;
         raw_sa.alloc(cap * 5, s); raw_lcp.alloc(cap * 5, s); d_bwt.alloc(cap + 64, s); d_sa.alloc(cap, s); d_lcp.alloc(cap + 64, s);

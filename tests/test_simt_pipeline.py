@@ -118,8 +118,8 @@ def test_simt_errors(simt_lib, tmp_path):
     open(tmp_path / "empty.fa", "w").write(">only a header\n")
     with pytest.raises(MumemtoError, match="Empty input file"):
         api.find_files([p[0], str(tmp_path / "empty.fa")], str(tmp_path / "x"), _lib=simt_lib)
-    with pytest.raises(MumemtoError, match="not supported"):
-        api.find_files(p, str(tmp_path / "x"), rare_freq=0, max_mem_freq=0, _lib=simt_lib)
+    with pytest.raises(MumemtoError, match="direct route only"):         # no frequency limit at all: needs the whole stream in one view
+        api.find_files(p, str(tmp_path / "x"), rare_freq=0, max_mem_freq=0, route="pfp", _lib=simt_lib)
 
 
 @pytest.mark.parametrize("parts", [[[0, 1, 2], [0, 3]], [[0, 1], [0, 2], [0, 3]], [[0, 3, 1], [0, 2]]])
@@ -169,6 +169,22 @@ def test_simt_walk_kernel_fallback(simt_lib, oracle_bin, small, tmp_path, flags,
     """The leftward-walk detector (used when more than 64 interval sizes can qualify) must agree with the windowed one."""
     monkeypatch.setenv("MMB_FORCE_WALK", "1")
     both(simt_lib, oracle_bin, str(tmp_path), small, flags)
+
+
+def test_simt_unbounded_frequency(simt_lib, oracle_bin, small, tmp_path):
+    """-f 0 without -F: LCP intervals of any size; includes a collection with a 1200-fold repeat."""
+    rng = np.random.default_rng(17)
+    unit, body = util.random_dna(rng, 37), util.random_dna(rng, 3000)
+    docs = ["A" * 900 + body + unit * 40 + "ACGT" * 100 + body[:700] + "G" * 450,
+            "A" * 300 + util.mutate(rng, body, 0.01) + unit * 26 + "C" * 150 + body[200:900],
+            util.mutate(rng, body, 0.02) + "AC" * 270 + unit * 12 + "A" * 100]
+    rep = [util.write_fasta(str(tmp_path / f"r{i}.fa"), [(f"r{i}", s)], width=77) for i, s in enumerate(docs)]
+    for name, paths in (("small", small), ("rep", rep)):
+        for i, flags in enumerate((["-f", "0"], ["-f", "0", "-k", "2"], ["-f", "0", "-k", "2", "-l", "12", "-r"])):
+            os.makedirs(str(tmp_path / f"{name}{i}"), exist_ok=True)
+            out = both(simt_lib, oracle_bin, str(tmp_path / f"{name}{i}"), paths, flags)
+            if name == "rep" and i == 0:
+                assert max(len(l.split(b"\t")[1].split(b",")) for l in out[".mems"].splitlines()) > 1000
 
 
 @pytest.mark.parametrize("flags", [[], ["-k", "-1"], ["-f", "3", "-F", "100"], ["-M", "-n"]])

@@ -31,3 +31,21 @@ def test_arrays_in_gpu(cuda_lib, oracle_bin, tmp_path):
         r = subprocess.run([EXE, "-o", c, "-a", full, *flags], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-2000:]
         assert util.outputs(c) == util.outputs(want), flags
+
+
+def test_unbounded_frequency_gpu(cuda_lib, oracle_bin, tmp_path):
+    """-f 0 without -F on the GPU: the leftward-walk detector over the whole stream (direct route), two-pass report order."""
+    import numpy as np
+    rng = np.random.default_rng(17)
+    unit, body = util.random_dna(rng, 37), util.random_dna(rng, 3000)
+    docs = ["A" * 900 + body + unit * 40 + "ACGT" * 100 + body[:700] + "G" * 450,
+            "A" * 300 + util.mutate(rng, body, 0.01) + unit * 26 + "C" * 150 + body[200:900],
+            util.mutate(rng, body, 0.02) + "AC" * 270 + unit * 12 + "A" * 100]
+    rep = [util.write_fasta(str(tmp_path / f"r{i}.fa"), [(f"r{i}", s)], width=77) for i, s in enumerate(docs)]
+    t2 = util.appendix_a(str(tmp_path / "t2"), N=5, L=20000, seed=42, identical_ends=True)
+    for name, paths in (("t2", t2), ("rep", rep)):
+        for i, flags in enumerate((["-f", "0"], ["-f", "0", "-k", "2", "-l", "12"])):
+            o, g = str(tmp_path / f"o_{name}{i}"), str(tmp_path / f"g_{name}{i}")
+            util.run_cli(oracle_bin, ["-o", o, *flags, *paths])
+            api.find_files(paths, g, _lib=cuda_lib, **util.flags_to_kwargs(flags))
+            assert util.outputs(g) == util.outputs(o), (name, flags)
