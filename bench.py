@@ -202,30 +202,76 @@ def run_reference(exe, sample, repeats, warmup):
     return float(np.mean(times))
 
 
+def run_reference_partitioned(exe, merge_exe, sample, procs, repeats, warmup):
+    """The reference's own way to use many cores (README "mumemto merge", mumemto/merge_mums.py:171-192): split the collection into
+    partitions that share document 0, run one `mumemto_exec -M -n` PROCESS per partition concurrently, then `anchor_merge` the partition
+    outputs.  The merged .mums is set-equal to a direct run on the whole collection.  Returns (seconds per run, partitions)."""
+    imgs = make_collection(sample, seed=1)
+    N = len(imgs)
+    procs = max(2, min(procs, N - 1))
+    times = []
+    with tempfile.TemporaryDirectory() as d:
+        paths = []
+        for i, im in enumerate(imgs):
+            p = os.path.join(d, f"h{i}.fa"); im.tofile(p); paths.append(p)
+        groups = [[paths[0]] + paths[1 + g::procs] for g in range(procs)]
+        for it in range(warmup + repeats):
+            t0 = time.perf_counter()
+            running = [subprocess.Popen([exe, "-o", os.path.join(d, f"part{g}"), "-M", "-n", *grp], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                       for g, grp in enumerate(groups)]
+            for pr in running:
+                if pr.wait() != 0:
+                    raise RuntimeError("a reference partition run failed")
+            subprocess.run([merge_exe, *[os.path.join(d, f"part{g}.mums") for g in range(procs)], "-o", os.path.join(d, "merged")],
+                           check=True, capture_output=True)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    return float(np.mean(times)), procs
+
+
+def reference_best(spec, repeats, warmup):
+    """Both ways the reference can run the path on this host: one process (it has no threads), and its partition-merge workflow with
+    one process per core.  Returns the faster one as (bases/s, seconds per run, cores, kind, sample note, both modes)."""
+    exe, kind = reference_exe()
+    sample, note = bounded_sample(spec)
+    t1 = run_reference(exe, sample, repeats, warmup)
+    modes = {"single_process": {"value": sample["N"] * sample["L"] / t1, "cores": 1, "seconds": t1, "sample": note}}
+    best = (modes["single_process"]["value"], t1, 1, kind,
+            note + "; reference sources compiled unmodified with sdsl/gsacak stand-ins (oracle/ref_shims), 1 thread: the reference has no threads or OpenMP")
+    merge_exe = os.path.join(ROOT, "oracle", "_ref", "anchor_merge")
+    cores = os.cpu_count() or 1
+    if kind == "reference" and os.path.exists(merge_exe) and cores >= 4 and spec["N"] >= 5 and spec["kind"] == "pangenome":
+        big, bnote = bounded_sample(spec, budget_bases=8_000_000 * min(cores, spec["N"] - 1) // 2)
+        try:
+            tp, procs = run_reference_partitioned(exe, merge_exe, big, cores, repeats, warmup)
+            vp = big["N"] * big["L"] / tp
+            modes["partition_processes"] = {"value": vp, "cores": procs, "seconds": tp, "sample": bnote}
+            if vp > best[0]:
+                best = (vp, tp, procs, kind, bnote + f"; the reference's own parallel workflow: {procs} concurrent mumemto_exec -M -n processes (one partition each, "
+                        "sharing document 0) + anchor_merge; reference sources compiled unmodified with sdsl/gsacak stand-ins")
+        except Exception as ex:      # the single-process number stands
+            modes["partition_processes"] = {"error": str(ex)[:200]}
+    return best + (modes,)
+
+
 def reference_arm(args, spec, rank):
     """The reference's own CPU implementation of the path, timed on the host cores (rank 0 only; the other ranks exit)."""
     if rank != 0:
         return
-    exe, kind = reference_exe()
-    sample, note = bounded_sample(spec)
-    t = run_reference(exe, sample, args.steps, min(args.warmup, 1))
-    v = sample["N"] * sample["L"] / t
-    desc = "reference sources compiled unmodified with sdsl/gsacak stand-ins (oracle/ref_shims), 1 thread: the reference has no threads or OpenMP"
+    v, t, cores, kind, note, modes = reference_best(spec, args.steps, min(args.warmup, 1))
     line = {"impl": "reference", "metric": "input bases/sec end-to-end (FASTA->.mums)", "value": v, "unit": "bases/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "config": {"workload": spec["desc"], "name": args.workload},
-            "cpu_baseline": {"value": v, "unit": "bases/s", "cores": 1, "kind": kind, "sample": note + "; " + desc},
-            "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "cpu_baseline": {"value": v, "unit": "bases/s", "cores": cores, "kind": kind, "sample": note},
+            "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "reference_modes": modes}
     print(json.dumps(line))
 
 
 def cpu_baseline_sample(spec):
-    """Bounded CPU run beside the GPU number (rank 0, N = 1): the reference build on (a sample of) the workload."""
-    exe, kind = reference_exe()
-    sample, note = bounded_sample(spec)
-    dt = run_reference(exe, sample, 1, 0)
-    return {"value": sample["N"] * sample["L"] / dt, "unit": "bases/s", "cores": 1, "kind": kind,
-            "sample": note + "; 1 thread (the reference is single-threaded); sdsl/gsacak replaced by stand-ins", "seconds": dt}
+    """Bounded CPU run beside the GPU number (rank 0, N = 1): the reference build on (a sample of) the workload, in the faster of its
+    two modes (one process; one process per core through its partition-merge workflow)."""
+    v, t, cores, kind, note, modes = reference_best(spec, 1, 0)
+    return {"value": v, "unit": "bases/s", "cores": cores, "kind": kind, "sample": note, "seconds": t, "modes": modes}
 
 
 def main():
