@@ -143,6 +143,31 @@ def test_simt_anchor_merge(simt_lib, oracle_bin, small, tmp_path, parts):
         assert open(tmp_path / "gm.athresh", "rb").read() == open(tmp_path / "all.athresh", "rb").read()
 
 
+@pytest.mark.parametrize("minlen", [9, 31])
+def test_simt_anchor_merge_ignores_min_match_len(simt_lib, oracle_bin, small, tmp_path, minlen):
+    """Quirk Q7: the merge keeps a match iff it is longer than the next-best threshold and at least 20 long -- hard-coded
+    (src/merge_candidates.cpp:141), whatever -l the partitions were computed with.  Checked against the reference's own anchor_merge
+    when oracle/_ref is built, else the oracle's fold."""
+    ref_merge = os.path.join(util.ROOT, "oracle", "_ref", "anchor_merge")
+    names = []
+    for i, idx in enumerate(([0, 1, 2], [0, 3])):
+        g = str(tmp_path / f"g{i}")
+        api.find_files([small[j] for j in idx], g, merge=True, anchor_merge=True, min_match_len=minlen, _lib=simt_lib)
+        names.append(g + ".mums")
+    api.merge_files(names, str(tmp_path / "gm"), _lib=simt_lib)
+    if os.path.exists(ref_merge):
+        import subprocess
+        subprocess.run([ref_merge, *names, "-o", str(tmp_path / "om")], check=True, capture_output=True)
+    else:
+        util.run_cli(oracle_bin, ["merge", *names, "-o", str(tmp_path / "om")])
+    got = util.outputs(str(tmp_path / "gm"))
+    assert got == util.outputs(str(tmp_path / "om"))
+    lens = [int(l.split(b"\t")[0]) for l in got[".mums"].splitlines()]
+    assert lens and min(lens) >= 20
+    if minlen < 20:         # the partitions did hold shorter matches
+        assert any(int(l.split("\t")[0]) < 20 for n in names for l in open(n))
+
+
 @pytest.mark.parametrize("block_order", [0, 1, 2])
 def test_simt_repeats_all_group_size_classes(simt_lib, oracle_bin, tmp_path, block_order):
     """Low-complexity and tandem-repeat inputs: the doubling rounds see groups of every size class (sub-warp ... warp x8, block sort,
