@@ -303,6 +303,7 @@ def main():
 
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's banner / debug lines must not mix with the JSON line on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.current_stream()
     eng = Engine(device=local, stream=stream.cuda_stream)
