@@ -407,6 +407,45 @@ __device__ __forceinline__ void verify_mum_candidate(u64 cj, u32 cs, u32 cv, u32
     }
 }
 
+// The same check from a document-id byte per rank (StreamTile::doc, experimental): count bytes instead of count gathered SA values and
+// lookups; SA is read once, by the lane that holds document 0, for the -M threshold.  leftmax must be known (0 / 1).
+template <class SAT, int W>
+__device__ __forceinline__ void verify_mum_candidate_docs(u64 cj, u32 cs, u32 cv, u32 ccur, u32 cbefore, int leftmax, const SAT* __restrict__ sa,
+                                                          const u8* __restrict__ docs, const DetectParams& prm, Report* __restrict__ reports,
+                                                          u32 cap, u32* __restrict__ count, u16* __restrict__ thresh, u32 lane) {
+    const u64 s0 = cj - cs;
+    u64 bits[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) bits[w] = 0;
+    u64 anchor_rank = ~0ull;
+    bool bad = false;                                   // a rank without a document (the sentinel) cannot be part of a match
+    for (u32 t = lane; t < cs; t += 32) {
+        u32 dd = docs[s0 + t];
+        if (dd >= prm.ndocs) { bad = true; continue; }
+        bits[(W == 1) ? 0 : (dd >> 6)] |= 1ull << (dd & 63);
+        if (dd == 0) anchor_rank = s0 + t;
+    }
+    u32 distinct = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+#ifdef MMB_SIMT
+        u64 bb = bits[w];
+        for (u32 dd = 16; dd > 0; dd >>= 1) bb |= __shfl_xor_sync(0xffffffffu, bb, dd);
+        distinct += (u32)__popcll(bb);
+#else
+        distinct += (u32)__popc(__reduce_or_sync(0xffffffffu, (u32)bits[w])) + (u32)__popc(__reduce_or_sync(0xffffffffu, (u32)(bits[w] >> 32)));
+#endif
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (!bad && distinct == cs && distinct >= prm.num_distinct) {          // every document at most once
+        if (prm.merge && anchor_rank != ~0ull) thresh[(u64)sa[anchor_rank]] = (u16)min(max(cbefore, ccur), 65535u);
+        if (leftmax && lane == 0) {
+            u32 slot = atomicAdd(count, 1u);
+            if (slot < cap) { Report rp; rp.key = (cj << 20) | cs; rp.s = s0; rp.len = cv; rp.pad = 0; reports[slot] = rp; }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ chunked window-minimum detector
 // Same test as detect_window_kernel, but the minimum of the smallest window (size_lo - 1 entries ending at j-1) costs O(1) per rank
 // instead of one shared-memory pass per power of two: the staged tile is cut into chunks of C = (size_lo - 1) | 1 ranks (C >= the
@@ -435,7 +474,7 @@ template <class SAT, int W, int P, bool FAST>
 __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restrict__ lcp, const SAT* __restrict__ sa, const u8* __restrict__ bwt,
                                                              const u8* __restrict__ text, u64 m, u64 j_first, DetectParams prm, ChunkPlan plan,
                                                              const u64* __restrict__ doc_start_g, Report* __restrict__ reports, u32 cap,
-                                                             u32* __restrict__ count, u16* __restrict__ thresh) {
+                                                             u32* __restrict__ count, u16* __restrict__ thresh, const u8* __restrict__ docs) {
     MMB_DYN_SMEM(u64, smem64);
     u64* bar = smem64;                                  // 2 mbarriers (16 bytes)
     u64* doc_start = smem64 + 2;                        // ndocs + 1 (+1 pad to keep 16-byte alignment)
@@ -560,7 +599,8 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
                         u64 cj = __shfl_sync(0xffffffffu, jc, src);
                         u32 cv = __shfl_sync(0xffffffffu, vv, src), ccur = __shfl_sync(0xffffffffu, curc, src), cbef = __shfl_sync(0xffffffffu, befc, src);
                         int clm = __shfl_sync(0xffffffffu, lmc, src);
-                        verify_mum_candidate<SAT, W>(cj, S, cv, ccur, cbef, clm, sa, bwt, text, doc_start, prm, reports, cap, count, thresh, lane);
+                        if (docs) verify_mum_candidate_docs<SAT, W>(cj, S, cv, ccur, cbef, clm, sa, docs, prm, reports, cap, count, thresh, lane);
+                        else verify_mum_candidate<SAT, W>(cj, S, cv, ccur, cbef, clm, sa, bwt, text, doc_start, prm, reports, cap, count, thresh, lane);
                     }
                 }
             }
@@ -681,6 +721,7 @@ struct DetectArgs {
     const u32* lcp; const u8* bwt; const u8* text; u64 m; u64 j_first; DetectParams prm; const u64* d_doc_start; Report* rep; u32 cap; u32* count; u16* thresh;
     bool use_window; WindowPlan plan;
     bool use_chunk = false; ChunkPlan cplan;
+    const u8* docs = nullptr;
 };
 
 template <class SAT, int W, int P>
@@ -693,7 +734,7 @@ void launch_detect(const SAT* sa, const DetectArgs& a, cudaStream_t s) {
         if (smem > 48 * 1024) MMB_CUDA(cudaFuncSetAttribute(detect_chunk_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
         u64 per_block = (u64)(a.cplan.rounds * DC_TPB - a.cplan.halo_chunks) * a.cplan.chunk;
-        MMB_LAUNCH(detect_chunk_k, ceil_div(a.m, per_block), DC_TPB, smem, s, a.lcp, sa, a.bwt, a.text, a.m, a.j_first, a.prm, a.cplan, a.d_doc_start, a.rep, a.cap, a.count, a.thresh);
+        MMB_LAUNCH(detect_chunk_k, ceil_div(a.m, per_block), DC_TPB, smem, s, a.lcp, sa, a.bwt, a.text, a.m, a.j_first, a.prm, a.cplan, a.d_doc_start, a.rep, a.cap, a.count, a.thresh, fast ? a.docs : (const u8*)nullptr);
     } else if (a.use_window) {
         auto detect_window_k = detect_window_kernel<SAT, W, P>;
         size_t smem = 16 + (size_t)((a.prm.ndocs + 2) & ~1u) * 8 + (size_t)a.plan.span * 4 * (2 + a.plan.nkept);
@@ -758,7 +799,7 @@ bool make_plan(const DetectParams& prm, bool& use_window, WindowPlan& pl) {
 
 template <class SAT>
 void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, const u8* text, u64 m, u64 j_first, const DetectParams& prm,
-                      const u64* d_doc_start, u16* thresh, Reports& out, cudaStream_t s) {
+                      const u64* d_doc_start, u16* thresh, Reports& out, cudaStream_t s, const u8* docs) {
     // the leftward walk is bounded by max_freq, or else by max_doc_freq * ndocs (a document overflows); with neither it is unbounded
     const bool unbounded = prm.max_freq == 0 && prm.max_doc_freq == 0;
     if (unbounded && !(prm.whole_stream && j_first == 0))
@@ -768,6 +809,7 @@ void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, const u8* te
     out.count = 0;
     DetectArgs a;
     a.lcp = lcp; a.bwt = bwt; a.text = text; a.m = m; a.j_first = j_first; a.prm = prm; a.d_doc_start = d_doc_start; a.thresh = thresh;
+    a.docs = prm.ndocs < 255 ? docs : nullptr;
     if (m < 2 || !make_plan(prm, a.use_window, a.plan)) { out.rep.alloc(0, s); return; }
     {
         u64 hi = prm.max_freq;
@@ -807,7 +849,7 @@ void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, const u8* te
     MMB_LAUNCH(report_gather, ceil_div(n, 256), 256, 0, s, raw.p, ib.p, n, out.rep.p);
 }
 
-template void detect_intervals<u32>(const u32*, const u32*, const u8*, const u8*, u64, u64, const DetectParams&, const u64*, u16*, Reports&, cudaStream_t);
-template void detect_intervals<u64>(const u32*, const u64*, const u8*, const u8*, u64, u64, const DetectParams&, const u64*, u16*, Reports&, cudaStream_t);
+template void detect_intervals<u32>(const u32*, const u32*, const u8*, const u8*, u64, u64, const DetectParams&, const u64*, u16*, Reports&, cudaStream_t, const u8*);
+template void detect_intervals<u64>(const u32*, const u64*, const u8*, const u8*, u64, u64, const DetectParams&, const u64*, u16*, Reports&, cudaStream_t, const u8*);
 
 }  // namespace mmb

@@ -39,9 +39,10 @@ struct Reports {
 // read from text[sa - 1] for the few ranks that need it.  lcp must be readable (zero) for 64 entries past m.
 // The arrays are a view of the suffix stream (the whole stream, or one tile with a halo in front); only closing ranks j >= j_first
 // of the view are examined, and report keys / starts are view indices.
+// docs (optional): one document-id byte per rank of the view (StreamTile::doc); the strict-MUM path then checks candidates from them.
 template <class SAT>
 void detect_intervals(const u32* lcp, const SAT* sa, const u8* bwt, const u8* text, u64 m, u64 j_first, const DetectParams& prm,
-                      const u64* d_doc_start, u16* thresh, Reports& out, cudaStream_t s);
+                      const u64* d_doc_start, u16* thresh, Reports& out, cudaStream_t s, const u8* docs = nullptr);
 
 struct MumTable {           // strict / partial multi-MUMs that survive the strand rules, in output order
     u64 count = 0;

@@ -462,7 +462,7 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
                 void consume(const StreamTile& tile) override {
                     ++tiles;
                     Reports rep;
-                    detect_intervals<u64>(tile.lcp, tile.sa, tile.bwt, e->text.text.p, tile.count, tile.first, e->prm, e->text.doc_start.p, thresh, rep, s);
+                    detect_intervals<u64>(tile.lcp, tile.sa, tile.bwt, e->text.text.p, tile.count, tile.first, e->prm, e->text.doc_start.p, thresh, rep, s, tile.doc);
                     if (e->mum_mode) { MumTable part; mum_rows<u64>(rep, tile.sa, e->prm, e->text.doc_start.p, e->text.doc_len.p, part, s); mparts.push_back(std::move(part)); }
                     else { MemTable part; mem_rows<u64>(rep, tile.sa, e->prm, e->text.doc_start.p, e->text.doc_len.p, part, s); eparts.push_back(std::move(part)); }
                     if (keep) {
@@ -476,7 +476,10 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
             consumer.e = e; consumer.s = s; consumer.thresh = thresh; consumer.keep = opts->keep_arrays != 0;
             if (consumer.keep) { e->full_sa.alloc(n + 1, s); e->full_lcp.alloc(n + 1, s); }
             t.start();
-            stream_suffixes(e->text.text.p, ix, tile_ranks, halo, consumer, s);
+            // experimental (not yet measured on a GPU, off by default): a document-id byte per rank for the -M candidate checks
+            DocLookup dl{e->doc_coarse.p, e->coarse_shift, e->text.doc_start.p, N};
+            const bool doc_stream = merge && N < 255 && getenv("MMB_DOC_STREAM") && atoi(getenv("MMB_DOC_STREAM"));
+            stream_suffixes(e->text.text.p, ix, tile_ranks, halo, consumer, s, doc_stream ? &dl : nullptr);
             e->stats.ms_detect = t.stop();
             e->stats.pfp_tiles = consumer.tiles;
             t.start();

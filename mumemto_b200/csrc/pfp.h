@@ -65,11 +65,17 @@ struct StreamTile {
     const u64* sa = nullptr;        // [count]
     const u32* lcp = nullptr;       // [count + 64], zero padded
     const u8* bwt = nullptr;        // [count] symbol preceding each suffix (0 for text position 0)
+    const u8* doc = nullptr;        // [count] document of each suffix (255 for the sentinel), only when stream_suffixes was given a DocLookup
     bool last = false;
 };
 
+// Optional: have every tile carry one document-id byte per rank (collections of at most 254 documents).  Experimental (MMB_DOC_STREAM=1):
+// with -M every interval of the right size needs a document check, which then reads count bytes instead of gathering count SA values.
+struct DocLookup { const u16* coarse; u32 shift; const u64* doc_start; u32 ndocs; };
+
 // Calls consume(tile) for consecutive tiles of about tile_ranks ranks, each carrying `halo` ranks of overlap.
 struct TileConsumer { virtual void consume(const StreamTile& t) = 0; virtual ~TileConsumer() {} };
-void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 halo, TileConsumer& consumer, cudaStream_t s);
+void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 halo, TileConsumer& consumer, cudaStream_t s,
+                     const DocLookup* docs = nullptr);
 
 }  // namespace mmb

@@ -325,9 +325,20 @@ __global__ void bwt_of_groups(const u64* __restrict__ groups, u32 k0, const u64*
     for (u64 e = (u64)blockIdx.y * blockDim.x + threadIdx.x; e < G; e += (u64)gridDim.y * blockDim.x) { u64 p = sa[base + e]; bwt[base + e] = p ? text[p - 1] : (u8)0; }
 }
 
+// document of every rank of the finished view (DocLookup): coarse table, then forward while the next document starts at or before p
+__global__ void __launch_bounds__(TPB) tile_docs(const u64* __restrict__ sa, u64 count, DocLookup L, u64 n, u8* __restrict__ doc) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= count) return;
+    u64 p = sa[r];
+    if (p >= n) { doc[r] = 255; return; }
+    u32 d = L.coarse[p >> L.shift];
+    while (L.doc_start[d + 1] <= p) ++d;
+    doc[r] = (u8)d;
+}
+
 }  // namespace
 
-void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 halo, TileConsumer& consumer, cudaStream_t s) {
+void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 halo, TileConsumer& consumer, cudaStream_t s, const DocLookup* docs) {
     u32 dsize = ix.dsize;
     PhaseTimer* pt = new PhaseTimer("stream members+bounds", s);
     // ---- members (owned dictionary suffixes in suffix order)
@@ -380,6 +391,8 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
     DevBuf<u64> sa, halo_sa, small, large; DevBuf<u32> lcp, key, halo_lcp, counts; DevBuf<u8> bwt, halo_bwt;
     sa.alloc(cap, s); lcp.alloc(cap + 64, s); key.alloc(cap, s); bwt.alloc(cap + 64, s); halo_sa.alloc(halo + 1, s); halo_lcp.alloc(halo + 1, s);
     halo_bwt.alloc(halo + 1, s); counts.alloc(2, s);
+    DevBuf<u8> doc;
+    if (docs) doc.alloc(cap, s);
     const int expand_variant = getenv("MMB_EXPAND_VARIANT") ? atoi(getenv("MMB_EXPAND_VARIANT")) : 0;
     u64 rank_next = 0;                  // global rank of the first new entry of the coming tile
     u64 halo_have = 0;
@@ -441,6 +454,10 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
         StreamTile tile;
         tile.rank0 = first_tile ? 0 : rank_next - halo_have;
         tile.count = count; tile.first = first_tile ? 0 : halo_have; tile.sa = sa.p; tile.lcp = lcp.p; tile.bwt = bwt.p; tile.last = last_tile;
+        if (docs) {
+            MMB_LAUNCH(tile_docs, ceil_div(count, TPB), TPB, 0, s, (const u64*)sa.p, count, *docs, ix.n, doc.p);
+            tile.doc = doc.p;
+        }
         delete tt;
         { PhaseTimer ct("stream tile: consume", s); consumer.consume(tile); }
         // stash the tail as the next tile's halo

@@ -212,6 +212,14 @@ def test_simt_unbounded_frequency(simt_lib, oracle_bin, small, tmp_path):
                 assert max(len(l.split(b"\t")[1].split(b",")) for l in out[".mems"].splitlines()) > 1000
 
 
+def test_simt_doc_stream_switch(simt_lib, oracle_bin, small, tmp_path, monkeypatch):
+    """MMB_DOC_STREAM=1 (experimental): with -M the tiles carry a document-id byte per rank and candidates are checked from it."""
+    monkeypatch.setenv("MMB_DOC_STREAM", "1")
+    for i, (flags, tile) in enumerate(((["-M", "-n"], 700), (["-M", "-n", "-l", "12"], 100000), (["-M", "-n", "-r"], 900))):
+        os.makedirs(str(tmp_path / f"d{i}"), exist_ok=True)
+        both_pfp(simt_lib, oracle_bin, str(tmp_path / f"d{i}"), small, flags, tile_ranks=tile)
+
+
 @pytest.mark.parametrize("flags", [[], ["-k", "-1"], ["-f", "3", "-F", "100"], ["-M", "-n"]])
 def test_simt_window_kernel(simt_lib, oracle_bin, small, tmp_path, flags, monkeypatch):
     """The power-of-two window-minimum detector (the default when the smallest interval size exceeds 128) must agree with the chunked
