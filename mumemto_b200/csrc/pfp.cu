@@ -225,13 +225,19 @@ __global__ void __launch_bounds__(TPB) owned_from_keys(const u64* __restrict__ s
 }
 
 // The one exception: the last phrase ends with w padding zeros that ARE symbols of its string, so its last w owned suffixes show a
-// zero at symbol w.  They contain padding, hence are unique strings, and isa_d gives their exact final rank.
+// zero at symbol w.  Their rank is looked up through isa_d: that is the head rank of their group, and because a padding zero and a
+// terminator are the same key symbol such a suffix can share its group with shorter strings that end where its padding starts
+// (e.g. "$" + padding with the "$" that ends some other phrase) -- so walk the group to the rank that really holds the suffix.
 __global__ void owned_fix_last_phrase(const u32* __restrict__ pid, u32 np, const u32* __restrict__ doff, const u32* __restrict__ limit,
-                                      const u32* __restrict__ isa_d, u32* __restrict__ flag) {
+                                      const u32* __restrict__ isa_d, const u32* __restrict__ sa_d, u32 dsize, u32* __restrict__ flag) {
     u32 g = pid[np - 1];
     for (u32 i = doff[g] + threadIdx.x; i < doff[g + 1]; i += blockDim.x) {
         u32 lim = limit[i];
-        if (lim >= PFP_W + 2 && lim <= 2 * PFP_W + 1) flag[isa_d[i]] = 1;
+        if (lim >= PFP_W + 2 && lim <= 2 * PFP_W + 1) {
+            u32 q = isa_d[i];
+            while (q < dsize && sa_d[q] != i) ++q;
+            if (q < dsize) flag[q] = 1;
+        }
     }
 }
 
@@ -441,7 +447,7 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
         refine_by_doubling(ix.sa_d.p, isa2.p, dsize, cpk, ix.limit.p, groups, ix.stats_d, s, 2);
         MMB_LAUNCH(unpair_ranks, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)isa2.p, dsize, ix.isa_d.p);
         isa2.release();
-        if (ix.owned.p) MMB_LAUNCH(owned_fix_last_phrase, 1, 256, 0, s, (const u32*)pid.p, np, (const u32*)ix.doff.p, (const u32*)ix.limit.p, (const u32*)ix.isa_d.p, ix.owned.p);
+        if (ix.owned.p) MMB_LAUNCH(owned_fix_last_phrase, 1, 256, 0, s, (const u32*)pid.p, np, (const u32*)ix.doff.p, (const u32*)ix.limit.p, (const u32*)ix.isa_d.p, (const u32*)ix.sa_d.p, dsize, ix.owned.p);
         MMB_CUDA(cudaStreamSynchronize(s));       // lut lives on this stack frame
     }
 

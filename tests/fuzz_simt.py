@@ -1,0 +1,123 @@
+"""Differential fuzzing of the engine (SIMT unit-test build) against the CPU oracle: random small collections, random flags, both routes,
+random tile sizes.  Not collected by pytest (no test_ prefix); run it by hand:  python tests/fuzz_simt.py [iterations] [seed]"""
+import ctypes
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import util  # noqa: E402
+from mumemto_b200 import _binding, api  # noqa: E402
+
+ORACLE = os.path.join(ROOT, "oracle", "_build", "mumemto_oracle")
+
+
+def random_collection(rng, d):
+    n = int(rng.integers(2, 7))
+    base_len = int(rng.integers(40, 2500))
+    base = util.random_dna(rng, base_len)
+    if rng.random() < 0.4:            # tandem repeats / low complexity
+        unit = util.random_dna(rng, int(rng.integers(1, 12)))
+        at = int(rng.integers(0, base_len))
+        base = base[:at] + unit * int(rng.integers(2, 60)) + base[at:]
+    paths = []
+    for i in range(n):
+        s = util.mutate(rng, base, float(rng.choice([0.0, 0.002, 0.01, 0.05])))
+        if rng.random() < 0.3:
+            cut = int(rng.integers(0, len(s)))
+            s = s[cut:] + s[:cut]
+        if rng.random() < 0.2:
+            at = int(rng.integers(0, len(s)))
+            s = s[:at] + "N" * int(rng.integers(1, 30)) + s[at:]
+        if rng.random() < 0.15:
+            s = s.lower()
+        if rng.random() < 0.2:        # reverse complement of the whole document
+            s = s[::-1].translate(str.maketrans("ACGTacgt", "TGCAtgca"))
+        recs = [(f"r{i}", s)]
+        if rng.random() < 0.25 and len(s) > 20:
+            cut = int(rng.integers(1, len(s) - 1))
+            recs = [(f"r{i}a", s[:cut]), (f"r{i}b", s[cut:])]
+        paths.append(util.write_fasta(os.path.join(d, f"d{i}.fa"), recs, width=int(rng.choice([60, 80, 7, 1000]))))
+    return paths
+
+
+def random_flags(rng, n):
+    mode = rng.integers(0, 6)
+    flags = []
+    if mode == 0:
+        pass
+    elif mode == 1:
+        flags += ["-k", str(int(rng.integers(-n - 1, n + 2)))]
+    elif mode == 2:
+        flags += ["-f", str(int(rng.integers(2, 5)))]
+        if rng.random() < 0.5:
+            flags += ["-F", str(int(rng.integers(-n - 1, 4 * n)))]
+        if rng.random() < 0.5:
+            flags += ["-k", str(int(rng.integers(2, n + 1)))]
+    elif mode == 3:
+        flags += ["-M", "-n"]
+    elif mode == 4:
+        flags += ["-f", "0"]
+        if rng.random() < 0.6:
+            flags += ["-F", str(int(rng.integers(2, 40)))]
+        flags += ["-k", str(int(rng.integers(2, n + 1)))]
+    else:
+        flags += ["-b"] if rng.random() < 0.5 else ["-A"]
+    if rng.random() < 0.3:
+        flags += ["-l", str(int(rng.integers(3, 40)))]
+    if rng.random() < 0.25:
+        flags += ["-r"]
+    return flags
+
+
+def main():
+    iters = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    skip = int(sys.argv[3]) if len(sys.argv) > 3 else 0           # replay: draw the first `skip` cases without running them
+    keep = os.environ.get("FUZZ_KEEP")                            # directory that receives the inputs of every case before it runs
+    lib = _binding.declare(ctypes.CDLL(os.path.join(ROOT, "tests", "simt", "_build", "libmumemto_b200_simt.so")))
+    rng = np.random.default_rng(seed)
+    bad = 0
+    for it in range(iters):
+        d = tempfile.mkdtemp(prefix="fuzz")
+        try:
+            paths = random_collection(rng, d)
+            flags = random_flags(rng, len(paths))
+            o, g = os.path.join(d, "o"), os.path.join(d, "g")
+            route = str(rng.choice(["direct", "pfp", "auto"]))
+            tile = int(rng.choice([0, 64, 300, 1500, 100000]))
+            if it < skip:
+                continue
+            if keep:
+                shutil.rmtree(keep, ignore_errors=True); shutil.copytree(d, keep)
+                with open(os.path.join(keep, "case.txt"), "w") as f:
+                    f.write(f"{it} {flags} {route} {tile}\n")
+            ok_o = util.run_cli(ORACLE, ["-o", o, *flags, *paths], check=False).returncode == 0
+            unbounded = "-f" in flags and flags[flags.index("-f") + 1] == "0" and "-F" not in flags
+            if unbounded and route == "pfp":
+                route = "direct"
+            kw = util.flags_to_kwargs(flags)
+            try:
+                api.find_files(paths, g, route=route, tile_ranks=tile, _lib=lib, **kw); ok_g = True
+            except Exception as ex:
+                ok_g = False; err = str(ex)
+            if ok_o != ok_g:
+                too_short = (not ok_g) and "too short" in err
+                if not too_short:
+                    bad += 1; print("MISMATCH status", it, flags, route, tile, ok_o, ok_g, "" if ok_g else err[:200]); shutil.copytree(d, f"/tmp/fuzz_fail_{seed}_{it}")
+            elif ok_o and util.outputs(g) != util.outputs(o):
+                bad += 1; print("MISMATCH output", it, flags, route, tile); shutil.copytree(d, f"/tmp/fuzz_fail_{seed}_{it}")
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+        if (it + 1) % 50 == 0:
+            print(f"{it + 1} iterations, {bad} mismatches", flush=True)
+    print("done:", iters, "iterations,", bad, "mismatches")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -212,6 +212,17 @@ def test_simt_unbounded_frequency(simt_lib, oracle_bin, small, tmp_path):
                 assert max(len(l.split(b"\t")[1].split(b",")) for l in out[".mems"].splitlines()) > 1000
 
 
+def test_simt_pfp_last_phrase_suffix_tied_with_a_phrase_end(simt_lib, oracle_bin, tmp_path):
+    """Found by tests/fuzz_simt.py: a phrase of this collection ends in '$' / 'A$', so the last phrase's suffixes '$' + padding and
+    'A$' + padding share their dictionary group with those shorter strings (padding zero = terminator in the sort key); their rank
+    must be looked up inside the group, else a non-member is expanded with a wrapped text position."""
+    src = os.path.join(util.ROOT, "tests", "golden", "pfp_last_phrase_tie")
+    paths = [os.path.join(src, f"d{i}.fa") for i in range(5)]
+    for i, (flags, tile) in enumerate(((["-A"], 0), ([], 300), (["-M", "-n"], 1500), (["-f", "2", "-k", "2", "-l", "8"], 64))):
+        os.makedirs(str(tmp_path / f"c{i}"), exist_ok=True)
+        both_pfp(simt_lib, oracle_bin, str(tmp_path / f"c{i}"), paths, flags, tile_ranks=tile)
+
+
 def test_simt_doc_stream_switch(simt_lib, oracle_bin, small, tmp_path, monkeypatch):
     """MMB_DOC_STREAM=1 (experimental): with -M the tiles carry a document-id byte per rank and candidates are checked from it."""
     monkeypatch.setenv("MMB_DOC_STREAM", "1")

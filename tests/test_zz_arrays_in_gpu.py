@@ -49,3 +49,15 @@ def test_unbounded_frequency_gpu(cuda_lib, oracle_bin, tmp_path):
             util.run_cli(oracle_bin, ["-o", o, *flags, *paths])
             api.find_files(paths, g, _lib=cuda_lib, **util.flags_to_kwargs(flags))
             assert util.outputs(g) == util.outputs(o), (name, flags)
+
+
+def test_pfp_last_phrase_suffix_tied_with_a_phrase_end_gpu(cuda_lib, oracle_bin, tmp_path):
+    """GPU twin of test_simt_pfp_last_phrase_suffix_tied_with_a_phrase_end (a case found by tests/fuzz_simt.py)."""
+    src = os.path.join(util.ROOT, "tests", "golden", "pfp_last_phrase_tie")
+    paths = [os.path.join(src, f"d{i}.fa") for i in range(5)]
+    for i, (flags, tile) in enumerate(((["-A"], 0), ([], 300), (["-M", "-n"], 1500))):
+        o, g = str(tmp_path / f"o{i}"), str(tmp_path / f"g{i}")
+        util.run_cli(oracle_bin, ["-o", o, *flags, *paths])
+        st = api.find_files(paths, g, route="pfp", tile_ranks=tile, _lib=cuda_lib, **util.flags_to_kwargs(flags))
+        assert st["route"] == 2
+        assert util.outputs(g) == util.outputs(o), flags
