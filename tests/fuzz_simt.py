@@ -14,6 +14,7 @@ import util  # noqa: E402
 from mumemto_b200 import _binding, api  # noqa: E402
 
 ORACLE = os.path.join(ROOT, "oracle", "_build", "mumemto_oracle")
+REF = os.path.join(ROOT, "oracle", "_ref", "mumemto_exec")
 
 
 def random_collection(rng, d):
@@ -96,6 +97,21 @@ def main():
                 shutil.rmtree(keep, ignore_errors=True); shutil.copytree(d, keep)
                 with open(os.path.join(keep, "case.txt"), "w") as f:
                     f.write(f"{it} {flags} {route} {tile}\n")
+            os.environ["MMB_DOC_STREAM"] = "1" if rng.random() < 0.5 else "0"
+            if os.path.exists(REF) and rng.random() < 0.15 and "-A" not in flags and not ("-f" in flags and flags[flags.index("-f") + 1] == "0" and "-F" not in flags):
+                # array input: the reference's own -A dump, then its own -a run against ours
+                import subprocess
+                full = os.path.join(d, "full")
+                rc = [f for f in flags if f == "-r"]
+                if subprocess.run([REF, "-o", full, "-A", *rc, *paths], capture_output=True).returncode == 0:
+                    ok_o = subprocess.run([REF, "-o", o, "-a", full, *flags], capture_output=True).returncode == 0
+                    try:
+                        api.find_arrays(full, g, tile_ranks=tile, _lib=lib, **util.flags_to_kwargs(flags)); ok_g = True
+                    except Exception as ex:
+                        ok_g = False; err = str(ex)
+                    if ok_o != ok_g or (ok_o and util.outputs(g) != util.outputs(o)):
+                        bad += 1; print("MISMATCH arrays", it, flags, tile, ok_o, ok_g); shutil.copytree(d, f"/tmp/fuzz_fail_{seed}_{it}")
+                continue
             ok_o = util.run_cli(ORACLE, ["-o", o, *flags, *paths], check=False).returncode == 0
             unbounded = "-f" in flags and flags[flags.index("-f") + 1] == "0" and "-F" not in flags
             if unbounded and route == "pfp":
