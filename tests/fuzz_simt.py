@@ -20,6 +20,8 @@ REF = os.path.join(ROOT, "oracle", "_ref", "mumemto_exec")
 def random_collection(rng, d):
     n = int(rng.integers(2, 7))
     base_len = int(rng.integers(40, 2500))
+    if rng.random() < 0.25:           # many similar documents: multi-member dictionary groups, multi-word document masks
+        n = int(rng.integers(7, 75)); base_len = int(rng.integers(150, 900))
     base = util.random_dna(rng, base_len)
     if rng.random() < 0.4:            # tandem repeats / low complexity
         unit = util.random_dna(rng, int(rng.integers(1, 12)))
@@ -111,6 +113,27 @@ def main():
                         ok_g = False; err = str(ex)
                     if ok_o != ok_g or (ok_o and util.outputs(g) != util.outputs(o)):
                         bad += 1; print("MISMATCH arrays", it, flags, tile, ok_o, ok_g); shutil.copytree(d, f"/tmp/fuzz_fail_{seed}_{it}")
+                continue
+            if len(paths) >= 3 and rng.random() < 0.12:
+                # partition -> anchor merge: random partitions sharing document 0, ours against the oracle's fold
+                k = int(rng.integers(2, min(4, len(paths) - 1) + 1))
+                rest = list(rng.permutation(np.arange(1, len(paths))))
+                groups = [[0] + [int(x) for x in rest[j::k]] for j in range(k)]
+                extra = ["-r"] if "-r" in flags else []
+                no, ng = [], []
+                try:
+                    for j, grp in enumerate(groups):
+                        sel = [paths[x] for x in grp]
+                        util.run_cli(ORACLE, ["-o", os.path.join(d, f"po{j}"), "-M", "-n", *extra, *sel])
+                        api.find_files(sel, os.path.join(d, f"pg{j}"), merge=True, anchor_merge=True, revcomp=not extra, route=route, tile_ranks=tile, _lib=lib)
+                        no.append(os.path.join(d, f"po{j}.mums")); ng.append(os.path.join(d, f"pg{j}.mums"))
+                    util.run_cli(ORACLE, ["merge", *no, "-o", os.path.join(d, "om")])
+                    api.merge_files(ng, os.path.join(d, "gm"), _lib=lib)
+                    if util.outputs(os.path.join(d, "gm")) != util.outputs(os.path.join(d, "om")):
+                        bad += 1; print("MISMATCH merge", it, groups, route, tile); shutil.copytree(d, f"/tmp/fuzz_fail_{seed}_{it}")
+                except Exception as ex:
+                    if "too short" not in str(ex):
+                        bad += 1; print("ERROR merge", it, groups, route, tile, str(ex)[:300]); shutil.copytree(d, f"/tmp/fuzz_fail_{seed}_{it}")
                 continue
             ok_o = util.run_cli(ORACLE, ["-o", o, *flags, *paths], check=False).returncode == 0
             unbounded = "-f" in flags and flags[flags.index("-f") + 1] == "0" and "-F" not in flags
