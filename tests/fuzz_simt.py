@@ -100,6 +100,7 @@ def main():
                 with open(os.path.join(keep, "case.txt"), "w") as f:
                     f.write(f"{it} {flags} {route} {tile}\n")
             os.environ["MMB_DOC_STREAM"] = "1" if rng.random() < 0.5 else "0"
+            lib.simt_set_block_order(int(rng.integers(0, 3)))           # block scheduling order of the SIMT harness: forward, reverse, shuffled
             if os.path.exists(REF) and rng.random() < 0.15 and "-A" not in flags and not ("-f" in flags and flags[flags.index("-f") + 1] == "0" and "-F" not in flags):
                 # array input: the reference's own -A dump, then its own -a run against ours
                 import subprocess
