@@ -54,10 +54,10 @@ typedef struct mmb_options {
     uint8_t anchor_merge;        /* -n */
     uint8_t cli_normalise;       /* 1: apply BuildOptions::validate/set_parameters; 0: library rules (mumemto_api.cpp:332-411) */
     uint8_t want_text;           /* 1: also format the .mums/.mems bytes on the device */
-    uint8_t route;               /* 0 auto; 1 direct suffix sorting of the text (|T| < 2^31); 2 prefix-free parse (dictionary + parse), any |T| < 2^40 */
+    uint8_t route;               /* 0 auto; 1 direct suffix sorting of the text (|T| < 2^31); 2 prefix-free parse (dictionary + parse), any |T| < 2^40 with -F below 2^20 */
     uint8_t keep_arrays;         /* 1: keep SA/LCP of the whole stream for mmb_copy_arrays even on the tiled (route 2) path */
     uint8_t reserved[6];
-    uint64_t tile_ranks;         /* route 2: ranks per stream tile, 0 = default (2^28) */
+    uint64_t tile_ranks;         /* route 2: ranks per stream tile, 0 = default (2^30 in mmb_find = ~18 GB of tile buffers; 2^26 in mmb_find_from_arrays) */
 } mmb_options;
 
 typedef struct mmb_stats {

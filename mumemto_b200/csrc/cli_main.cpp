@@ -227,6 +227,7 @@ int main(int argc, char** argv) {
     mmb_options mo; mmb_default_options(&mo);
     mo.min_match_len = (uint32_t)o.min_match_len; mo.num_distinct_docs = o.num_distinct_docs; mo.rare_freq = o.rare_freq; mo.max_mem_freq = o.max_mem_freq;
     mo.merge = o.merge; mo.anchor_merge = o.anchor_merge; mo.cli_normalise = 1; mo.want_text = o.binary ? 0 : 1;
+    mo.keep_arrays = o.arrays_out ? 1 : 0;      // the tiled route only keeps the whole stream when asked
     bool mum_mode = (o.rare_freq == 1);
     status(mum_mode ? "finding multi-MUMs on the GPU" : "finding multi-MEMs on the GPU");
     if (!o.arrays_in.empty()) {

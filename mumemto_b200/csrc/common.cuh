@@ -4,6 +4,7 @@
 // compiled is the unit-test build under tests/simt/ (-DMMB_SIMT), which runs the kernel bodies on CPU fibers so that index logic
 // can be tested in a container without a GPU; that build is never shipped or loaded by the product.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -32,7 +33,7 @@ struct Error : std::runtime_error {
     Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
 };
 
-extern unsigned long long g_kernel_launches;   // every MMB_LAUNCH, for bench.py's "gpu_launches"
+extern std::atomic<unsigned long long> g_kernel_launches;   // every MMB_LAUNCH, for bench.py's "gpu_launches"
 extern double g_host_alloc_ms, g_host_free_ms, g_host_sync_ms;      // host time inside cudaMallocAsync / cudaFreeAsync / stream syncs
 extern unsigned long long g_host_allocs, g_host_syncs;
 inline double host_now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }

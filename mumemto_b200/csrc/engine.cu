@@ -12,55 +12,72 @@
 #include "sa.h"
 #include "text.h"
 
+#include <atomic>
 #include <cctype>
 #include <map>
 #include <mutex>
 #include <unordered_map>
 
 namespace mmb {
-unsigned long long g_kernel_launches = 0;
+std::atomic<unsigned long long> g_kernel_launches{0};
 double g_host_alloc_ms = 0, g_host_free_ms = 0, g_host_sync_ms = 0;
 unsigned long long g_host_allocs = 0, g_host_syncs = 0;
 }
 
 // ---------------------------------------------------------------------------------------------- cached device allocator
+// Free lists are keyed by (device, stream): a block released by one stage may be handed out again at once only to work that is
+// ordered on the SAME stream.  Two engines in one process (concurrent mumemto_mum / mumemto_mem calls, engines on different GPUs)
+// therefore never see each other's blocks.
 namespace mmb {
 namespace poolimpl {
+typedef std::pair<int, cudaStream_t> Key;
 struct BlockCache {
     std::mutex mu;
-    std::multimap<size_t, void*> free_blocks;          // size -> block
-    std::unordered_map<void*, size_t> live;            // blocks handed out
-    size_t cached_bytes = 0;
+    std::map<Key, std::multimap<size_t, void*>> free_blocks;      // (device, stream) -> size -> block
+    std::unordered_map<void*, std::pair<size_t, Key>> live;      // blocks handed out
 } g_cache;
 size_t round_block(size_t b) { return b <= (1u << 20) ? ((b + 511) & ~(size_t)511) : ((b + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1)); }
+int current_device() { int d = 0; cudaGetDevice(&d); return d; }
+// give the cached blocks of one key (or of every key on `device` when stream_only is false) back to the driver
+void trim(int device, cudaStream_t s, bool stream_only) {
+    std::vector<void*> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        for (auto& kv : g_cache.free_blocks) {
+            if (kv.first.first != device || (stream_only && kv.first.second != s)) continue;
+            for (auto& b : kv.second) drop.push_back(b.second);
+            kv.second.clear();
+        }
+    }
+    if (drop.empty()) return;
+    if (stream_only) cudaStreamSynchronize(s); else cudaDeviceSynchronize();
+    for (void* p : drop) cudaFree(p);
+}
 }  // namespace poolimpl
 using poolimpl::g_cache;
 using poolimpl::round_block;
 
-void pool_trim() {
-    std::lock_guard<std::mutex> lk(g_cache.mu);
-    cudaDeviceSynchronize();
-    for (auto& kv : g_cache.free_blocks) cudaFree(kv.second);
-    g_cache.free_blocks.clear(); g_cache.cached_bytes = 0;
-}
+void pool_trim() { poolimpl::trim(poolimpl::current_device(), nullptr, false); }
 
-void* pool_alloc(size_t bytes, cudaStream_t) {
+void* pool_alloc(size_t bytes, cudaStream_t s) {
     size_t want = round_block(bytes);
+    poolimpl::Key key(poolimpl::current_device(), s);
     {
         std::lock_guard<std::mutex> lk(g_cache.mu);
-        auto it = g_cache.free_blocks.lower_bound(want);
-        if (it != g_cache.free_blocks.end() && it->first <= want + want / 4 + 4096) {      // best fit, at most 25 % slack
+        auto& fl = g_cache.free_blocks[key];
+        auto it = fl.lower_bound(want);
+        if (it != fl.end() && it->first <= want + want / 4 + 4096) {      // best fit, at most 25 % slack
             void* p = it->second; size_t sz = it->first;
-            g_cache.free_blocks.erase(it); g_cache.cached_bytes -= sz; g_cache.live[p] = sz;
+            fl.erase(it); g_cache.live[p] = {sz, key};
             return p;
         }
     }
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) { cudaGetLastError(); pool_trim(); e = cudaMalloc(&p, want); }
+    if (e != cudaSuccess) { cudaGetLastError(); poolimpl::trim(key.first, nullptr, false); e = cudaMalloc(&p, want); }
     check(e, "cudaMalloc", __FILE__, __LINE__);
     std::lock_guard<std::mutex> lk(g_cache.mu);
-    g_cache.live[p] = want;
+    g_cache.live[p] = {want, key};
     return p;
 }
 
@@ -69,7 +86,7 @@ void pool_free(void* p, cudaStream_t) {
     std::lock_guard<std::mutex> lk(g_cache.mu);
     auto it = g_cache.live.find(p);
     if (it == g_cache.live.end()) return;
-    g_cache.free_blocks.emplace(it->second, p); g_cache.cached_bytes += it->second;
+    g_cache.free_blocks[it->second.second].emplace(it->second.first, p);      // back to the list of the stream it was allocated for
     g_cache.live.erase(it);
 }
 }  // namespace mmb
@@ -77,12 +94,16 @@ void pool_free(void* p, cudaStream_t) {
 // ---------------------------------------------------------------------------------------------- per-kernel event timing
 namespace mmb {
 namespace profimpl {
+std::mutex mu;
+std::atomic<bool> on{false};
 std::string filter;                                    // empty = off
 std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pairs;
 bool open_pair = false;
 }  // namespace profimpl
 void profile_before(const char* name, cudaStream_t s) {
     using namespace profimpl;
+    if (!on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(mu);
     if (filter.empty() || !strstr(name, filter.c_str())) return;
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
@@ -91,6 +112,8 @@ void profile_before(const char* name, cudaStream_t s) {
 }
 void profile_after(const char* name, cudaStream_t s) {
     using namespace profimpl;
+    if (!on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(mu);
     if (!open_pair) return;
     (void)name;
     cudaEventRecord(pairs.back().second, s); open_pair = false;
@@ -108,8 +131,9 @@ int fail(int code, const std::string& msg) { g_error = msg; return code; }
 int map_error(const Error& e) {
     int c = e.code;
     if (c == 10) return MMB_ERR_CUDA;
-    if (c == 13 || c == 21 || c == 40 || c == 41 || c == 42) return MMB_ERR_INPUT;
-    if (c == 12 || c == 20 || (c >= 30 && c <= 39) || (c >= 50 && c <= 59)) return MMB_ERR_PARAM;
+    if (c == 1 || c == 11 || c == 61) return MMB_ERR_ARG;                          // null destination, misaligned offsets, partition shape
+    if (c == 13 || c == 21 || c == 40 || c == 41 || c == 42 || c == 60 || c == 70) return MMB_ERR_INPUT;
+    if (c == 12 || c == 20 || (c >= 30 && c <= 39) || (c >= 50 && c <= 59) || (c >= 71 && c <= 75)) return MMB_ERR_PARAM;   // 71-75: sizes the engine does not support
     return MMB_ERR_INTERNAL;
 }
 
@@ -320,7 +344,7 @@ int mmb_create(int device, void* cuda_stream, mmb_engine** out) {
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
 #endif
-        e->launches_at_create = g_kernel_launches;
+        e->launches_at_create = g_kernel_launches.load();
         *out = e;
     });
 }
@@ -328,10 +352,11 @@ int mmb_create(int device, void* cuda_stream, mmb_engine** out) {
 void mmb_destroy(mmb_engine* e) {
     if (!e) return;
     cudaStreamSynchronize(e->stream);
-    cudaStream_t s = e->stream; bool own = e->own_stream;
+    cudaStream_t s = e->stream; bool own = e->own_stream; int dev = e->device;
+    cudaSetDevice(dev);
     delete e;
+    poolimpl::trim(dev, s, true);
     if (own) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
-    pool_trim();
 }
 
 int mmb_load_fasta(mmb_engine* e, const uint8_t* const* files, const uint64_t* sizes, size_t nfiles, int use_revcomp) {
@@ -349,6 +374,8 @@ int mmb_load_fasta_device(mmb_engine* e, const void* d_raw, const uint64_t* offs
     return guarded([&] {
         MMB_CUDA(cudaSetDevice(e->device));
         std::vector<u64> off(offsets, offsets + nfiles), size(sizes, sizes + nfiles);
+        for (size_t i = 0; i < nfiles; ++i)
+            if (off[i] & 15) throw Error(11, "mmb_load_fasta_device: offsets[" + std::to_string(i) + "] is not a multiple of 16");
         load_common(e, (const u8*)d_raw, nullptr, off, size, use_revcomp != 0, false);
     });
 }
@@ -584,7 +611,7 @@ int mmb_find_from_arrays(mmb_engine* e, const uint64_t* doc_lengths, size_t ndoc
 int mmb_get_stats(const mmb_engine* e, mmb_stats* out) {
     if (!e || !out) return fail(MMB_ERR_ARG, "null argument");
     *out = e->stats;
-    out->kernel_launches = g_kernel_launches - e->launches_at_create;
+    out->kernel_launches = g_kernel_launches.load() - e->launches_at_create;
     return MMB_OK;
 }
 
@@ -770,14 +797,17 @@ int mmb_merge_copy_text(mmb_engine* e, void* host_dst) {
 }
 
 int mmb_profile_kernel(const char* name_substring) {
+    std::lock_guard<std::mutex> lk(profimpl::mu);
     for (auto& p : profimpl::pairs) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     profimpl::pairs.clear(); profimpl::open_pair = false;
     profimpl::filter = name_substring ? name_substring : "";
+    profimpl::on.store(!profimpl::filter.empty());
     return MMB_OK;
 }
 
 int mmb_profile_result(double* total_ms, uint64_t* launches) {
     cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(profimpl::mu);
     double t = 0;
     for (auto& p : profimpl::pairs) { float ms = 0; if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) t += ms; }
     if (total_ms) *total_ms = t;

@@ -288,7 +288,7 @@ void build_text(const u8* d_raw, const std::vector<u64>& file_off, const std::ve
     std::vector<u32> chunk_first(nfiles + 1, 0);
     std::vector<u64> file_end(nfiles);
     for (u32 f = 0; f < nfiles; ++f) {
-        if (file_off[f] % 16) throw Error(11, "internal: file slot not 16-byte aligned");
+        if (file_off[f] % 16) throw Error(11, "file image offsets must be multiples of 16");
         u64 nch = (file_size[f] + CHUNK - 1) / CHUNK;
         if ((u64)chunk_first[f] + nch > 0xfffffff0ull) throw Error(12, "input too large for one device");
         chunk_first[f + 1] = chunk_first[f] + (u32)nch;
