@@ -170,14 +170,24 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax or None, "reasons": sorted(self.reasons)}
 
 
-def bounded_sample(spec, budget_bases=8_000_000):
-    """A collection of the same generator small enough for the single-threaded reference: ~5-10 s of CPU per run."""
-    sample = dict(spec)
-    note = "whole workload"
-    if spec["N"] * spec["L"] > budget_bases:
-        sample["L"] = max(10_000, budget_bases // spec["N"])
-        note = f"{spec['N']}x{sample['L']} bp collection from the same generator (the reference's time grows linearly with input size)"
-    return sample, note
+FLAGSETS = {      # reference CLI flags, keyword arguments of Engine.find
+    "strict": ([], {}),
+    "partial": (["-k", "-1"], {"num_distinct_docs": -1}),
+    "mem": (["-f", "3", "-F", "100"], {"rare_freq": 3, "max_mem_freq": 100}),
+}
+REF_CAVEAT = ("reference sources compiled unmodified (oracle/Makefile: -O3 -march=x86-64-v3) against definitional stand-ins for its two un-vendored "
+              "dependencies: sdsl (oracle/ref_shims/sdsl) and gsacak -> our SA-IS (oracle/sais.hpp, int64; slower than gsacak, which flatters the GPU/CPU ratio); "
+              "the reference has no threads or OpenMP: 1 thread per process")
+
+
+def sample_of(spec, L):
+    """The same generator at L bases per document (the reference's time grows linearly with input size: see reference_modes)."""
+    s = dict(spec); s["L"] = min(L, spec["L"])
+    return s
+
+
+def sample_name(sample):
+    return f"{sample['N']}x{sample['L']} bp, generator of the workload with seed 1"
 
 
 def reference_exe():
@@ -190,91 +200,241 @@ def reference_exe():
     return exe, "port"
 
 
-def run_reference(exe, sample, repeats, warmup):
-    imgs = make_collection(sample, seed=1)
-    times = []
-    with tempfile.TemporaryDirectory() as d:
-        paths = []
-        for i, im in enumerate(imgs):
-            p = os.path.join(d, f"h{i}.fa"); im.tofile(p); paths.append(p)
-        for it in range(warmup + repeats):
-            t0 = time.perf_counter()
-            subprocess.run([exe, "-o", os.path.join(d, "ref"), *paths], check=True, capture_output=True)
-            if it >= warmup:
-                times.append(time.perf_counter() - t0)
-    return float(np.mean(times))
+class SampleFiles:
+    """A sample collection written to a scratch directory once; reference runs and the GPU parity check read the same images."""
+
+    def __init__(self, sample):
+        self.sample = sample
+        self.imgs = make_collection(sample, seed=1)
+        self.tmp = tempfile.TemporaryDirectory()
+        self.dir = self.tmp.name
+        self.paths = []
+        for i, im in enumerate(self.imgs):
+            p = os.path.join(self.dir, f"h{i}.fa"); im.tofile(p); self.paths.append(p)
+        self.bases = sample["N"] * sample["L"]
+
+    def groups(self, procs):
+        """Partitions that share document 0 (reference README "mumemto merge"): [0] + every procs-th of the others."""
+        procs = max(2, min(procs, len(self.paths) - 1))
+        return [[0] + list(range(1 + g, len(self.paths), procs)) for g in range(procs)]
+
+    def close(self):
+        self.tmp.cleanup()
 
 
-def run_reference_partitioned(exe, merge_exe, sample, procs, repeats, warmup):
+def run_reference(exe, files, flags, tag="ref"):
+    """One single-process run of the reference on the sample; returns (seconds, output bytes)."""
+    prefix = os.path.join(files.dir, tag)
+    t0 = time.perf_counter()
+    subprocess.run([exe, "-o", prefix, *flags, *files.paths], check=True, capture_output=True)
+    secs = time.perf_counter() - t0
+    out = b""
+    for ext in (".mums", ".mems"):
+        if os.path.exists(prefix + ext):
+            with open(prefix + ext, "rb") as f:
+                out = f.read()
+    return secs, out
+
+
+def run_reference_partitioned(exe, merge_exe, files, procs):
     """The reference's own way to use many cores (README "mumemto merge", mumemto/merge_mums.py:171-192): split the collection into
     partitions that share document 0, run one `mumemto_exec -M -n` PROCESS per partition concurrently, then `anchor_merge` the partition
-    outputs.  The merged .mums is set-equal to a direct run on the whole collection.  Returns (seconds per run, partitions)."""
-    imgs = make_collection(sample, seed=1)
-    N = len(imgs)
-    procs = max(2, min(procs, N - 1))
-    times = []
-    with tempfile.TemporaryDirectory() as d:
-        paths = []
-        for i, im in enumerate(imgs):
-            p = os.path.join(d, f"h{i}.fa"); im.tofile(p); paths.append(p)
-        groups = [[paths[0]] + paths[1 + g::procs] for g in range(procs)]
-        for it in range(warmup + repeats):
-            t0 = time.perf_counter()
-            running = [subprocess.Popen([exe, "-o", os.path.join(d, f"part{g}"), "-M", "-n", *grp], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-                       for g, grp in enumerate(groups)]
-            for pr in running:
-                if pr.wait() != 0:
-                    raise RuntimeError("a reference partition run failed")
-            subprocess.run([merge_exe, *[os.path.join(d, f"part{g}.mums") for g in range(procs)], "-o", os.path.join(d, "merged")],
-                           check=True, capture_output=True)
-            if it >= warmup:
-                times.append(time.perf_counter() - t0)
-    return float(np.mean(times)), procs
+    outputs.  The merged .mums is set-equal to a direct run on the whole collection.
+    Returns (seconds, partitions as lists of document indices, merged .mums bytes, merged .athresh bytes)."""
+    groups = files.groups(procs)
+    d = files.dir
+    t0 = time.perf_counter()
+    running = [subprocess.Popen([exe, "-o", os.path.join(d, f"part{g}"), "-M", "-n", *[files.paths[i] for i in grp]],
+                                stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for g, grp in enumerate(groups)]
+    for pr in running:
+        if pr.wait() != 0:
+            raise RuntimeError("a reference partition run failed")
+    subprocess.run([merge_exe, *[os.path.join(d, f"part{g}.mums") for g in range(len(groups))], "-o", os.path.join(d, "merged")],
+                   check=True, capture_output=True)
+    secs = time.perf_counter() - t0
+    with open(os.path.join(d, "merged.mums"), "rb") as f:
+        mums = f.read()
+    with open(os.path.join(d, "merged.athresh"), "rb") as f:
+        athresh = f.read()
+    return secs, groups, mums, athresh
 
 
-def reference_best(spec, repeats, warmup):
-    """Both ways the reference can run the path on this host: one process (it has no threads), and its partition-merge workflow with
-    one process per core.  Returns the faster one as (bases/s, seconds per run, cores, kind, sample note, both modes)."""
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_modes_table(spec, flagset, sizes=(1_000_000, 4_000_000, 16_000_000), budget_s=170.0):
+    """bases/s of the reference per mode and sample size (64 x {1, 4, 16} Mbp, linearity shown, the full-size
+    figure is an extrapolation).  A size is skipped when the time predicted from the previous one does not fit what is left of the budget
+    or the host lacks the memory (about 45 bytes per text symbol and process)."""
     exe, kind = reference_exe()
-    sample, note = bounded_sample(spec)
-    t1 = run_reference(exe, sample, repeats, warmup)
-    modes = {"single_process": {"value": sample["N"] * sample["L"] / t1, "cores": 1, "seconds": t1, "sample": note}}
-    best = (modes["single_process"]["value"], t1, 1, kind,
-            note + "; reference sources compiled unmodified with sdsl/gsacak stand-ins (oracle/ref_shims), 1 thread: the reference has no threads or OpenMP")
     merge_exe = os.path.join(ROOT, "oracle", "_ref", "anchor_merge")
-    cores = os.cpu_count() or 1
-    if kind == "reference" and os.path.exists(merge_exe) and cores >= 4 and spec["N"] >= 5 and spec["kind"] == "pangenome":
-        big, bnote = bounded_sample(spec, budget_bases=8_000_000 * min(cores, spec["N"] - 1) // 2)
-        try:
-            tp, procs = run_reference_partitioned(exe, merge_exe, big, cores, repeats, warmup)
-            vp = big["N"] * big["L"] / tp
-            modes["partition_processes"] = {"value": vp, "cores": procs, "seconds": tp, "sample": bnote}
-            if vp > best[0]:
-                best = (vp, tp, procs, kind, bnote + f"; the reference's own parallel workflow: {procs} concurrent mumemto_exec -M -n processes (one partition each, "
-                        "sharing document 0) + anchor_merge; reference sources compiled unmodified with sdsl/gsacak stand-ins")
-        except Exception as ex:      # the single-process number stands
-            modes["partition_processes"] = {"error": str(ex)[:200]}
-    return best + (modes,)
+    flags = FLAGSETS[flagset][0]
+    cores = host_cores()
+    can_partition = kind == "reference" and os.path.exists(merge_exe) and flagset == "strict" and spec["N"] >= 5 and spec["kind"] == "pangenome" and cores >= 2
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 32 << 30
+    table = {"single_process": {"cores": 1, "sizes": {}}, "partition_processes": {"cores": 0, "sizes": {}}}
+    t_start = time.perf_counter()
+    last = {"single_process": None, "partition_processes": None}
+    for L in sizes:
+        if L > spec["L"]:
+            break
+        sample = sample_of(spec, L)
+        symbols = 2 * sample["N"] * (L + 1)
+        files = None
+        for mode in ("partition_processes", "single_process"):
+            if mode == "partition_processes" and not can_partition:
+                continue
+            left = budget_s - (time.perf_counter() - t_start)
+            prev = last[mode]
+            predicted = prev[1] * (L / prev[0]) if prev else 0.0
+            need_mem = 45 * symbols * (1.3 if mode == "partition_processes" else 1.0)
+            if predicted > left or need_mem > 0.8 * avail:
+                table[mode]["sizes"][str(L)] = {"skipped": f"predicted {predicted:.0f} s with {left:.0f} s of the budget left" if predicted > left else "host memory"}
+                continue
+            if files is None:
+                files = SampleFiles(sample)
+            if mode == "single_process":
+                secs, _ = run_reference(exe, files, flags, tag=f"lin{L}")
+            else:
+                secs, groups, _, _ = run_reference_partitioned(exe, merge_exe, files, cores)
+                table[mode]["cores"] = len(groups)
+            last[mode] = (L, secs)
+            table[mode]["sizes"][str(L)] = {"bases_per_s": files.bases / secs, "seconds": secs, "sample": sample_name(sample)}
+        if files is not None:
+            files.close()
+    return table
 
 
 def reference_arm(args, spec, rank):
-    """The reference's own CPU implementation of the path, timed on the host cores (rank 0 only; the other ranks exit)."""
+    """The reference's own CPU implementation of the path, timed on the host cores (rank 0 only; the other ranks exit).  Every step is
+    one run of a bounded sample of the workload (config.workload names the sample that was timed, not the full size); the faster of
+    the reference's two modes (one process; its partition-merge workflow with one process per core) is the line's value."""
     if rank != 0:
         return
-    v, t, cores, kind, note, modes = reference_best(spec, args.steps, min(args.warmup, 1))
+    flagset = spec.get("flagset", "strict")
+    exe, kind = reference_exe()
+    merge_exe = os.path.join(ROOT, "oracle", "_ref", "anchor_merge")
+    cores = host_cores()
+    sample = sample_of(spec, int(os.environ.get("MMB_REF_SAMPLE_L", "1000000")))
+    files = SampleFiles(sample)
+    flags = FLAGSETS[flagset][0]
+    partition_ok = kind == "reference" and os.path.exists(merge_exe) and flagset == "strict" and spec["N"] >= 5 and spec["kind"] == "pangenome" and cores >= 4
+    procs = 0
+
+    def step():
+        nonlocal procs
+        if partition_ok:
+            secs, groups, _, _ = run_reference_partitioned(exe, merge_exe, files, cores)
+            procs = len(groups)
+            return secs
+        return run_reference(exe, files, flags)[0]
+
+    for _ in range(args.warmup):
+        step()
+    times = [step() for _ in range(max(1, args.steps))]
+    files.close()
+    t = float(np.mean(times))
+    v = sample["N"] * sample["L"] / t
+    used = procs if partition_ok else 1
+    mode = (f"the reference's own parallel workflow: {procs} concurrent `mumemto_exec -M -n` processes (one partition each, sharing document 0) + anchor_merge"
+            if partition_ok else "one process")
+    modes = reference_modes_table(spec, flagset) if not os.environ.get("MMB_REF_NO_TABLE") else None
     line = {"impl": "reference", "metric": "input bases/sec end-to-end (FASTA->.mums)", "value": v, "unit": "bases/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic", "config": {"workload": spec["desc"], "name": args.workload},
-            "cpu_baseline": {"value": v, "unit": "bases/s", "cores": cores, "kind": kind, "sample": note},
-            "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "reference_modes": modes}
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"SAMPLE of {args.workload}: {sample_name(sample)} ({spec['desc']} is the full workload; the CPU figure for it is an extrapolation)",
+                       "name": args.workload, "sample_bases": sample["N"] * sample["L"], "full_workload_bases": spec["N"] * spec["L"], "extrapolated": True,
+                       "flags": flags},
+            "cpu_baseline": {"value": v, "unit": "bases/s", "cores": used, "kind": kind, "sample": f"{sample_name(sample)}; {mode}; {REF_CAVEAT}", "host_cores": cores},
+            "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "reference_modes": modes, "extrapolated": True}
     print(json.dumps(line))
 
 
-def cpu_baseline_sample(spec):
-    """Bounded CPU run beside the GPU number (rank 0, N = 1): the reference build on (a sample of) the workload, in the faster of its
-    two modes (one process; one process per core through its partition-merge workflow)."""
-    v, t, cores, kind, note, modes = reference_best(spec, 1, 0)
-    return {"value": v, "unit": "bases/s", "cores": cores, "kind": kind, "sample": note, "seconds": t, "modes": modes}
+def snapshot_partition(eng, tdev):
+    """Clone the engine's last MUM table + thresholds into torch tensors on the device (the engine's own buffers die at the next find)."""
+    from mumemto_b200 import partition
+    part = partition.local_partition(eng, tdev)
+    return tuple(x.clone() for x in part)
+
+
+def merge_on_device(eng, parts):
+    """mmb_anchor_merge(inputs_on_device = 1) over cloned partition tables; returns (merged .mums bytes, merged .athresh bytes)."""
+    args = [(p[0].data_ptr(), p[1].data_ptr(), p[2].data_ptr(), p[3].data_ptr(), int(p[0].shape[0]), int(p[1].shape[1])) for p in parts]
+    eng.anchor_merge(args, int(parts[0][3].shape[0]), on_device=True)
+    _, _, _, thr = eng.merge_result()
+    return eng.merge_text(), thr.tobytes()
+
+
+def cpu_baseline_and_parity(eng, tdev, spec, sample_L=1_000_000, procs=None):
+    """Rank 0, N = 1, off the clock: the reference on a bounded sample of the workload (both modes), AND the byte-for-byte comparison of
+    the GPU engine with the reference's output on that same sample -- direct run with the workload's flags, and (strict multi-MUMs)
+    partitions with -M -n -> anchor_merge against the engine's partitions -> device-input merge.  Raises when any byte differs."""
+    flagset = spec.get("flagset", "strict")
+    flags, kw = FLAGSETS[flagset]
+    exe, kind = reference_exe()
+    merge_exe = os.path.join(ROOT, "oracle", "_ref", "anchor_merge")
+    cores = procs or host_cores()
+    sample = sample_of(spec, sample_L)
+    files = SampleFiles(sample)
+    parity = {}
+    modes = {}
+    # the reference's partition workflow first (a few seconds on >= 8 cores), then one process
+    if kind == "reference" and os.path.exists(merge_exe) and flagset == "strict" and spec["kind"] == "pangenome" and spec["N"] >= 5 and cores >= 2:
+        tp, groups, ref_mums, ref_athresh = run_reference_partitioned(exe, merge_exe, files, cores)
+        modes["partition_processes"] = {"value": files.bases / tp, "cores": len(groups), "seconds": tp}
+        parts = []
+        for grp in groups:
+            eng.load_fasta_bytes([files.imgs[i] for i in grp])
+            eng.find(merge=True, anchor_merge=True, want_text=False)
+            parts.append(snapshot_partition(eng, tdev))
+        got_mums, got_athresh = merge_on_device(eng, parts)
+        if got_mums != ref_mums or got_athresh != ref_athresh:
+            raise AssertionError("parity_sample: device partition merge differs from the reference's anchor_merge output")
+        parity["partitions_anchor_merge"] = {"partitions": len(groups), "mums_bytes": len(ref_mums), "athresh_bytes": len(ref_athresh), "result": "ok"}
+    t1, ref_out = run_reference(exe, files, flags)
+    modes["single_process"] = {"value": files.bases / t1, "cores": 1, "seconds": t1}
+    eng.load_fasta_bytes(files.imgs)
+    eng.find(want_text=True, **kw)
+    got = eng.text()
+    if got != ref_out:
+        raise AssertionError(f"parity_sample: GPU output differs from the reference on {sample_name(sample)} with flags {flags}")
+    parity["direct"] = {"flags": flags, "bytes": len(ref_out), "lines": ref_out.count(b"\n"), "result": "ok"}
+    files.close()
+    best = max(modes, key=lambda m: modes[m]["value"])
+    return ({"value": modes[best]["value"], "unit": "bases/s", "cores": modes[best]["cores"], "kind": kind, "seconds": modes[best]["seconds"],
+             "sample": f"{sample_name(sample)}; mode {best}; {REF_CAVEAT}", "modes": modes, "extrapolated": True, "host_cores": cores},
+            {"result": "ok", "sample": sample_name(sample), "checks": parity})
+
+
+def golden_md5(workload, flagset):
+    """md5 of the reference's output on the FULL workload, when scripts/make_fullsize_golden.py has recorded it (tests/golden/md5_table.json)."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "md5_table.json")) as f:
+            e = json.load(f).get(f"full:{workload}:{flagset}")
+        return e
+    except Exception:
+        return None
+
+
+# Algorithmic bytes per unit of the kernels that can dominate a step (DESIGN.md section 4); unit = one text suffix unless stated.
+ROOF = {
+    "expand_members": (29.0, "suffix"),      # occurrence list 16 B read; SA 8 + LCP 4 + BWT 1 B written
+    "detect_chunk": (5.0, "suffix"),         # LCP 4 B + BWT 1 B read
+    "detect_window": (4.0, "suffix"),
+    "sort_groups_warp": (16.0, "listed suffix and round"),
+    "fasta_pass": (1.5, "suffix"),           # half a FASTA byte read, one symbol written
+    "trigger_masks": (1.125, "suffix"),      # 1 B read + 1/8 B written
+    "cub_radix_sort": (None, None),          # library kernel: time only
+}
 
 
 def main():
@@ -284,17 +444,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("MMB_WORKLOAD", "c2"))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline AND the parity-sample check (profiling runs only)")
     ap.add_argument("--route", default=os.environ.get("MMB_ROUTE", "auto"), choices=["auto", "direct", "pfp"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--merge-mode", action="store_true", help="N = 1 only: run the partition flags (-M -n) without an exchange, to time that mode")
     ap.add_argument("--tile-ranks", type=int, default=0, help="ranks per stream tile on the PFP route (0 = engine default)")
     ap.add_argument("--roofline-kernel", default=None, help="kernel (name substring) whose launches are timed with CUDA events for the roofline line")
+    ap.add_argument("--kernel-table-steps", type=int, default=2, help="extra steps after the timed region with every launch bracketed by events (per-kernel table)")
+    ap.add_argument("--dump-output", default=None, help="write the .mums/.mems bytes of the last end-to-end step to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and args.workload == "c2":
         args.workload = "c5"            # several GPUs: the partition-merge configuration, one 32-genome partition per GPU
     spec = WORKLOADS[args.workload]
+    flagset = spec.get("flagset", "strict")
+    find_kw = dict(FLAGSETS[flagset][1])
 
     if args.impl == "reference":
         reference_arm(args, spec, rank)
@@ -351,16 +515,30 @@ def main():
     dev = host.cuda(non_blocking=False)
     pinned_imgs = [hv[o:o + s] for o, s in zip(offsets, sizes)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
-    opts = dict(merge=multi or args.merge_mode, anchor_merge=multi or args.merge_mode, route=args.route, tile_ranks=args.tile_ranks)
+    merge_flags = multi or args.merge_mode
+    opts = dict(merge=merge_flags, anchor_merge=merge_flags, route=args.route, tile_ranks=args.tile_ranks, **find_kw)
 
     from mumemto_b200 import partition
     tdev = torch.device("cuda", local)
+    exchange_ev = []       # (start, gathered, merged) events of the exchange step inside timed steps (N > 1)
 
-    def step_device():
+    def exchange(record):
+        """The exchange step of the path (N > 1): ONE all-gather of the partition tables, then the merge kernels on every rank."""
+        if record:
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(stream)
+        parts = partition.gather_partitions(partition.local_partition(eng, tdev), dist, world)
+        if record:
+            e1.record(stream)
+        partition.merge_gathered(eng, parts, fetch=False)
+        if record:
+            e2.record(stream); exchange_ev.append((e0, e1, e2))
+
+    def step_device(record=False):
         eng.load_fasta_device(dev.data_ptr(), offsets, sizes)
         st = eng.find(want_text=True, **opts)
-        if multi:       # the exchange step of the path: one all-gather of the partition tables, then the merge kernels on every rank
-            partition.partition_merge(eng, dist, world, tdev, fetch=False)
+        if multi:
+            exchange(record)
         return st
 
     out_host = None
@@ -375,7 +553,7 @@ def main():
             out_host = torch.empty(max(n, 1), dtype=torch.uint8).pin_memory()
         eng.copy_text_into(out_host.numpy())
         if multi:       # partition .mums above, then exchange + merge; rank 0 brings the merged .mums back to the host (pinned buffer)
-            partition.partition_merge(eng, dist, world, tdev, fetch=False)
+            exchange(False)
             if rank == 0:
                 mn = eng.merge_text_size()
                 if merged_host is None or merged_host.numel() < mn:
@@ -389,13 +567,9 @@ def main():
         torch.cuda.synchronize()
 
     min_warm = int(os.environ.get("MMB_MIN_WARMUP", "3"))      # profiling runs only; a bench line always has >= 3 warm-up steps
-    for _ in range(max(args.warmup, min_warm, 1)):
+    n_warm = max(args.warmup, min_warm, 1)
+    for _ in range(n_warm):
         flush.zero_(); st_warm = step_device()
-    # dominant kernel per route (profiles/README.md): algorithmic bytes per suffix it must move
-    ROOF = {"expand_members": 29.0,      # occurrence list 16 B read; SA 8 + LCP 4 + BWT 1 B written
-            "detect_window": 4.0,        # the LCP tile; SA/BWT only for surviving candidates
-            "sort_groups_warp": 16.0,    # per listed suffix and round: sa 4+4, isa 4 (random), nh 4
-            "fasta_scatter_pass": 1.5}   # per suffix: half a FASTA byte read, one symbol written
     roof_kernel = args.roofline_kernel or ("expand_members" if st_warm["route"] == 2 else "sort_groups_warp")
     eng.profile_kernel(roof_kernel)
     sampler = ClockSampler(local); sampler.start()
@@ -409,7 +583,7 @@ def main():
     for a, b in ev:
         flush.zero_()
         a.record(stream)
-        st = step_device()
+        st = step_device(record=True)
         b.record(stream)
         for k in stage:
             stage[k] += st[k]
@@ -426,6 +600,33 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = total_bases / (ms_max * 1e-3)
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    exchange_ms = None
+    if exchange_ev:
+        exchange_ms = {"allgather_ms": float(np.mean([a.elapsed_time(b) for a, b, _ in exchange_ev])),
+                       "merge_ms": float(np.mean([b.elapsed_time(c) for _, b, c in exchange_ev]))}
+
+    # ---- per-kernel table: a few extra steps with EVERY launch bracketed by events (outside the timed region: the brackets add no work
+    # but the table is not part of the headline number)
+    kernel_table = None
+    if args.kernel_table_steps > 0:
+        eng.profile_kernel("*")
+        for _ in range(args.kernel_table_steps):
+            flush.zero_(); step_device()
+        torch.cuda.synchronize()
+        tab = eng.profile_table()
+        eng.profile_kernel(None)
+        tot = sum(v[0] for v in tab.values()) or 1.0
+        top = sorted(tab.items(), key=lambda kv: -kv[1][0])[:12]
+        kernel_table = []
+        for name, (kms, kn) in top:
+            per_step = kms / args.kernel_table_steps
+            entry = {"kernel": name, "ms_per_step": round(per_step, 3), "launches_per_step": kn / args.kernel_table_steps, "share_of_kernel_time": round(kms / tot, 4)}
+            for key, (bpu, unit) in ROOF.items():
+                if key in name and bpu:
+                    gbs = bpu * float(st["text_symbols"]) / (per_step * 1e-3) / 1e9
+                    entry.update({"algorithmic_bytes_per_unit": bpu, "unit": unit, "achieved_gbs": round(gbs, 1)})
+            kernel_table.append(entry)
 
     # ---- end to end through the host-buffer call
     for _ in range(0 if args.no_e2e else 2):
@@ -445,13 +646,40 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = total_bases / float(te.item())
-    sampler.stop_flag = True; sampler.join(timeout=2)
-    verified = verify_sample(imgs, bytes(out_host.numpy()[:out_bytes]) if (out_host is not None and rank == 0 and not multi) else b"")
 
-    # ---- partition merge (N > 1): one NCCL all-gather of the partition tables, then the merge kernels on every rank
+    # ---- checks off the clock (rank 0): sampled lines against the sequences, md5 of the whole output against the reference's run on the
+    # full workload when that is on record, and the byte-for-byte parity sample against the reference executed here
+    verified = 0
+    output_md5 = None
+    golden_check = None
+    if rank == 0 and not multi and out_host is not None:
+        out_np = out_host.numpy()[:out_bytes]
+        if eng.mum_mode:
+            verified = verify_sample(imgs, bytes(out_np))
+        import hashlib
+        output_md5 = hashlib.md5(out_np).hexdigest()
+        if args.dump_output:
+            out_np.tofile(args.dump_output)
+        g = golden_md5(args.workload, flagset) if not args.merge_mode else None
+        if g:
+            ext = ".mums" if eng.mum_mode else ".mems"
+            golden_check = {"reference_md5": g["md5"].get(ext), "reference_lines": g["lines"].get(ext), "match": g["md5"].get(ext) == output_md5}
+            if not golden_check["match"]:
+                raise AssertionError(f"output md5 {output_md5} differs from the reference's {g['md5'].get(ext)} on the full workload {args.workload}")
+
+    # ---- partition merge (N > 1): the same exchange once more with wall-clock brackets and the table sizes
     merge_info = None
     if multi:
         merge_info = partition_merge(eng, dist, world, rank, spec)
+        if exchange_ms:
+            merge_info.update(exchange_ms)
+
+    cpu_base = parity = None
+    if rank == 0 and not args.no_cpu_baseline:
+        # at N > 1 rank 0 runs the same parity sample (the partition-merge check is the one that covers the multi-GPU path)
+        cpu_base, parity = cpu_baseline_and_parity(eng, tdev, spec if not multi else dict(WORKLOADS["c2"], L=spec["L"]))
+    if world > 1:
+        dist.barrier()
 
     if rank == 0:
         peaks = {}
@@ -468,36 +696,44 @@ def main():
             units = float(st["text_symbols"]) * max(1, int(st["sa_rounds"])) * args.steps      # upper bound: every suffix listed in every round
         # DRAM bytes per suffix of that kernel from its ncu --set full capture (dram__bytes_read.sum + dram__bytes_write.sum of one launch
         # divided by the suffixes that launch produced); the capture and its summary are under profiles/ncu/
-        traffic = None
+        traffic = None; traffic_src = None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu", "traffic.json")) as f:
                 tr = json.load(f).get(roof_kernel)
             if tr and roof_launches:
                 traffic = tr["dram_bytes_per_suffix"] * float(st["text_symbols"]) * args.steps / roof_launches
+                traffic_src = f"profiles/ncu/traffic.json: {tr['dram_bytes_per_suffix']} B per suffix from {tr.get('capture', 'an ncu --set full capture')} x the suffixes of one launch (a constant of the capture, not measured in this run)"
         except Exception:
             pass
-        k_bytes = ROOF.get(roof_kernel, 0.0) * units
+        bpu = (ROOF.get(roof_kernel) or (0.0, None))[0] or 0.0
+        k_bytes = bpu * units
         k_achieved = (k_bytes / (roof_ms * 1e-3) / 1e9) if roof_ms > 0 else None
         line = {"metric": "input bases/sec end-to-end (FASTA->.mums)", "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-                "data": "synthetic", "config": {"workload": spec["desc"], "name": args.workload, "l2": "flushed between steps (256 MiB write)",
+                "warmup": n_warm, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic", "config": {"workload": spec["desc"], "name": args.workload, "flags": FLAGSETS[flagset][0] + (["-M", "-n"] if merge_flags else []),
+                                                "l2": "flushed between steps (256 MiB write)",
                                                 "partitioning": "1 collection" if not multi else f"{world} partitions sharing anchor h0, -M -n, 1 per GPU"},
+                "value_region": "device: FASTA images resident in HBM -> formatted output bytes in HBM (CUDA events); e2e adds the host<->device copies; e2e_cli (when present) is process start -> closed file",
                 "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(sum(sizes)), "d2h_bytes_per_step": int(out_bytes)},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": k_achieved, "peak": peak, "unit": "GB/s",
-                             "frac": (k_achieved / peak) if k_achieved else None, "traffic": traffic, "achieved_per_launch_bytes": (k_bytes / roof_launches) if roof_launches else None,
+                             "frac": (k_achieved / peak) if k_achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                             "achieved_per_launch_bytes": (k_bytes / roof_launches) if roof_launches else None,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "kernel_ms_per_step": roof_ms / args.steps,
                              "kernel_launches_per_step": roof_launches / args.steps, "kernel_share_of_step": (roof_ms / args.steps) / ms if ms else None,
-                             "algorithmic_bytes_per_suffix": ROOF.get(roof_kernel),
-                             "whole_path": {"achieved": achieved, "frac": achieved / peak, "algorithmic_bytes_per_base": 60.0}},
+                             "algorithmic_bytes_per_suffix": bpu,
+                             "whole_path": {"achieved": achieved, "frac": achieved / peak, "algorithmic_bytes_per_base": 60.0},
+                             "kernels": kernel_table},
                 "stages_ms": {k: v / args.steps for k, v in stage.items()}, "step_ms": step_ms, "per_step_stages": per_step_stages, "e2e_stages_ms": e2e_stage,
-                "matches": int(st["num_matches"]), "verified_sample_lines": int(verified), "sa_rounds": int(st["sa_rounds"]), "sa_sorted_elements": int(st["sa_sorted_elements"]),
+                "matches": int(st["num_matches"]), "verified_sample_lines": int(verified), "output_md5": output_md5, "golden_full_size": golden_check,
+                "parity_sample": parity["result"] if parity else None, "parity_sample_detail": parity,
+                "sa_rounds": int(st["sa_rounds"]), "sa_sorted_elements": int(st["sa_sorted_elements"]),
                 "text_symbols": int(st["text_symbols"]), "wall_s_timed_region": t_wall, "clocks": sampler.summary(),
                 "route": int(st["route"]), "pfp": {k: int(st[k]) for k in ("pfp_phrases", "pfp_distinct_phrases", "pfp_dict_bytes", "pfp_tiles")}}
         if merge_info:
             line["partition_merge"] = merge_info
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_sample(spec)
+        if cpu_base and not multi:                          # the CPU figure is reported at N = 1 only; at N > 1 the run above serves the parity check
+            line["cpu_baseline"] = cpu_base
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -511,7 +747,7 @@ def partition_merge(eng, dist, world, rank, spec):
     torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
     parts = partition.gather_partitions(partition.local_partition(eng, dev), dist, world)
     torch.cuda.synchronize(); t1 = time.perf_counter()
-    partition.merge_gathered(eng, parts)
+    partition.merge_gathered(eng, parts, fetch=False)
     torch.cuda.synchronize(); t2 = time.perf_counter()
     return {"in_timed_step": True, "allgather_s": t1 - t0, "merge_s": t2 - t1, "merged_mums": int(eng.lib.mmb_merge_num_mums(eng.h)),
             "merged_columns": int(eng.lib.mmb_merge_num_docs(eng.h)), "partition_mums": [int(p[4]) for p in parts],

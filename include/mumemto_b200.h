@@ -141,6 +141,9 @@ MMB_API int mmb_merge_copy_text(mmb_engine* e, void* host_dst);
  * launching stream (NULL or "" switches it off and clears the record); mmb_profile_result adds up the recorded launches. */
 MMB_API int mmb_profile_kernel(const char* name_substring);
 MMB_API int mmb_profile_result(double* total_ms, uint64_t* launches);
+/* With mmb_profile_kernel("*") every launch is bracketed; this returns one line "kernel\tms\tlaunches\n" per kernel name (library
+ * sorts and scans appear as cub_radix_sort / cub_scan).  *needed = bytes required including the terminating NUL. */
+MMB_API int mmb_profile_table(char* dst, size_t cap, size_t* needed);
 
 /* The text T itself (|T| bytes), for tests. */
 MMB_API int mmb_copy_symbols(mmb_engine* e, uint8_t* dst);

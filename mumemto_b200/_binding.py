@@ -70,6 +70,7 @@ _SIGNATURES = {
     "mmb_find_from_arrays": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                        C.POINTER(Options)]),
     "mmb_profile_result": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "mmb_profile_table": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "mmb_mum_table_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "mmb_anchor_merge": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_uint64, C.c_int]),
@@ -273,6 +274,18 @@ class Engine:
         ms, n = C.c_double(), C.c_uint64()
         self.lib.mmb_profile_result(C.byref(ms), C.byref(n))
         return ms.value, n.value
+
+    def profile_table(self):
+        """{kernel name: (ms, launches)} of everything recorded since profile_kernel("*")."""
+        need = C.c_size_t()
+        self.lib.mmb_profile_table(None, 0, C.byref(need))
+        buf = C.create_string_buffer(need.value + 16)
+        self.lib.mmb_profile_table(buf, need.value + 16, C.byref(need))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, n = line.split("\t")
+            out[name] = (float(ms), int(n))
+        return out
 
     # ------------------------------------------------------------------ partition merge
     def mum_table_device(self):

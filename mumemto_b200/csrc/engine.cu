@@ -98,17 +98,18 @@ std::mutex mu;
 std::atomic<bool> on{false};
 std::string filter;                                    // empty = off
 std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pairs;
+std::vector<std::string> names;                        // kernel of each pair
 bool open_pair = false;
 }  // namespace profimpl
 void profile_before(const char* name, cudaStream_t s) {
     using namespace profimpl;
     if (!on.load(std::memory_order_relaxed)) return;
     std::lock_guard<std::mutex> lk(mu);
-    if (filter.empty() || !strstr(name, filter.c_str())) return;
+    if (filter.empty() || (filter != "*" && !strstr(name, filter.c_str()))) return;
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, s);
-    pairs.emplace_back(a, b); open_pair = true;
+    pairs.emplace_back(a, b); names.emplace_back(name); open_pair = true;
 }
 void profile_after(const char* name, cudaStream_t s) {
     using namespace profimpl;
@@ -799,7 +800,7 @@ int mmb_merge_copy_text(mmb_engine* e, void* host_dst) {
 int mmb_profile_kernel(const char* name_substring) {
     std::lock_guard<std::mutex> lk(profimpl::mu);
     for (auto& p : profimpl::pairs) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-    profimpl::pairs.clear(); profimpl::open_pair = false;
+    profimpl::pairs.clear(); profimpl::names.clear(); profimpl::open_pair = false;
     profimpl::filter = name_substring ? name_substring : "";
     profimpl::on.store(!profimpl::filter.empty());
     return MMB_OK;
@@ -812,6 +813,22 @@ int mmb_profile_result(double* total_ms, uint64_t* launches) {
     for (auto& p : profimpl::pairs) { float ms = 0; if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) t += ms; }
     if (total_ms) *total_ms = t;
     if (launches) *launches = profimpl::pairs.size();
+    return MMB_OK;
+}
+
+int mmb_profile_table(char* dst, size_t cap, size_t* needed) {
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(profimpl::mu);
+    std::map<std::string, std::pair<double, uint64_t>> agg;
+    for (size_t i = 0; i < profimpl::pairs.size(); ++i) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, profimpl::pairs[i].first, profimpl::pairs[i].second) != cudaSuccess) continue;
+        auto& a = agg[profimpl::names[i]]; a.first += ms; ++a.second;
+    }
+    std::string out;
+    for (auto& kv : agg) out += kv.first + "\t" + std::to_string(kv.second.first) + "\t" + std::to_string(kv.second.second) + "\n";
+    if (needed) *needed = out.size() + 1;
+    if (dst && cap) { size_t k = std::min(cap - 1, out.size()); memcpy(dst, out.data(), k); dst[k] = 0; }
     return MMB_OK;
 }
 

@@ -44,7 +44,9 @@ static void sort_impl(const u64* ki, u64* ko, const V* vi, V* vo, size_t n, int 
     MMB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ki, ko, vi, vo, (int64_t)n, b, e, s));
     Temp t(bytes, s);
     ++g_kernel_launches;
+    profile_before("cub_radix_sort", s);
     MMB_CUDA(cub::DeviceRadixSort::SortPairs(t.p, bytes, ki, ko, vi, vo, (int64_t)n, b, e, s));
+    profile_after("cub_radix_sort", s);
 }
 void sort_pairs(const u64* ki, u64* ko, const u32* vi, u32* vo, size_t n, int b, int e, cudaStream_t s) { sort_impl(ki, ko, vi, vo, n, b, e, s); }
 void sort_pairs64(const u64* ki, u64* ko, const u64* vi, u64* vo, size_t n, int b, int e, cudaStream_t s) { sort_impl(ki, ko, vi, vo, n, b, e, s); }
@@ -56,7 +58,9 @@ static void exsum_impl(const I* in, O* out, size_t n, cudaStream_t s) {
     MMB_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, bytes, in, out, cub::Sum(), (O)0, (int64_t)n, s));
     Temp t(bytes, s);
     ++g_kernel_launches;
+    profile_before("cub_scan", s);
     MMB_CUDA(cub::DeviceScan::ExclusiveScan(t.p, bytes, in, out, cub::Sum(), (O)0, (int64_t)n, s));
+    profile_after("cub_scan", s);
 }
 void exclusive_sum(const u32* in, u32* out, size_t n, cudaStream_t s) { exsum_impl(in, out, n, s); }
 void exclusive_sum(const u32* in, u64* out, size_t n, cudaStream_t s) { exsum_impl(in, out, n, s); }
@@ -69,7 +73,9 @@ static void incmax_impl(const T* in, T* out, size_t n, cudaStream_t s) {
     MMB_CUDA(cub::DeviceScan::InclusiveScan(nullptr, bytes, in, out, MaxOp(), (int64_t)n, s));
     Temp t(bytes, s);
     ++g_kernel_launches;
+    profile_before("cub_scan", s);
     MMB_CUDA(cub::DeviceScan::InclusiveScan(t.p, bytes, in, out, MaxOp(), (int64_t)n, s));
+    profile_after("cub_scan", s);
 }
 void inclusive_max(const u32* in, u32* out, size_t n, cudaStream_t s) { incmax_impl(in, out, n, s); }
 void inclusive_max(const u64* in, u64* out, size_t n, cudaStream_t s) { incmax_impl(in, out, n, s); }

@@ -86,5 +86,26 @@ def test_reference_partition_mode_gives_the_direct_result(tmp_path):
 
     inv = [order.index(i) for i in range(len(paths))]
     assert rows(tmp_path / "merged.mums", inv) == rows(tmp_path / "direct.mums", range(len(paths)))
-    t, secs = bench.run_reference_partitioned(REF, REF_MERGE, dict(spec, L=8000), 3, 1, 0)
-    assert t > 0 and secs == 3
+    files = bench.SampleFiles(dict(spec, L=8000))
+    secs, groups, mums, athresh = bench.run_reference_partitioned(REF, REF_MERGE, files, 3)
+    files.close()
+    assert secs > 0 and len(groups) == 3 and len(athresh) == 2 * 8001 and mums.count(b"\n") > 10
+
+
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(REF_MERGE)), reason="oracle/_ref is not built")
+@pytest.mark.parametrize("workload_flags", ["strict", "partial", "mem"])
+def test_parity_sample_check_runs_and_catches_a_difference(simt_lib, workload_flags, monkeypatch):
+    """bench.py's off-the-clock parity check (reference output vs engine output on the same sample, byte for byte; partitions ->
+    anchor_merge vs the device-input merge) driven through the CPU unit-test build of the kernels."""
+    import torch
+    from mumemto_b200 import Engine
+    spec = dict(N=7, L=30000, kind="pangenome", flagset=workload_flags, desc="t")
+    eng = Engine(0, _lib=simt_lib)
+    base, parity = bench.cpu_baseline_and_parity(eng, torch.device("cpu"), spec, sample_L=12000, procs=3)
+    assert parity["result"] == "ok" and parity["checks"]["direct"]["lines"] > 5
+    assert ("partitions_anchor_merge" in parity["checks"]) == (workload_flags == "strict")
+    assert base["value"] > 0 and base["extrapolated"]
+    monkeypatch.setattr(bench, "run_reference", lambda *a, **k: (1.0, b"20\t1,2\t+,+\n"))
+    with pytest.raises(AssertionError):
+        bench.cpu_baseline_and_parity(eng, torch.device("cpu"), spec, sample_L=12000, procs=3)
+    eng.close()

