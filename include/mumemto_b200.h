@@ -134,7 +134,7 @@ MMB_API int mmb_anchor_merge(mmb_engine* e, size_t nparts, const void* const* le
 MMB_API uint64_t mmb_merge_num_mums(const mmb_engine* e);
 MMB_API uint64_t mmb_merge_num_docs(const mmb_engine* e);
 MMB_API int mmb_merge_copy(mmb_engine* e, uint32_t* lengths, int64_t* offsets, uint8_t* strands /* 1 = '+' */, uint16_t* thresholds);
-MMB_API uint64_t mmb_merge_text_size(const mmb_engine* e);          /* merged .mums bytes (include/mumsio.hpp:283-296,318-326) */
+MMB_API uint64_t mmb_merge_text_size(mmb_engine* e);                /* merged .mums bytes (include/mumsio.hpp:283-296,318-326); formatted on first use */
 MMB_API int mmb_merge_copy_text(mmb_engine* e, void* host_dst);
 
 /* Measurement aid for bench.py: bracket every launch of the kernels whose name contains `name_substring` with CUDA events on the

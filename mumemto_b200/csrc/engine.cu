@@ -182,7 +182,7 @@ struct mmb_engine {
     MergePartition merged;              // result of the last mmb_anchor_merge
     DevBuf<u8> merged_text;
     u64 merged_text_bytes = 0, merged_anchor_len = 0;
-    bool has_merged = false;
+    bool has_merged = false, has_merged_text = false;
 };
 
 namespace {
@@ -743,42 +743,42 @@ int mmb_anchor_merge(mmb_engine* e, size_t nparts, const void* const* lengths, c
         MMB_CUDA(cudaSetDevice(e->device));
         cudaStream_t s = e->stream;
         e->has_merged = false;
-        auto prepare = [&](size_t p, MergePartition& out) {
+        std::vector<MergeSource> src(nparts);
+        std::vector<DevBuf<u32>> hl(nparts); std::vector<DevBuf<i64>> ho(nparts); std::vector<DevBuf<u8>> hs(nparts); std::vector<DevBuf<u16>> ht(nparts);
+        for (size_t p = 0; p < nparts; ++p) {
             u64 n = n_mums[p], nd = ndocs[p];
             if (nd < 2 || nd > 0xffffffffull) throw Error(61, "a partition needs at least two sequences");
-            if (inputs_on_device) {
-                merge_prepare((const u32*)lengths[p], (const i64*)offsets[p], (const u8*)strands[p], n, (u32)nd, (const u16*)thresholds[p], anchor_len, out, s);
-                return;
-            }
-            DevBuf<u32> l; DevBuf<i64> o; DevBuf<u8> st; DevBuf<u16> t;
-            l.alloc(n, s); o.alloc(n * nd, s); st.alloc(n * nd, s); t.alloc(anchor_len, s);
+            if (inputs_on_device) { src[p] = MergeSource{(const u32*)lengths[p], (const i64*)offsets[p], (const u8*)strands[p], (const u16*)thresholds[p], n, (u32)nd}; continue; }
+            hl[p].alloc(n, s); ho[p].alloc(n * nd, s); hs[p].alloc(n * nd, s); ht[p].alloc(anchor_len, s);
             if (n) {
-                MMB_CUDA(cudaMemcpyAsync(l.p, lengths[p], n * 4, cudaMemcpyHostToDevice, s));
-                MMB_CUDA(cudaMemcpyAsync(o.p, offsets[p], n * nd * 8, cudaMemcpyHostToDevice, s));
-                MMB_CUDA(cudaMemcpyAsync(st.p, strands[p], n * nd, cudaMemcpyHostToDevice, s));
+                MMB_CUDA(cudaMemcpyAsync(hl[p].p, lengths[p], n * 4, cudaMemcpyHostToDevice, s));
+                MMB_CUDA(cudaMemcpyAsync(ho[p].p, offsets[p], n * nd * 8, cudaMemcpyHostToDevice, s));
+                MMB_CUDA(cudaMemcpyAsync(hs[p].p, strands[p], n * nd, cudaMemcpyHostToDevice, s));
             }
-            if (anchor_len) MMB_CUDA(cudaMemcpyAsync(t.p, thresholds[p], anchor_len * 2, cudaMemcpyHostToDevice, s));
-            merge_prepare(l.p, o.p, st.p, n, (u32)nd, t.p, anchor_len, out, s);
-            MMB_CUDA(cudaStreamSynchronize(s));
-        };
-        MergePartition acc, next, res;
-        prepare(0, acc);
-        for (size_t p = 1; p < nparts; ++p) {
-            prepare(p, next);
-            merge_fold(acc, next, anchor_len, res, s);
-            std::swap(acc, res);
+            if (anchor_len) MMB_CUDA(cudaMemcpyAsync(ht[p].p, thresholds[p], anchor_len * 2, cudaMemcpyHostToDevice, s));
+            src[p] = MergeSource{hl[p].p, ho[p].p, hs[p].p, ht[p].p, n, (u32)nd};
         }
-        e->merged = std::move(acc);
+        merge_partitions(src.data(), nparts, anchor_len, e->merged, s);
         e->merged_anchor_len = anchor_len;
-        merge_text(e->merged, e->merged_text, e->merged_text_bytes, s);
+        e->merged_text.release(); e->merged_text_bytes = 0; e->has_merged_text = false;      // formatted on demand (mmb_merge_text_size / _copy_text)
         MMB_CUDA(cudaStreamSynchronize(s));
         e->has_merged = true;
     });
 }
 
+static int ensure_merged_text(mmb_engine* e) {
+    if (!e || !e->has_merged) return fail(MMB_ERR_STATE, "no merge result");
+    if (e->has_merged_text) return MMB_OK;
+    return guarded([&] {
+        MMB_CUDA(cudaSetDevice(e->device));
+        merge_text(e->merged, e->merged_text, e->merged_text_bytes, e->stream);
+        e->has_merged_text = true;
+    });
+}
+
 uint64_t mmb_merge_num_mums(const mmb_engine* e) { return (e && e->has_merged) ? e->merged.n : 0; }
 uint64_t mmb_merge_num_docs(const mmb_engine* e) { return (e && e->has_merged) ? e->merged.ndocs : 0; }
-uint64_t mmb_merge_text_size(const mmb_engine* e) { return (e && e->has_merged) ? e->merged_text_bytes : 0; }
+uint64_t mmb_merge_text_size(mmb_engine* e) { return ensure_merged_text(e) == MMB_OK ? e->merged_text_bytes : 0; }
 
 int mmb_merge_copy(mmb_engine* e, uint32_t* lengths, int64_t* offsets, uint8_t* strands, uint16_t* thresholds) {
     if (!e || !e->has_merged) return fail(MMB_ERR_STATE, "no merge result");
@@ -793,7 +793,7 @@ int mmb_merge_copy(mmb_engine* e, uint32_t* lengths, int64_t* offsets, uint8_t* 
 }
 
 int mmb_merge_copy_text(mmb_engine* e, void* host_dst) {
-    if (!e || !e->has_merged) return fail(MMB_ERR_STATE, "no merge result");
+    if (int rc = ensure_merged_text(e)) return rc;
     return guarded([&] { copy_out(e->merged_text.p, (u8*)host_dst, e->merged_text_bytes, e->stream); MMB_CUDA(cudaStreamSynchronize(e->stream)); });
 }
 

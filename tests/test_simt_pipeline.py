@@ -290,3 +290,30 @@ def test_simt_pfp_route_edge_inputs(simt_lib, oracle_bin, tmp_path):
     p.append(util.write_fasta(str(tmp_path / "iupac.fna"), [("y", util.mutate(rng, core, 0.01)[:300] + "NNNNNRYKMSWBDHVNU" + core[317:])], width=50, newline="\r\n"))
     for flags in ([], ["-f", "2"], ["-k", "-1", "-l", "10", "-A"]):
         both_pfp(simt_lib, oracle_bin, str(tmp_path), p, flags, tile_ranks=0)
+
+
+def test_simt_anchor_merge_is_the_fold_not_a_kway_min(simt_lib, ref_dir, tmp_path):
+    """MUMs of one partition may overlap.  When the fold suppresses an intermediate candidate (here: a zero threshold at 120), the next
+    fold step sees the EARLIER intermediate MUM (start 100, 20 symbols left at 130), not the latest-started source MUMs (90 left) that a
+    K-way min/max over the sources would use.  Hand-made partition files, reference anchor_merge (src/merge_candidates.cpp:106-157)."""
+    import subprocess
+    L = 400
+
+    def part(name, rows, nb):
+        with open(tmp_path / f"{name}.mums", "w") as f:
+            for ln, offs, strands in rows:
+                f.write(f"{ln}\t{','.join(map(str, offs))}\t{','.join(strands)}\n")
+        t = np.zeros(L, dtype=np.uint16)
+        for k, v in nb.items():
+            t[k] = v
+        t.tofile(tmp_path / f"{name}.athresh")
+        return str(tmp_path / f"{name}.mums")
+
+    a = part("a", [(50, (100, 7), "+-"), (100, (120, 1000), "++")], {100: 5, 130: 5})
+    b = part("b", [(200, (90, 300), "+-")], {90: 5, 100: 5, 120: 5, 130: 5})
+    c = part("c", [(100, (130, 40), "++")], {130: 5})
+    subprocess.run([os.path.join(ref_dir, "anchor_merge"), a, b, c, "-o", str(tmp_path / "om")], check=True, capture_output=True)
+    api.merge_files([a, b, c], str(tmp_path / "gm"), _lib=simt_lib)
+    got = util.outputs(str(tmp_path / "gm"))
+    assert got == util.outputs(str(tmp_path / "om"))
+    assert got[".mums"] == b"20\t130,7,440,40\t+,-,-,+\n"          # a K-way min over the latest-started sources would report 90
