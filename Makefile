@@ -27,9 +27,11 @@ $(LIB): $(OBJ)
 	@mkdir -p mumemto_b200/lib
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
 
-mumemto_b200/bin/mumemto_exec: $(CSRC)/cli_main.cpp $(LIB) $(HDRS)
+CUDA_HOME ?= /usr/local/cuda
+mumemto_b200/bin/mumemto_exec: $(CSRC)/cli_main.cpp $(CSRC)/multi_gpu.cpp $(CSRC)/multi_gpu.h $(LIB) $(HDRS)
 	@mkdir -p mumemto_b200/bin
-	$(CXX) -O2 -std=c++17 -Wall -Iinclude $< -o $@ -Lmumemto_b200/lib -lmumemto_b200 -lz -Wl,-rpath,'$$ORIGIN/../lib'
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude -I$(CUDA_HOME)/include $(CSRC)/cli_main.cpp $(CSRC)/multi_gpu.cpp -o $@ -Lmumemto_b200/lib -lmumemto_b200 \
+	    -L$(CUDA_HOME)/lib64 -lcudart -lnccl -lz -lpthread -Wl,-rpath,'$$ORIGIN/../lib' -Wl,-rpath,$(CUDA_HOME)/lib64
 mumemto_b200/bin/anchor_merge: $(CSRC)/anchor_merge_main.cpp $(LIB) $(HDRS)
 	@mkdir -p mumemto_b200/bin
 	$(CXX) -O2 -std=c++17 -Wall -Iinclude $< -o $@ -Lmumemto_b200/lib -lmumemto_b200 -Wl,-rpath,'$$ORIGIN/../lib'

@@ -56,7 +56,8 @@ typedef struct mmb_options {
     uint8_t want_text;           /* 1: also format the .mums/.mems bytes on the device */
     uint8_t route;               /* 0 auto; 1 direct suffix sorting of the text (|T| < 2^31); 2 prefix-free parse (dictionary + parse), any |T| < 2^40 with -F below 2^20 */
     uint8_t keep_arrays;         /* 1: keep SA/LCP of the whole stream for mmb_copy_arrays even on the tiled (route 2) path */
-    uint8_t reserved[6];
+    uint8_t no_prune;            /* 1: enumerate every suffix on route 2 (no segment pruning; results are identical) */
+    uint8_t reserved[5];
     uint64_t tile_ranks;         /* route 2: ranks per stream tile, 0 = default (2^30 in mmb_find = ~18 GB of tile buffers; 2^26 in mmb_find_from_arrays) */
 } mmb_options;
 
@@ -70,6 +71,9 @@ typedef struct mmb_stats {
     float ms_text, ms_sa, ms_lcp, ms_detect, ms_emit, ms_total;   /* CUDA-event times of the last mmb_find (ms_text: last load) */
     uint32_t route;              /* route taken by the last mmb_find (1 direct, 2 prefix-free parse, 3 arrays given by the caller) */
     uint32_t pfp_phrases, pfp_distinct_phrases, pfp_dict_bytes, pfp_tiles;
+    uint32_t pruned;             /* route 2: 1 when segments that cannot hold a match were left out of the suffix stream */
+    uint64_t stream_suffixes;    /* ranks that were enumerated and scanned (|T| + 1 without pruning) */
+    uint64_t threshold_segments; /* -M, pruned: segments whose threshold was taken without enumerating them */
 } mmb_stats;
 
 MMB_API const char* mmb_last_error(void);
@@ -78,6 +82,11 @@ MMB_API void mmb_default_options(mmb_options* o);
 /* cuda_stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL for the engine's own stream. */
 MMB_API int mmb_create(int device, void* cuda_stream, mmb_engine** out);
 MMB_API void mmb_destroy(mmb_engine* e);
+
+/* Page-locked host memory for inputs and outputs (copies to and from it run at full PCIe speed).  An engine must exist on the calling
+ * thread's device before the first call.  NULL on failure. */
+MMB_API void* mmb_alloc_pinned(size_t bytes);
+MMB_API void mmb_free_pinned(void* p);
 
 /* Input.  files[i] is the (decompressed) byte image of FASTA file i in host memory.  The copy to the device happens here. */
 MMB_API int mmb_load_fasta(mmb_engine* e, const uint8_t* const* files, const uint64_t* sizes, size_t nfiles, int use_revcomp);

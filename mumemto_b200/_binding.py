@@ -19,7 +19,7 @@ u8p = C.POINTER(C.c_uint8)
 class Options(C.Structure):
     _fields_ = [("min_match_len", C.c_uint32), ("num_distinct_docs", C.c_int32), ("rare_freq", C.c_int32), ("max_mem_freq", C.c_int32),
                 ("merge", C.c_uint8), ("anchor_merge", C.c_uint8), ("cli_normalise", C.c_uint8), ("want_text", C.c_uint8),
-                ("route", C.c_uint8), ("keep_arrays", C.c_uint8), ("reserved", C.c_uint8 * 6), ("tile_ranks", C.c_uint64)]
+                ("route", C.c_uint8), ("keep_arrays", C.c_uint8), ("no_prune", C.c_uint8), ("reserved", C.c_uint8 * 5), ("tile_ranks", C.c_uint64)]
 
 
 class Stats(C.Structure):
@@ -27,7 +27,8 @@ class Stats(C.Structure):
                 ("sa_rounds", C.c_uint32), ("sa_sorted_elements", C.c_uint64),
                 ("ms_text", C.c_float), ("ms_sa", C.c_float), ("ms_lcp", C.c_float), ("ms_detect", C.c_float), ("ms_emit", C.c_float),
                 ("ms_total", C.c_float), ("route", C.c_uint32), ("pfp_phrases", C.c_uint32), ("pfp_distinct_phrases", C.c_uint32),
-                ("pfp_dict_bytes", C.c_uint32), ("pfp_tiles", C.c_uint32)]
+                ("pfp_dict_bytes", C.c_uint32), ("pfp_tiles", C.c_uint32), ("pruned", C.c_uint32), ("stream_suffixes", C.c_uint64),
+                ("threshold_segments", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -44,6 +45,8 @@ _SIGNATURES = {
     "mmb_default_options": (None, [C.POINTER(Options)]),
     "mmb_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mmb_destroy": (None, [C.c_void_p]),
+    "mmb_alloc_pinned": (C.c_void_p, [C.c_size_t]),
+    "mmb_free_pinned": (None, [C.c_void_p]),
     "mmb_load_fasta": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_size_t, C.c_int]),
     "mmb_load_fasta_device": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_size_t, C.c_int]),
     "mmb_load_records": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t, C.c_int]),
@@ -167,9 +170,9 @@ class Engine:
     ROUTES = {"auto": 0, "direct": 1, "pfp": 2}
 
     def find(self, min_match_len=20, num_distinct_docs=0, rare_freq=1, max_mem_freq=0, merge=False, anchor_merge=False, cli_normalise=True,
-             want_text=True, route="auto", keep_arrays=False, tile_ranks=0):
+             want_text=True, route="auto", keep_arrays=False, tile_ranks=0, no_prune=False):
         o = Options(min_match_len, num_distinct_docs, rare_freq, max_mem_freq, int(merge), int(anchor_merge), int(cli_normalise), int(want_text),
-                    self.ROUTES[route], int(keep_arrays), (C.c_uint8 * 6)(), int(tile_ranks))
+                    self.ROUTES[route], int(keep_arrays), int(no_prune), (C.c_uint8 * 5)(), int(tile_ranks))
         self._check(self.lib.mmb_find(self.h, C.byref(o)))
         return self.stats()
 
@@ -177,7 +180,7 @@ class Engine:
                          max_mem_freq=0, merge=False, anchor_merge=False, cli_normalise=True, want_text=True, tile_ranks=0):
         """Detection over pre-computed arrays in the reference's file format (uint8 arrays: 5-byte LE SA / LCP entries, BWT bytes)."""
         o = Options(min_match_len, num_distinct_docs, rare_freq, max_mem_freq, int(merge), int(anchor_merge), int(cli_normalise), int(want_text),
-                    0, 0, (C.c_uint8 * 6)(), int(tile_ranks))
+                    0, 0, 0, (C.c_uint8 * 5)(), int(tile_ranks))
         dl = np.ascontiguousarray(doc_lengths, dtype=np.uint64)
         self._keep_arrays = (dl, sa5, lcp5, bwt)
         self._check(self.lib.mmb_find_from_arrays(self.h, dl.ctypes.data_as(C.POINTER(C.c_uint64)), len(dl), int(revcomp), _ptr(sa5), _ptr(lcp5),

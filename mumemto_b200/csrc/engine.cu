@@ -360,6 +360,13 @@ void mmb_destroy(mmb_engine* e) {
     if (own) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
 }
 
+void* mmb_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void mmb_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
 int mmb_load_fasta(mmb_engine* e, const uint8_t* const* files, const uint64_t* sizes, size_t nfiles, int use_revcomp) {
     if (!e || !files || !sizes) return fail(MMB_ERR_ARG, "null argument");
     return guarded([&] {
@@ -450,6 +457,7 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
         e->route = use_pfp ? 2 : 1;
         e->full_sa.release(); e->full_lcp.release(); e->bwt.release();
         e->stats.pfp_phrases = e->stats.pfp_distinct_phrases = e->stats.pfp_dict_bytes = e->stats.pfp_tiles = 0;
+        e->stats.stream_suffixes = n + 1; e->stats.pruned = 0; e->stats.threshold_segments = 0;
         if (!use_pfp) {
             t.start();
             build_suffix_array(e->text.text.p, n, e->sa, s);
@@ -472,7 +480,11 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
             e->sa.sa.release(); e->sa.isa.release(); e->lcp.release();
             t.start();
             if (!parsed) pfp_parse(e->text.text.p, n, ix, pp, s);
-            pfp_finish(e->text.text.p, n, ix, pp, s);
+            // segment pruning (pfp.h): off when the caller wants the whole suffix stream back
+            PfpPrune prune;
+            prune.enabled = (opts->keep_arrays || opts->no_prune) ? 0 : 1;
+            prune.min_len = e->prm.min_len; prune.size_lo = std::max<u32>(2, e->prm.num_distinct); prune.merge = merge ? 1 : 0; prune.ndocs = N;
+            pfp_finish(e->text.text.p, n, ix, pp, s, prune);
             pp = PfpParse();
             e->stats.ms_sa = t.stop() + ms_parse;
             e->stats.ms_lcp = 0;
@@ -489,6 +501,10 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
                 mmb_engine* e; cudaStream_t s; u16* thresh; bool keep; std::vector<MumTable> mparts; std::vector<MemTable> eparts; u32 tiles = 0;
                 void consume(const StreamTile& tile) override {
                     ++tiles;
+                    if (getenv("MMB_DEBUG_TILE")) {
+                        std::vector<u64> hs = to_host(tile.sa, tile.count, s); std::vector<u32> hl = to_host(tile.lcp, tile.count, s); std::vector<u8> hb = to_host(tile.bwt, tile.count, s);
+                        for (u64 r = 0; r < tile.count; ++r) fprintf(stderr, "[tile] %llu sa %llu lcp %u bwt %u\n", (unsigned long long)(tile.rank0 + r), (unsigned long long)hs[r], hl[r], hb[r]);
+                    }
                     Reports rep;
                     detect_intervals<u64>(tile.lcp, tile.sa, tile.bwt, e->text.text.p, tile.count, tile.first, e->prm, e->text.doc_start.p, thresh, rep, s, tile.doc);
                     if (e->mum_mode) { MumTable part; mum_rows<u64>(rep, tile.sa, e->prm, e->text.doc_start.p, e->text.doc_len.p, part, s); mparts.push_back(std::move(part)); }
@@ -508,6 +524,9 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
             DocLookup dl{e->doc_coarse.p, e->coarse_shift, e->text.doc_start.p, N};
             const bool doc_stream = merge && N < 255 && getenv("MMB_DOC_STREAM") && atoi(getenv("MMB_DOC_STREAM"));
             stream_suffixes(e->text.text.p, ix, tile_ranks, halo, consumer, s, doc_stream ? &dl : nullptr);
+            if (merge) segment_thresholds(ix, dl, thresh, s);
+            e->stats.stream_suffixes = ix.stream_ranks + 1; e->stats.pruned = ix.full_stream ? 0 : 1;
+            e->stats.threshold_segments = ix.n_closers;
             e->stats.ms_detect = t.stop();
             e->stats.pfp_tiles = consumer.tiles;
             t.start();

@@ -1,0 +1,35 @@
+// mumemto_b200/csrc/multi_gpu.h -- partition-merge over several GPUs inside ONE process (the drop-in executable's --gpus N).
+//
+// Replaces the reference's multi-core workflow `mumemto merge` (mumemto/merge_mums.py:171-183): P x `mumemto_exec -M -n` on partitions
+// that share their first sequence, then `anchor_merge` (src/merge_candidates.cpp:170-255).  Here: one host thread per GPU runs its
+// partition through the C ABI (include/mumemto_b200.h), ONE ncclAllGather moves the packed partition tables (lengths, offsets, strands,
+// thresholds) between the GPUs, and the merge kernels fold them on the first device; PREFIX.mums / PREFIX.athresh are byte-identical
+// to what `anchor_merge p0.mums p1.mums ...` writes for the same partitions.  Host code only: plain C++ on top of the C ABI, the CUDA
+// runtime (buffers, peer-less copies) and NCCL.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace mgpu {
+
+struct Request {
+    std::vector<std::string> files;             // input paths (for PREFIX.lengths), anchor first
+    std::vector<const uint8_t*> images;         // decompressed FASTA images, host memory (ideally pinned)
+    std::vector<uint64_t> sizes;
+    int gpus = 1;                               // devices first_device .. first_device + gpus - 1
+    int partitions = 0;                         // 0 = one per GPU; > gpus only with gpus == 1 (run one after the other, no NCCL)
+    int first_device = 0;
+    bool use_rcomp = true;
+    uint32_t min_match_len = 20;
+    bool binary = false;                        // PREFIX.bumbl instead of PREFIX.mums
+    std::string output_prefix;
+};
+
+// Partition p holds the anchor (file 0) and a contiguous slice of the other files, so the merged columns come out in input order.
+std::vector<std::vector<size_t>> make_partitions(size_t nfiles, size_t parts);
+
+// Returns false with `error` set on failure.
+bool run(const Request& rq, std::string& error);
+
+}  // namespace mgpu

@@ -241,6 +241,164 @@ __global__ void owned_fix_last_phrase(const u32* __restrict__ pid, u32 np, const
     }
 }
 
+
+// ================================================================================================ pruned route: rank words and segments
+// rank word (one u32 per rank of the initial key order):
+//   bit 31      the rank starts a segment (shares fewer than t key symbols with the rank before it)
+//   bit 30      the suffix is longer than w (it owns text suffixes)
+//   bit 29      the suffix is shorter than t symbols (its text suffixes may share fewer than t symbols with each other)
+//   bits 28..9  occurrences of its phrase (saturating)
+//   bits 8..0   symbol that precedes the suffix inside its phrase, 0x100 = the suffix is a whole phrase
+constexpr u32 RK_HB = 1u << 31, RK_OWN = 1u << 30, RK_SHORT = 1u << 29, RK_CNT_MAX = (1u << 20) - 1, RK_START = 0x100u;
+constexpr u32 SEG_LIMIT = 128;           // segments of more ranks than this are kept as they are (low-complexity repeats)
+constexpr u8 CLS_STREAM = 1, CLS_REFINE = 2, CLS_THRESH = 4, CLS_HAS_START = 8;
+
+__device__ __forceinline__ u32 key_shared(u64 a, u64 b, u32 bits, u32 cpk) {
+    u64 x = a ^ b;
+    return x ? cpk - 1 - (u32)(63 - __clzll((long long)x)) / bits : cpk;
+}
+
+__global__ void __launch_bounds__(TPB) phrase_counts(const u32* __restrict__ pid, u32 np, u32* __restrict__ count) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < np) atomicAdd(&count[pid[j]], 1u);
+}
+__global__ void __launch_bounds__(TPB) dict_info(const u32* __restrict__ dphrase, const u32* __restrict__ doff, const u8* __restrict__ dict,
+                                                 const u32* __restrict__ count, u32 dsize, u32* __restrict__ pinfo) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dsize) return;
+    u32 g = dphrase[i];
+    u32 before = i > doff[g] ? (u32)dict[i - 1] : RK_START;
+    pinfo[i] = (min(count[g], RK_CNT_MAX) << 9) | before;
+}
+__global__ void __launch_bounds__(TPB) rank_words(const u64* __restrict__ keys, const u32* __restrict__ sa_d, const u32* __restrict__ pinfo, u32 dsize,
+                                                  u32 bits, u32 cpk, u32 t, u32* __restrict__ rk) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= dsize) return;
+    u64 key = keys[p];
+    u32 w = pinfo[sa_d[p]];
+    if ((u32)(key >> (bits * (cpk - 1 - PFP_W))) & ((1u << bits) - 1)) w |= RK_OWN;
+    if (((u32)(key >> (bits * (cpk - t))) & ((1u << bits) - 1)) == 0) w |= RK_SHORT;           // symbol t - 1 is the terminator or past it
+    if (p == 0 || key_shared(keys[p - 1], key, bits, cpk) < t) w |= RK_HB;
+    rk[p] = w;
+}
+// the last phrase's w padding zeros are symbols of its string: its last w suffixes that are longer than w look short in their keys
+// (see owned_fix_last_phrase); one block per such suffix finds its rank among the equal keys and sets the bit
+__global__ void __launch_bounds__(TPB) rank_words_fix_last_phrase(const u32* __restrict__ pid, u32 np, const u32* __restrict__ doff, const u32* __restrict__ limit,
+                                                                  const u8* __restrict__ dict, const u8* __restrict__ lut, u32 bits, u32 cpk,
+                                                                  const u64* __restrict__ keys, const u32* __restrict__ sa_d, u32 dsize,
+                                                                  u32* __restrict__ rk) {
+    u32 g = pid[np - 1];
+    u32 i = doff[g + 1] - 1 - (PFP_W + 1) - blockIdx.x;                // positions with limit = w + 2 + blockIdx.x
+    if (i < doff[g] || i >= doff[g + 1]) return;
+    u32 lim = limit[i];
+    if (lim < PFP_W + 2 || lim > 2 * PFP_W + 1) return;
+    u64 key = 0;
+    for (u32 t = 0; t < cpk; ++t) key = (key << bits) | (u64)(t < lim ? lut[dict[i + t]] : 0);
+    u32 lo = 0, hi = dsize;                                             // first rank whose key is >= key
+    while (lo < hi) { u32 mid = lo + ((hi - lo) >> 1); if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+    for (u32 q = lo + threadIdx.x; q < dsize && keys[q] == key; q += blockDim.x)
+        if (sa_d[q] == i) rk[q] |= RK_OWN;
+}
+
+// Class of every rank that is longer than w: what its segment needs (CLS_*).  Each thread walks its segment in a shared-memory tile.
+__global__ void __launch_bounds__(TPB) classify_segments(const u32* __restrict__ rk, u32 dsize, PfpPrune prune, u32 seg_is_interval, u8* __restrict__ cls) {
+    __shared__ u32 tile[TPB + 2 * SEG_LIMIT + 1];
+    const i64 base = (i64)blockIdx.x * TPB - SEG_LIMIT;
+    for (u32 x = threadIdx.x; x < TPB + 2 * SEG_LIMIT + 1; x += TPB) {
+        i64 q = base + x;
+        tile[x] = (q >= 0 && q < (i64)dsize) ? rk[q] : RK_HB;       // outside the array: a segment start that owns nothing
+    }
+    __syncthreads();
+    u32 p = blockIdx.x * TPB + threadIdx.x;
+    if (p >= dsize) return;
+    u32 x = threadIdx.x + SEG_LIMIT, w = tile[x];
+    if (!(w & RK_OWN)) { cls[p] = 0; return; }
+    u8 all = CLS_STREAM | CLS_REFINE | CLS_HAS_START;     // without the walk: assume the segment may hold a whole phrase
+    if (!prune.enabled) { cls[p] = all; return; }
+    // walk to the segment's first and last rank
+    u32 a = x, steps = 0;
+    while (!(tile[a] & RK_HB) && steps < SEG_LIMIT) { --a; ++steps; }
+    if (!(tile[a] & RK_HB)) { cls[p] = all; return; }
+    u32 b = x;
+    while (!(tile[b + 1] & RK_HB) && steps < SEG_LIMIT) { ++b; ++steps; }
+    if (!(tile[b + 1] & RK_HB)) { cls[p] = all; return; }
+    u64 total = 0; u32 sym = 0xffffffffu; bool uniform = true, has_start = false, saturated = false, has_short = false;
+    for (u32 y = a; y <= b; ++y) {
+        u32 v = tile[y];
+        if (!(v & RK_OWN)) continue;
+        u32 c = (v >> 9) & RK_CNT_MAX, bsym = v & 0x1ffu;
+        total += c; saturated |= c == RK_CNT_MAX; has_short |= (v & RK_SHORT) != 0;
+        if (bsym == RK_START) { has_start = true; uniform = false; }
+        else if (sym == 0xffffffffu) sym = bsym;
+        else if (sym != bsym) uniform = false;
+    }
+    const u8 general = CLS_STREAM | CLS_REFINE;
+    u8 c = 0;
+    if (saturated) c = general;
+    else if (total >= prune.size_lo) {
+        if (!uniform) c = general;
+        // -M: a segment of exactly N suffixes, all at least t = -l symbols long, is one interval of length >= -l
+        else if (prune.merge) c = (seg_is_interval && !has_short && total == prune.ndocs) ? CLS_THRESH : general;
+    }
+    if (has_start) c |= CLS_REFINE | CLS_HAS_START;     // phrase ranks need the exact place of every whole phrase
+    cls[p] = c;
+}
+
+__global__ void __launch_bounds__(TPB) owned_positions(const u32* __restrict__ rk, u32 dsize, u32* __restrict__ out) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < dsize) out[p] = (rk[p] & RK_OWN) ? p + 1 : 0u;
+}
+
+// Per rank that is longer than w: key symbols shared with the previous such rank; member flags of the stream (surviving ranks and the
+// stand-in that follows a surviving segment); -M: the ranks that close a threshold-only segment.
+__global__ void __launch_bounds__(TPB) member_flags(const u64* __restrict__ keys, const u32* __restrict__ rk, const u8* __restrict__ cls,
+                                                    const u32* __restrict__ prev_owned, u32 dsize, u32 bits, u32 cpk, u32 t, u8* __restrict__ klcp,
+                                                    u32* __restrict__ member, u8* __restrict__ mkind, u8* __restrict__ refine,
+                                                    u32* __restrict__ closers, u32* __restrict__ n_closers) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    bool closes = false;
+    if (p < dsize) {
+        u32 w = rk[p];
+        u8 c = cls[p], kind = 0; u32 shared = 0;
+        if (w & RK_OWN) {
+            u32 q = p ? prev_owned[p - 1] : 0u;          // 1 + previous rank that is longer than w
+            if (q) shared = key_shared(keys[q - 1], keys[p], bits, cpk);
+            u8 cq = q ? cls[q - 1] : (u8)0;
+            if (c & CLS_STREAM) kind = 1;
+            else if (cq & CLS_STREAM) kind = 2;          // first rank after a surviving segment: carries the true LCP that closes it
+            closes = q && (cq & CLS_THRESH) && shared < t;
+        }
+        klcp[p] = (u8)shared; member[p] = kind ? 1u : 0u; mkind[p] = kind;
+        refine[p] = (u8)(((c & CLS_REFINE) ? 1 : 0) | ((c & CLS_HAS_START) ? 2 : 0));
+    }
+    if (p == dsize) member[p] = 0;
+    unsigned m = __ballot_sync(FULL, closes);
+    if (m) {
+        u32 lane = threadIdx.x & 31, base = 0;
+        if (lane == (u32)__ffs((int)m) - 1) base = atomicAdd(n_closers, (u32)__popc(m));
+        base = __shfl_sync(FULL, base, __ffs((int)m) - 1);
+        if (closes) closers[base + __popc(m & ((1u << lane) - 1))] = p;
+    }
+}
+
+// after the refinement (which permutes sa_d inside key groups, so the rank words' per-suffix fields no longer line up): ranks that hold
+// a whole phrase, looked up only in the segments that have one
+__global__ void __launch_bounds__(TPB) phrase_start_flags(const u8* __restrict__ refine, const u32* __restrict__ sa_d, const u32* __restrict__ dphrase,
+                                                          const u32* __restrict__ doff, u32 dsize, u32* __restrict__ flag) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < dsize) {
+        u32 f = 0;
+        if (refine[p] & 2) { u32 i = sa_d[p]; f = doff[dphrase[i]] == i ? 1u : 0u; }
+        flag[p] = f;
+    }
+    if (p == dsize) flag[p] = 0;
+}
+__global__ void __launch_bounds__(TPB) phrase_ranks_from_order(const u32* __restrict__ flag, const u32* __restrict__ before, const u32* __restrict__ sa_d,
+                                                               const u32* __restrict__ dphrase, u32 dsize, u32* __restrict__ prank) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < dsize && flag[p]) prank[dphrase[sa_d[p]]] = before[p] + 1;
+}
+
 __global__ void __launch_bounds__(TPB) phrase_rank_keys(const u32* __restrict__ isa_d, const u32* __restrict__ doff, u32 nd, u64* __restrict__ keys,
                                                         u32* __restrict__ vals) {
     u32 g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -416,11 +574,13 @@ void pfp_parse(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s
 }
 
 // stages 4-8
-void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s) {
+void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s, const PfpPrune& prune) {
     u32 np = ix.np, nd = ix.nd, dsize = ix.dsize;
     DevBuf<u32>& pid = pp.pid;
     // ---- 4. suffix order of the dictionary (ties allowed)
     PhaseTimer* pt = new PhaseTimer("pfp 4 dictionary SA", s);
+    bool pruned_done = false;
+    ix.prank.alloc(nd, s);
     {
         DevBuf<u32> hist; hist.alloc(256, s); hist.zero();
         MMB_LAUNCH(dict_histogram, 148 * 8, TPB, 0, s, (const u8*)ix.dict.p, dsize, hist.p);
@@ -431,30 +591,81 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
         u32 cpk = 64 / bits;
         DevBuf<u8> d_lut; d_lut.alloc(256, s);
         MMB_CUDA(cudaMemcpyAsync(d_lut.p, lut.data(), 256, cudaMemcpyHostToDevice, s));
-        ix.sa_d.alloc(dsize, s); ix.isa_d.alloc(dsize, s);
-        DevBuf<u32> isa2; isa2.alloc(2 * (u64)dsize, s);
-        MMB_LAUNCH(phrase_offsets, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.limit.p, (const u32*)ix.dphrase.p, (const u32*)ix.doff.p, dsize, isa2.p);
-        GroupStore groups;
-        {
-            DevBuf<u64> ka, kb; DevBuf<u32> va; ka.alloc(dsize, s); kb.alloc(dsize, s); va.alloc(dsize, s);
-            MMB_LAUNCH(dict_keys, ceil_div(dsize, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const u32*)ix.limit.p, dsize, (const u8*)d_lut.p, bits, cpk, ka.p, va.p);
+        MMB_CUDA(cudaStreamSynchronize(s));       // lut lives on this stack frame
+        ix.sa_d.alloc(dsize, s);
+        DevBuf<u64> ka, kb; DevBuf<u32> va; ka.alloc(dsize, s); kb.alloc(dsize, s); va.alloc(dsize, s);
+        MMB_LAUNCH(dict_keys, ceil_div(dsize, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const u32*)ix.limit.p, dsize, (const u8*)d_lut.p, bits, cpk, ka.p, va.p);
+        // Pruned route: needs the longer-than-w flag in the key (cpk > w) and a segment prefix of at least w + 1 symbols.
+        const u32 t = std::min(prune.min_len, cpk);
+        const bool try_pruned = cpk > PFP_W && t > PFP_W && !getenv("MMB_NO_PRUNE");
+        if (try_pruned) {
+            prim::sort_pairs(ka.p, kb.p, va.p, ix.sa_d.p, dsize, 0, (int)(bits * cpk), s);
+            ka.release(); va.release();
+            DevBuf<u32> count, pinfo; count.alloc(nd, s); count.zero(); pinfo.alloc(dsize, s);
+            MMB_LAUNCH(phrase_counts, ceil_div(np, TPB), TPB, 0, s, (const u32*)pid.p, np, count.p);
+            MMB_LAUNCH(dict_info, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.dphrase.p, (const u32*)ix.doff.p, (const u8*)ix.dict.p, (const u32*)count.p, dsize, pinfo.p);
+            ix.rk.alloc(dsize, s);
+            MMB_LAUNCH(rank_words, ceil_div(dsize, TPB), TPB, 0, s, (const u64*)kb.p, (const u32*)ix.sa_d.p, (const u32*)pinfo.p, dsize, bits, cpk, t, ix.rk.p);
+            MMB_LAUNCH(rank_words_fix_last_phrase, PFP_W, TPB, 0, s, (const u32*)pid.p, np, (const u32*)ix.doff.p, (const u32*)ix.limit.p, (const u8*)ix.dict.p,
+                       (const u8*)d_lut.p, bits, cpk, (const u64*)kb.p, (const u32*)ix.sa_d.p, dsize, ix.rk.p);
+            pinfo.release(); count.release();
+            DevBuf<u8> cls, refine; cls.alloc(dsize, s); refine.alloc(dsize, s);
+            MMB_LAUNCH(classify_segments, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.rk.p, dsize, prune, (u32)(t == prune.min_len ? 1 : 0), cls.p);
+            ix.prev_owned.alloc(dsize, s);
+            {
+                DevBuf<u32> own_pos; own_pos.alloc(dsize, s);
+                MMB_LAUNCH(owned_positions, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.rk.p, dsize, own_pos.p);
+                prim::inclusive_max(own_pos.p, ix.prev_owned.p, dsize, s);
+            }
+            ix.owned.alloc((u64)dsize + 1, s); ix.klcp.alloc(dsize, s); ix.mkind.alloc(dsize, s); ix.key_symbols = cpk; ix.seg_symbols = t;
+            DevBuf<u32> n_closers; n_closers.alloc(1, s); n_closers.zero();
+            if (prune.merge && prune.enabled) ix.closers.alloc(dsize, s);
+            MMB_LAUNCH(member_flags, ceil_div((u64)dsize + 1, TPB), TPB, 0, s, (const u64*)kb.p, (const u32*)ix.rk.p, (const u8*)cls.p, (const u32*)ix.prev_owned.p, dsize,
+                       bits, cpk, t, ix.klcp.p, ix.owned.p, ix.mkind.p, refine.p, ix.closers.p, n_closers.p);
+            cls.release();
+            ix.ghead.alloc(dsize, s);
+            const u32 max_rounds = getenv("MMB_CHUNK_ROUNDS") ? (u32)atoi(getenv("MMB_CHUNK_ROUNDS")) : 64u;
+            pruned_done = refine_dictionary_chunks(kb.p, ix.sa_d.p, dsize, cpk, bits, ix.dict.p, ix.limit.p, d_lut.p, refine.p, ix.ghead.p, ix.stats_d, s, max_rounds);
+            if (pruned_done) {
+                ix.pruned = true; ix.full_stream = !prune.enabled;
+                ix.n_closers = to_host(n_closers.p, 1, s)[0];
+                // phrase ranks: whole phrases in suffix order
+                DevBuf<u32> flag, before; flag.alloc((u64)dsize + 1, s); before.alloc((u64)dsize + 1, s);
+                MMB_LAUNCH(phrase_start_flags, ceil_div((u64)dsize + 1, TPB), TPB, 0, s, (const u8*)refine.p, (const u32*)ix.sa_d.p, (const u32*)ix.dphrase.p,
+                           (const u32*)ix.doff.p, dsize, flag.p);
+                prim::exclusive_sum(flag.p, before.p, (u64)dsize + 1, s);
+                MMB_LAUNCH(phrase_ranks_from_order, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)flag.p, (const u32*)before.p, (const u32*)ix.sa_d.p,
+                           (const u32*)ix.dphrase.p, dsize, ix.prank.p);
+            } else {
+                // a phrase with a very long low-complexity stretch: start over with the doubling engine, nothing pruned
+                ix.rk.release(); ix.prev_owned.release(); ix.owned.release(); ix.klcp.release(); ix.mkind.release(); ix.closers.release(); ix.ghead.release();
+                ix.stats_d = SaStats();
+                ka.alloc(dsize, s); va.alloc(dsize, s);
+                MMB_LAUNCH(dict_keys, ceil_div(dsize, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const u32*)ix.limit.p, dsize, (const u8*)d_lut.p, bits, cpk, ka.p, va.p);
+            }
+        }
+        if (!pruned_done) {
+            ix.isa_d.alloc(dsize, s);
+            DevBuf<u32> isa2; isa2.alloc(2 * (u64)dsize, s);
+            MMB_LAUNCH(phrase_offsets, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.limit.p, (const u32*)ix.dphrase.p, (const u32*)ix.doff.p, dsize, isa2.p);
+            GroupStore groups;
             order_by_initial_keys(ka.p, kb.p, va.p, dsize, (int)(bits * cpk), cpk, ix.limit.p, ix.sa_d.p, isa2.p, groups, s, 2);
             if (cpk > PFP_W) {
                 ix.owned.alloc((u64)dsize + 1, s); ix.klcp.alloc(dsize, s); ix.key_symbols = cpk;
                 MMB_LAUNCH(owned_from_keys, ceil_div((u64)dsize + 1, TPB), TPB, 0, s, (const u64*)kb.p, dsize, bits, cpk, ix.owned.p, ix.klcp.p);
             }
+            ka.release(); kb.release(); va.release();
+            refine_by_doubling(ix.sa_d.p, isa2.p, dsize, cpk, ix.limit.p, groups, ix.stats_d, s, 2);
+            MMB_LAUNCH(unpair_ranks, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)isa2.p, dsize, ix.isa_d.p);
+            isa2.release();
+            if (ix.owned.p) MMB_LAUNCH(owned_fix_last_phrase, 1, 256, 0, s, (const u32*)pid.p, np, (const u32*)ix.doff.p, (const u32*)ix.limit.p, (const u32*)ix.isa_d.p, (const u32*)ix.sa_d.p, dsize, ix.owned.p);
         }
-        refine_by_doubling(ix.sa_d.p, isa2.p, dsize, cpk, ix.limit.p, groups, ix.stats_d, s, 2);
-        MMB_LAUNCH(unpair_ranks, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)isa2.p, dsize, ix.isa_d.p);
-        isa2.release();
-        if (ix.owned.p) MMB_LAUNCH(owned_fix_last_phrase, 1, 256, 0, s, (const u32*)pid.p, np, (const u32*)ix.doff.p, (const u32*)ix.limit.p, (const u32*)ix.isa_d.p, (const u32*)ix.sa_d.p, dsize, ix.owned.p);
-        MMB_CUDA(cudaStreamSynchronize(s));       // lut lives on this stack frame
+        MMB_CUDA(cudaStreamSynchronize(s));
     }
 
     // ---- 5. phrase ranks and the parse
     delete pt; pt = new PhaseTimer("pfp 5 phrase ranks", s);
-    ix.prank.alloc(nd, s);
-    {
+    if (!pruned_done) {
         DevBuf<u64> ka, kb; DevBuf<u32> va, vb; ka.alloc(nd, s); kb.alloc(nd, s); va.alloc(nd, s); vb.alloc(nd, s);
         MMB_LAUNCH(phrase_rank_keys, ceil_div(nd, TPB), TPB, 0, s, (const u32*)ix.isa_d.p, (const u32*)ix.doff.p, nd, ka.p, va.p);
         prim::sort_pairs(ka.p, kb.p, va.p, vb.p, nd, 0, 32, s);

@@ -35,10 +35,22 @@ struct PfpIndex {
     u32 dsize = 0;                  // |D'|
     DevBuf<u8> dict;                // [dsize + 64]
     DevBuf<u32> limit;              // [dsize] symbols from here up to and including the terminator
-    DevBuf<u32> sa_d, isa_d;        // suffix order of D' (equal strings share one head rank in isa_d)
-    DevBuf<u32> owned;              // [dsize + 1] by rank in sa_d: 1 = the suffix is longer than w (may be empty: stream.cu then derives it)
-    DevBuf<u8> klcp;                // [dsize] by rank in sa_d: symbols shared with the previous rank inside the initial sort key, capped at
-    u32 key_symbols = 0;            //   key_symbols (both from the sorted keys; empty when `owned` is)
+    DevBuf<u32> sa_d, isa_d;        // suffix order of D' (equal strings share one head rank in isa_d; isa_d is empty on the pruned route)
+    DevBuf<u32> owned;              // [dsize + 1] by rank in sa_d: 1 = the suffix is a member of the stream: longer than w and (pruned route)
+                                    //   not pruned, or the stand-in that follows a surviving segment (may be empty: stream.cu then derives it)
+    DevBuf<u8> klcp;                // [dsize] by rank in sa_d: symbols shared inside the initial sort key with the previous rank (full route) or
+    u32 key_symbols = 0;            //   with the previous rank that is longer than w (pruned route), capped at key_symbols
+    // ---- pruned route only (see PfpPrune)
+    bool pruned = false;            // the dictionary order came from the chunk engine (rank words, ghead ... are filled)
+    bool full_stream = true;        // nothing was left out: the stream has all |T| suffixes
+    DevBuf<u32> ghead;              // [dsize] by rank: first rank of the run of equal strings the rank belongs to
+    DevBuf<u8> mkind;               // [dsize] by rank: 1 = ordinary member, 2 = stand-in rank after a surviving segment
+    DevBuf<u32> rk;                 // [dsize] by rank: segment start / longer-than-w / occurrences / preceding symbol (pfp.cu: rank words)
+    DevBuf<u32> prev_owned;         // [dsize] by rank: 1 + the last rank <= p that is longer than w (0 = none)
+    DevBuf<u32> closers;            // -M: ranks that close a segment whose only possible interval is the whole segment (threshold only)
+    u32 n_closers = 0;
+    u32 seg_symbols = 0;            // symbols that define a segment (min(-l, key_symbols))
+    u64 stream_ranks = 0;           // text suffixes that are enumerated (members' occurrences + stand-ins)
     DevBuf<u32> dphrase;            // [dsize] distinct-phrase id (in D' order) of every dictionary position
     DevBuf<u32> doff;               // [nd + 1] start of each distinct phrase in D'
     DevBuf<u32> prank;              // [nd] lexicographic rank (1-based) of each distinct phrase
@@ -52,10 +64,27 @@ struct PfpIndex {
 
 struct PfpParse { DevBuf<u32> pid; };      // provisional phrase id of every phrase occurrence, handed from pfp_parse to pfp_finish
 
+// Segment pruning.  Sorted by their first t = min(-l, key symbols) symbols the dictionary suffixes fall into
+// SEGMENTS; text suffixes of different segments share fewer than -l symbols, so no reportable interval crosses a segment boundary.  A
+// segment can be left out of the suffix stream when none of its intervals can be reported:
+//   * fewer text suffixes than the smallest interval size that qualifies (max(2, -k)), or
+//   * every suffix is preceded by the same symbol inside its phrase: no interval is left-maximal (the reference's check_bwt_range,
+//     include/mem_finder.hpp:189-192).  With -M the thresholds of such intervals are still needed (recorded before the BWT test,
+//     :326-336): a segment of exactly N suffixes is one interval, whose threshold needs no suffix order at all (stream.cu,
+//     segment_thresholds); any other same-symbol segment stays in the stream.
+// Only surviving segments (and the key groups that hold a whole phrase: phrase ranks) are sorted beyond the initial key.
+struct PfpPrune {
+    u32 enabled = 0;
+    u32 min_len = 20;       // -l
+    u32 size_lo = 2;        // smallest interval size that can qualify
+    u32 merge = 0;          // -M
+    u32 ndocs = 0;
+};
+
 void build_pfp_index(const u8* text, u64 n, PfpIndex& out, cudaStream_t s);
 // The same in two steps: parse + dictionary (stages 1-3, cheap) and everything else; `auto` routing looks at ix.dsize in between.
 void pfp_parse(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s);
-void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s);
+void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s, const PfpPrune& prune = PfpPrune());
 
 // One window of the suffix stream in rank order, with `halo` ranks of the previous window in front of it.
 struct StreamTile {
@@ -77,5 +106,7 @@ struct DocLookup { const u16* coarse; u32 shift; const u64* doc_start; u32 ndocs
 struct TileConsumer { virtual void consume(const StreamTile& t) = 0; virtual ~TileConsumer() {} };
 void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 halo, TileConsumer& consumer, cudaStream_t s,
                      const DocLookup* docs = nullptr);
+// -M on the pruned route: thresholds of the segments listed in ix.closers (every one is a single interval of ndocs suffixes).
+void segment_thresholds(const PfpIndex& ix, const DocLookup& docs, u16* thresh, cudaStream_t s);
 
 }  // namespace mmb

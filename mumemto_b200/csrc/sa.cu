@@ -26,7 +26,7 @@ namespace {
 
 constexpr u32 TPB = 256;
 constexpr u32 FULL = 0xffffffffu;
-constexpr u32 BLOCK_SORT_MAX = 4096;      // elements one block sorts in shared memory
+constexpr u32 BLOCK_SORT_MAX = 2048;      // elements one block sorts in shared memory
 constexpr int NCLASS = 9;                 // size classes: <=4, <=8, <=16, <=32, <=64, <=128, <=256, <=BLOCK_SORT_MAX, larger
 
 typedef u64 Group;                        // head << 32 | size
@@ -331,6 +331,209 @@ void launch_apply_class(const Group* groups, u32 n, const u32* sa, const u32* nh
     MMB_LAUNCH(apply_groups_warp_k, ceil_div((u64)n * WIDTH, TPB), TPB, 0, s, groups, n, sa, nh, changed, isa);
 }
 
+// ================================================================================================ dictionary refinement by symbol chunks
+// The pruned prefix-free-parse route (pfp.cu) only needs the exact order of the dictionary suffixes inside the few key groups whose
+// text suffixes can still take part in a match (or that hold a whole phrase).  Those groups are refined WITHOUT a rank array: round r
+// compares the next `cpk` symbols of every listed suffix, packed from the dictionary bytes themselves (one or two random sectors per
+// listed suffix and round, nothing written back but the permuted sa entries).  A suffix whose string has ended sorts with key 0 and ties
+// with every other ended suffix of its group (equal strings: a member group of the stream).
+// Output: sa reordered inside the listed groups; ghead[rank] = first rank of the run of equal strings the rank belongs to.
+struct DictView {
+    const u8* dict; const u32* limit; const u8* lut; u32 bits, cpk;
+};
+
+__device__ __forceinline__ u64 chunk_key(const DictView& D, const u8* code, u32 s, u32 h) {
+    u32 lim = D.limit[s];                            // symbols from s up to and including the terminator
+    if (lim <= h) return 0ull;
+    u32 take = min(D.cpk, lim - h);
+    const u8* q = D.dict + (u64)s + h;
+    u64 key = 0;
+    for (u32 t = 0; t < D.cpk; ++t) key = (key << D.bits) | (u64)(t < take ? code[q[t]] : 0);
+    return key;
+}
+
+template <int WIDTH, int K>
+__global__ void __launch_bounds__(TPB) sort_dgroups_warp(const Group* __restrict__ groups, u32 ngroups, u32 h, DictView D, u32* __restrict__ sa,
+                                                         u32* __restrict__ ghead, GroupLists next) {
+    __shared__ u8 code[256];
+    code[threadIdx.x] = D.lut[threadIdx.x];
+    __syncthreads();
+    u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 gi = tid / WIDTH, lane = tid % WIDTH;
+    bool have = gi < ngroups;
+    Group g = have ? groups[gi] : 0;
+    u32 head = g_head(g), size = have ? g_size(g) : 0u;
+    u32 s[K]; u64 key[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        u32 e = lane + (u32)WIDTH * k;
+        s[k] = 0; key[k] = 0;
+        if (e < size) { s[k] = sa[head + e]; key[k] = chunk_key(D, code, s[k], h); }
+    }
+    u32 lt[K], eq[K], before[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { lt[k] = 0; eq[k] = 0; before[k] = 0; }
+#pragma unroll
+    for (int k2 = 0; k2 < K; ++k2) {
+        for (int j = 0; j < WIDTH; ++j) {
+            u64 kj = __shfl_sync(FULL, key[k2], j, WIDTH);
+            u32 ej = (u32)j + (u32)WIDTH * k2;
+            if (ej < size) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    u32 e = lane + (u32)WIDTH * k;
+                    lt[k] += kj < key[k];
+                    eq[k] += kj == key[k];
+                    before[k] += (kj == key[k]) && (ej < e);
+                }
+            }
+        }
+    }
+    bool split = (size > 0) && (eq[0] != size);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        u32 e = lane + (u32)WIDTH * k;
+        bool valid = e < size;
+        u32 run = head + lt[k], slot = run + before[k];
+        if (valid) {
+            if (split) sa[slot] = s[k];
+            if (eq[k] == 1 || key[k] == 0) ghead[slot] = run;          // final: alone, or tied with equal strings
+        }
+        append_group_warp(valid && before[k] == 0 && eq[k] > 1 && key[k] != 0, run, eq[k], next);
+    }
+}
+
+__global__ void __launch_bounds__(TPB) sort_dgroups_block(const Group* __restrict__ groups, u32 h, DictView D, u32* __restrict__ sa,
+                                                          u32* __restrict__ ghead, GroupLists next) {
+    __shared__ u64 key[BLOCK_SORT_MAX];
+    __shared__ u32 suf[BLOCK_SORT_MAX];
+    __shared__ u16 idx[BLOCK_SORT_MAX];           // element index carried through the sort
+    __shared__ u16 start_of[BLOCK_SORT_MAX];
+    __shared__ u8 code[256];
+    code[threadIdx.x] = D.lut[threadIdx.x];
+    __syncthreads();
+    Group g = groups[blockIdx.x];
+    u32 head = g_head(g), size = g_size(g);
+    u32 n2 = 1; while (n2 < size) n2 <<= 1;
+    for (u32 e = threadIdx.x; e < n2; e += blockDim.x) {
+        u64 v = ~0ull;
+        if (e < size) { u32 s = sa[head + e]; suf[e] = s; v = chunk_key(D, code, s, h); }
+        key[e] = v; idx[e] = (u16)e;
+    }
+    __syncthreads();
+    for (u32 k = 2; k <= n2; k <<= 1) {
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            for (u32 e = threadIdx.x; e < n2; e += blockDim.x) {
+                u32 partner = e ^ j;
+                if (partner > e) {
+                    u64 a = key[e], b = key[partner]; u16 ia = idx[e], ib = idx[partner];
+                    bool up = (e & k) == 0;
+                    bool gt = a > b || (a == b && ia > ib);
+                    if (gt == up) { key[e] = b; key[partner] = a; idx[e] = ib; idx[partner] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    __shared__ u32 slice_max[TPB];
+    u32 per = (size + blockDim.x - 1) / blockDim.x;
+    u32 lo = min(threadIdx.x * per, size), hi = min(lo + per, size);
+    u32 run = 0;
+    for (u32 e = lo; e < hi; ++e) {
+        if (e == 0 || key[e] != key[e - 1]) run = e + 1;
+        start_of[e] = (u16)run;
+    }
+    slice_max[threadIdx.x] = run;
+    __syncthreads();
+    for (u32 d = 1; d < blockDim.x; d <<= 1) {
+        u32 v = (threadIdx.x >= d) ? slice_max[threadIdx.x - d] : 0u;
+        __syncthreads();
+        slice_max[threadIdx.x] = max(slice_max[threadIdx.x], v);
+        __syncthreads();
+    }
+    u32 carry = threadIdx.x ? slice_max[threadIdx.x - 1] : 0u;
+    for (u32 e = lo; e < hi; ++e) {
+        u32 st = max((u32)start_of[e], carry) - 1;
+        u64 kk = key[e];
+        sa[head + e] = suf[idx[e]];
+        bool last = (e + 1 == size) || key[e + 1] != kk;
+        bool first = e == st;
+        if (kk == 0 || (first && last)) ghead[head + e] = head + st;
+        if (last && e != st && kk != 0) append_group_single(head + st, e - st + 1, next);
+    }
+}
+
+// groups larger than one block sorts: flat list, sorted by chunk key and then (stably) by group
+__global__ void __launch_bounds__(TPB) dlarge_gather(const Group* __restrict__ groups, const u32* __restrict__ base, u32 h, DictView D,
+                                                     const u32* __restrict__ sa, u64* __restrict__ keys, u32* __restrict__ gid, u32* __restrict__ sfx,
+                                                     u32* __restrict__ iota) {
+    __shared__ u8 code[256];
+    code[threadIdx.x] = D.lut[threadIdx.x];
+    __syncthreads();
+    Group g = groups[blockIdx.x];
+    u32 head = g_head(g), size = g_size(g), b = base[blockIdx.x];
+    for (u32 e = blockIdx.y * blockDim.x + threadIdx.x; e < size; e += gridDim.y * blockDim.x) {
+        u32 s = sa[head + e];
+        keys[b + e] = chunk_key(D, code, s, h); gid[b + e] = blockIdx.x; sfx[b + e] = s; iota[b + e] = b + e;
+    }
+}
+__global__ void __launch_bounds__(TPB) dlarge_gid_keys(const u32* __restrict__ perm, const u32* __restrict__ gid, u32 A, u64* __restrict__ out) {
+    u32 a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < A) out[a] = gid[perm[a]];
+}
+__global__ void __launch_bounds__(TPB) dlarge_scatter(const u32* __restrict__ perm, const u64* __restrict__ keys, const u32* __restrict__ gid,
+                                                      const u32* __restrict__ sfx, const Group* __restrict__ groups, const u32* __restrict__ base, u32 A,
+                                                      u32* __restrict__ sa, u64* __restrict__ skey, u32* __restrict__ pos, u32* __restrict__ head_cand) {
+    u32 a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= A) return;
+    u32 src = perm[a], g = gid[src];
+    u32 p = g_head(groups[g]) + (a - base[g]);
+    u64 k = keys[src];
+    sa[p] = sfx[src]; skey[a] = k; pos[a] = p;
+    bool first = (a == base[g]) || keys[perm[a - 1]] != k;
+    head_cand[a] = first ? p : 0u;
+}
+__global__ void __launch_bounds__(TPB) dlarge_finish(const u32* __restrict__ pos, const u64* __restrict__ skey, const u32* __restrict__ head,
+                                                     const u32* __restrict__ perm, const u32* __restrict__ gid, u32 A, u32* __restrict__ ghead,
+                                                     GroupLists next) {
+    u32 a = blockIdx.x * blockDim.x + threadIdx.x;
+    bool want = false; u32 hd = 0, p = 0;
+    if (a < A) {
+        hd = head[a]; p = pos[a];
+        u64 k = skey[a];
+        bool last = (a + 1 == A) || skey[a + 1] != k || gid[perm[a + 1]] != gid[perm[a]];
+        if (k == 0 || (last && hd == p)) ghead[p] = hd;
+        want = last && hd != p && k != 0;
+    }
+    append_group_warp(want, hd, p - hd + 1, next);
+}
+
+template <int WIDTH, int K>
+void launch_dwarp_class(const Group* groups, u32 n, u32 h, const DictView& D, u32* sa, u32* ghead, const GroupLists& next, cudaStream_t s) {
+    if (!n) return;
+    auto sort_dgroups_warp_k = sort_dgroups_warp<WIDTH, K>;
+    MMB_LAUNCH(sort_dgroups_warp_k, ceil_div((u64)n * WIDTH, TPB), TPB, 0, s, groups, n, h, D, sa, ghead, next);
+}
+
+// Key groups after the initial sort: ghead of every rank, and the groups that need refinement (refine[p] != 0 on their ranks, more than
+// one member, and strings that continue past the key).  Equal keys whose last symbol is 0 (terminator or the padding after it) are
+// strings that ended inside the key: equal strings, a final tie.
+__global__ void __launch_bounds__(TPB) list_dict_groups(const u64* __restrict__ keys, const u32* __restrict__ head, u32 m, u32 bits,
+                                                        const u8* __restrict__ refine, u32* __restrict__ ghead, GroupLists L) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    bool want = false; u32 hd = 0;
+    if (p < m) {
+        hd = head[p];
+        u64 key = keys[p];
+        bool last = (p + 1 == m) || keys[p + 1] != key;
+        bool multi = hd != p || !last;
+        bool final_tie = multi && (key & ((1ull << bits) - 1)) == 0;
+        ghead[p] = final_tie ? hd : p;              // refined groups overwrite this when their runs become final
+        want = last && hd != p && refine[p] && !final_tie;
+    }
+    append_group_warp(want, hd, p - hd + 1, L);
+}
+
 const u32 kClassMinSize[NCLASS] = {2, 5, 9, 17, 33, 65, 129, 257, BLOCK_SORT_MAX + 1};
 
 }  // namespace
@@ -431,6 +634,77 @@ void order_by_initial_keys(u64* keys_in, u64* keys_tmp, u32* vals_in, u32 m, int
     MMB_LAUNCH(first_flags, ceil_div(m, TPB), TPB, 0, s, (const u64*)keys_tmp, m, cand.p);
     prim::inclusive_max(cand.p, head.p, m, s);
     MMB_LAUNCH(first_ranks, ceil_div(m, TPB), TPB, 0, s, (const u64*)keys_tmp, (const u32*)sa, (const u32*)head.p, m, h0, limit, isa, lists_of(groups));
+}
+
+bool refine_dictionary_chunks(const u64* sorted_keys, u32* sa, u32 m, u32 cpk, u32 bits, const u8* dict, const u32* limit, const u8* lut,
+                              const u8* refine, u32* ghead, SaStats& st, cudaStream_t s, u32 max_rounds) {
+    DictView D{dict, limit, lut, bits, cpk};
+    GroupStore cur, nxt;
+    cur.alloc(m, s); nxt.alloc(m, s);
+    {
+        DevBuf<u32> cand, head; cand.alloc(m, s); head.alloc(m, s);
+        MMB_LAUNCH(first_flags, ceil_div(m, TPB), TPB, 0, s, sorted_keys, m, cand.p);
+        prim::inclusive_max(cand.p, head.p, m, s);
+        MMB_LAUNCH(list_dict_groups, ceil_div(m, TPB), TPB, 0, s, sorted_keys, (const u32*)head.p, m, bits, refine, ghead, lists_of(cur));
+    }
+    for (u32 r = 1;; ++r) {
+        std::vector<u32> cnt = to_host(cur.counts.p, NCLASS, s);
+        u64 total = 0;
+        for (int c = 0; c < NCLASS; ++c) {
+            if ((u64)cnt[c] > cur.first[c + 1] - cur.first[c]) throw Error(23, "internal: group list overflow");
+            total += cnt[c];
+        }
+        if (getenv("MMB_DEBUG")) {
+            fprintf(stderr, "[dsort] m=%u round=%u classes:", m, r);
+            for (int c = 0; c < NCLASS; ++c) fprintf(stderr, " %u", cnt[c]);
+            fprintf(stderr, "\n");
+        }
+        if (total == 0) return true;
+        if (r > max_rounds) return false;            // very long shared prefixes (long low-complexity phrases): the caller falls back to doubling
+        u64 h64 = (u64)cpk * r;
+        if (h64 >= 0xffffffffull) return false;
+        u32 h = (u32)h64;
+        nxt.counts.zero();
+        GroupLists next = lists_of(nxt);
+        const Group* G[NCLASS];
+        for (int c = 0; c < NCLASS; ++c) G[c] = cur.groups.p + cur.first[c];
+        launch_dwarp_class<4, 1>(G[0], cnt[0], h, D, sa, ghead, next, s);
+        launch_dwarp_class<8, 1>(G[1], cnt[1], h, D, sa, ghead, next, s);
+        launch_dwarp_class<16, 1>(G[2], cnt[2], h, D, sa, ghead, next, s);
+        launch_dwarp_class<32, 1>(G[3], cnt[3], h, D, sa, ghead, next, s);
+        launch_dwarp_class<32, 2>(G[4], cnt[4], h, D, sa, ghead, next, s);
+        launch_dwarp_class<32, 4>(G[5], cnt[5], h, D, sa, ghead, next, s);
+        launch_dwarp_class<32, 8>(G[6], cnt[6], h, D, sa, ghead, next, s);
+        if (cnt[7]) MMB_LAUNCH(sort_dgroups_block, cnt[7], TPB, 0, s, G[7], h, D, sa, ghead, next);
+        u32 A = 0;
+        if (cnt[8]) {
+            u32 nl = cnt[8];
+            DevBuf<u32> sizes, base, gid, sfx, perm_a, perm_b, perm_c, pos, cand, head; DevBuf<u64> ck, ck_b, gk, gk_b, skey, by_head;
+            sizes.alloc(nl + 1, s); base.alloc(nl + 1, s);
+            // groups were appended in arbitrary order; the run-start scan below needs them in suffix-array order
+            by_head.alloc(nl, s); perm_a.alloc(nl, s); perm_b.alloc(nl, s);
+            MMB_CUDA(cudaMemsetAsync(perm_a.p, 0, (size_t)nl * 4, s));
+            prim::sort_pairs(G[8], by_head.p, perm_a.p, perm_b.p, nl, 32, 64, s);
+            G[8] = by_head.p;
+            MMB_LAUNCH(large_sizes, ceil_div(nl + 1, TPB), TPB, 0, s, G[8], nl, sizes.p);
+            prim::exclusive_sum(sizes.p, base.p, nl + 1, s);
+            A = to_host(base.p + nl, 1, s)[0];
+            ck.alloc(A, s); ck_b.alloc(A, s); gk.alloc(A, s); gk_b.alloc(A, s); skey.alloc(A, s); gid.alloc(A, s); sfx.alloc(A, s);
+            perm_a.alloc(A, s); perm_b.alloc(A, s); perm_c.alloc(A, s); pos.alloc(A, s); cand.alloc(A, s); head.alloc(A, s);
+            dim3 grid(nl, 32);
+            MMB_LAUNCH(dlarge_gather, grid, TPB, 0, s, G[8], (const u32*)base.p, h, D, (const u32*)sa, ck.p, gid.p, sfx.p, perm_a.p);
+            prim::sort_pairs(ck.p, ck_b.p, perm_a.p, perm_b.p, A, 0, (int)(bits * cpk), s);
+            MMB_LAUNCH(dlarge_gid_keys, ceil_div(A, TPB), TPB, 0, s, (const u32*)perm_b.p, (const u32*)gid.p, A, gk.p);
+            prim::sort_pairs(gk.p, gk_b.p, perm_b.p, perm_c.p, A, 0, (int)bits_for(nl), s);
+            MMB_LAUNCH(dlarge_scatter, ceil_div(A, TPB), TPB, 0, s, (const u32*)perm_c.p, (const u64*)ck.p, (const u32*)gid.p, (const u32*)sfx.p, G[8],
+                       (const u32*)base.p, A, sa, skey.p, pos.p, cand.p);
+            prim::inclusive_max(cand.p, head.p, A, s);
+            MMB_LAUNCH(dlarge_finish, ceil_div(A, TPB), TPB, 0, s, (const u32*)pos.p, (const u64*)skey.p, (const u32*)head.p, (const u32*)perm_c.p,
+                       (const u32*)gid.p, A, ghead, next);
+        }
+        cur.groups.swap(nxt.groups); cur.counts.swap(nxt.counts);
+        ++st.rounds; st.groups_sorted += total; st.large_elements += A;
+    }
 }
 
 void build_suffix_array(const u8* text, u64 n, SuffixArray& out, cudaStream_t s) {

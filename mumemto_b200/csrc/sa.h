@@ -38,6 +38,13 @@ void order_by_initial_keys(u64* keys_in, u64* keys_tmp, u32* vals_in, u32 m, int
                            GroupStore& groups, cudaStream_t s, u32 isa_stride = 1);
 void refine_by_doubling(u32* sa, u32* isa, u32 m, u32 h0, const u32* limit, GroupStore& groups, SaStats& st, cudaStream_t s, u32 isa_stride = 1);
 
+// Pruned prefix-free-parse route: exact order of the dictionary suffixes inside the key groups whose ranks are marked in refine[]
+// (sorted_keys = the initial cpk-symbol keys in rank order, sa = positions in that order), by comparing further cpk-symbol chunks of the
+// dictionary bytes; ghead[rank] = first rank of the run of EQUAL strings the rank belongs to (its own rank when it is alone).  Returns
+// false when max_rounds chunks were not enough (the caller falls back to the doubling engine above).
+bool refine_dictionary_chunks(const u64* sorted_keys, u32* sa, u32 m, u32 cpk, u32 bits, const u8* dict, const u32* limit, const u8* lut,
+                              const u8* refine, u32* ghead, SaStats& st, cudaStream_t s, u32 max_rounds);
+
 // lcp[r] = longest common prefix of suffixes sa[r-1] and sa[r] (lcp[0] = 0), followed by 64 zero entries.
 void build_lcp(const u8* text, u64 n, const SuffixArray& sa, DevBuf<u32>& lcp, cudaStream_t s);
 // bwt[r] = text[sa[r]-1] (0 when sa[r] = 0)

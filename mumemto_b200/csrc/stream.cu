@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(TPB) owned_flags(const u32* __restrict__ sa_d,
 }
 
 // Everything expand_members needs to know about a member, gathered once (16 bytes, read coalesced there).
+constexpr u8 MEMBER_STAND_IN = 2;        // MemberMeta::inside of a stand-in rank (pruned route)
 struct MemberMeta {
     u32 q0;         // first entry of the phrase's occurrence list
     u32 cnt;        // occurrences of the phrase
@@ -60,19 +61,21 @@ __global__ void __launch_bounds__(TPB) dict_records(const u32* __restrict__ limi
                                                     const u32* __restrict__ doff, const u8* __restrict__ dict, u32 dsize, DictRecord* __restrict__ rec) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dsize) return;
-    DictRecord r; r.limit = limit[i]; r.phrase = dphrase[i]; r.head = isa_d[i];
+    DictRecord r; r.limit = limit[i]; r.phrase = dphrase[i]; r.head = isa_d ? isa_d[i] : 0u;
     r.before = i > doff[r.phrase] ? (u32)dict[i - 1] : 0x100u;
     rec[i] = r;
 }
 
 __global__ void __launch_bounds__(TPB) members_fill(const u32* __restrict__ sa_d, const DictRecord* __restrict__ rec, const u32* __restrict__ prank,
                                                     const u32* __restrict__ occ_first, const u32* __restrict__ flag, const u32* __restrict__ idx, u32 dsize,
-                                                    const u8* __restrict__ klcp, u32* __restrict__ mem_i, u32* __restrict__ mem_head,
+                                                    const u8* __restrict__ klcp, const u32* __restrict__ ghead, const u8* __restrict__ mkind,
+                                                    u32* __restrict__ mem_i, u32* __restrict__ mem_head,
                                                     u32* __restrict__ mem_cnt, MemberMeta* __restrict__ meta, u8* __restrict__ mem_klcp) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= dsize || !flag[p]) return;
     u32 k = idx[p], i = sa_d[p];
-    if (klcp) {         // key symbols shared with the previous MEMBER: minimum over the ranks skipped in between (suffixes of <= w symbols)
+    if (klcp && ghead) mem_klcp[k] = klcp[p];      // pruned route: already the symbols shared with the previous suffix longer than w
+    else if (klcp) {    // key symbols shared with the previous MEMBER: minimum over the ranks skipped in between (suffixes of <= w symbols)
         // Runs of skipped ranks are usually a few entries, but equal short strings (phrase ends) form runs of millions: give up after
         // 64 steps and let group_lcp compare the bytes from the start (KLCP_UNKNOWN).
         u32 mn = klcp[p], q = p, steps = 0;
@@ -83,10 +86,12 @@ __global__ void __launch_bounds__(TPB) members_fill(const u32* __restrict__ sa_d
     DictRecord d = rec[i];
     u32 r = prank[d.phrase];
     u32 q0 = occ_first[r], cnt = occ_first[r + 1] - q0;
-    mem_i[k] = i; mem_head[k] = d.head; mem_cnt[k] = cnt;
+    const bool stand_in = mkind && mkind[p] == 2;      // one rank that stands for the pruned suffixes after a surviving segment
+    if (stand_in) cnt = 1;
+    mem_i[k] = i; mem_head[k] = ghead ? ghead[p] : d.head; mem_cnt[k] = cnt;
     MemberMeta m;
     m.q0 = q0; m.cnt = cnt; m.shift = d.limit - 1 - PFP_W;
-    m.inside = d.before < 0x100u ? 1 : 0; m.before = (u8)d.before; m.back = 0; m.members = 1;
+    m.inside = stand_in ? MEMBER_STAND_IN : (d.before < 0x100u ? 1 : 0); m.before = (u8)d.before; m.back = 0; m.members = 1;
     meta[k] = m;
 }
 
@@ -97,12 +102,18 @@ __global__ void __launch_bounds__(TPB) group_lcp(const u8* __restrict__ dict, co
                                                  u32* __restrict__ glcp) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
-    if (k == 0) { glcp[0] = 0; return; }
+    if (k == 0) {       // the first member follows the sentinel suffix -- or, on the pruned route, suffixes that were left out
+        u32 shared = mem_klcp ? mem_klcp[0] : 0u;
+        glcp[0] = shared < key_symbols ? min(shared, meta[0].shift + PFP_W) : 0u;
+        return;
+    }
     if (mem_head[k] == mem_head[k - 1]) { glcp[k] = NOT_START; return; }
     u32 cap = min(meta[k - 1].shift, meta[k].shift) + PFP_W, l = 0;      // |alpha| of the shorter; different strings of a prefix-free set differ before either ends
     if (mem_klcp) {
         u32 shared = mem_klcp[k];
-        if (shared < key_symbols) { glcp[k] = min(shared, cap); return; }
+        // the two differ inside the key (on the pruned route member k - 1 need not be the suffix this count was taken against: the
+        // suffixes in between were pruned -- only the member's own length bounds it)
+        if (shared < key_symbols) { glcp[k] = min(shared, meta[k].shift + PFP_W); return; }
         if (shared != KLCP_UNKNOWN) l = min(key_symbols, cap);
     }
     u32 a = mem_i[k - 1], b = mem_i[k];
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(EXP_TPB, MINB) expand_members(u32 k0, u32 k1, 
                                                                 const u32* __restrict__ glcp, const u32* __restrict__ occ_next_rank,
                                                                 const u64* __restrict__ occ_next_start, const u32* __restrict__ occ_lcp,
                                                                 const u32* __restrict__ s_lcp, const u32* __restrict__ rmq, u32 rmq_blocks,
-                                                                const u8* __restrict__ text, u64 lead, u64* __restrict__ sa, u32* __restrict__ lcp,
+                                                                const u8* __restrict__ text, u64 text_len, u64 lead, u64* __restrict__ sa, u32* __restrict__ lcp,
                                                                 u32* __restrict__ key, u8* __restrict__ bwt) {
     __shared__ MemberMeta smeta[EXP_TPB / 32][32];
     __shared__ u32 soff[EXP_TPB / 32][33];
@@ -201,6 +212,10 @@ __global__ void __launch_bounds__(EXP_TPB, MINB) expand_members(u32 k0, u32 k1, 
             asm volatile("prefetch.global.L2 [%0];" ::"l"(occ_next_start + qn));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(occ_lcp + qn));
 #endif
+        }
+        if (m.inside == MEMBER_STAND_IN) {                 // pruned route: closes the segment before it with the true LCP, matches nothing
+            sa[wbase + e] = text_len; bwt[wbase + e] = 0; lcp[wbase + e] = glcp[kk];
+            continue;
         }
         u64 pos = occ_next_start[q] - m.shift;
         u8 sym = m.inside ? m.before : (pos ? text[pos - 1] : (u8)0);
@@ -336,7 +351,94 @@ __global__ void __launch_bounds__(TPB) tile_docs(const u64* __restrict__ sa, u64
     doc[r] = (u8)d;
 }
 
+
+// ---------------------------------------------------------------------------------------------- -M on the pruned route
+// A threshold-only segment (pfp.h, PfpPrune) is ONE LCP interval: its N text suffixes share at least -l symbols, its neighbours share
+// fewer.  The reference records a threshold for it when the N suffixes come from N distinct documents (include/mem_finder.hpp:326-336):
+// thresh[position of the document-0 suffix] = min(max(LCP[first rank], LCP[closing rank]), 65535) -- and both LCPs are shared key symbols
+// at the two segment boundaries.  No order inside the segment is needed: one warp gathers the occurrences of the segment's dictionary
+// suffixes straight from the occurrence lists.  rk word layout: pfp.cu.
+constexpr u32 RKW_HB = 1u << 31, RKW_OWN = 1u << 30;
+
+template <int W>
+__global__ void __launch_bounds__(TPB) segment_thresholds_kernel(const u32* __restrict__ closers, u32 n_closers, const u32* __restrict__ rk,
+                                                                 const u32* __restrict__ prev_owned, const u8* __restrict__ klcp,
+                                                                 const u32* __restrict__ sa_d, const u32* __restrict__ limit, const u32* __restrict__ dphrase,
+                                                                 const u32* __restrict__ prank, const u32* __restrict__ occ_first,
+                                                                 const u64* __restrict__ occ_next_start, DocLookup L, u16* __restrict__ thresh) {
+    u32 wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wi >= n_closers) return;                                    // whole warp
+    const u32 c = closers[wi];
+    const u32 last = prev_owned[c - 1] - 1;                         // last rank of the segment that is longer than w (exists: c closes it)
+    const u32 lcp_close = klcp[c];
+    u64 bits[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) bits[w] = 0;
+    u64 anchor = ~0ull; u32 lcp_open = 0, seen = 0;
+    // walk the segment from its last rank to its first, 32 ranks at a time
+    for (u32 hi = last;;) {
+        u32 x = hi >= lane ? hi - lane : 0u;
+        bool in_range = hi >= lane;
+        u32 w = in_range ? rk[x] : RKW_HB;
+        unsigned starts = __ballot_sync(0xffffffffu, (w & RKW_HB) != 0);
+        int first_lane = __ffs((int)starts) - 1;                    // nearest segment start at or below hi (-1: further down)
+        bool mine = in_range && (w & RKW_OWN) && (first_lane < 0 || (int)lane <= first_lane);
+        // metadata of my dictionary suffix
+        u32 q0 = 0, cnt = 0, shift = 0;
+        if (mine) {
+            u32 i = sa_d[x];
+            shift = limit[i] - 1 - PFP_W;
+            u32 r = prank[dphrase[i]];
+            q0 = occ_first[r]; cnt = occ_first[r + 1] - q0;
+        }
+        unsigned owners = __ballot_sync(0xffffffffu, mine);
+        if (owners) {                                               // the lowest rank seen so far that is longer than w opens the segment
+            int low = 31 - __clz((int)owners);
+            lcp_open = __shfl_sync(0xffffffffu, (u32)klcp[mine ? x : 0], low);
+        }
+        while (owners) {
+            int src = __ffs((int)owners) - 1; owners &= owners - 1;
+            u32 mq = __shfl_sync(0xffffffffu, q0, src), mc = __shfl_sync(0xffffffffu, cnt, src), ms = __shfl_sync(0xffffffffu, shift, src);
+            for (u32 t = lane; t < mc; t += 32) {
+                u64 p = occ_next_start[mq + t] - ms;
+                u32 d = L.coarse[p >> L.shift];
+                while (L.doc_start[d + 1] <= p) ++d;
+                bits[(W == 1) ? 0 : (d >> 6)] |= 1ull << (d & 63);
+                if (d == 0) anchor = p;
+            }
+            seen += mc;
+        }
+        if (first_lane >= 0 || hi < 32) break;
+        hi -= 32;
+    }
+    u32 distinct = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+#ifdef MMB_SIMT
+        u64 bb = bits[w];
+        for (u32 dd = 16; dd > 0; dd >>= 1) bb |= __shfl_xor_sync(0xffffffffu, bb, dd);
+        distinct += (u32)__popcll(bb);
+#else
+        distinct += (u32)__popc(__reduce_or_sync(0xffffffffu, (u32)bits[w])) + (u32)__popc(__reduce_or_sync(0xffffffffu, (u32)(bits[w] >> 32)));
+#endif
+    }
+    if (distinct == seen && distinct == L.ndocs && anchor != ~0ull) thresh[anchor] = (u16)min(max(lcp_open, lcp_close), 65535u);
+}
+
 }  // namespace
+
+void segment_thresholds(const PfpIndex& ix, const DocLookup& docs, u16* thresh, cudaStream_t s) {
+    if (!ix.pruned || !ix.n_closers || !thresh) return;
+    u32 grid = ceil_div((u64)ix.n_closers * 32, TPB);
+    auto launch = [&](auto segment_thresholds_k) {
+        MMB_LAUNCH(segment_thresholds_k, grid, TPB, 0, s, (const u32*)ix.closers.p, ix.n_closers, (const u32*)ix.rk.p, (const u32*)ix.prev_owned.p, (const u8*)ix.klcp.p,
+                   (const u32*)ix.sa_d.p, (const u32*)ix.limit.p, (const u32*)ix.dphrase.p, (const u32*)ix.prank.p, (const u32*)ix.occ_first.p,
+                   (const u64*)ix.occ_next_start.p, docs, thresh);
+    };
+    if (docs.ndocs <= 64) launch(segment_thresholds_kernel<1>);
+    else if (docs.ndocs <= 256) launch(segment_thresholds_kernel<4>);
+    else launch(segment_thresholds_kernel<16>);
+}
 
 void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 halo, TileConsumer& consumer, cudaStream_t s, const DocLookup* docs) {
     u32 dsize = ix.dsize;
@@ -351,6 +453,7 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
     }
     prim::exclusive_sum(flag, idx.p, (u64)dsize + 1, s);
     u32 K = to_host(idx.p + dsize, 1, s)[0];
+    if (K == 0) { const_cast<PfpIndex&>(ix).stream_ranks = 0; return; }      // pruned route: no segment can hold a match
     DevBuf<u32> mem_i, mem_head, mem_cnt, glcp; DevBuf<u64> out_base; DevBuf<MemberMeta> meta; DevBuf<u8> mem_klcp;
     if (ix.klcp.p) mem_klcp.alloc(K, s);
     meta.alloc(K, s); mem_i.alloc(K, s); mem_head.alloc(K, s); mem_cnt.alloc((u64)K + 1, s); glcp.alloc((u64)K + 1, s); out_base.alloc((u64)K + 1, s);
@@ -360,19 +463,22 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
         MMB_LAUNCH(dict_records, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.limit.p, (const u32*)ix.dphrase.p, (const u32*)ix.isa_d.p, (const u32*)ix.doff.p,
                    (const u8*)ix.dict.p, dsize, rec.p);
         MMB_LAUNCH(members_fill, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.sa_d.p, (const DictRecord*)rec.p, (const u32*)ix.prank.p,
-                   (const u32*)ix.occ_first.p, flag, (const u32*)idx.p, dsize, (const u8*)ix.klcp.p, mem_i.p, mem_head.p, mem_cnt.p, meta.p, mem_klcp.p);
+                   (const u32*)ix.occ_first.p, flag, (const u32*)idx.p, dsize, (const u8*)ix.klcp.p, (const u32*)ix.ghead.p, (const u8*)ix.mkind.p, mem_i.p, mem_head.p,
+                   mem_cnt.p, meta.p, mem_klcp.p);
     }
     flag_own.release(); idx.release();
     prim::exclusive_sum(mem_cnt.p, out_base.p, (u64)K + 1, s);
     u64 total = to_host(out_base.p + K, 1, s)[0];
-    if (total != ix.n) throw Error(76, "internal: the parse does not cover the text (" + std::to_string(total) + " of " + std::to_string(ix.n) + ")");
+    const_cast<PfpIndex&>(ix).stream_ranks = total;
+    if (getenv("MMB_DEBUG")) fprintf(stderr, "[stream] members %u, ranks %llu of %llu\n", K, (unsigned long long)total, (unsigned long long)ix.n);
+    if ((!ix.pruned || ix.full_stream) && total != ix.n) throw Error(76, "internal: the parse does not cover the text (" + std::to_string(total) + " of " + std::to_string(ix.n) + ")");
     MMB_LAUNCH(group_lcp, ceil_div(K, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const MemberMeta*)meta.p, (const u32*)mem_i.p, (const u32*)mem_head.p, (const u8*)mem_klcp.p, ix.key_symbols, K, glcp.p);
     mem_klcp.release();
     mem_head.release();
     MMB_LAUNCH(group_shape, ceil_div(K, TPB), TPB, 0, s, (const u32*)glcp.p, K, meta.p);
 
     // ---- tile boundaries on group starts
-    u32 nt = (u32)((ix.n + tile_ranks - 1) / tile_ranks);
+    u32 nt = (u32)((total + tile_ranks - 1) / tile_ranks);
     DevBuf<u32> d_bounds; d_bounds.alloc(nt + 1, s);
     MMB_LAUNCH(tile_bounds, ceil_div(nt + 1, 128), 128, 0, s, (const u64*)out_base.p, (const u32*)glcp.p, K, tile_ranks, nt, d_bounds.p);
     std::vector<u32> raw_bounds = to_host(d_bounds.p, nt + 1, s);
@@ -413,7 +519,7 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
             auto launch_expand = [&](auto expand_members_k) {
                 MMB_LAUNCH(expand_members_k, ceil_div(nm, EXP_TPB), EXP_TPB, 0, s, k0, k1, (const MemberMeta*)meta.p, (const u64*)out_base.p, (const u32*)glcp.p,
                            (const u32*)ix.occ_next_rank.p, (const u64*)ix.occ_next_start.p, (const u32*)ix.occ_lcp.p, (const u32*)ix.s_lcp.p,
-                           (const u32*)ix.rmq.p, ix.rmq_blocks, text, lead, sa.p, lcp.p, key.p, bwt.p);
+                           (const u32*)ix.rmq.p, ix.rmq_blocks, text, ix.n, lead, sa.p, lcp.p, key.p, bwt.p);
             };
             switch (expand_variant) {
                 case 1: launch_expand(expand_members<8, 0>); break;

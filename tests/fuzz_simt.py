@@ -100,6 +100,16 @@ def main():
                 with open(os.path.join(keep, "case.txt"), "w") as f:
                     f.write(f"{it} {flags} {route} {tile}\n")
             os.environ["MMB_DOC_STREAM"] = "1" if rng.random() < 0.5 else "0"
+            # dictionary order of the prefix-free-parse route: chunk engine with segment pruning (default), the same without pruning,
+            # the doubling engine (MMB_NO_PRUNE), and the fallback from the chunk engine after too few rounds
+            variant = rng.random()
+            no_prune = bool(variant < 0.15)
+            for k in ("MMB_NO_PRUNE", "MMB_CHUNK_ROUNDS"):
+                os.environ.pop(k, None)
+            if 0.15 <= variant < 0.25:
+                os.environ["MMB_NO_PRUNE"] = "1"
+            elif 0.25 <= variant < 0.35:
+                os.environ["MMB_CHUNK_ROUNDS"] = str(int(rng.integers(1, 4)))
             lib.simt_set_block_order(int(rng.integers(0, 3)))           # block scheduling order of the SIMT harness: forward, reverse, shuffled
             if os.path.exists(REF) and rng.random() < 0.15 and "-A" not in flags and not ("-f" in flags and flags[flags.index("-f") + 1] == "0" and "-F" not in flags):
                 # array input: the reference's own -A dump, then its own -a run against ours
@@ -126,7 +136,7 @@ def main():
                     for j, grp in enumerate(groups):
                         sel = [paths[x] for x in grp]
                         util.run_cli(ORACLE, ["-o", os.path.join(d, f"po{j}"), "-M", "-n", *extra, *sel])
-                        api.find_files(sel, os.path.join(d, f"pg{j}"), merge=True, anchor_merge=True, revcomp=not extra, route=route, tile_ranks=tile, _lib=lib)
+                        api.find_files(sel, os.path.join(d, f"pg{j}"), merge=True, anchor_merge=True, revcomp=not extra, route=route, tile_ranks=tile, no_prune=no_prune, _lib=lib)
                         no.append(os.path.join(d, f"po{j}.mums")); ng.append(os.path.join(d, f"pg{j}.mums"))
                     util.run_cli(ORACLE, ["merge", *no, "-o", os.path.join(d, "om")])
                     api.merge_files(ng, os.path.join(d, "gm"), _lib=lib)
@@ -142,7 +152,7 @@ def main():
                 route = "direct"
             kw = util.flags_to_kwargs(flags)
             try:
-                api.find_files(paths, g, route=route, tile_ranks=tile, _lib=lib, **kw); ok_g = True
+                api.find_files(paths, g, route=route, tile_ranks=tile, no_prune=no_prune, _lib=lib, **kw); ok_g = True
             except Exception as ex:
                 ok_g = False; err = str(ex)
             if ok_o != ok_g:
@@ -150,7 +160,7 @@ def main():
                 if not too_short:
                     bad += 1; print("MISMATCH status", it, flags, route, tile, ok_o, ok_g, "" if ok_g else err[:200]); shutil.copytree(d, f"/tmp/fuzz_fail_{seed}_{it}")
             elif ok_o and util.outputs(g) != util.outputs(o):
-                bad += 1; print("MISMATCH output", it, flags, route, tile); shutil.copytree(d, f"/tmp/fuzz_fail_{seed}_{it}")
+                bad += 1; print("MISMATCH output", it, flags, route, tile, no_prune, os.environ.get("MMB_NO_PRUNE"), os.environ.get("MMB_CHUNK_ROUNDS")); shutil.copytree(d, f"/tmp/fuzz_fail_{seed}_{it}")
         finally:
             shutil.rmtree(d, ignore_errors=True)
         if (it + 1) % 50 == 0:

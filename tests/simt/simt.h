@@ -177,6 +177,8 @@ inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
 inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+enum { cudaHostAllocPortable = 1 };
+inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMalloc(p, n); }
 inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
 inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }

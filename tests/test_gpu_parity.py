@@ -173,10 +173,16 @@ def test_size_independent_properties(cuda_lib, tmp_path):
 def test_c1_golden_pfp_route(cuda_lib, c1, name):
     """C1 through the dictionary/parse route with 64 stream tiles: same golden md5s."""
     d, paths, table = c1
-    st = api.find_files(paths, os.path.join(d, "p_" + name), route="pfp", tile_ranks=160000, _lib=cuda_lib, **util.flags_to_kwargs(table["outputs"][name]["flags"]))
+    kw = util.flags_to_kwargs(table["outputs"][name]["flags"])
+    st = api.find_files(paths, os.path.join(d, "p_" + name), route="pfp", tile_ranks=160000, no_prune=True, _lib=cuda_lib, **kw)
     got = {ext: util.md5(b) for ext, b in util.outputs(os.path.join(d, "p_" + name)).items()}
     assert got == table["outputs"][name]["md5"]
-    assert st["route"] == 2 and st["pfp_tiles"] >= 60
+    assert st["route"] == 2 and st["pfp_tiles"] >= 60 and not st["pruned"]
+    # default: segment pruning (DESIGN.md 5b) -- the same bytes from a fraction of the ranks
+    st = api.find_files(paths, os.path.join(d, "q_" + name), route="pfp", tile_ranks=160000, _lib=cuda_lib, **kw)
+    got = {ext: util.md5(b) for ext, b in util.outputs(os.path.join(d, "q_" + name)).items()}
+    assert got == table["outputs"][name]["md5"]
+    assert st["pruned"] and st["stream_suffixes"] < st["text_symbols"] // 2
 
 
 @pytest.mark.parametrize("name", ["strict", "arrays", "memF", "bumbl", "norc"])
@@ -222,7 +228,15 @@ def test_pfp_route_equals_direct_route_pangenome(cuda_lib, tmp_path):
         api.find_files(paths, a, route="direct", _lib=cuda_lib, **util.flags_to_kwargs(flags))
         st = api.find_files(paths, b, route="pfp", tile_ranks=1 << 22, _lib=cuda_lib, **util.flags_to_kwargs(flags))
         assert util.outputs(a) == util.outputs(b), flags
-        assert st["pfp_dict_bytes"] < 0.2 * st["text_symbols"]
+        assert st["pfp_dict_bytes"] < 0.2 * st["text_symbols"] and st["pruned"] and st["stream_suffixes"] < 0.2 * st["text_symbols"]
+        c = str(tmp_path / f"c{i}")
+        st = api.find_files(paths, c, route="pfp", tile_ranks=1 << 22, no_prune=True, _lib=cuda_lib, **util.flags_to_kwargs(flags))
+        assert util.outputs(a) == util.outputs(c), flags
+        assert st["stream_suffixes"] == st["text_symbols"] + 1
+    # -M -n: thresholds of the pruned segments come from the segment kernel, not from the stream
+    for i, extra in enumerate(({}, {"no_prune": True}, {"route": "direct"})):
+        api.find_files(paths, str(tmp_path / f"m{i}"), merge=True, anchor_merge=True, _lib=cuda_lib, **({"route": "pfp", **extra}))
+    assert util.outputs(str(tmp_path / "m0")) == util.outputs(str(tmp_path / "m2")) == util.outputs(str(tmp_path / "m1"))
 
 
 # ------------------------------------------------------------------------------------------------ the drop-in executables

@@ -243,10 +243,10 @@ def test_simt_window_kernel(simt_lib, oracle_bin, small, tmp_path, flags, monkey
 
 
 # ------------------------------------------------------------------------------------------------ prefix-free-parse route (tiled stream)
-def both_pfp(simt_lib, oracle_bin, tmp, paths, flags, tile_ranks):
+def both_pfp(simt_lib, oracle_bin, tmp, paths, flags, tile_ranks, no_prune=False):
     o, g = os.path.join(tmp, "o"), os.path.join(tmp, "g")
     util.run_cli(oracle_bin, ["-o", o, *flags, *paths])
-    st = api.find_files(paths, g, route="pfp", tile_ranks=tile_ranks, _lib=simt_lib, **util.flags_to_kwargs(flags))
+    st = api.find_files(paths, g, route="pfp", tile_ranks=tile_ranks, no_prune=no_prune, _lib=simt_lib, **util.flags_to_kwargs(flags))
     assert st["route"] == 2
     assert util.outputs(g) == util.outputs(o), flags
     return st
@@ -256,8 +256,12 @@ def both_pfp(simt_lib, oracle_bin, tmp, paths, flags, tile_ranks):
 def test_simt_pfp_route_equals_oracle(simt_lib, oracle_bin, small, tmp_path, name):
     """Dictionary + parse suffix arrays, tiled enumeration (SA/LCP per tile with halo), same detector: byte-identical outputs, including the
     .sa/.lcp/.bwt arrays, with tiles so small that intervals straddle tile boundaries."""
-    st = both_pfp(simt_lib, oracle_bin, str(tmp_path), small, FLAGSETS[name], tile_ranks=700)
-    assert st["pfp_tiles"] > 10 and st["pfp_distinct_phrases"] < st["pfp_phrases"]
+    st = both_pfp(simt_lib, oracle_bin, str(tmp_path), small, FLAGSETS[name], tile_ranks=700, no_prune=True)
+    assert st["pfp_tiles"] > 10 and st["pfp_distinct_phrases"] < st["pfp_phrases"] and not st["pruned"]
+    # the default: segments that cannot hold a match are left out of the stream (same bytes, fewer ranks)
+    st = both_pfp(simt_lib, oracle_bin, str(tmp_path), small, FLAGSETS[name], tile_ranks=200)
+    if name != "arrays":
+        assert st["pruned"] and st["stream_suffixes"] < st["text_symbols"]
 
 
 @pytest.mark.parametrize("block_order", [0, 2])
