@@ -415,6 +415,40 @@ def cpu_baseline_and_parity(eng, tdev, spec, sample_L=1_000_000, procs=None):
             {"result": "ok", "sample": sample_name(sample), "checks": parity})
 
 
+def cli_end_to_end(imgs, spec, flagset, expect_md5, runs=2):
+    """Wall clock of `mumemto_exec` as a user runs it: process start, FASTA files on local disk (page cache), all the way to the closed
+    .mums / .mems file.  The bench process keeps its own device buffers meanwhile (the executable needs the rest of the GPU's memory)."""
+    import hashlib
+    import shutil
+    exe = os.path.join(ROOT, "mumemto_b200", "bin", "mumemto_exec")
+    if not os.path.exists(exe):
+        return {"error": "bin/mumemto_exec is not built"}
+    d = tempfile.mkdtemp(prefix="mmb_cli_", dir=os.environ.get("MMB_CLI_DIR", "/tmp"))
+    try:
+        paths = []
+        for i, im in enumerate(imgs):
+            p = os.path.join(d, f"h{i}.fa"); np.asarray(im).tofile(p); paths.append(p)
+        flags = FLAGSETS[flagset][0]
+        times = []
+        for _ in range(runs):
+            t0 = time.perf_counter()
+            r = subprocess.run([exe, "-o", os.path.join(d, "out"), *flags, *paths], capture_output=True)
+            times.append(time.perf_counter() - t0)
+            if r.returncode != 0:
+                return {"error": r.stderr.decode(errors="replace")[-400:]}
+        out = os.path.join(d, "out.mums" if flagset != "mem" else "out.mems")
+        h = hashlib.md5()
+        with open(out, "rb") as f:
+            for blk in iter(lambda: f.read(1 << 24), b""):
+                h.update(blk)
+        best = min(times)
+        return {"value": spec["N"] * spec["L"] / best, "unit": "bases/s", "seconds": best, "all_seconds": times, "output_bytes": os.path.getsize(out),
+                "md5_matches_engine_output": h.hexdigest() == expect_md5, "stderr_tail": r.stderr.decode(errors="replace")[-300:],
+                "region": "wall clock of bin/mumemto_exec: process start, FASTA files in the page cache -> closed output file (pooled pread into pinned memory, H2D, path, D2H, write)"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def golden_md5(workload, flagset):
     """md5 of the reference's output on the FULL workload, when scripts/make_fullsize_golden.py has recorded it (tests/golden/md5_table.json)."""
     try:
@@ -473,6 +507,7 @@ def main():
     ap.add_argument("--tile-ranks", type=int, default=0, help="ranks per stream tile on the PFP route (0 = engine default)")
     ap.add_argument("--roofline-kernel", default=None, help="kernel (name substring) whose launches are timed with CUDA events for the roofline line")
     ap.add_argument("--kernel-table-steps", type=int, default=2, help="extra steps after the timed region with every launch bracketed by events (per-kernel table)")
+    ap.add_argument("--cli-e2e", action="store_true", help="also time bin/mumemto_exec on the workload written to local disk (wall clock of the whole process)")
     ap.add_argument("--dump-output", default=None, help="write the .mums/.mems bytes of the last end-to-end step to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -708,6 +743,15 @@ def main():
     if world > 1:
         dist.barrier()
 
+    # ---- the real end to end: the drop-in executable, process start with FASTA files on local disk -> closed output file.
+    # Last: this process gives its device memory back first (the executable is a separate process on the same GPU).
+    e2e_cli = None
+    if rank == 0 and not multi and args.cli_e2e and not args.merge_mode:
+        eng.close()
+        del dev, flush
+        torch.cuda.empty_cache()
+        e2e_cli = cli_end_to_end(imgs, spec, flagset, output_md5)
+
     if rank == 0:
         peaks = {}
         try:
@@ -760,6 +804,8 @@ def main():
                 "text_symbols": int(st["text_symbols"]), "wall_s_timed_region": t_wall, "clocks": sampler.summary(),
                 "route": int(st["route"]), "pruned": int(st.get("pruned", 0)), "stream_suffixes": int(st.get("stream_suffixes", 0)),
                 "threshold_segments": int(st.get("threshold_segments", 0)), "pfp": {k: int(st[k]) for k in ("pfp_phrases", "pfp_distinct_phrases", "pfp_dict_bytes", "pfp_tiles")}}
+        if e2e_cli:
+            line["e2e_cli"] = e2e_cli
         if merge_info:
             line["partition_merge"] = merge_info
         if cpu_base and not multi:                          # the CPU figure is reported at N = 1 only; at N > 1 the run above serves the parity check

@@ -90,7 +90,8 @@ MMB_API void mmb_free_pinned(void* p);
 
 /* Input.  files[i] is the (decompressed) byte image of FASTA file i in host memory.  The copy to the device happens here. */
 MMB_API int mmb_load_fasta(mmb_engine* e, const uint8_t* const* files, const uint64_t* sizes, size_t nfiles, int use_revcomp);
-/* Same, but the images already sit in device memory at d_raw + offsets[i] (offsets multiples of 16). */
+/* Same, but the images already sit in device memory at d_raw + offsets[i] (offsets multiples of 16; the buffer must be readable for 64
+ * bytes past the last image).  Record names for PREFIX.lengths are fetched from the device copy (cut at 255 bytes). */
 MMB_API int mmb_load_fasta_device(mmb_engine* e, const void* d_raw, const uint64_t* offsets, const uint64_t* sizes, size_t nfiles, int use_revcomp);
 /* Library-style input: document d has n_records[d] NUL-terminated records, flattened in records[] (no FASTA syntax). */
 MMB_API int mmb_load_records(mmb_engine* e, const char* const* records, const size_t* n_records, size_t ndocs, int use_revcomp);
@@ -145,6 +146,7 @@ MMB_API uint64_t mmb_merge_num_docs(const mmb_engine* e);
 MMB_API int mmb_merge_copy(mmb_engine* e, uint32_t* lengths, int64_t* offsets, uint8_t* strands /* 1 = '+' */, uint16_t* thresholds);
 MMB_API uint64_t mmb_merge_text_size(mmb_engine* e);                /* merged .mums bytes (include/mumsio.hpp:283-296,318-326); formatted on first use */
 MMB_API int mmb_merge_copy_text(mmb_engine* e, void* host_dst);
+MMB_API const void* mmb_merge_text_device(mmb_engine* e);           /* device pointer of the merged .mums bytes, valid until the next merge */
 
 /* Measurement aid for bench.py: bracket every launch of the kernels whose name contains `name_substring` with CUDA events on the
  * launching stream (NULL or "" switches it off and clears the record); mmb_profile_result adds up the recorded launches. */

@@ -82,6 +82,7 @@ _SIGNATURES = {
     "mmb_merge_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmb_merge_text_size": (C.c_uint64, [C.c_void_p]),
     "mmb_merge_copy_text": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mmb_merge_text_device": (C.c_void_p, [C.c_void_p]),
 }
 
 

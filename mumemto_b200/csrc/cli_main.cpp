@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "mumemto_b200.h"
+#include "fasta_io.h"
 #include "multi_gpu.h"
 
 namespace fs = std::filesystem;
@@ -85,75 +86,6 @@ static int usage() {
         "\t                                writes PREFIX.mums / PREFIX.athresh like `anchor_merge` (rows in anchor order)\n"
         "\t    --partitions      [INT]     the same workflow with P partitions run one after the other on one GPU\n\n");
     return 0;
-}
-
-static std::string slurp(const std::string& path) {          // gzopen reads plain and gzip files alike, like the reference
-    gzFile f = gzopen(path.c_str(), "r");
-    if (!f) fatal("cannot open " + path);
-    gzbuffer(f, 1 << 20);
-    std::string out; std::vector<char> buf(1 << 22); int k;
-    while ((k = gzread(f, buf.data(), (unsigned)buf.size())) > 0) out.append(buf.data(), k);
-    gzclose(f);
-    return out;
-}
-
-// All input files at once: plain files are read by a pool of threads straight into ONE pinned buffer (16-byte aligned slots), gzip
-// files are inflated by the same pool and copied in afterwards.  Returns the buffer; ptrs / sizes describe the images.
-struct InputImages {
-    uint8_t* pinned = nullptr; std::vector<const uint8_t*> ptrs; std::vector<uint64_t> sizes; std::vector<std::string> inflated;
-};
-static bool is_gzip(const std::string& path) {
-    unsigned char h[2] = {0, 0};
-    int fd = open(path.c_str(), O_RDONLY);
-    if (fd < 0) fatal("cannot open " + path);
-    ssize_t k = read(fd, h, 2); close(fd);
-    return k == 2 && h[0] == 0x1f && h[1] == 0x8b;
-}
-static void read_inputs(const std::vector<std::string>& files, InputImages& in) {
-    size_t n = files.size();
-    std::vector<char> gz(n); std::vector<uint64_t> off(n, 0);
-    in.sizes.assign(n, 0); in.inflated.assign(n, std::string());
-    unsigned workers = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)n));
-    std::atomic<size_t> next{0};
-    auto pool = [&](auto&& job) {
-        next = 0;
-        std::vector<std::thread> th;
-        for (unsigned w = 0; w < workers; ++w) th.emplace_back([&] { for (size_t i; (i = next++) < n;) job(i); });
-        for (auto& t : th) t.join();
-    };
-    pool([&](size_t i) {
-        gz[i] = is_gzip(files[i]);
-        if (gz[i]) { in.inflated[i] = slurp(files[i]); in.sizes[i] = in.inflated[i].size(); }
-        else { struct stat st; if (stat(files[i].c_str(), &st) != 0) fatal("cannot stat " + files[i]); in.sizes[i] = (uint64_t)st.st_size; }
-    });
-    uint64_t total = 0;
-    for (size_t i = 0; i < n; ++i) { off[i] = total; total += (in.sizes[i] + 15) & ~15ull; }
-    in.pinned = (uint8_t*)mmb_alloc_pinned(total + 64);
-    if (!in.pinned) fatal("cannot allocate pinned host memory for the input files");
-    pool([&](size_t i) {
-        uint8_t* dst = in.pinned + off[i];
-        if (gz[i]) { memcpy(dst, in.inflated[i].data(), in.sizes[i]); std::string().swap(in.inflated[i]); return; }
-        int fd = open(files[i].c_str(), O_RDONLY);
-        if (fd < 0) fatal("cannot open " + files[i]);
-        uint64_t got = 0;
-        while (got < in.sizes[i]) {
-            ssize_t k = pread(fd, dst + got, std::min<uint64_t>(in.sizes[i] - got, 1ull << 30), (off_t)got);
-            if (k <= 0) fatal("short read on " + files[i]);
-            got += (uint64_t)k;
-        }
-        close(fd);
-    });
-    in.ptrs.resize(n);
-    for (size_t i = 0; i < n; ++i) in.ptrs[i] = in.pinned + off[i];
-}
-
-// device -> pinned host -> write(2)
-static void put_file_fd(const std::string& path, const void* p, size_t n) {
-    int fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
-    if (fd < 0) fatal("cannot write " + path);
-    const char* q = (const char*)p;
-    while (n) { ssize_t k = write(fd, q, std::min<size_t>(n, 1ull << 30)); if (k <= 0) fatal("short write on " + path); q += k; n -= (size_t)k; }
-    close(fd);
 }
 
 static std::string slurp_plain(const std::string& path) {    // binary array files: no transparent gzip detection
@@ -278,28 +210,33 @@ int main(int argc, char** argv) {
 
 
     status("parsing input files");
-    CHECK(mmb_create(o.device, nullptr, &e));           // first: the pinned staging buffer needs a CUDA context
-    InputImages in;
-    read_inputs(inputs, in);
+    std::vector<fio::Source> sources;
+    try { sources = fio::probe(inputs); } catch (const std::exception& ex) { fatal(ex.what()); }
     if (o.gpus > 1 || o.partitions > 1) {
         // partition-merge inside this process (multi_gpu.cpp): replaces `mumemto_exec -M -n` x P + `anchor_merge` of the reference
         // workflow (mumemto/merge_mums.py:171-183 -> src/merge_candidates.cpp:170-255)
         if (o.rare_freq != 1 || o.num_distinct_docs != 0) fatal("Merging not available for partial multi-MUM/MEMs");
-        mmb_destroy(e); e = nullptr;
         std::fprintf(stderr, " done.  (%.3f sec)\n", lap());
         mgpu::Request rq;
-        rq.files = inputs; rq.images = in.ptrs; rq.sizes = in.sizes; rq.gpus = std::max(1, o.gpus); rq.partitions = o.partitions; rq.first_device = o.device;
+        rq.sources = &sources; rq.gpus = std::max(1, o.gpus); rq.partitions = o.partitions; rq.first_device = o.device;
         rq.use_rcomp = o.use_rcomp; rq.min_match_len = (uint32_t)o.min_match_len; rq.binary = o.binary; rq.output_prefix = o.output_prefix;
         std::string err;
         status("finding multi-MUMs: one partition per GPU, all-gather, merge");
         if (!mgpu::run(rq, err)) fatal(err);
         std::fprintf(stderr, " done.  (%.3f sec)\n", lap());
-        mmb_free_pinned(in.pinned);
         return 0;
     }
-    if (mmb_load_fasta(e, in.ptrs.data(), in.sizes.data(), in.ptrs.size(), o.use_rcomp) != 0)
-        fatal(std::string(mmb_last_error()) + "\nPlease check the input files and ensure that it contains valid FASTA files.");
-    mmb_free_pinned(in.pinned); in.pinned = nullptr;
+    CHECK(mmb_create(o.device, nullptr, &e));
+    {   // pooled pread -> pinned slices -> device (fasta_io.h), then the text build on the device
+        std::vector<const fio::Source*> all;
+        for (auto& sc : sources) all.push_back(&sc);
+        fio::DeviceImages img;
+        try { img = fio::upload(all, o.device); } catch (const std::exception& ex) { fatal(ex.what()); }
+        if (mmb_load_fasta_device(e, img.d_raw, img.offsets.data(), img.sizes.data(), img.sizes.size(), o.use_rcomp) != 0)
+            fatal(std::string(mmb_last_error()) + "\nPlease check the input files and ensure that it contains valid FASTA files.");
+        img.release();
+        std::vector<fio::Source>().swap(sources);
+    }
     std::fprintf(stderr, " done.  (%.3f sec)\n", lap());
     {   // PREFIX.lengths
         std::ofstream L(o.output_prefix + ".lengths");
@@ -334,12 +271,9 @@ int main(int argc, char** argv) {
     size_t N = mmb_num_docs(e);
     uint64_t count = mmb_num_matches(e);
     if (!mum_mode || !o.binary) {
-        size_t tn = mmb_text_size(e);
-        void* text = mmb_alloc_pinned(tn + 1);
-        if (!text) fatal("cannot allocate pinned host memory for the output");
-        CHECK(mmb_copy_text(e, text));
-        put_file_fd(o.output_prefix + (mum_mode ? ".mums" : ".mems"), text, tn);
-        mmb_free_pinned(text);
+        // device -> pinned slices -> write(2), copy and write overlapped (fasta_io.h)
+        try { fio::write_device_buffer(o.output_prefix + (mum_mode ? ".mums" : ".mems"), mmb_text_device(e), mmb_text_size(e)); }
+        catch (const std::exception& ex) { fatal(ex.what()); }
     } else {
         if (count == 0) fatal("no multi-MUMs found: nothing to write in binary format");
         long n = (long)N, k = o.num_distinct_docs;

@@ -213,7 +213,22 @@ std::string record_name(const u8* img, u64 size, u64 at) {
     return s;
 }
 
-void finish_load(mmb_engine* e, const u8* const* host_imgs, const std::vector<u64>& off, const std::vector<u64>& size, bool raw_mode) {
+// record names when the images only exist on the device: up to NAME_MAX_LEN bytes after each header marker, cut at the first whitespace
+constexpr u32 NAME_MAX_LEN = 255;
+__global__ void gather_record_names(const u8* __restrict__ raw, const u64* __restrict__ pos, const u64* __restrict__ end, u32 nrec, u8* __restrict__ out) {
+    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrec) return;
+    u8* o = out + (u64)r * (NAME_MAX_LEN + 1);
+    u32 k = 0;
+    for (u64 i = pos[r] + 1; i < end[r] && k < NAME_MAX_LEN; ++i) {
+        u8 c = raw[i];
+        if (c == ' ' || (c >= 9 && c <= 13)) break;          // isspace
+        o[k++] = c;
+    }
+    o[k] = 0;
+}
+
+void finish_load(mmb_engine* e, const u8* d_raw, const u8* const* host_imgs, const std::vector<u64>& off, const std::vector<u64>& size, bool raw_mode) {
     u32 N = (u32)off.size();
     for (u32 d = 0; d < N; ++d)
         if (e->text.h_doc_len[d] == 0) throw Error(40, "Empty input file found (document " + std::to_string(d) + ")");
@@ -221,6 +236,19 @@ void finish_load(mmb_engine* e, const u8* const* host_imgs, const std::vector<u6
     if (raw_mode) return;
     // FASTA records: boundaries from the device scan, names from the host image when we have one
     const auto& pos = e->text.h_rec_pos; const auto& before = e->text.h_rec_before;
+    std::vector<u8> dev_names;
+    if (!host_imgs && d_raw && !pos.empty()) {
+        // images were uploaded by the caller: fetch the names from the device copy (header lines longer than 255 bytes are cut)
+        std::vector<u64> ends(pos.size());
+        size_t rr = 0;
+        for (u32 d = 0; d < N; ++d) while (rr < pos.size() && pos[rr] < off[d] + size[d]) { ends[rr] = off[d] + size[d]; ++rr; }
+        DevBuf<u64> d_pos, d_end; DevBuf<u8> d_names;
+        d_pos.alloc(pos.size(), e->stream); d_end.alloc(pos.size(), e->stream); d_names.alloc(pos.size() * (NAME_MAX_LEN + 1), e->stream);
+        MMB_CUDA(cudaMemcpyAsync(d_pos.p, pos.data(), pos.size() * 8, cudaMemcpyHostToDevice, e->stream));
+        MMB_CUDA(cudaMemcpyAsync(d_end.p, ends.data(), ends.size() * 8, cudaMemcpyHostToDevice, e->stream));
+        MMB_LAUNCH(gather_record_names, ceil_div(pos.size(), 128), 128, 0, e->stream, d_raw, (const u64*)d_pos.p, (const u64*)d_end.p, (u32)pos.size(), d_names.p);
+        dev_names = to_host(d_names.p, pos.size() * (NAME_MAX_LEN + 1), e->stream);
+    }
     u64 cum = 0; size_t r = 0;
     for (u32 d = 0; d < N; ++d) {
         u64 doc_end_bases = cum + e->text.h_doc_len[d];
@@ -228,6 +256,7 @@ void finish_load(mmb_engine* e, const u8* const* host_imgs, const std::vector<u6
             u64 next = (r + 1 < pos.size() && pos[r + 1] < off[d] + size[d]) ? before[r + 1] : doc_end_bases;
             RecordInfo ri; ri.length = next - before[r];
             if (host_imgs) ri.name = record_name(host_imgs[d], size[d], pos[r] - off[d]);
+            else if (!dev_names.empty()) ri.name = (const char*)&dev_names[r * (NAME_MAX_LEN + 1)];
             e->records[d].push_back(std::move(ri));
             ++r;
         }
@@ -260,7 +289,7 @@ void load_common(mmb_engine* e, const u8* d_raw, const u8* const* host_imgs, con
     build_text(d_raw, off, size, revcomp, raw_mode, e->text, e->stream);
     e->stats.ms_text = t.stop();
     build_doc_coarse(e);
-    finish_load(e, host_imgs, off, size, raw_mode);
+    finish_load(e, d_raw, host_imgs, off, size, raw_mode);
     e->stats.text_symbols = e->text.n; e->stats.input_bases = e->text.total_bases;
     e->loaded = true;
 }
@@ -810,6 +839,8 @@ int mmb_merge_copy(mmb_engine* e, uint32_t* lengths, int64_t* offsets, uint8_t* 
         MMB_CUDA(cudaStreamSynchronize(s));
     });
 }
+
+const void* mmb_merge_text_device(mmb_engine* e) { return ensure_merged_text(e) == MMB_OK ? (const void*)e->merged_text.p : nullptr; }
 
 int mmb_merge_copy_text(mmb_engine* e, void* host_dst) {
     if (int rc = ensure_merged_text(e)) return rc;

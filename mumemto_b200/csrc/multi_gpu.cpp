@@ -67,12 +67,13 @@ bool run(const Request& rq, std::string& error) {
     try {
         int ndev = 0;
         cu(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount");
-        if (rq.files.size() < 3) throw Fail("partition-merge needs an anchor and at least two other sequences");
+        const std::vector<fio::Source>& src = *rq.sources;
+        if (src.size() < 3) throw Fail("partition-merge needs an anchor and at least two other sequences");
         if (rq.gpus < 1 || rq.first_device < 0 || rq.first_device + rq.gpus > ndev)
             throw Fail("--gpus " + std::to_string(rq.gpus) + " from device " + std::to_string(rq.first_device) + ": only " + std::to_string(ndev) + " CUDA devices");
         if (rq.gpus > 1 && rq.partitions > 0 && rq.partitions != rq.gpus) throw Fail("--partitions must equal --gpus when several GPUs are used (one partition per GPU)");
         size_t want = rq.gpus > 1 ? (size_t)rq.gpus : (size_t)std::max(2, rq.partitions);
-        auto groups = make_partitions(rq.files.size(), want);
+        auto groups = make_partitions(src.size(), want);
         if (groups.size() < 2) throw Fail("not enough sequences for two partitions");
         const size_t P = groups.size();
         const int G = (int)std::min<size_t>((size_t)rq.gpus, P);
@@ -87,15 +88,18 @@ bool run(const Request& rq, std::string& error) {
             try {
                 cu(cudaSetDevice(pt.device), "cudaSetDevice");
                 mm(mmb_create(pt.device, nullptr, &pt.e));
-                std::vector<const uint8_t*> im; std::vector<uint64_t> sz;
-                for (size_t f : pt.files) { im.push_back(rq.images[f]); sz.push_back(rq.sizes[f]); }
-                mm(mmb_load_fasta(pt.e, im.data(), sz.data(), im.size(), rq.use_rcomp ? 1 : 0));
+                std::vector<const fio::Source*> mine;
+                for (size_t f : pt.files) mine.push_back(&src[f]);
+                fio::DeviceImages img = fio::upload(mine, pt.device);
+                int rc = mmb_load_fasta_device(pt.e, img.d_raw, img.offsets.data(), img.sizes.data(), img.sizes.size(), rq.use_rcomp ? 1 : 0);
+                img.release();
+                mm(rc);
                 mm(mmb_find(pt.e, &mo));
                 pt.n = mmb_num_matches(pt.e); pt.nd = mmb_num_docs(pt.e); pt.L = mmb_threshold_count(pt.e) / 2;
                 mm(mmb_mum_table_device(pt.e, &pt.len, &pt.off, &pt.str, &pt.thr));
                 // PREFIX.lengths lines (src/ref_builder.cpp:193-209); the anchor is listed by the first partition only
                 for (size_t d = (pt.files[0] == 0 && &pt != &parts[0]) ? 1 : 0; d < pt.files.size(); ++d) {
-                    std::string cp = std::filesystem::canonical(rq.files[pt.files[d]]).string();
+                    std::string cp = std::filesystem::canonical(src[pt.files[d]].path).string();
                     uint64_t total = 0; size_t nr = mmb_num_records(pt.e, d);
                     for (size_t r = 0; r < nr; ++r) { uint64_t len; mmb_record(pt.e, d, r, nullptr, &len); total += len; }
                     pt.lengths_lines += cp + " * " + std::to_string(total) + "\n";
@@ -202,11 +206,7 @@ bool run(const Request& rq, std::string& error) {
             b.write((char*)len.data(), nm * 4); b.write((char*)off.data(), nm * ns * 8); b.write((char*)bits.data(), bits.size());
         } else {
             size_t tn = mmb_merge_text_size(e0);
-            void* text = mmb_alloc_pinned(tn + 1);
-            if (!text) throw Fail("cannot allocate pinned host memory for the output");
-            mm(mmb_merge_copy_text(e0, text));
-            put(rq.output_prefix + ".mums", text, tn);
-            mmb_free_pinned(text);
+            fio::write_device_buffer(rq.output_prefix + ".mums", mmb_merge_text_device(e0), tn);
             mm(mmb_merge_copy(e0, nullptr, nullptr, nullptr, nb.data()));
         }
         put(rq.output_prefix + ".athresh", nb.data(), nb.size() * 2);

@@ -11,12 +11,12 @@
 #include <string>
 #include <vector>
 
+#include "fasta_io.h"
+
 namespace mgpu {
 
 struct Request {
-    std::vector<std::string> files;             // input paths (for PREFIX.lengths), anchor first
-    std::vector<const uint8_t*> images;         // decompressed FASTA images, host memory (ideally pinned)
-    std::vector<uint64_t> sizes;
+    const std::vector<fio::Source>* sources = nullptr;      // the input files (fio::probe), anchor first
     int gpus = 1;                               // devices first_device .. first_device + gpus - 1
     int partitions = 0;                         // 0 = one per GPU; > gpus only with gpus == 1 (run one after the other, no NCCL)
     int first_device = 0;

@@ -624,7 +624,9 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
                        bits, cpk, t, ix.klcp.p, ix.owned.p, ix.mkind.p, refine.p, ix.closers.p, n_closers.p);
             cls.release();
             ix.ghead.alloc(dsize, s);
-            const u32 max_rounds = getenv("MMB_CHUNK_ROUNDS") ? (u32)atoi(getenv("MMB_CHUNK_ROUNDS")) : 64u;
+            // rounds of 21 symbols: phrase lengths are geometric (mean ~100), the longest of 1e8 phrases has ~2000 symbols = ~100 rounds, and
+            // the late rounds only touch the few groups of such phrases; give up (and sort by doubling) beyond ~86 000 shared symbols
+            const u32 max_rounds = getenv("MMB_CHUNK_ROUNDS") ? (u32)atoi(getenv("MMB_CHUNK_ROUNDS")) : 4096u;
             pruned_done = refine_dictionary_chunks(kb.p, ix.sa_d.p, dsize, cpk, bits, ix.dict.p, ix.limit.p, d_lut.p, refine.p, ix.ghead.p, ix.stats_d, s, max_rounds);
             if (pruned_done) {
                 ix.pruned = true; ix.full_stream = !prune.enabled;

@@ -368,3 +368,37 @@ def test_cli_arrays_out_on_the_tiled_route(cuda_lib, ref_dir, tmp_path):
     a, b = util.outputs(got), util.outputs(ref)
     assert set(a) == {".mums", ".sa", ".lcp", ".bwt"} and a == b
     files.close()
+
+
+@pytest.mark.parametrize("mode", ["partitions", "gpus"])
+def test_cli_partition_merge_in_one_process(ref_dir, tmp_path, mode):
+    """`mumemto_exec --partitions P` (one GPU, partitions one after the other) and `--gpus N` (one host thread per GPU + ncclAllGather,
+    csrc/multi_gpu.cpp) against the reference workflow on the same partitions: P x `mumemto_exec -M -n`, then `anchor_merge`
+    (mumemto/merge_mums.py:171-183, src/merge_candidates.cpp:170-255): PREFIX.mums, PREFIX.athresh byte for byte, PREFIX.lengths lines."""
+    import bench
+    import subprocess
+    import torch
+    P = 3
+    if mode == "gpus":
+        if torch.cuda.device_count() < 2:
+            pytest.skip("needs two GPUs")
+        P = min(torch.cuda.device_count(), 4)
+    files = bench.SampleFiles(dict(N=13, L=150000, kind="pangenome"))
+    rest = len(files.paths) - 1
+    groups, at = [], 1
+    for p in range(P):                          # contiguous slices, like mgpu::make_partitions
+        take = rest // P + (1 if p < rest % P else 0)
+        groups.append([0] + list(range(at, at + take))); at += take
+    names = []
+    for g, grp in enumerate(groups):
+        pre = str(tmp_path / f"ref{g}")
+        subprocess.run([os.path.join(ref_dir, "mumemto_exec"), "-o", pre, "-M", "-n", *[files.paths[i] for i in grp]], check=True, capture_output=True)
+        names.append(pre + ".mums")
+    subprocess.run([os.path.join(ref_dir, "anchor_merge"), *names, "-o", str(tmp_path / "refm")], check=True, capture_output=True)
+    flag = ["--partitions", str(P)] if mode == "partitions" else ["--gpus", str(P)]
+    util.run_cli(os.path.join(BIN, "mumemto_exec"), ["-o", str(tmp_path / "got"), *flag, *files.paths])
+    a, b = util.outputs(str(tmp_path / "got")), util.outputs(str(tmp_path / "refm"))
+    assert a == b and len(b[".mums"]) > 1000
+    lines = open(tmp_path / "got.lengths").read().splitlines()
+    assert len(lines) == 2 * len(files.paths) and lines[0].endswith(" * 150000") and lines[1].endswith(" h0 150000")
+    files.close()
