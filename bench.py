@@ -432,7 +432,7 @@ def cli_end_to_end(imgs, spec, flagset, expect_md5, runs=2):
         times = []
         for _ in range(runs):
             t0 = time.perf_counter()
-            r = subprocess.run([exe, "-o", os.path.join(d, "out"), *flags, *paths], capture_output=True)
+            r = subprocess.run([exe, "-o", os.path.join(d, "out"), *flags, *paths], capture_output=True, env=dict(os.environ, MMB_CLI_TIMING="1"))
             times.append(time.perf_counter() - t0)
             if r.returncode != 0:
                 return {"error": r.stderr.decode(errors="replace")[-400:]}
@@ -443,7 +443,7 @@ def cli_end_to_end(imgs, spec, flagset, expect_md5, runs=2):
                 h.update(blk)
         best = min(times)
         return {"value": spec["N"] * spec["L"] / best, "unit": "bases/s", "seconds": best, "all_seconds": times, "output_bytes": os.path.getsize(out),
-                "md5_matches_engine_output": h.hexdigest() == expect_md5, "stderr_tail": r.stderr.decode(errors="replace")[-300:],
+                "md5_matches_engine_output": h.hexdigest() == expect_md5, "stderr_tail": r.stderr.decode(errors="replace")[-1200:],
                 "region": "wall clock of bin/mumemto_exec: process start, FASTA files in the page cache -> closed output file (pooled pread into pinned memory, H2D, path, D2H, write)"}
     finally:
         shutil.rmtree(d, ignore_errors=True)
@@ -507,6 +507,7 @@ def main():
     ap.add_argument("--tile-ranks", type=int, default=0, help="ranks per stream tile on the PFP route (0 = engine default)")
     ap.add_argument("--roofline-kernel", default=None, help="kernel (name substring) whose launches are timed with CUDA events for the roofline line")
     ap.add_argument("--kernel-table-steps", type=int, default=2, help="extra steps after the timed region with every launch bracketed by events (per-kernel table)")
+    ap.add_argument("--kernel-table-rows", type=int, default=16)
     ap.add_argument("--cli-e2e", action="store_true", help="also time bin/mumemto_exec on the workload written to local disk (wall clock of the whole process)")
     ap.add_argument("--dump-output", default=None, help="write the .mums/.mems bytes of the last end-to-end step to this file")
     args = ap.parse_args()
@@ -678,7 +679,7 @@ def main():
         tab = eng.profile_table()
         eng.profile_kernel(None)
         tot = sum(v[0] for v in tab.values()) or 1.0
-        top = sorted(tab.items(), key=lambda kv: -kv[1][0])[:12]
+        top = sorted(tab.items(), key=lambda kv: -kv[1][0])[:args.kernel_table_rows]
         kernel_table = []
         for name, (kms, kn) in top:
             per_step = kms / args.kernel_table_steps

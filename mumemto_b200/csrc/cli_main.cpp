@@ -210,8 +210,16 @@ int main(int argc, char** argv) {
 
 
     status("parsing input files");
+    const bool timing = std::getenv("MMB_CLI_TIMING") != nullptr;
+    auto mark = [&, tm = std::chrono::steady_clock::now()](const char* what) mutable {
+        if (!timing) return;
+        auto t = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "\n\t[timing] %-28s %8.3f s", what, std::chrono::duration<double>(t - tm).count());
+        tm = t;
+    };
     std::vector<fio::Source> sources;
     try { sources = fio::probe(inputs); } catch (const std::exception& ex) { fatal(ex.what()); }
+    mark("probe input files");
     if (o.gpus > 1 || o.partitions > 1) {
         // partition-merge inside this process (multi_gpu.cpp): replaces `mumemto_exec -M -n` x P + `anchor_merge` of the reference
         // workflow (mumemto/merge_mums.py:171-183 -> src/merge_candidates.cpp:170-255)
@@ -227,15 +235,18 @@ int main(int argc, char** argv) {
         return 0;
     }
     CHECK(mmb_create(o.device, nullptr, &e));
+    mark("CUDA context + engine");
     {   // pooled pread -> pinned slices -> device (fasta_io.h), then the text build on the device
         std::vector<const fio::Source*> all;
         for (auto& sc : sources) all.push_back(&sc);
         fio::DeviceImages img;
         try { img = fio::upload(all, o.device); } catch (const std::exception& ex) { fatal(ex.what()); }
+        mark("read + upload");
         if (mmb_load_fasta_device(e, img.d_raw, img.offsets.data(), img.sizes.data(), img.sizes.size(), o.use_rcomp) != 0)
             fatal(std::string(mmb_last_error()) + "\nPlease check the input files and ensure that it contains valid FASTA files.");
         img.release();
         std::vector<fio::Source>().swap(sources);
+        mark("text build on the device");
     }
     std::fprintf(stderr, " done.  (%.3f sec)\n", lap());
     {   // PREFIX.lengths

@@ -513,6 +513,7 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
             PfpPrune prune;
             prune.enabled = (opts->keep_arrays || opts->no_prune) ? 0 : 1;
             prune.min_len = e->prm.min_len; prune.size_lo = std::max<u32>(2, e->prm.num_distinct); prune.merge = merge ? 1 : 0; prune.ndocs = N;
+            prune.doc_coarse = e->doc_coarse.p; prune.coarse_shift = e->coarse_shift; prune.doc_start = e->text.doc_start.p;
             pfp_finish(e->text.text.p, n, ix, pp, s, prune);
             pp = PfpParse();
             e->stats.ms_sa = t.stop() + ms_parse;

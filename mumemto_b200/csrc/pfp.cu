@@ -383,6 +383,27 @@ __global__ void __launch_bounds__(TPB) member_flags(const u64* __restrict__ keys
 
 // after the refinement (which permutes sa_d inside key groups, so the rank words' per-suffix fields no longer line up): ranks that hold
 // a whole phrase, looked up only in the segments that have one
+// -M, at most 64 documents: document mask / anchor occurrence of every distinct phrase (PhraseDocs)
+__global__ void __launch_bounds__(TPB) phrase_docs_init(const u32* __restrict__ doff, u32 nd, PhraseDocs* __restrict__ rec) {
+    u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < nd) { PhraseDocs r; r.mask = 0; r.anchor = 0; r.flags = 0; r.total = doff[g + 1] - doff[g]; rec[g] = r; }
+}
+__global__ void __launch_bounds__(TPB) phrase_docs_fill(const u64* __restrict__ pstart, const u32* __restrict__ pid, u32 np, PfpPrune L,
+                                                        PhraseDocs* __restrict__ rec) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= np) return;
+    u64 a = pstart[j], b = pstart[j + 1] - 1;              // the text suffixes this occurrence owns start in [a, b]
+    u32 d = L.doc_coarse[a >> L.coarse_shift];
+    while (L.doc_start[d + 1] <= a) ++d;
+    PhraseDocs* r = rec + pid[j];
+    u32 fl = L.doc_start[d + 1] <= b ? PD_CROSSES : 0u;
+    u64 bit = 1ull << (d & 63);
+    u64 old = atomicOr((unsigned long long*)&r->mask, (unsigned long long)bit);
+    if (old & bit) fl |= PD_DUPLICATE;
+    if (d == 0) { fl |= PD_HAS_ANCHOR; r->anchor = a; }     // a second occurrence in document 0 sets PD_DUPLICATE: the value is then unused
+    if (fl) atomicOr(&r->flags, fl);
+}
+
 __global__ void __launch_bounds__(TPB) phrase_start_flags(const u8* __restrict__ refine, const u32* __restrict__ sa_d, const u32* __restrict__ dphrase,
                                                           const u32* __restrict__ doff, u32 dsize, u32* __restrict__ flag) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -603,6 +624,11 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
             ka.release(); va.release();
             DevBuf<u32> count, pinfo; count.alloc(nd, s); count.zero(); pinfo.alloc(dsize, s);
             MMB_LAUNCH(phrase_counts, ceil_div(np, TPB), TPB, 0, s, (const u32*)pid.p, np, count.p);
+            if (prune.enabled && prune.merge && prune.ndocs <= 64 && prune.doc_coarse) {
+                ix.phrase_docs.alloc(nd, s);
+                MMB_LAUNCH(phrase_docs_init, ceil_div(nd, TPB), TPB, 0, s, (const u32*)ix.doff.p, nd, ix.phrase_docs.p);
+                MMB_LAUNCH(phrase_docs_fill, ceil_div(np, TPB), TPB, 0, s, (const u64*)ix.pstart.p, (const u32*)pid.p, np, prune, ix.phrase_docs.p);
+            }
             MMB_LAUNCH(dict_info, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.dphrase.p, (const u32*)ix.doff.p, (const u8*)ix.dict.p, (const u32*)count.p, dsize, pinfo.p);
             ix.rk.alloc(dsize, s);
             MMB_LAUNCH(rank_words, ceil_div(dsize, TPB), TPB, 0, s, (const u64*)kb.p, (const u32*)ix.sa_d.p, (const u32*)pinfo.p, dsize, bits, cpk, t, ix.rk.p);
@@ -625,8 +651,9 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
             cls.release();
             ix.ghead.alloc(dsize, s);
             // rounds of 21 symbols: phrase lengths are geometric (mean ~100), the longest of 1e8 phrases has ~2000 symbols = ~100 rounds, and
-            // the late rounds only touch the few groups of such phrases; give up (and sort by doubling) beyond ~86 000 shared symbols
-            const u32 max_rounds = getenv("MMB_CHUNK_ROUNDS") ? (u32)atoi(getenv("MMB_CHUNK_ROUNDS")) : 4096u;
+            // the late rounds only touch the few groups of such phrases; beyond ~5 000 shared symbols (a long single-symbol run inside
+            // one phrase: one suffix leaves its group per symbol) give up and sort by doubling, which needs log rounds there
+            const u32 max_rounds = getenv("MMB_CHUNK_ROUNDS") ? (u32)atoi(getenv("MMB_CHUNK_ROUNDS")) : 256u;
             pruned_done = refine_dictionary_chunks(kb.p, ix.sa_d.p, dsize, cpk, bits, ix.dict.p, ix.limit.p, d_lut.p, refine.p, ix.ghead.p, ix.stats_d, s, max_rounds);
             if (pruned_done) {
                 ix.pruned = true; ix.full_stream = !prune.enabled;
@@ -640,7 +667,7 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
                            (const u32*)ix.dphrase.p, dsize, ix.prank.p);
             } else {
                 // a phrase with a very long low-complexity stretch: start over with the doubling engine, nothing pruned
-                ix.rk.release(); ix.prev_owned.release(); ix.owned.release(); ix.klcp.release(); ix.mkind.release(); ix.closers.release(); ix.ghead.release();
+                ix.rk.release(); ix.prev_owned.release(); ix.owned.release(); ix.klcp.release(); ix.mkind.release(); ix.closers.release(); ix.ghead.release(); ix.phrase_docs.release();
                 ix.stats_d = SaStats();
                 ka.alloc(dsize, s); va.alloc(dsize, s);
                 MMB_LAUNCH(dict_keys, ceil_div(dsize, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const u32*)ix.limit.p, dsize, (const u8*)d_lut.p, bits, cpk, ka.p, va.p);

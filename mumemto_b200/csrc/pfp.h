@@ -19,6 +19,15 @@ namespace mmb {
 constexpr u32 PFP_W = 10;           // window (reference default -w 10)
 constexpr u32 PFP_P = 100;          // modulus (reference default -m 100)
 
+// -M on the pruned route, collections of at most 64 documents: which documents the occurrences of a phrase lie in.
+struct PhraseDocs {
+    u64 mask;               // bit d: an occurrence of the phrase starts in document d
+    u64 anchor;             // text position where the phrase's occurrence in document 0 starts (valid with PD_HAS_ANCHOR)
+    u32 flags;              // PD_*
+    u32 total;              // phrase length + 1 (the terminator), = limit of its first dictionary position
+};
+enum : u32 { PD_DUPLICATE = 1, PD_CROSSES = 2, PD_HAS_ANCHOR = 4 };     // a document twice; an occurrence spans a document boundary
+
 struct PfpIndex {
     u64 n = 0;                      // |T|
     // parse
@@ -49,6 +58,7 @@ struct PfpIndex {
     DevBuf<u32> prev_owned;         // [dsize] by rank: 1 + the last rank <= p that is longer than w (0 = none)
     DevBuf<u32> closers;            // -M: ranks that close a segment whose only possible interval is the whole segment (threshold only)
     u32 n_closers = 0;
+    DevBuf<PhraseDocs> phrase_docs; // -M, at most 64 documents: per distinct phrase (dictionary order)
     u32 seg_symbols = 0;            // symbols that define a segment (min(-l, key_symbols))
     u64 stream_ranks = 0;           // text suffixes that are enumerated (members' occurrences + stand-ins)
     DevBuf<u32> dphrase;            // [dsize] distinct-phrase id (in D' order) of every dictionary position
@@ -79,7 +89,10 @@ struct PfpPrune {
     u32 size_lo = 2;        // smallest interval size that can qualify
     u32 merge = 0;          // -M
     u32 ndocs = 0;
+    // -M: position -> document lookup (device pointers; coarse table + document starts, as DetectParams::doc_coarse)
+    const u16* doc_coarse = nullptr; u32 coarse_shift = 0; const u64* doc_start = nullptr;
 };
+
 
 void build_pfp_index(const u8* text, u64 n, PfpIndex& out, cudaStream_t s);
 // The same in two steps: parse + dictionary (stages 1-3, cheap) and everything else; `auto` routing looks at ix.dsize in between.

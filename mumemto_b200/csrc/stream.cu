@@ -425,13 +425,65 @@ __global__ void __launch_bounds__(TPB) segment_thresholds_kernel(const u32* __re
     if (distinct == seen && distinct == L.ndocs && anchor != ~0ull) thresh[anchor] = (u16)min(max(lcp_open, lcp_close), 65535u);
 }
 
+
+// The same for collections of at most 64 documents, one THREAD per segment: the documents of a segment are the union of its phrases'
+// document masks (PhraseDocs, L2 resident: one record per distinct phrase), and the document-0 suffix sits at the phrase's document-0
+// occurrence + the offset of the dictionary suffix inside the phrase.  Segments that touch a phrase with a repeated document or an
+// occurrence across a document boundary go to `slow` (the warp kernel above decides them exactly from the occurrence lists).
+__global__ void __launch_bounds__(TPB) segment_thresholds_masks(const u32* __restrict__ closers, u32 n_closers, const u32* __restrict__ rk,
+                                                                const u32* __restrict__ prev_owned, const u8* __restrict__ klcp,
+                                                                const u32* __restrict__ sa_d, const u32* __restrict__ limit, const u32* __restrict__ dphrase,
+                                                                const PhraseDocs* __restrict__ pdocs, u32 ndocs, u16* __restrict__ thresh,
+                                                                u32* __restrict__ slow, u32* __restrict__ n_slow) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool defer = false; u32 c = 0;
+    if (t < n_closers) {
+        c = closers[t];
+        u32 x = prev_owned[c - 1] - 1;                      // last rank of the segment that is longer than w
+        const u32 lcp_close = klcp[c];
+        u64 mask = 0, anchor = ~0ull; u32 lcp_open = 0;
+        for (;; --x) {
+            u32 w = rk[x];
+            if (w & RKW_OWN) {
+                u32 i = sa_d[x];
+                PhraseDocs r = pdocs[dphrase[i]];
+                defer |= (r.flags & (PD_DUPLICATE | PD_CROSSES)) != 0;
+                mask |= r.mask;
+                if (r.flags & PD_HAS_ANCHOR) anchor = r.anchor + (r.total - limit[i]);
+                lcp_open = klcp[x];
+            }
+            if ((w & RKW_HB) || x == 0) break;
+        }
+        if (!defer && (u32)__popcll(mask) == ndocs && anchor != ~0ull) thresh[anchor] = (u16)min(max(lcp_open, lcp_close), 65535u);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, defer);
+    if (m) {
+        u32 lane = threadIdx.x & 31, base = 0;
+        int leader = __ffs((int)m) - 1;
+        if ((int)lane == leader) base = atomicAdd(n_slow, (u32)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (defer) slow[base + __popc(m & ((1u << lane) - 1))] = c;
+    }
+}
+
 }  // namespace
 
 void segment_thresholds(const PfpIndex& ix, const DocLookup& docs, u16* thresh, cudaStream_t s) {
     if (!ix.pruned || !ix.n_closers || !thresh) return;
-    u32 grid = ceil_div((u64)ix.n_closers * 32, TPB);
+    const u32* list = ix.closers.p; u32 count = ix.n_closers;
+    DevBuf<u32> slow, n_slow;
+    if (ix.phrase_docs.p && docs.ndocs <= 64 && !getenv("MMB_THRESH_SLOW")) {
+        slow.alloc(ix.n_closers, s); n_slow.alloc(1, s); n_slow.zero();
+        MMB_LAUNCH(segment_thresholds_masks, ceil_div(ix.n_closers, TPB), TPB, 0, s, (const u32*)ix.closers.p, ix.n_closers, (const u32*)ix.rk.p,
+                   (const u32*)ix.prev_owned.p, (const u8*)ix.klcp.p, (const u32*)ix.sa_d.p, (const u32*)ix.limit.p, (const u32*)ix.dphrase.p,
+                   (const PhraseDocs*)ix.phrase_docs.p, docs.ndocs, thresh, slow.p, n_slow.p);
+        count = to_host(n_slow.p, 1, s)[0];
+        list = slow.p;
+        if (!count) return;
+    }
+    u32 grid = ceil_div((u64)count * 32, TPB);
     auto launch = [&](auto segment_thresholds_k) {
-        MMB_LAUNCH(segment_thresholds_k, grid, TPB, 0, s, (const u32*)ix.closers.p, ix.n_closers, (const u32*)ix.rk.p, (const u32*)ix.prev_owned.p, (const u8*)ix.klcp.p,
+        MMB_LAUNCH(segment_thresholds_k, grid, TPB, 0, s, list, count, (const u32*)ix.rk.p, (const u32*)ix.prev_owned.p, (const u8*)ix.klcp.p,
                    (const u32*)ix.sa_d.p, (const u32*)ix.limit.p, (const u32*)ix.dphrase.p, (const u32*)ix.prank.p, (const u32*)ix.occ_first.p,
                    (const u64*)ix.occ_next_start.p, docs, thresh);
     };

@@ -49,7 +49,7 @@ def random_collection(rng, d):
 
 
 def random_flags(rng, n):
-    mode = rng.integers(0, 6)
+    mode = rng.integers(0, 6) if rng.random() > float(os.environ.get("FUZZ_MERGE_SHARE", "0")) else 3
     flags = []
     if mode == 0:
         pass
@@ -104,8 +104,10 @@ def main():
             # the doubling engine (MMB_NO_PRUNE), and the fallback from the chunk engine after too few rounds
             variant = rng.random()
             no_prune = bool(variant < 0.15)
-            for k in ("MMB_NO_PRUNE", "MMB_CHUNK_ROUNDS"):
+            for k in ("MMB_NO_PRUNE", "MMB_CHUNK_ROUNDS", "MMB_THRESH_SLOW"):
                 os.environ.pop(k, None)
+            if rng.random() < 0.3:
+                os.environ["MMB_THRESH_SLOW"] = "1"         # -M thresholds of pruned segments from the occurrence lists instead of the phrase masks
             if 0.15 <= variant < 0.25:
                 os.environ["MMB_NO_PRUNE"] = "1"
             elif 0.25 <= variant < 0.35:

@@ -176,7 +176,7 @@ def test_simt_repeats_all_group_size_classes(simt_lib, oracle_bin, tmp_path, blo
     unit = util.random_dna(rng, 37)
     body = util.random_dna(rng, 1500)
     docs = [
-        "A" * 5200 + body + unit * 90 + "ACGT" * 40 + body[:700],
+        "A" * 1300 + body + unit * 90 + "ACGT" * 40 + body[:700],
         "A" * 300 + util.mutate(rng, body, 0.01) + unit * 60 + "C" * 150 + body[200:900],
         util.mutate(rng, body, 0.02) + "AC" * 700 + unit * 20 + "A" * 100,
     ]
@@ -265,14 +265,14 @@ def test_simt_pfp_route_equals_oracle(simt_lib, oracle_bin, small, tmp_path, nam
 
 
 @pytest.mark.parametrize("block_order", [0, 2])
-def test_simt_pfp_route_repeats(simt_lib, oracle_bin, tmp_path, block_order):
+def test_simt_pfp_route_repeats(simt_lib, oracle_bin, tmp_path, block_order, monkeypatch):
     """Tandem repeats and low-complexity runs: dictionary suffixes shared by many phrases (multi-member groups beyond one block's
     shared-memory sort), long phrases, phrases of minimum length."""
     rng = np.random.default_rng(17)
     unit = util.random_dna(rng, 37)
     body = util.random_dna(rng, 1500)
     docs = [
-        "A" * 5200 + body + unit * 90 + "ACGT" * 40 + body[:700],
+        "A" * 1300 + body + unit * 90 + "ACGT" * 40 + body[:700],
         "A" * 300 + util.mutate(rng, body, 0.01) + unit * 60 + "C" * 150 + body[200:900],
         util.mutate(rng, body, 0.02) + "AC" * 700 + unit * 20 + "A" * 100,
     ]
@@ -281,6 +281,11 @@ def test_simt_pfp_route_repeats(simt_lib, oracle_bin, tmp_path, block_order):
     try:
         for flags in ([], ["-f", "4", "-k", "2", "-l", "15", "-A"], ["-r", "-f", "2"]):
             both_pfp(simt_lib, oracle_bin, str(tmp_path), p, flags, tile_ranks=3000)
+        if block_order == 0:
+            # the 1300-symbol run needs ~60 chunk rounds: with a limit of 12 the dictionary falls back to the doubling engine (nothing pruned)
+            monkeypatch.setenv("MMB_CHUNK_ROUNDS", "12")
+            st = both_pfp(simt_lib, oracle_bin, str(tmp_path), p, [], tile_ranks=3000)
+            assert not st["pruned"] and st["stream_suffixes"] == st["text_symbols"] + 1
     finally:
         simt_lib.simt_set_block_order(0)
 
