@@ -59,6 +59,10 @@ typedef struct mmb_options {
     uint8_t no_prune;            /* 1: enumerate every suffix on route 2 (no segment pruning; results are identical) */
     uint8_t reserved[5];
     uint64_t tile_ranks;         /* route 2: ranks per stream tile, 0 = default (2^30 in mmb_find = ~18 GB of tile buffers; 2^26 in mmb_find_from_arrays) */
+    uint32_t trim_min_len;       /* 0 = off (the reference's output, bit-exact).  > 0: multi-MUM rows are post-processed like the reference's
+                                    `mumemto trim` (mumemto/trim_mums.py:51-86): shortened by their overhang past the end of a sequence,
+                                    dropped when shorter than this afterwards (its default is 20) */
+    uint32_t reserved2;
 } mmb_options;
 
 typedef struct mmb_stats {

@@ -50,6 +50,7 @@ struct Options {
     int device = 0;
     int gpus = 1;           // --gpus N: partition-merge over N GPUs in this process (anchor = first sequence), NCCL all-gather + device merge
     int partitions = 0;     // --partitions P (with one GPU): the same workflow with the partitions run one after the other
+    int trim = 0;           // --trim[=MINLEN]: post-process multi-MUMs like `mumemto trim` (mumemto/trim_mums.py); 0 = off
 };
 
 static bool ends_with(const std::string& s, const std::string& suf) { return s.size() >= suf.size() && !s.compare(s.size() - suf.size(), suf.size(), suf); }
@@ -84,7 +85,9 @@ static int usage() {
         "\t    --gpus            [INT]     partition-merge on N GPUs: the first sequence is the anchor of every partition, the others are\n"
         "\t                                split into N groups (one per GPU, -M -n), one NCCL all-gather, merge on the device;\n"
         "\t                                writes PREFIX.mums / PREFIX.athresh like `anchor_merge` (rows in anchor order)\n"
-        "\t    --partitions      [INT]     the same workflow with P partitions run one after the other on one GPU\n\n");
+        "\t    --partitions      [INT]     the same workflow with P partitions run one after the other on one GPU\n"
+        "\t    --trim[=INT]                shorten multi-MUMs that run past the end of a sequence and drop those shorter than INT (default 20)\n"
+        "\t                                afterwards, like `mumemto trim`; off by default (the reference's output, bit for bit)\n\n");
     return 0;
 }
 
@@ -115,7 +118,7 @@ int main(int argc, char** argv) {
         {"arrays-in", required_argument, nullptr, 'a'}, {"keep-temp-files", no_argument, nullptr, 'K'}, {"window", required_argument, nullptr, 'w'},
         {"rare", required_argument, nullptr, 'f'}, {"binary", no_argument, nullptr, 'b'}, {"merge", no_argument, nullptr, 'M'},
         {"anchor", no_argument, nullptr, 'n'}, {"use-gsacak", no_argument, nullptr, 'g'}, {"device", required_argument, nullptr, 'd'},
-        {"gpus", required_argument, nullptr, 1000}, {"partitions", required_argument, nullptr, 1001},
+        {"gpus", required_argument, nullptr, 1000}, {"partitions", required_argument, nullptr, 1001}, {"trim", optional_argument, nullptr, 1002},
         {nullptr, 0, nullptr, 0}};
     Options o;
     int c;
@@ -139,6 +142,7 @@ int main(int argc, char** argv) {
             case 'd': o.device = std::atoi(optarg); break;
             case 1000: o.gpus = std::atoi(optarg); break;
             case 1001: o.partitions = std::atoi(optarg); break;
+            case 1002: o.trim = optarg ? std::atoi(optarg) : 20; break;
             case 'p': case 'P': case 'K':
                 fatal("-p/-P/-K use stage files of the CPU algorithm (.dict/.parse); the GPU engine has no such stages");
             default: usage(); return 1;
@@ -266,6 +270,7 @@ int main(int argc, char** argv) {
     mo.min_match_len = (uint32_t)o.min_match_len; mo.num_distinct_docs = o.num_distinct_docs; mo.rare_freq = o.rare_freq; mo.max_mem_freq = o.max_mem_freq;
     mo.merge = o.merge; mo.anchor_merge = o.anchor_merge; mo.cli_normalise = 1; mo.want_text = o.binary ? 0 : 1;
     mo.keep_arrays = o.arrays_out ? 1 : 0;      // the tiled route only keeps the whole stream when asked
+    mo.trim_min_len = (o.rare_freq == 1 && o.trim > 0) ? (uint32_t)o.trim : 0;
     bool mum_mode = (o.rare_freq == 1);
     status(mum_mode ? "finding multi-MUMs on the GPU" : "finding multi-MEMs on the GPU");
     if (!o.arrays_in.empty()) {

@@ -76,6 +76,8 @@ void emit_mems(const Reports& rep, const SAT* sa, const DetectParams& prm, const
 template <class SAT>
 void mum_rows(const Reports& rep, const SAT* sa, const DetectParams& prm, const u64* d_doc_start, const u64* d_doc_len, MumTable& out, cudaStream_t s);
 void mum_text(MumTable& t, u32 ndocs, cudaStream_t s);
+// optional post-processing of the reference (mumemto/trim_mums.py:51-86): shorten rows that overhang their document, drop rows below min_length
+void trim_mum_table(MumTable& t, u32 ndocs, const u64* d_doc_len, u32 min_length, cudaStream_t s);
 template <class SAT>
 void mem_rows(const Reports& rep, const SAT* sa, const DetectParams& prm, const u64* d_doc_start, const u64* d_doc_len, MemTable& out, cudaStream_t s);
 void mem_text(MemTable& t, cudaStream_t s);

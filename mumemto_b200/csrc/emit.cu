@@ -191,7 +191,51 @@ __global__ void rebase_first(const u64* __restrict__ in, u64 n, u64 add, u64* __
 
 u32 warps_grid(u32 n) { return ceil_div((u64)n * 32, TPB); }
 
+// --trim (optional, off by default): mumemto/trim_mums.py:51-86 of the reference.  A '+' multi-MUM may run through the '$' that ends its
+// document (quirk Q1); the reference's post-processing shortens such a row by its largest overhang max_d(start_d + len - L_d) -- the
+// start coordinates stay as they are -- and drops every row that is then shorter than min_length.  One warp per row.
+__global__ void __launch_bounds__(TPB) trim_lengths(const u32* __restrict__ len, const i64* __restrict__ off, u32 n, u32 N, const u64* __restrict__ doc_len,
+                                                    u32 min_length, u32* __restrict__ new_len, u32* __restrict__ keep) {
+    u32 r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= n) return;
+    i64 l = len[r], worst = INT64_MIN;
+    for (u32 d = lane; d < N; d += 32) { i64 o = off[(u64)r * N + d]; if (o != -1) worst = max(worst, o + l - (i64)doc_len[d]); }
+#pragma unroll
+    for (u32 k = 16; k > 0; k >>= 1) worst = max(worst, __shfl_xor_sync(0xffffffffu, worst, k));
+    if (lane == 0) {
+        i64 nl = worst > 0 ? l - worst : l;
+        bool ok = nl >= (i64)min_length;
+        new_len[r] = ok ? (u32)nl : 0u; keep[r] = ok ? 1u : 0u;
+    }
+}
+__global__ void __launch_bounds__(TPB) trim_gather(const u32* __restrict__ new_len, const i64* __restrict__ off, const u8* __restrict__ strand,
+                                                   const u32* __restrict__ keep, const u32* __restrict__ slot, u32 n, u32 N, u32* __restrict__ len_o,
+                                                   i64* __restrict__ off_o, u8* __restrict__ strand_o) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (u64)n * N) return;
+    u32 r = (u32)(t / N), d = (u32)(t % N);
+    if (!keep[r]) return;
+    u64 dst = (u64)slot[r] * N + d;
+    off_o[dst] = off[t]; strand_o[dst] = strand[t];
+    if (d == 0) len_o[slot[r]] = new_len[r];
+}
+
 }  // namespace
+
+void trim_mum_table(MumTable& t, u32 N, const u64* d_doc_len, u32 min_length, cudaStream_t s) {
+    u32 n = (u32)t.count;
+    if (!n) return;
+    DevBuf<u32> nl, keep, slot; nl.alloc(n, s); keep.alloc((u64)n + 1, s); slot.alloc((u64)n + 1, s);
+    MMB_CUDA(cudaMemsetAsync(keep.p + n, 0, 4, s));
+    MMB_LAUNCH(trim_lengths, warps_grid(n), TPB, 0, s, (const u32*)t.len.p, (const i64*)t.off.p, n, N, d_doc_len, min_length, nl.p, keep.p);
+    prim::exclusive_sum(keep.p, slot.p, (u64)n + 1, s);
+    u32 kept = to_host(slot.p + n, 1, s)[0];
+    DevBuf<u32> len_o; DevBuf<i64> off_o; DevBuf<u8> strand_o;
+    len_o.alloc(kept, s); off_o.alloc((u64)kept * N, s); strand_o.alloc((u64)kept * N, s);
+    if (kept) MMB_LAUNCH(trim_gather, ceil_div((u64)n * N, TPB), TPB, 0, s, (const u32*)nl.p, (const i64*)t.off.p, (const u8*)t.strand.p, (const u32*)keep.p,
+                         (const u32*)slot.p, n, N, len_o.p, off_o.p, strand_o.p);
+    t.len = std::move(len_o); t.off = std::move(off_o); t.strand = std::move(strand_o); t.count = kept;
+}
 
 template <class SAT>
 void mum_rows(const Reports& rep, const SAT* sa, const DetectParams& prm, const u64* d_doc_start, const u64* d_doc_len, MumTable& out, cudaStream_t s) {

@@ -470,13 +470,17 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
         // dictionary (stages 1-3 of the PFP route) are cheap, and the route pays off when the dictionary is a small fraction of the text
         PfpIndex ix; PfpParse pp;
         bool parsed = false;
-        const bool unbounded = e->prm.max_freq == 0 && e->prm.max_doc_freq == 0;      // -f 0 without -F: intervals of any size
-        if (unbounded && (opts->route == 2 || n + 1 >= (1ull << 31)))
-            throw Error(31, "unbounded total frequency (-f 0 with -F 0) needs the whole suffix stream on the device: direct route only (text below 2^31 symbols)");
+        // -f 0 without -F: intervals of any size.  The interval walk then needs the whole suffix stream in ONE view: the direct route below
+        // 2^31 symbols, or the prefix-free-parse route when the PRUNED stream fits one tile (segment pruning holds for any interval size:
+        // a segment is left out because it is too small or has a uniform BWT)
+        const bool unbounded = e->prm.max_freq == 0 && e->prm.max_doc_freq == 0;
+        const bool prune_ok = !(opts->keep_arrays || opts->no_prune);
+        if (unbounded && !prune_ok && (opts->route == 2 || n + 1 >= (1ull << 31)))
+            throw Error(31, "unbounded total frequency (-f 0 with -F 0) needs the whole suffix stream in one view: not together with keep_arrays / no_prune on the prefix-free-parse route");
         e->prm.whole_stream = 0;
-        bool use_pfp = !unbounded && (opts->route == 2 || (opts->route == 0 && n + 1 >= (1ull << 31)));
+        bool use_pfp = (opts->route == 2 || (opts->route == 0 && n + 1 >= (1ull << 31)));
         Timer tparse(s); float ms_parse = 0;
-        if (opts->route == 0 && !use_pfp && !unbounded && n >= (1u << 16)) {
+        if (opts->route == 0 && !use_pfp && !unbounded && n >= (1u << 16)) {      // unbounded + auto: the direct route whenever it fits
             tparse.start();
             pfp_parse(e->text.text.p, n, ix, pp, s); parsed = true;
             ms_parse = tparse.stop();
@@ -501,7 +505,11 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
             MMB_CUDA(cudaStreamSynchronize(s));
             e->stats.ms_detect = t.stop();
             t.start();
-            if (e->mum_mode) emit_mums<u32>(e->reports, e->sa.sa.p, e->prm, e->text.doc_start.p, e->text.doc_len.p, want_text, e->mums, s);
+            if (e->mum_mode && opts->trim_min_len) {
+                mum_rows<u32>(e->reports, e->sa.sa.p, e->prm, e->text.doc_start.p, e->text.doc_len.p, e->mums, s);
+                trim_mum_table(e->mums, N, e->text.doc_len.p, opts->trim_min_len, s);
+                if (want_text) mum_text(e->mums, N, s);
+            } else if (e->mum_mode) emit_mums<u32>(e->reports, e->sa.sa.p, e->prm, e->text.doc_start.p, e->text.doc_len.p, want_text, e->mums, s);
             else emit_mems<u32>(e->reports, e->sa.sa.p, e->prm, e->text.doc_start.p, e->text.doc_len.p, want_text, e->mems, s);
             e->stats.ms_emit = t.stop();
             e->stats.sa_rounds = e->sa.stats.rounds; e->stats.sa_sorted_elements = e->sa.stats.groups_sorted;
@@ -523,10 +531,13 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
             // how far back an interval can reach: the detector's halo
             u64 hi = e->prm.max_freq;
             if (e->prm.max_doc_freq) { u64 bound = (u64)e->prm.max_doc_freq * N; hi = hi ? std::min(hi, bound) : bound; }
-            if (hi == 0) throw Error(31, "unbounded total frequency (-f 0 with -F 0) is not supported by the windowed interval scan");
             u32 halo = (u32)std::min<u64>((hi + 8) & ~3ull, 1u << 22);
             // ranks per stream tile: 17 B per rank of tile buffers; C2 measured 745 / 731 / 722 ms per step at 2^28 / 2^29 / 2^30
             u64 tile_ranks = opts->tile_ranks ? opts->tile_ranks : (1ull << 30);
+            if (hi == 0) {          // unbounded: one tile or nothing
+                if (!ix.pruned || ix.full_stream) throw Error(31, "unbounded total frequency (-f 0 with -F 0): the suffix stream could not be pruned (-l below 11, or a very long low-complexity phrase); use the direct route (text below 2^31 symbols)");
+                tile_ranks = 1ull << 62; halo = 0; e->prm.whole_stream = 1;
+            }
             struct Consumer : TileConsumer {
                 mmb_engine* e; cudaStream_t s; u16* thresh; bool keep; std::vector<MumTable> mparts; std::vector<MemTable> eparts; u32 tiles = 0;
                 void consume(const StreamTile& tile) override {
@@ -560,7 +571,11 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
             e->stats.ms_detect = t.stop();
             e->stats.pfp_tiles = consumer.tiles;
             t.start();
-            if (e->mum_mode) { concat_mums(consumer.mparts, N, e->mums, s); if (want_text) mum_text(e->mums, N, s); }
+            if (e->mum_mode) {
+                concat_mums(consumer.mparts, N, e->mums, s);
+                if (opts->trim_min_len) trim_mum_table(e->mums, N, e->text.doc_len.p, opts->trim_min_len, s);
+                if (want_text) mum_text(e->mums, N, s);
+            }
             else { concat_mems(consumer.eparts, e->mems, s); if (want_text) mem_text(e->mems, s); }
             e->stats.ms_emit = t.stop();
         }

@@ -523,6 +523,8 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
     u64 total = to_host(out_base.p + K, 1, s)[0];
     const_cast<PfpIndex&>(ix).stream_ranks = total;
     if (getenv("MMB_DEBUG")) fprintf(stderr, "[stream] members %u, ranks %llu of %llu\n", K, (unsigned long long)total, (unsigned long long)ix.n);
+    if (tile_ranks >= (1ull << 62) && total >= (1ull << 32))
+        throw Error(31, "unbounded total frequency (-f 0 with -F 0): the pruned suffix stream still has " + std::to_string(total) + " ranks, too many for one view");
     if ((!ix.pruned || ix.full_stream) && total != ix.n) throw Error(76, "internal: the parse does not cover the text (" + std::to_string(total) + " of " + std::to_string(ix.n) + ")");
     MMB_LAUNCH(group_lcp, ceil_div(K, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const MemberMeta*)meta.p, (const u32*)mem_i.p, (const u32*)mem_head.p, (const u8*)mem_klcp.p, ix.key_symbols, K, glcp.p);
     mem_klcp.release();

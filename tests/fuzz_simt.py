@@ -151,7 +151,10 @@ def main():
             ok_o = util.run_cli(ORACLE, ["-o", o, *flags, *paths], check=False).returncode == 0
             unbounded = "-f" in flags and flags[flags.index("-f") + 1] == "0" and "-F" not in flags
             if unbounded and route == "pfp":
-                route = "direct"
+                # one view of the PRUNED stream: only when pruning is on and possible (-l above 10, chunk engine not forced to fall back)
+                minlen = int(flags[flags.index("-l") + 1]) if "-l" in flags else 20
+                if no_prune or minlen <= 10 or os.environ.get("MMB_NO_PRUNE") or os.environ.get("MMB_CHUNK_ROUNDS"):
+                    route = "direct"
             kw = util.flags_to_kwargs(flags)
             try:
                 api.find_files(paths, g, route=route, tile_ranks=tile, no_prune=no_prune, _lib=lib, **kw); ok_g = True

@@ -118,8 +118,8 @@ def test_simt_errors(simt_lib, tmp_path):
     open(tmp_path / "empty.fa", "w").write(">only a header\n")
     with pytest.raises(MumemtoError, match="Empty input file"):
         api.find_files([p[0], str(tmp_path / "empty.fa")], str(tmp_path / "x"), _lib=simt_lib)
-    with pytest.raises(MumemtoError, match="direct route only"):         # no frequency limit at all: needs the whole stream in one view
-        api.find_files(p, str(tmp_path / "x"), rare_freq=0, max_mem_freq=0, route="pfp", _lib=simt_lib)
+    with pytest.raises(MumemtoError, match="one view"):                  # no frequency limit at all: needs the whole (pruned) stream in one view
+        api.find_files(p, str(tmp_path / "x"), rare_freq=0, max_mem_freq=0, route="pfp", no_prune=True, _lib=simt_lib)
 
 
 @pytest.mark.parametrize("parts", [[[0, 1, 2], [0, 3]], [[0, 1], [0, 2], [0, 3]], [[0, 3, 1], [0, 2]]])
@@ -210,6 +210,29 @@ def test_simt_unbounded_frequency(simt_lib, oracle_bin, small, tmp_path):
             out = both(simt_lib, oracle_bin, str(tmp_path / f"{name}{i}"), paths, flags)
             if name == "rep" and i == 0:
                 assert max(len(l.split(b"\t")[1].split(b",")) for l in out[".mems"].splitlines()) > 1000
+            if i < 2:       # the same on the prefix-free-parse route: the pruned stream in one view (section 8(f).4 on the tiled route)
+                st = both_pfp(simt_lib, oracle_bin, str(tmp_path / f"{name}{i}"), paths, flags, tile_ranks=0)
+                assert st["pruned"] and st["pfp_tiles"] == 1
+
+
+def test_simt_trim_option(simt_lib, oracle_bin, small, tmp_path):
+    """--trim (off by default): the reference's `mumemto trim` post-processing (mumemto/trim_mums.py:51-86) applied on the device: rows that
+    run past the end of a sequence are shortened by their largest overhang, rows shorter than the minimum afterwards are dropped.  Checked
+    against a numpy restatement on the untrimmed output; t2-like documents with identical ends hold such a MUM."""
+    paths = util.appendix_a(str(tmp_path / "t"), N=4, L=3000, seed=42, identical_ends=True)
+    for route in ("direct", "pfp"):
+        a, b = str(tmp_path / f"plain_{route}"), str(tmp_path / f"trim_{route}")
+        api.find_files(paths, a, route=route, _lib=simt_lib)
+        api.find_files(paths, b, route=route, trim_min_len=20, _lib=simt_lib)
+        want, changed = [], 0
+        for line in open(a + ".mums"):
+            l, o, sg = line.rstrip("\n").split("\t")
+            over = max(int(x) + int(l) - 3000 for x in o.split(",") if x != "")
+            nl = int(l) - over if over > 0 else int(l)
+            changed += over > 0
+            if nl >= 20:
+                want.append(f"{nl}\t{o}\t{sg}\n")
+        assert changed >= 1 and open(b + ".mums").read() == "".join(want)
 
 
 def test_simt_pfp_last_phrase_suffix_tied_with_a_phrase_end(simt_lib, oracle_bin, tmp_path):
