@@ -529,7 +529,18 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's banner / debug lines must not mix with the JSON line on stdout
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints "NCCL version ..." straight to fd 1 when its first communicator comes up: point fd 1 at stderr until that has happened
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     stream = torch.cuda.current_stream()
     eng = Engine(device=local, stream=stream.cuda_stream)
 

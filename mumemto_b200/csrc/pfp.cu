@@ -300,48 +300,63 @@ __global__ void __launch_bounds__(TPB) rank_words_fix_last_phrase(const u32* __r
         if (sa_d[q] == i) rk[q] |= RK_OWN;
 }
 
-// Class of every rank that is longer than w: what its segment needs (CLS_*).  Each thread walks its segment in a shared-memory tile.
+// Class of every rank that is longer than w: what its segment needs (CLS_*).  The block stages the rank words of its ranks plus
+// SEG_LIMIT ranks of context on both sides; the thread that finds a segment START walks the segment once and leaves its class at the
+// start's slot, then every rank looks up the class of the start to its left (a few steps on pangenome-like input).
 __global__ void __launch_bounds__(TPB) classify_segments(const u32* __restrict__ rk, u32 dsize, PfpPrune prune, u32 seg_is_interval, u8* __restrict__ cls) {
-    __shared__ u32 tile[TPB + 2 * SEG_LIMIT + 1];
+    constexpr u32 SPAN = TPB + 2 * SEG_LIMIT + 1;
+    constexpr u8 TOO_LONG = 0x80;
+    __shared__ u32 tile[SPAN];
+    __shared__ u8 head_cls[SPAN];
     const i64 base = (i64)blockIdx.x * TPB - SEG_LIMIT;
-    for (u32 x = threadIdx.x; x < TPB + 2 * SEG_LIMIT + 1; x += TPB) {
+    for (u32 x = threadIdx.x; x < SPAN; x += TPB) {
         i64 q = base + x;
         tile[x] = (q >= 0 && q < (i64)dsize) ? rk[q] : RK_HB;       // outside the array: a segment start that owns nothing
     }
     __syncthreads();
+    const u8 all = CLS_STREAM | CLS_REFINE | CLS_HAS_START;         // without a verdict: keep, and assume the segment may hold a whole phrase
+    const u8 general = CLS_STREAM | CLS_REFINE;
+    if (prune.enabled) {
+        for (u32 y = threadIdx.x; y < TPB + SEG_LIMIT; y += TPB) {     // every start this block's ranks can belong to
+            if (!(tile[y] & RK_HB)) continue;
+            u64 total = 0; u32 sym = 0xffffffffu; bool uniform = true, has_start = false, saturated = false, has_short = false;
+            u32 b = y, steps = 0;
+            for (;;) {
+                u32 v = tile[b];
+                if (v & RK_OWN) {
+                    u32 c = (v >> 9) & RK_CNT_MAX, bsym = v & 0x1ffu;
+                    total += c; saturated |= c == RK_CNT_MAX; has_short |= (v & RK_SHORT) != 0;
+                    if (bsym == RK_START) { has_start = true; uniform = false; }
+                    else if (sym == 0xffffffffu) sym = bsym;
+                    else if (sym != bsym) uniform = false;
+                }
+                if ((tile[b + 1] & RK_HB) || steps == SEG_LIMIT) break;
+                ++b; ++steps;
+            }
+            u8 c = 0;
+            if (!(tile[b + 1] & RK_HB)) c = TOO_LONG;                   // more than SEG_LIMIT + 1 ranks: low-complexity repeats, kept as they are
+            else {
+                if (saturated) c = general;
+                else if (total >= prune.size_lo) {
+                    if (!uniform) c = general;
+                    // -M: a segment of exactly N suffixes, all at least t = -l symbols long, is one interval of length >= -l
+                    else if (prune.merge) c = (seg_is_interval && !has_short && total == prune.ndocs) ? CLS_THRESH : general;
+                }
+                if (has_start) c |= CLS_REFINE | CLS_HAS_START;         // phrase ranks need the exact place of every whole phrase
+            }
+            head_cls[y] = c;
+        }
+    }
+    __syncthreads();
     u32 p = blockIdx.x * TPB + threadIdx.x;
     if (p >= dsize) return;
-    u32 x = threadIdx.x + SEG_LIMIT, w = tile[x];
-    if (!(w & RK_OWN)) { cls[p] = 0; return; }
-    u8 all = CLS_STREAM | CLS_REFINE | CLS_HAS_START;     // without the walk: assume the segment may hold a whole phrase
+    u32 x = threadIdx.x + SEG_LIMIT;
+    if (!(tile[x] & RK_OWN)) { cls[p] = 0; return; }
     if (!prune.enabled) { cls[p] = all; return; }
-    // walk to the segment's first and last rank
     u32 a = x, steps = 0;
     while (!(tile[a] & RK_HB) && steps < SEG_LIMIT) { --a; ++steps; }
-    if (!(tile[a] & RK_HB)) { cls[p] = all; return; }
-    u32 b = x;
-    while (!(tile[b + 1] & RK_HB) && steps < SEG_LIMIT) { ++b; ++steps; }
-    if (!(tile[b + 1] & RK_HB)) { cls[p] = all; return; }
-    u64 total = 0; u32 sym = 0xffffffffu; bool uniform = true, has_start = false, saturated = false, has_short = false;
-    for (u32 y = a; y <= b; ++y) {
-        u32 v = tile[y];
-        if (!(v & RK_OWN)) continue;
-        u32 c = (v >> 9) & RK_CNT_MAX, bsym = v & 0x1ffu;
-        total += c; saturated |= c == RK_CNT_MAX; has_short |= (v & RK_SHORT) != 0;
-        if (bsym == RK_START) { has_start = true; uniform = false; }
-        else if (sym == 0xffffffffu) sym = bsym;
-        else if (sym != bsym) uniform = false;
-    }
-    const u8 general = CLS_STREAM | CLS_REFINE;
-    u8 c = 0;
-    if (saturated) c = general;
-    else if (total >= prune.size_lo) {
-        if (!uniform) c = general;
-        // -M: a segment of exactly N suffixes, all at least t = -l symbols long, is one interval of length >= -l
-        else if (prune.merge) c = (seg_is_interval && !has_short && total == prune.ndocs) ? CLS_THRESH : general;
-    }
-    if (has_start) c |= CLS_REFINE | CLS_HAS_START;     // phrase ranks need the exact place of every whole phrase
-    cls[p] = c;
+    u8 c = (tile[a] & RK_HB) ? head_cls[a] : TOO_LONG;
+    cls[p] = c == TOO_LONG ? all : c;
 }
 
 __global__ void __launch_bounds__(TPB) owned_positions(const u32* __restrict__ rk, u32 dsize, u32* __restrict__ out) {
@@ -350,11 +365,11 @@ __global__ void __launch_bounds__(TPB) owned_positions(const u32* __restrict__ r
 }
 
 // Per rank that is longer than w: key symbols shared with the previous such rank; member flags of the stream (surviving ranks and the
-// stand-in that follows a surviving segment); -M: the ranks that close a threshold-only segment.
+// stand-in that follows a surviving segment); -M: mkind 3 = the rank closes a threshold-only segment (stream.cu, segment_thresholds).
 __global__ void __launch_bounds__(TPB) member_flags(const u64* __restrict__ keys, const u32* __restrict__ rk, const u8* __restrict__ cls,
                                                     const u32* __restrict__ prev_owned, u32 dsize, u32 bits, u32 cpk, u32 t, u8* __restrict__ klcp,
                                                     u32* __restrict__ member, u8* __restrict__ mkind, u8* __restrict__ refine,
-                                                    u32* __restrict__ closers, u32* __restrict__ n_closers) {
+                                                    u32* __restrict__ n_closers) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     bool closes = false;
     if (p < dsize) {
@@ -368,17 +383,18 @@ __global__ void __launch_bounds__(TPB) member_flags(const u64* __restrict__ keys
             else if (cq & CLS_STREAM) kind = 2;          // first rank after a surviving segment: carries the true LCP that closes it
             closes = q && (cq & CLS_THRESH) && shared < t;
         }
-        klcp[p] = (u8)shared; member[p] = kind ? 1u : 0u; mkind[p] = kind;
+        klcp[p] = (u8)shared; member[p] = kind ? 1u : 0u; mkind[p] = closes ? (u8)(kind | 4) : kind;
         refine[p] = (u8)(((c & CLS_REFINE) ? 1 : 0) | ((c & CLS_HAS_START) ? 2 : 0));
     }
     if (p == dsize) member[p] = 0;
+    // how many segments get their threshold that way (statistics): one atomic per block
+    __shared__ u32 s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
     unsigned m = __ballot_sync(FULL, closes);
-    if (m) {
-        u32 lane = threadIdx.x & 31, base = 0;
-        if (lane == (u32)__ffs((int)m) - 1) base = atomicAdd(n_closers, (u32)__popc(m));
-        base = __shfl_sync(FULL, base, __ffs((int)m) - 1);
-        if (closes) closers[base + __popc(m & ((1u << lane) - 1))] = p;
-    }
+    if (m && (threadIdx.x & 31) == 0) atomicAdd(&s_cnt, (u32)__popc(m));
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) atomicAdd(n_closers, s_cnt);
 }
 
 // after the refinement (which permutes sa_d inside key groups, so the rank words' per-suffix fields no longer line up): ranks that hold
@@ -386,7 +402,7 @@ __global__ void __launch_bounds__(TPB) member_flags(const u64* __restrict__ keys
 // -M, at most 64 documents: document mask / anchor occurrence of every distinct phrase (PhraseDocs)
 __global__ void __launch_bounds__(TPB) phrase_docs_init(const u32* __restrict__ doff, u32 nd, PhraseDocs* __restrict__ rec) {
     u32 g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < nd) { PhraseDocs r; r.mask = 0; r.anchor = 0; r.flags = 0; r.total = doff[g + 1] - doff[g]; rec[g] = r; }
+    if (g < nd) { PhraseDocs r; r.mask = 0; r.anchor = 0; r.flags = 0; r.first = doff[g]; rec[g] = r; }
 }
 __global__ void __launch_bounds__(TPB) phrase_docs_fill(const u64* __restrict__ pstart, const u32* __restrict__ pid, u32 np, PfpPrune L,
                                                         PhraseDocs* __restrict__ rec) {
@@ -453,7 +469,9 @@ __device__ __forceinline__ u64 text_lcp(const u8* __restrict__ t, u64 a, u64 b, 
     return l;
 }
 
-constexpr u32 KASAI_CHUNK = 32;
+// consecutive phrases per thread: the first one of a chunk pays the whole common prefix (hundreds of phrases between haplotypes), the
+// others inherit it minus one (Kasai); ncu at 64 x 16 Mbp showed 81 sectors per phrase with chunks of 32
+constexpr u32 KASAI_CHUNK = 256;
 __global__ void __launch_bounds__(128) parse_lcp(const u8* __restrict__ text, u64 n, const u64* __restrict__ pstart, const u32* __restrict__ parse,
                                                  const u32* __restrict__ sa_p, const u32* __restrict__ isa_p, u32 m, u32* __restrict__ s_lcp,
                                                  u32* __restrict__ overflow) {
@@ -645,9 +663,8 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
             }
             ix.owned.alloc((u64)dsize + 1, s); ix.klcp.alloc(dsize, s); ix.mkind.alloc(dsize, s); ix.key_symbols = cpk; ix.seg_symbols = t;
             DevBuf<u32> n_closers; n_closers.alloc(1, s); n_closers.zero();
-            if (prune.merge && prune.enabled) ix.closers.alloc(dsize, s);
             MMB_LAUNCH(member_flags, ceil_div((u64)dsize + 1, TPB), TPB, 0, s, (const u64*)kb.p, (const u32*)ix.rk.p, (const u8*)cls.p, (const u32*)ix.prev_owned.p, dsize,
-                       bits, cpk, t, ix.klcp.p, ix.owned.p, ix.mkind.p, refine.p, ix.closers.p, n_closers.p);
+                       bits, cpk, t, ix.klcp.p, ix.owned.p, ix.mkind.p, refine.p, n_closers.p);
             cls.release();
             ix.ghead.alloc(dsize, s);
             // rounds of 21 symbols: phrase lengths are geometric (mean ~100), the longest of 1e8 phrases has ~2000 symbols = ~100 rounds, and
@@ -667,7 +684,7 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
                            (const u32*)ix.dphrase.p, dsize, ix.prank.p);
             } else {
                 // a phrase with a very long low-complexity stretch: start over with the doubling engine, nothing pruned
-                ix.rk.release(); ix.prev_owned.release(); ix.owned.release(); ix.klcp.release(); ix.mkind.release(); ix.closers.release(); ix.ghead.release(); ix.phrase_docs.release();
+                ix.rk.release(); ix.prev_owned.release(); ix.owned.release(); ix.klcp.release(); ix.mkind.release(); ix.ghead.release(); ix.phrase_docs.release();
                 ix.stats_d = SaStats();
                 ka.alloc(dsize, s); va.alloc(dsize, s);
                 MMB_LAUNCH(dict_keys, ceil_div(dsize, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const u32*)ix.limit.p, dsize, (const u8*)d_lut.p, bits, cpk, ka.p, va.p);

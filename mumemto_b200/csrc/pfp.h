@@ -24,7 +24,7 @@ struct PhraseDocs {
     u64 mask;               // bit d: an occurrence of the phrase starts in document d
     u64 anchor;             // text position where the phrase's occurrence in document 0 starts (valid with PD_HAS_ANCHOR)
     u32 flags;              // PD_*
-    u32 total;              // phrase length + 1 (the terminator), = limit of its first dictionary position
+    u32 first;              // dictionary position where the phrase starts (doff)
 };
 enum : u32 { PD_DUPLICATE = 1, PD_CROSSES = 2, PD_HAS_ANCHOR = 4 };     // a document twice; an occurrence spans a document boundary
 
@@ -53,11 +53,11 @@ struct PfpIndex {
     bool pruned = false;            // the dictionary order came from the chunk engine (rank words, ghead ... are filled)
     bool full_stream = true;        // nothing was left out: the stream has all |T| suffixes
     DevBuf<u32> ghead;              // [dsize] by rank: first rank of the run of equal strings the rank belongs to
-    DevBuf<u8> mkind;               // [dsize] by rank: 1 = ordinary member, 2 = stand-in rank after a surviving segment
+    DevBuf<u8> mkind;               // [dsize] by rank: 1 = ordinary member, 2 = stand-in rank after a surviving segment; bit 2 (4): the rank
+                                    //   closes a threshold-only segment (-M)
     DevBuf<u32> rk;                 // [dsize] by rank: segment start / longer-than-w / occurrences / preceding symbol (pfp.cu: rank words)
     DevBuf<u32> prev_owned;         // [dsize] by rank: 1 + the last rank <= p that is longer than w (0 = none)
-    DevBuf<u32> closers;            // -M: ranks that close a segment whose only possible interval is the whole segment (threshold only)
-    u32 n_closers = 0;
+    u32 n_closers = 0;              // -M: segments whose only possible interval is the whole segment (threshold only)
     DevBuf<PhraseDocs> phrase_docs; // -M, at most 64 documents: per distinct phrase (dictionary order)
     u32 seg_symbols = 0;            // symbols that define a segment (min(-l, key_symbols))
     u64 stream_ranks = 0;           // text suffixes that are enumerated (members' occurrences + stand-ins)
@@ -119,7 +119,7 @@ struct DocLookup { const u16* coarse; u32 shift; const u64* doc_start; u32 ndocs
 struct TileConsumer { virtual void consume(const StreamTile& t) = 0; virtual ~TileConsumer() {} };
 void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 halo, TileConsumer& consumer, cudaStream_t s,
                      const DocLookup* docs = nullptr);
-// -M on the pruned route: thresholds of the segments listed in ix.closers (every one is a single interval of ndocs suffixes).
+// -M on the pruned route: thresholds of the segments whose closing rank is flagged in ix.mkind (every one is a single interval of ndocs suffixes).
 void segment_thresholds(const PfpIndex& ix, const DocLookup& docs, u16* thresh, cudaStream_t s);
 
 }  // namespace mmb

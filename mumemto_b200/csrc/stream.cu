@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(TPB) members_fill(const u32* __restrict__ sa_d
     DictRecord d = rec[i];
     u32 r = prank[d.phrase];
     u32 q0 = occ_first[r], cnt = occ_first[r + 1] - q0;
-    const bool stand_in = mkind && mkind[p] == 2;      // one rank that stands for the pruned suffixes after a surviving segment
+    const bool stand_in = mkind && (mkind[p] & 3) == 2;      // one rank that stands for the pruned suffixes after a surviving segment
     if (stand_in) cnt = 1;
     mem_i[k] = i; mem_head[k] = ghead ? ghead[p] : d.head; mem_cnt[k] = cnt;
     MemberMeta m;
@@ -426,35 +426,38 @@ __global__ void __launch_bounds__(TPB) segment_thresholds_kernel(const u32* __re
 }
 
 
-// The same for collections of at most 64 documents, one THREAD per segment: the documents of a segment are the union of its phrases'
-// document masks (PhraseDocs, L2 resident: one record per distinct phrase), and the document-0 suffix sits at the phrase's document-0
-// occurrence + the offset of the dictionary suffix inside the phrase.  Segments that touch a phrase with a repeated document or an
-// occurrence across a document boundary go to `slow` (the warp kernel above decides them exactly from the occurrence lists).
-__global__ void __launch_bounds__(TPB) segment_thresholds_masks(const u32* __restrict__ closers, u32 n_closers, const u32* __restrict__ rk,
+// The same for collections of at most 64 documents, one THREAD per closing rank (threads of the other ranks leave at once, so that the
+// rank-indexed arrays are read coalesced): the documents of a segment are the union of its phrases' document masks (PhraseDocs, L2
+// resident: one record per distinct phrase), and the document-0 suffix sits at the phrase's document-0 occurrence + the offset of the
+// dictionary suffix inside the phrase.  Segments that touch a phrase with a repeated document or an occurrence across a document
+// boundary go to `slow` (the warp kernel above decides them exactly from the occurrence lists).
+__global__ void __launch_bounds__(TPB) segment_thresholds_masks(const u8* __restrict__ mkind, u32 dsize, const u32* __restrict__ rk,
                                                                 const u32* __restrict__ prev_owned, const u8* __restrict__ klcp,
-                                                                const u32* __restrict__ sa_d, const u32* __restrict__ limit, const u32* __restrict__ dphrase,
+                                                                const u32* __restrict__ sa_d, const u32* __restrict__ dphrase,
                                                                 const PhraseDocs* __restrict__ pdocs, u32 ndocs, u16* __restrict__ thresh,
-                                                                u32* __restrict__ slow, u32* __restrict__ n_slow) {
-    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    bool defer = false; u32 c = 0;
-    if (t < n_closers) {
-        c = closers[t];
-        u32 x = prev_owned[c - 1] - 1;                      // last rank of the segment that is longer than w
-        const u32 lcp_close = klcp[c];
-        u64 mask = 0, anchor = ~0ull; u32 lcp_open = 0;
-        for (;; --x) {
-            u32 w = rk[x];
-            if (w & RKW_OWN) {
-                u32 i = sa_d[x];
-                PhraseDocs r = pdocs[dphrase[i]];
-                defer |= (r.flags & (PD_DUPLICATE | PD_CROSSES)) != 0;
-                mask |= r.mask;
-                if (r.flags & PD_HAS_ANCHOR) anchor = r.anchor + (r.total - limit[i]);
-                lcp_open = klcp[x];
+                                                                u32* __restrict__ slow, u32* __restrict__ n_slow, int list_all) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    bool defer = false;
+    if (c < dsize && (mkind[c] & 4)) {
+        if (list_all) defer = true;                         // more than 64 documents: every segment goes to the warp kernel
+        else {
+            u32 x = prev_owned[c - 1] - 1;                  // last rank of the segment that is longer than w
+            const u32 lcp_close = klcp[c];
+            u64 mask = 0, anchor = ~0ull; u32 lcp_open = 0;
+            for (;; --x) {
+                u32 w = rk[x];
+                if (w & RKW_OWN) {
+                    u32 i = sa_d[x];
+                    PhraseDocs r = pdocs[dphrase[i]];
+                    defer |= (r.flags & (PD_DUPLICATE | PD_CROSSES)) != 0;
+                    mask |= r.mask;
+                    if (r.flags & PD_HAS_ANCHOR) anchor = r.anchor + (i - r.first);
+                    lcp_open = klcp[x];
+                }
+                if ((w & RKW_HB) || x == 0) break;
             }
-            if ((w & RKW_HB) || x == 0) break;
+            if (!defer && (u32)__popcll(mask) == ndocs && anchor != ~0ull) thresh[anchor] = (u16)min(max(lcp_open, lcp_close), 65535u);
         }
-        if (!defer && (u32)__popcll(mask) == ndocs && anchor != ~0ull) thresh[anchor] = (u16)min(max(lcp_open, lcp_close), 65535u);
     }
     unsigned m = __ballot_sync(0xffffffffu, defer);
     if (m) {
@@ -470,17 +473,23 @@ __global__ void __launch_bounds__(TPB) segment_thresholds_masks(const u32* __res
 
 void segment_thresholds(const PfpIndex& ix, const DocLookup& docs, u16* thresh, cudaStream_t s) {
     if (!ix.pruned || !ix.n_closers || !thresh) return;
-    const u32* list = ix.closers.p; u32 count = ix.n_closers;
+    const bool masks = ix.phrase_docs.p && docs.ndocs <= 64 && !getenv("MMB_THRESH_SLOW");
     DevBuf<u32> slow, n_slow;
-    if (ix.phrase_docs.p && docs.ndocs <= 64 && !getenv("MMB_THRESH_SLOW")) {
-        slow.alloc(ix.n_closers, s); n_slow.alloc(1, s); n_slow.zero();
-        MMB_LAUNCH(segment_thresholds_masks, ceil_div(ix.n_closers, TPB), TPB, 0, s, (const u32*)ix.closers.p, ix.n_closers, (const u32*)ix.rk.p,
-                   (const u32*)ix.prev_owned.p, (const u8*)ix.klcp.p, (const u32*)ix.sa_d.p, (const u32*)ix.limit.p, (const u32*)ix.dphrase.p,
-                   (const PhraseDocs*)ix.phrase_docs.p, docs.ndocs, thresh, slow.p, n_slow.p);
+    slow.alloc(masks ? std::max<u32>(ix.n_closers / 8, 1u << 16) : ix.n_closers, s); n_slow.alloc(1, s); n_slow.zero();
+    // (with masks the deferred segments are the few that touch a document boundary or a phrase repeated inside a document; if they
+    // ever outnumber the list, the kernel is simply run again with every segment deferred)
+    MMB_LAUNCH(segment_thresholds_masks, ceil_div(ix.dsize, TPB), TPB, 0, s, (const u8*)ix.mkind.p, ix.dsize, (const u32*)ix.rk.p, (const u32*)ix.prev_owned.p,
+               (const u8*)ix.klcp.p, (const u32*)ix.sa_d.p, (const u32*)ix.dphrase.p, (const PhraseDocs*)ix.phrase_docs.p, docs.ndocs, thresh, slow.p, n_slow.p,
+               masks ? 0 : 1);
+    u32 count = to_host(n_slow.p, 1, s)[0];
+    if (count > slow.n) {
+        slow.alloc(ix.n_closers, s); n_slow.zero();
+        MMB_LAUNCH(segment_thresholds_masks, ceil_div(ix.dsize, TPB), TPB, 0, s, (const u8*)ix.mkind.p, ix.dsize, (const u32*)ix.rk.p, (const u32*)ix.prev_owned.p,
+                   (const u8*)ix.klcp.p, (const u32*)ix.sa_d.p, (const u32*)ix.dphrase.p, (const PhraseDocs*)ix.phrase_docs.p, docs.ndocs, thresh, slow.p, n_slow.p, 1);
         count = to_host(n_slow.p, 1, s)[0];
-        list = slow.p;
-        if (!count) return;
     }
+    const u32* list = slow.p;
+    if (!count) return;
     u32 grid = ceil_div((u64)count * 32, TPB);
     auto launch = [&](auto segment_thresholds_k) {
         MMB_LAUNCH(segment_thresholds_k, grid, TPB, 0, s, list, count, (const u32*)ix.rk.p, (const u32*)ix.prev_owned.p, (const u8*)ix.klcp.p,
