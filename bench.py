@@ -432,7 +432,7 @@ def cli_end_to_end(imgs, spec, flagset, expect_md5, runs=2):
         times = []
         for _ in range(runs):
             t0 = time.perf_counter()
-            r = subprocess.run([exe, "-o", os.path.join(d, "out"), *flags, *paths], capture_output=True, env=dict(os.environ, MMB_CLI_TIMING="1"))
+            r = subprocess.run([exe, "-o", os.path.join(d, "out"), *flags, *paths], capture_output=True, env=dict(os.environ, MMB_CLI_TIMING="1", MMB_PROFILE_HOST="1"))
             times.append(time.perf_counter() - t0)
             if r.returncode != 0:
                 return {"error": r.stderr.decode(errors="replace")[-400:]}
@@ -443,7 +443,7 @@ def cli_end_to_end(imgs, spec, flagset, expect_md5, runs=2):
                 h.update(blk)
         best = min(times)
         return {"value": spec["N"] * spec["L"] / best, "unit": "bases/s", "seconds": best, "all_seconds": times, "output_bytes": os.path.getsize(out),
-                "md5_matches_engine_output": h.hexdigest() == expect_md5, "stderr_tail": r.stderr.decode(errors="replace")[-1200:],
+                "md5_matches_engine_output": h.hexdigest() == expect_md5, "stderr_tail": r.stderr.decode(errors="replace")[-1600:],
                 "region": "wall clock of bin/mumemto_exec: process start, FASTA files in the page cache -> closed output file (pooled pread into pinned memory, H2D, path, D2H, write)"}
     finally:
         shutil.rmtree(d, ignore_errors=True)
