@@ -469,12 +469,36 @@ __device__ __forceinline__ u64 text_lcp(const u8* __restrict__ t, u64 a, u64 b, 
     return l;
 }
 
-// consecutive phrases per thread: the first one of a chunk pays the whole common prefix (hundreds of phrases between haplotypes), the
-// others inherit it minus one (Kasai); ncu at 64 x 16 Mbp showed 81 sectors per phrase with chunks of 32
-constexpr u32 KASAI_CHUNK = 256;
-__global__ void __launch_bounds__(128) parse_lcp(const u8* __restrict__ text, u64 n, const u64* __restrict__ pstart, const u32* __restrict__ parse,
-                                                 const u32* __restrict__ sa_p, const u32* __restrict__ isa_p, u32 m, u32* __restrict__ s_lcp,
-                                                 u32* __restrict__ overflow) {
+// consecutive phrases per thread (Kasai inheritance inside a chunk).  Measured at C2: chunks of 32 -> 33.0 ms, chunks of 256 -> 39.4 ms.
+constexpr u32 KASAI_CHUNK = 32;
+// LCP of the phrases of adjacent rank (dictionary strings; by_rank[r - 1] = distinct phrase with rank r): plcp[r] for r = 2 .. nd,
+// plcp[0] = plcp[1] = 0.  With a range-minimum index over it the LCP of ANY two phrases is one L2-resident query, so parse_lcp never
+// touches the text (the reference does the same through lcpD and an RMQ, include/dictionary.hpp:87-101).
+__global__ void __launch_bounds__(TPB) phrase_by_rank(const u32* __restrict__ prank, u32 nd, u32* __restrict__ by_rank) {
+    u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < nd) by_rank[prank[g] - 1] = g;
+}
+__global__ void __launch_bounds__(TPB) phrase_lcp(const u8* __restrict__ dict, const u32* __restrict__ doff, const u32* __restrict__ by_rank, u32 nd,
+                                                  u32* __restrict__ plcp) {
+    u32 r = blockIdx.x * blockDim.x + threadIdx.x;          // phrase rank, 1-based; slot 0 unused
+    if (r > nd) return;
+    if (r < 2) { plcp[r] = 0; return; }
+    u32 ga = by_rank[r - 2], gb = by_rank[r - 1];
+    u32 a = doff[ga], b = doff[gb];
+    u32 cap = min(doff[ga + 1] - a, doff[gb + 1] - b) - 1;   // symbols of the shorter phrase (terminator excluded)
+    u32 l = 0;
+    while (l + 8 <= cap) {
+        u64 x = load8(dict, (u64)a + l) ^ load8(dict, (u64)b + l);
+        if (x) { l += (u32)((__ffsll((long long)x) - 1) >> 3); plcp[r] = l; return; }
+        l += 8;
+    }
+    while (l < cap && dict[a + l] == dict[b + l]) ++l;
+    plcp[r] = l;
+}
+
+__global__ void __launch_bounds__(128) parse_lcp(const u64* __restrict__ pstart, const u32* __restrict__ parse,
+                                                 const u32* __restrict__ sa_p, const u32* __restrict__ isa_p, u32 m, const u32* __restrict__ plcp,
+                                                 const u32* __restrict__ prmq, u32 prmq_blocks, u32* __restrict__ s_lcp, u32* __restrict__ overflow) {
     u64 first = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * KASAI_CHUNK;
     u32 l = 0;
     for (u32 k = 0; k < KASAI_CHUNK; ++k) {
@@ -483,13 +507,10 @@ __global__ void __launch_bounds__(128) parse_lcp(const u8* __restrict__ text, u6
         u32 r = isa_p[j];
         if (r == 0) { s_lcp[0] = 0; l = 0; continue; }
         u64 j2 = sa_p[r - 1];
-        while (parse[j + l] == parse[j2 + l]) ++l;                   // the terminator 0 at m-1 is unique, so this stops inside the array
+        u32 ra, rb;
+        while ((ra = parse[j + l]) == (rb = parse[j2 + l])) ++l;       // the terminator 0 at m-1 is unique, so this stops inside the array
         u64 common = pstart[j + l] - pstart[j];
-        if (parse[j + l] && parse[j2 + l]) {
-            u64 pa = pstart[j + l], pb = pstart[j2 + l];
-            u64 cap = min(pstart[j + l + 1] - pa, pstart[j2 + l + 1] - pb) + PFP_W;     // shorter of the two phrases
-            common += text_lcp(text, pa, pb, cap);
-        }
+        if (ra && rb) common += range_min(plcp, prmq, prmq_blocks, min(ra, rb) + 1, max(ra, rb));      // LCP of the two differing phrases
         if (common > 0xfffffffeull) { *overflow = 1; common = 0xfffffffeull; }
         s_lcp[r] = (u32)common;
         if (l) --l;
@@ -741,10 +762,21 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
     delete pt; pt = new PhaseTimer("pfp 7 s_lcp", s);
     ix.s_lcp.alloc(m, s);
     {
+        // LCP of phrases of adjacent rank + range-minimum index (blocks of 32 + sparse table over the blocks: a few MB, L2 resident)
+        DevBuf<u32> by_rank, plcp, prmq; by_rank.alloc(nd, s); plcp.alloc((u64)nd + 1, s);
+        MMB_LAUNCH(phrase_by_rank, ceil_div(nd, TPB), TPB, 0, s, (const u32*)ix.prank.p, nd, by_rank.p);
+        MMB_LAUNCH(phrase_lcp, ceil_div((u64)nd + 1, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const u32*)ix.doff.p, (const u32*)by_rank.p, nd, plcp.p);
+        u32 pblocks = (nd + 1 + 31) / 32, plevels = 1;
+        while ((1u << plevels) <= pblocks) ++plevels;
+        prmq.alloc((u64)plevels * pblocks, s);
+        MMB_LAUNCH(rmq_block_minima, ceil_div(pblocks, TPB), TPB, 0, s, (const u32*)plcp.p, nd + 1, pblocks, prmq.p);
+        for (u32 k = 1; k < plevels; ++k)
+            MMB_LAUNCH(rmq_level, ceil_div(pblocks, TPB), TPB, 0, s, (const u32*)(prmq.p + (u64)(k - 1) * pblocks), pblocks, 1u << (k - 1),
+                       prmq.p + (u64)k * pblocks);
         DevBuf<u32> overflow; overflow.alloc(1, s); overflow.zero();
         u64 threads = ((u64)m + KASAI_CHUNK - 1) / KASAI_CHUNK;
-        MMB_LAUNCH(parse_lcp, ceil_div(threads, 128), 128, 0, s, text, n, (const u64*)ix.pstart.p, (const u32*)ix.parse.p, (const u32*)sa_p.p,
-                   (const u32*)ix.isa_p.p, m, ix.s_lcp.p, overflow.p);
+        MMB_LAUNCH(parse_lcp, ceil_div(threads, 128), 128, 0, s, (const u64*)ix.pstart.p, (const u32*)ix.parse.p, (const u32*)sa_p.p,
+                   (const u32*)ix.isa_p.p, m, (const u32*)plcp.p, (const u32*)prmq.p, pblocks, ix.s_lcp.p, overflow.p);
         if (to_host(overflow.p, 1, s)[0]) throw Error(75, "a common prefix longer than 2^32 symbols: not supported");
     }
     sa_p.release();

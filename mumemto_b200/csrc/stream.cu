@@ -441,7 +441,8 @@ __global__ void __launch_bounds__(TPB) segment_thresholds_masks(const u8* __rest
     if (c < dsize && (mkind[c] & 4)) {
         if (list_all) defer = true;                         // more than 64 documents: every segment goes to the warp kernel
         else {
-            u32 x = prev_owned[c - 1] - 1;                  // last rank of the segment that is longer than w
+            u32 x = c - 1;                                  // last rank of the segment that is longer than w: usually the rank before
+            if (!(rk[x] & RKW_OWN)) x = prev_owned[c - 1] - 1;
             const u32 lcp_close = klcp[c];
             u64 mask = 0, anchor = ~0ull; u32 lcp_open = 0;
             for (;; --x) {
