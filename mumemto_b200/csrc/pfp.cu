@@ -263,19 +263,21 @@ __global__ void __launch_bounds__(TPB) phrase_counts(const u32* __restrict__ pid
     if (j < np) atomicAdd(&count[pid[j]], 1u);
 }
 __global__ void __launch_bounds__(TPB) dict_info(const u32* __restrict__ dphrase, const u32* __restrict__ doff, const u8* __restrict__ dict,
-                                                 const u32* __restrict__ count, u32 dsize, u32* __restrict__ pinfo) {
+                                                 const u32* __restrict__ count, u32 dsize, u64* __restrict__ pinfo) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dsize) return;
     u32 g = dphrase[i];
     u32 before = i > doff[g] ? (u32)dict[i - 1] : RK_START;
-    pinfo[i] = (min(count[g], RK_CNT_MAX) << 9) | before;
+    pinfo[i] = ((u64)g << 32) | (min(count[g], RK_CNT_MAX) << 9) | before;      // phrase id rides along: the gather in rank_words fetches it for free
 }
-__global__ void __launch_bounds__(TPB) rank_words(const u64* __restrict__ keys, const u32* __restrict__ sa_d, const u32* __restrict__ pinfo, u32 dsize,
-                                                  u32 bits, u32 cpk, u32 t, u32* __restrict__ rk) {
+__global__ void __launch_bounds__(TPB) rank_words(const u64* __restrict__ keys, const u32* __restrict__ sa_d, const u64* __restrict__ pinfo, u32 dsize,
+                                                  u32 bits, u32 cpk, u32 t, u32* __restrict__ rk, u32* __restrict__ rank_phrase) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= dsize) return;
     u64 key = keys[p];
-    u32 w = pinfo[sa_d[p]];
+    u64 info = pinfo[sa_d[p]];
+    u32 w = (u32)info;
+    if (rank_phrase) rank_phrase[p] = (u32)(info >> 32);        // valid as long as the rank's key group is not refined (threshold-only segments never are)
     if ((u32)(key >> (bits * (cpk - 1 - PFP_W))) & ((1u << bits) - 1)) w |= RK_OWN;
     if (((u32)(key >> (bits * (cpk - t))) & ((1u << bits) - 1)) == 0) w |= RK_SHORT;           // symbol t - 1 is the terminator or past it
     if (p == 0 || key_shared(keys[p - 1], key, bits, cpk) < t) w |= RK_HB;
@@ -661,7 +663,7 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
         if (try_pruned) {
             prim::sort_pairs(ka.p, kb.p, va.p, ix.sa_d.p, dsize, 0, (int)(bits * cpk), s);
             ka.release(); va.release();
-            DevBuf<u32> count, pinfo; count.alloc(nd, s); count.zero(); pinfo.alloc(dsize, s);
+            DevBuf<u32> count; DevBuf<u64> pinfo; count.alloc(nd, s); count.zero(); pinfo.alloc(dsize, s);
             MMB_LAUNCH(phrase_counts, ceil_div(np, TPB), TPB, 0, s, (const u32*)pid.p, np, count.p);
             if (prune.enabled && prune.merge && prune.ndocs <= 64 && prune.doc_coarse) {
                 ix.phrase_docs.alloc(nd, s);
@@ -670,7 +672,9 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
             }
             MMB_LAUNCH(dict_info, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.dphrase.p, (const u32*)ix.doff.p, (const u8*)ix.dict.p, (const u32*)count.p, dsize, pinfo.p);
             ix.rk.alloc(dsize, s);
-            MMB_LAUNCH(rank_words, ceil_div(dsize, TPB), TPB, 0, s, (const u64*)kb.p, (const u32*)ix.sa_d.p, (const u32*)pinfo.p, dsize, bits, cpk, t, ix.rk.p);
+            if (ix.phrase_docs.p) ix.rank_phrase.alloc(dsize, s);
+            MMB_LAUNCH(rank_words, ceil_div(dsize, TPB), TPB, 0, s, (const u64*)kb.p, (const u32*)ix.sa_d.p, (const u64*)pinfo.p, dsize, bits, cpk, t, ix.rk.p,
+                       ix.rank_phrase.p);
             MMB_LAUNCH(rank_words_fix_last_phrase, PFP_W, TPB, 0, s, (const u32*)pid.p, np, (const u32*)ix.doff.p, (const u32*)ix.limit.p, (const u8*)ix.dict.p,
                        (const u8*)d_lut.p, bits, cpk, (const u64*)kb.p, (const u32*)ix.sa_d.p, dsize, ix.rk.p);
             pinfo.release(); count.release();
@@ -705,7 +709,7 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
                            (const u32*)ix.dphrase.p, dsize, ix.prank.p);
             } else {
                 // a phrase with a very long low-complexity stretch: start over with the doubling engine, nothing pruned
-                ix.rk.release(); ix.prev_owned.release(); ix.owned.release(); ix.klcp.release(); ix.mkind.release(); ix.ghead.release(); ix.phrase_docs.release();
+                ix.rk.release(); ix.prev_owned.release(); ix.owned.release(); ix.klcp.release(); ix.mkind.release(); ix.ghead.release(); ix.phrase_docs.release(); ix.rank_phrase.release();
                 ix.stats_d = SaStats();
                 ka.alloc(dsize, s); va.alloc(dsize, s);
                 MMB_LAUNCH(dict_keys, ceil_div(dsize, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const u32*)ix.limit.p, dsize, (const u8*)d_lut.p, bits, cpk, ka.p, va.p);

@@ -59,6 +59,8 @@ struct PfpIndex {
     DevBuf<u32> prev_owned;         // [dsize] by rank: 1 + the last rank <= p that is longer than w (0 = none)
     u32 n_closers = 0;              // -M: segments whose only possible interval is the whole segment (threshold only)
     DevBuf<PhraseDocs> phrase_docs; // -M, at most 64 documents: per distinct phrase (dictionary order)
+    DevBuf<u32> rank_phrase;        // -M, with phrase_docs: distinct phrase of the suffix at every rank of the INITIAL key order (stays valid for
+                                    //   ranks whose key group is never refined: the threshold-only segments)
     u32 seg_symbols = 0;            // symbols that define a segment (min(-l, key_symbols))
     u64 stream_ranks = 0;           // text suffixes that are enumerated (members' occurrences + stand-ins)
     DevBuf<u32> dphrase;            // [dsize] distinct-phrase id (in D' order) of every dictionary position

@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(TPB) segment_thresholds_kernel(const u32* __re
 // boundary go to `slow` (the warp kernel above decides them exactly from the occurrence lists).
 __global__ void __launch_bounds__(TPB) segment_thresholds_masks(const u8* __restrict__ mkind, u32 dsize, const u32* __restrict__ rk,
                                                                 const u32* __restrict__ prev_owned, const u8* __restrict__ klcp,
-                                                                const u32* __restrict__ sa_d, const u32* __restrict__ dphrase,
+                                                                const u32* __restrict__ sa_d, const u32* __restrict__ rank_phrase,
                                                                 const PhraseDocs* __restrict__ pdocs, u32 ndocs, u16* __restrict__ thresh,
                                                                 u32* __restrict__ slow, u32* __restrict__ n_slow, int list_all) {
     u32 c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(TPB) segment_thresholds_masks(const u8* __rest
                 u32 w = rk[x];
                 if (w & RKW_OWN) {
                     u32 i = sa_d[x];
-                    PhraseDocs r = pdocs[dphrase[i]];
+                    PhraseDocs r = pdocs[rank_phrase[x]];        // rank-indexed: coalesced with rk / sa_d / klcp
                     defer |= (r.flags & (PD_DUPLICATE | PD_CROSSES)) != 0;
                     mask |= r.mask;
                     if (r.flags & PD_HAS_ANCHOR) anchor = r.anchor + (i - r.first);
@@ -474,19 +474,19 @@ __global__ void __launch_bounds__(TPB) segment_thresholds_masks(const u8* __rest
 
 void segment_thresholds(const PfpIndex& ix, const DocLookup& docs, u16* thresh, cudaStream_t s) {
     if (!ix.pruned || !ix.n_closers || !thresh) return;
-    const bool masks = ix.phrase_docs.p && docs.ndocs <= 64 && !getenv("MMB_THRESH_SLOW");
+    const bool masks = ix.phrase_docs.p && ix.rank_phrase.p && docs.ndocs <= 64 && !getenv("MMB_THRESH_SLOW");
     DevBuf<u32> slow, n_slow;
     slow.alloc(masks ? std::max<u32>(ix.n_closers / 8, 1u << 16) : ix.n_closers, s); n_slow.alloc(1, s); n_slow.zero();
     // (with masks the deferred segments are the few that touch a document boundary or a phrase repeated inside a document; if they
     // ever outnumber the list, the kernel is simply run again with every segment deferred)
     MMB_LAUNCH(segment_thresholds_masks, ceil_div(ix.dsize, TPB), TPB, 0, s, (const u8*)ix.mkind.p, ix.dsize, (const u32*)ix.rk.p, (const u32*)ix.prev_owned.p,
-               (const u8*)ix.klcp.p, (const u32*)ix.sa_d.p, (const u32*)ix.dphrase.p, (const PhraseDocs*)ix.phrase_docs.p, docs.ndocs, thresh, slow.p, n_slow.p,
+               (const u8*)ix.klcp.p, (const u32*)ix.sa_d.p, (const u32*)ix.rank_phrase.p, (const PhraseDocs*)ix.phrase_docs.p, docs.ndocs, thresh, slow.p, n_slow.p,
                masks ? 0 : 1);
     u32 count = to_host(n_slow.p, 1, s)[0];
     if (count > slow.n) {
         slow.alloc(ix.n_closers, s); n_slow.zero();
         MMB_LAUNCH(segment_thresholds_masks, ceil_div(ix.dsize, TPB), TPB, 0, s, (const u8*)ix.mkind.p, ix.dsize, (const u32*)ix.rk.p, (const u32*)ix.prev_owned.p,
-                   (const u8*)ix.klcp.p, (const u32*)ix.sa_d.p, (const u32*)ix.dphrase.p, (const PhraseDocs*)ix.phrase_docs.p, docs.ndocs, thresh, slow.p, n_slow.p, 1);
+                   (const u8*)ix.klcp.p, (const u32*)ix.sa_d.p, (const u32*)ix.rank_phrase.p, (const PhraseDocs*)ix.phrase_docs.p, docs.ndocs, thresh, slow.p, n_slow.p, 1);
         count = to_host(n_slow.p, 1, s)[0];
     }
     const u32* list = slow.p;
