@@ -63,6 +63,13 @@ void profile_after(const char* kernel_name, cudaStream_t s);
     type* name = reinterpret_cast<type*>(name##_raw_)
 #endif
 
+// a 16-byte aligned static shared-memory array (the unit-test build spells the attribute order differently)
+#ifdef MMB_SIMT
+#define MMB_SHARED_ALIGNED16(type, name, count) alignas(16) static type name[count]
+#else
+#define MMB_SHARED_ALIGNED16(type, name, count) __shared__ __align__(16) type name[count]
+#endif
+
 inline u32 ceil_div(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
 
 // MMB_DEBUG=1: wall-clock of a host-side phase (synchronises the stream at both ends; never active in measured runs)

@@ -6,12 +6,13 @@
 //
 // The parse is a 4-state line automaton evaluated in parallel: every 4 KiB chunk summarises itself as a map state->state, the maps
 // are composed per file, and with the start state of each chunk known every byte decides locally whether it is sequence.
-//   pass 1  fasta_chunk_maps     read raw                      -> 1 B map per chunk
-//   (tiny)  fasta_chunk_states   one thread per file composes  -> start state per chunk
-//   pass 2  fasta_chunk_counts   read raw                      -> kept bases / header starts per chunk
+//   pass 1  fasta_chunk_maps     read raw                      -> per chunk: 1 B map + kept bases / header starts for EACH of the four
+//                                                                 states the chunk can start in (they only differ before the chunk's first
+//                                                                 newline, so most threads classify their bytes once)
+//   (tiny)  fasta_chunk_states   one thread per file composes  -> start state, kept bases and header starts per chunk
 //   (scan)  exclusive sums over chunks; fasta_doc_layout       -> doc_start[], doc_len[]
-//   pass 3  fasta_scatter        read raw, write T (fwd + rc)  -> 1 B read + 2 B written per base
-// Algorithmic traffic: 3 reads of the FASTA bytes + 2 bytes written per base.
+//   pass 2  fasta_scatter        read raw, write T (fwd + rc)  -> 1 B read + 2 B written per base
+// Algorithmic traffic: 2 reads of the FASTA bytes + 2 bytes written per base.
 #include "text.h"
 #include "prims.h"
 
@@ -177,35 +178,66 @@ __device__ __forceinline__ u32 block_sum_scan(u32 mine, u32* total) {
     return before + inc - mine;
 }
 
+// Sum of one u64 per thread over the block (every thread gets the total).
+__device__ __forceinline__ u64 block_sum64(u64 mine) {
+    __shared__ u64 warp_sums[TPB / 32];
+    u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (u32 d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(FULL, mine, d);
+    if (lane == 0) warp_sums[warp] = mine;
+    __syncthreads();
+    u64 all = 0;
+    for (u32 w = 0; w < TPB / 32; ++w) all += warp_sums[w];
+    __syncthreads();
+    return all;
+}
+
+// Pass 1: the chunk's state map, and its kept-base / header-start counts for each of the four states it may start in, packed as
+// four 16-bit fields (a chunk has at most 4096 bytes).
 __global__ void __launch_bounds__(TPB) fasta_chunk_maps(const u8* __restrict__ raw, const u64* __restrict__ file_off, const u64* __restrict__ file_end,
-                                                        const u32* __restrict__ chunk_first, u32 nfiles, u8* __restrict__ chunk_map) {
+                                                        const u32* __restrict__ chunk_first, u32 nfiles, int raw_mode, u8* __restrict__ chunk_map,
+                                                        u64* __restrict__ chunk_kept4, u64* __restrict__ chunk_hdr4) {
     ChunkView v; u32 file;
     load_view(raw, file_off, file_end, chunk_first, nfiles, v, file);
-    u32 total;
-    block_map_scan(thread_map(v), &total);
-    if (threadIdx.x == 0) chunk_map[blockIdx.x] = (u8)total;
+    u64 kept4 = 0, hdr4 = 0; u32 total = MAP_ID;
+    if (raw_mode) kept4 = (u64)v.nbytes * 0x0001000100010001ull;
+    else {
+        u32 prefix = block_map_scan(thread_map(v), &total);     // state before this thread's bytes, per chunk start state
+        u32 done = 0xffffffffu; u32 k_prev = 0, h_prev = 0;
+#pragma unroll
+        for (u32 cs = 0; cs < 4; ++cs) {
+            u32 st = (prefix >> (2 * cs)) & 3;
+            if (st != done) { ByteMasks bm = classify_bytes(v, st); k_prev = (u32)__popc(bm.keep); h_prev = (u32)__popc(bm.header); done = st; }
+            kept4 |= (u64)k_prev << (16 * cs); hdr4 |= (u64)h_prev << (16 * cs);
+        }
+    }
+    kept4 = block_sum64(kept4); hdr4 = block_sum64(hdr4);
+    if (threadIdx.x == 0) { chunk_map[blockIdx.x] = (u8)total; chunk_kept4[blockIdx.x] = kept4; chunk_hdr4[blockIdx.x] = hdr4; }
 }
 
-__global__ void fasta_chunk_states(const u8* __restrict__ chunk_map, const u32* __restrict__ chunk_first, u32 nfiles, u8* __restrict__ chunk_state) {
+__global__ void fasta_chunk_states(const u8* __restrict__ chunk_map, const u64* __restrict__ chunk_kept4, const u64* __restrict__ chunk_hdr4,
+                                   const u32* __restrict__ chunk_first, u32 nfiles, int raw_mode, u8* __restrict__ chunk_state,
+                                   u32* __restrict__ chunk_kept, u32* __restrict__ chunk_hdr) {
     u32 f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nfiles) return;
-    u32 st = ST_PRE;
-    for (u32 c = chunk_first[f]; c < chunk_first[f + 1]; ++c) { chunk_state[c] = (u8)st; st = (chunk_map[c] >> (2 * st)) & 3; }
+    u32 st = raw_mode ? ST_SEQ : ST_PRE;
+    for (u32 c = chunk_first[f]; c < chunk_first[f + 1]; ++c) {
+        chunk_state[c] = (u8)st;
+        chunk_kept[c] = (u32)(chunk_kept4[c] >> (16 * st)) & 0xffffu;
+        chunk_hdr[c] = (u32)(chunk_hdr4[c] >> (16 * st)) & 0xffffu;
+        if (!raw_mode) st = (chunk_map[c] >> (2 * st)) & 3;
+    }
 }
 
-// Write `total` staged symbols to text[dst0 ..): bytes up to the first 4-byte boundary, aligned words, trailing bytes.
-// REVERSE: the run is the reverse complement of the staged symbols.
-template <bool REVERSE>
-__device__ __forceinline__ void write_run(u8* __restrict__ text, u64 dst0, const u8* stage, u32 total) {
-    auto get = [&](u32 j) -> u32 { return REVERSE ? (u32)complement_upper(stage[total - 1 - j]) : (u32)stage[j]; };
-    u32 head = min(total, (u32)((4 - (dst0 & 3)) & 3));
-    for (u32 j = threadIdx.x; j < head; j += blockDim.x) text[dst0 + j] = (u8)get(j);
-    u32 nwords = (total - head) >> 2;
-    for (u32 w = threadIdx.x; w < nwords; w += blockDim.x) {
-        u32 j = head + 4 * w;
-        *reinterpret_cast<u32*>(text + dst0 + j) = get(j) | (get(j + 1) << 8) | (get(j + 2) << 16) | (get(j + 3) << 24);
-    }
-    for (u32 j = head + 4 * nwords + threadIdx.x; j < total; j += blockDim.x) text[dst0 + j] = (u8)get(j);
+// Copy `total` staged bytes to text[dst ..): src is shared memory staged at the same offset modulo 16 as dst, so after the bytes up to
+// the first 16-byte boundary the body moves as aligned 128-bit words.
+__device__ __forceinline__ void copy_run(u8* __restrict__ text, u64 dst, const u8* src, u32 total) {
+    u32 head = min(total, (u32)((16 - (dst & 15)) & 15));
+    for (u32 j = threadIdx.x; j < head; j += blockDim.x) text[dst + j] = src[j];
+    u32 nvec = (total - head) >> 4;
+    for (u32 w = threadIdx.x; w < nvec; w += blockDim.x)
+        *reinterpret_cast<uint4*>(text + dst + head + 16 * (u64)w) = *reinterpret_cast<const uint4*>(src + head + 16 * w);
+    for (u32 j = head + 16 * nvec + threadIdx.x; j < total; j += blockDim.x) text[dst + j] = src[j];
 }
 
 template <bool SCATTER>
@@ -230,31 +262,43 @@ __global__ void __launch_bounds__(TPB) fasta_pass(const u8* __restrict__ raw, co
     else bm = classify_bytes(v, st);
     u32 kept = (u32)__popc(bm.keep), hdr = (u32)__popc(bm.header);
     if (bm.fastq) *fastq_flag = 1;
-    u32 kept_total, hdr_total;
-    u32 kept_before = block_sum_scan(kept, &kept_total);
-    u32 hdr_before = block_sum_scan(hdr, &hdr_total);
+    u32 packed_total;                                           // one scan for both counts: each stays below 2^13 per block
+    u32 packed_before = block_sum_scan(kept | (hdr << 16), &packed_total);
+    u32 kept_total = packed_total & 0xffffu, hdr_total = packed_total >> 16;
+    u32 kept_before = packed_before & 0xffffu, hdr_before = packed_before >> 16;
     if (!SCATTER) {
         if (threadIdx.x == 0) { chunk_kept[blockIdx.x] = kept_total; chunk_hdr[blockIdx.x] = hdr_total; }
         return;
     }
     // kept symbols go to shared memory first (a chunk's kept symbols form ONE contiguous run in the forward text and one in the
-    // reverse complement), then the block writes both runs with aligned 4-byte stores
-    __shared__ u8 stage[CHUNK];
+    // reverse complement): both runs are staged in final order -- upper-cased, the second one reversed and complemented through a
+    // 256-byte table -- at the offset (mod 16) of their destination, then the block copies them with aligned 128-bit stores
+    MMB_SHARED_ALIGNED16(u8, stage_f, CHUNK + 16);
+    MMB_SHARED_ALIGNED16(u8, stage_r, CHUNK + 16);
+    __shared__ u8 lut_u[256], lut_c[256];
+    lut_u[threadIdx.x] = upper((u8)threadIdx.x); lut_c[threadIdx.x] = complement_upper(upper((u8)threadIdx.x));      // TPB = 256
     u64 kbase = chunk_kept_base[blockIdx.x] + kept_before;      // global index among kept bases of this thread's first kept byte
     u32 hidx = chunk_hdr_base[blockIdx.x] + hdr_before;
+    u64 base = doc_start[file], L = doc_len[file];
+    u64 q0 = chunk_kept_base[blockIdx.x] - chunk_kept_base[chunk_first[file]];      // document-relative index of the chunk's first kept base
+    u32 total = kept_total;
+    const u64 dst_f = base + q0, dst_r = base + 2 * L - (q0 + total - 1);
+    const u32 of = (u32)(dst_f & 15), orr = (u32)(dst_r & 15);
+    __syncthreads();                                            // the tables
     u32 local = kept_before;
 #pragma unroll
     for (u32 k = 0; k < 16; ++k) {
         if ((bm.header >> k) & 1) { rec_pos[hidx] = v.begin + k; rec_before[hidx] = kbase + (u32)__popc(bm.keep & ((1u << k) - 1)); ++hidx; }
-        if ((bm.keep >> k) & 1) stage[local++] = upper(v.b[k]);
+        if ((bm.keep >> k) & 1) {
+            stage_f[of + local] = lut_u[v.b[k]];
+            if (revcomp) stage_r[orr + (total - 1 - local)] = lut_c[v.b[k]];
+            ++local;
+        }
     }
     __syncthreads();
-    u64 base = doc_start[file], L = doc_len[file];
-    u64 q0 = chunk_kept_base[blockIdx.x] - chunk_kept_base[chunk_first[file]];      // document-relative index of the chunk's first kept base
-    u32 total = kept_total;
     if (total == 0) return;
-    write_run<false>(text, base + q0, stage, total);
-    if (revcomp) write_run<true>(text, base + 2 * L - (q0 + total - 1), stage, total);
+    copy_run(text, dst_f, stage_f + of, total);
+    if (revcomp) copy_run(text, dst_r, stage_r + orr, total);
 }
 
 __global__ void fasta_doc_layout(const u64* __restrict__ chunk_kept_base, const u32* __restrict__ chunk_first, u32 nfiles, u32 nchunks,
@@ -306,22 +350,17 @@ void build_text(const u8* d_raw, const std::vector<u64>& file_off, const std::ve
     out.doc_start.alloc(nfiles + 1, s); out.doc_len.alloc(nfiles, s);
 
     if (nchunks) {
-        if (!raw_mode) {
-            MMB_LAUNCH(fasta_chunk_maps, nchunks, TPB, 0, s, d_raw, d_off.p, d_end.p, d_first.p, nfiles, d_map.p);
-            MMB_LAUNCH(fasta_chunk_states, ceil_div(nfiles, 128), 128, 0, s, d_map.p, d_first.p, nfiles, d_state.p);
-        }
-        auto fasta_count_pass = fasta_pass<false>;
-        MMB_LAUNCH(fasta_count_pass, nchunks, TPB, 0, s, d_raw, d_off.p, d_end.p, d_first.p, nfiles, d_state.p, (int)raw_mode, d_kept.p, d_hdr.p, d_flag.p,
-                   (const u64*)nullptr, (const u32*)nullptr, (const u64*)nullptr, (const u64*)nullptr, (int)revcomp, (u8*)nullptr, (u64*)nullptr, (u64*)nullptr);
+        DevBuf<u64> d_kept4, d_hdr4; d_kept4.alloc(nchunks, s); d_hdr4.alloc(nchunks, s);
+        MMB_LAUNCH(fasta_chunk_maps, nchunks, TPB, 0, s, d_raw, d_off.p, d_end.p, d_first.p, nfiles, (int)raw_mode, d_map.p, d_kept4.p, d_hdr4.p);
+        MMB_LAUNCH(fasta_chunk_states, ceil_div(nfiles, 128), 128, 0, s, (const u8*)d_map.p, (const u64*)d_kept4.p, (const u64*)d_hdr4.p, d_first.p, nfiles,
+                   (int)raw_mode, d_state.p, d_kept.p, d_hdr.p);
     }
     prim::exclusive_sum(d_kept.p, d_kept_base.p, nchunks + 1, s);     // entry [nchunks] = total
     prim::exclusive_sum(d_hdr.p, d_hdr_base.p, nchunks + 1, s);
-    u64 total_kept = 0; u32 total_hdr = 0, fastq = 0;
+    u64 total_kept = 0; u32 total_hdr = 0;
     MMB_CUDA(cudaMemcpyAsync(&total_kept, d_kept_base.p + nchunks, 8, cudaMemcpyDeviceToHost, s));
     MMB_CUDA(cudaMemcpyAsync(&total_hdr, d_hdr_base.p + nchunks, 4, cudaMemcpyDeviceToHost, s));
-    MMB_CUDA(cudaMemcpyAsync(&fastq, d_flag.p, 4, cudaMemcpyDeviceToHost, s));
     MMB_CUDA(cudaStreamSynchronize(s));
-    if (fastq) throw Error(13, "FASTQ records ('+' separator line) are not supported");
 
     MMB_LAUNCH(fasta_doc_layout, 1, 1, 0, s, d_kept_base.p, d_first.p, nfiles, nchunks, total_kept, (int)revcomp, out.doc_start.p, out.doc_len.p);
     out.n = (revcomp ? 2 : 1) * (total_kept + nfiles);
@@ -335,6 +374,7 @@ void build_text(const u8* d_raw, const std::vector<u64>& file_off, const std::ve
         MMB_LAUNCH(fasta_scatter_pass, nchunks, TPB, 0, s, d_raw, d_off.p, d_end.p, d_first.p, nfiles, d_state.p, (int)raw_mode, d_kept.p, d_hdr.p, d_flag.p,
                    d_kept_base.p, d_hdr_base.p, out.doc_start.p, out.doc_len.p, (int)revcomp, out.text.p, d_rec_pos.p, d_rec_before.p);
     }
+    if (to_host(d_flag.p, 1, s)[0]) throw Error(13, "FASTQ records ('+' separator line) are not supported");      // seen by the scatter pass
     out.h_doc_start = to_host(out.doc_start.p, nfiles + 1, s);
     out.h_doc_len = to_host(out.doc_len.p, nfiles, s);
     out.h_rec_pos = to_host(d_rec_pos.p, total_hdr, s);
