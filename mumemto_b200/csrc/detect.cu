@@ -682,6 +682,11 @@ __global__ void __launch_bounds__(DC_TPB) detect_chunk_kernel(const u32* __restr
                     DocCounter<W, P> docs; docs.clear();
                     u64 s0 = j - size; bool ok = true, differs = false;
                     u8 psym = 0;
+                    if (bwt) {      // left-maximality first, from the staged symbols alone (no SA gather, no document lookup): most intervals fail it
+                        bool any = false;
+                        for (u32 t = 1; t < size && !any; ++t) any = bwt[s0 + t] != bwt[s0 + t - 1];
+                        ok = any;
+                    }
                     for (u32 t = 0; t < size && ok; ++t) {
                         u64 rk = s0 + t; u64 p = (u64)sa[rk];
                         ok = docs.add(find_doc(doc_start, prm.ndocs, p), prm.max_doc_freq);
