@@ -35,6 +35,8 @@ WORKLOADS = {
     "h64_4m": dict(N=64, L=4_000_000, kind="pangenome", desc="64x4 Mbp human-chr-like haplotypes, strict multi-MUMs"),
     "h64_16m": dict(N=64, L=16_000_000, kind="pangenome", desc="64x16 Mbp human-chr-like haplotypes, strict multi-MUMs"),
     "h64_40m": dict(N=64, L=40_000_000, kind="pangenome", desc="64x40 Mbp human-chr-like haplotypes (text crosses 2^32 symbols), strict multi-MUMs"),
+    "h64_40m_c3": dict(N=64, L=40_000_000, kind="pangenome", flagset="partial", desc="64x40 Mbp human-chr-like haplotypes (text crosses 2^32 symbols), partial multi-MUMs -k -1"),
+    "h64_40m_c4": dict(N=64, L=40_000_000, kind="pangenome", flagset="mem", desc="64x40 Mbp human-chr-like haplotypes (text crosses 2^32 symbols), multi-MEMs -f 3 -F 100"),
     "c2": dict(N=64, L=100_000_000, kind="pangenome", desc="64x100 Mbp synthetic human-chr-like haplotypes, strict multi-MUMs [BASELINE configs[1]]"),
     "c3": dict(N=64, L=100_000_000, kind="pangenome", flagset="partial", desc="64x100 Mbp synthetic human-chr-like haplotypes, partial multi-MUMs -k -1 [BASELINE configs[2]]"),
     "c4": dict(N=64, L=100_000_000, kind="pangenome", flagset="mem", desc="64x100 Mbp synthetic human-chr-like haplotypes, multi-MEMs -f 3 -F 100 [BASELINE configs[3]]"),

@@ -154,6 +154,8 @@ struct mmb_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;                 // uploads of mmb_load_fasta, so that they overlap the text build
+    std::vector<cudaEvent_t> upload_events;
     unsigned long long launches_at_create = 0;
 
     bool loaded = false, found = false;
@@ -281,12 +283,26 @@ void build_doc_coarse(mmb_engine* e) {
     MMB_CUDA(cudaStreamSynchronize(e->stream));       // tab lives on this stack frame
 }
 
+// groups: file ranges [f0, f1) whose bytes are on the device once the matching event has fired (nullptr / empty: everything is there)
+struct UploadGroup { size_t f0, f1; cudaEvent_t ready; };
+
 void load_common(mmb_engine* e, const u8* d_raw, const u8* const* host_imgs, const std::vector<u64>& off, const std::vector<u64>& size,
-                 bool revcomp, bool raw_mode) {
+                 bool revcomp, bool raw_mode, const std::vector<UploadGroup>* groups = nullptr) {
     if (off.size() < 2) throw Error(41, "Multiple FASTA inputs required. Perhaps split a multi-FASTA into multiple files?");
     e->found = false; e->loaded = false;
     Timer t(e->stream); t.start();
-    build_text(d_raw, off, size, revcomp, raw_mode, e->text, e->stream);
+    if (groups && groups->size() > 1) {
+        // the text build of the files that have arrived runs while the copy stream is still uploading the next ones
+        text_begin(size, revcomp, e->text, e->stream);
+        for (const UploadGroup& g : *groups) {
+            MMB_CUDA(cudaStreamWaitEvent(e->stream, g.ready, 0));
+            text_append(d_raw, off, size, g.f0, g.f1, raw_mode, e->text, e->stream);
+        }
+        text_finish(e->text, e->stream);
+    } else {
+        if (groups && groups->size() == 1) MMB_CUDA(cudaStreamWaitEvent(e->stream, (*groups)[0].ready, 0));
+        build_text(d_raw, off, size, revcomp, raw_mode, e->text, e->stream);
+    }
     e->stats.ms_text = t.stop();
     build_doc_coarse(e);
     finish_load(e, d_raw, host_imgs, off, size, raw_mode);
@@ -294,12 +310,30 @@ void load_common(mmb_engine* e, const u8* d_raw, const u8* const* host_imgs, con
     e->loaded = true;
 }
 
-void upload(mmb_engine* e, const u8* const* imgs, const u64* sizes, size_t n, std::vector<u64>& off, std::vector<u64>& size) {
+// Host images -> device, on the engine's copy stream, in groups of at least 256 MB: one event per group tells the text build which files
+// are in place (with pinned host memory the copies run asynchronously at PCIe speed; from pageable memory they are staged by the driver
+// and simply finish earlier than the events are waited for).
+void upload(mmb_engine* e, const u8* const* imgs, const u64* sizes, size_t n, std::vector<u64>& off, std::vector<u64>& size,
+            std::vector<UploadGroup>& groups) {
     u64 at = 0;
     for (size_t i = 0; i < n; ++i) { off.push_back(at); size.push_back(sizes[i]); at += (sizes[i] + 15) & ~15ull; }
-    e->raw.alloc(at + 32, e->stream);
-    for (size_t i = 0; i < n; ++i)
-        if (sizes[i]) MMB_CUDA(cudaMemcpyAsync(e->raw.p + off[i], imgs[i], sizes[i], cudaMemcpyHostToDevice, e->stream));
+    e->raw.alloc(at + 64, e->stream);
+    if (!e->copy_stream) MMB_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    MMB_CUDA(cudaStreamSynchronize(e->stream));        // nothing of an earlier call may still read the buffer the copy stream is about to fill
+    MMB_CUDA(cudaMemsetAsync(e->raw.p + at, 0, 64, e->copy_stream));
+    constexpr u64 GROUP_BYTES = 256ull << 20;
+    size_t f0 = 0; u64 acc = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (sizes[i]) MMB_CUDA(cudaMemcpyAsync(e->raw.p + off[i], imgs[i], sizes[i], cudaMemcpyHostToDevice, e->copy_stream));
+        acc += sizes[i];
+        if (acc >= GROUP_BYTES || i + 1 == n) {
+            while (e->upload_events.size() <= groups.size()) { cudaEvent_t ev; MMB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e->upload_events.push_back(ev); }
+            cudaEvent_t ev = e->upload_events[groups.size()];
+            MMB_CUDA(cudaEventRecord(ev, e->copy_stream));
+            groups.push_back(UploadGroup{f0, i + 1, ev});
+            f0 = i + 1; acc = 0;
+        }
+    }
 }
 
 template <class F>
@@ -384,6 +418,8 @@ void mmb_destroy(mmb_engine* e) {
     cudaStreamSynchronize(e->stream);
     cudaStream_t s = e->stream; bool own = e->own_stream; int dev = e->device;
     cudaSetDevice(dev);
+    if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+    for (cudaEvent_t ev : e->upload_events) cudaEventDestroy(ev);
     delete e;
     poolimpl::trim(dev, s, true);
     if (own) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
@@ -400,9 +436,9 @@ int mmb_load_fasta(mmb_engine* e, const uint8_t* const* files, const uint64_t* s
     if (!e || !files || !sizes) return fail(MMB_ERR_ARG, "null argument");
     return guarded([&] {
         MMB_CUDA(cudaSetDevice(e->device));
-        std::vector<u64> off, size;
-        upload(e, files, sizes, nfiles, off, size);
-        load_common(e, e->raw.p, files, off, size, use_revcomp != 0, false);
+        std::vector<u64> off, size; std::vector<UploadGroup> groups;
+        upload(e, files, sizes, nfiles, off, size, groups);
+        load_common(e, e->raw.p, files, off, size, use_revcomp != 0, false, &groups);
     });
 }
 
@@ -433,9 +469,9 @@ int mmb_load_records(mmb_engine* e, const char* const* records, const size_t* n_
             }
         std::vector<const u8*> imgs; std::vector<u64> sizes;
         for (auto& d : docs) { imgs.push_back((const u8*)d.data()); sizes.push_back(d.size()); }
-        std::vector<u64> off, size;
-        upload(e, imgs.data(), sizes.data(), ndocs, off, size);
-        MMB_CUDA(cudaStreamSynchronize(e->stream));       // the host strings die at the end of this scope
+        std::vector<u64> off, size; std::vector<UploadGroup> groups;
+        upload(e, imgs.data(), sizes.data(), ndocs, off, size, groups);
+        MMB_CUDA(cudaStreamSynchronize(e->copy_stream));  // the host strings die at the end of this scope
         load_common(e, e->raw.p, nullptr, off, size, use_revcomp != 0, true);
         e->records = std::move(recs);
     });

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(EXP_TPB, MINB) expand_members(u32 k0, u32 k1, 
             sa[wbase + e] = pos; bwt[wbase + e] = sym;
             lcp[wbase + e] = t ? m.shift + occ_lcp[q] : glcp[kk];
         } else if (m.members > FUSE_MAX_MEMBERS) {
-            sa[wbase + e] = pos; key[wbase + e] = occ_next_rank[q];            // bwt of these is filled after the sort (bwt_of_groups)
+            sa[wbase + e] = pos; key[wbase + e] = occ_next_rank[q]; bwt[wbase + e] = sym;      // merge_small permutes all three; the large path re-reads the text
         } else {
             u32 ks = kk - m.back;
             u64 gbase = (ks >= kw) ? wbase + soff[w][ks - kw] : out_base[ks] - tile_base + lead;
@@ -247,24 +247,73 @@ __global__ void __launch_bounds__(EXP_TPB, MINB) expand_members(u32 k0, u32 k1, 
 }
 
 // group starts that have more than one member -> (first member, end member) by size
+constexpr u32 MERGE_WARP_MAX = 256;      // groups of at most this many suffixes are ordered by one warp (merge_warp)
 __global__ void __launch_bounds__(TPB) collect_multi(u32 k0, u32 k1, u32 K, const u32* __restrict__ glcp, const u64* __restrict__ out_base,
-                                                     u64* __restrict__ small, u64* __restrict__ large, u32* __restrict__ counts) {
+                                                     u64* __restrict__ tiny, u64* __restrict__ small, u64* __restrict__ large, u32* __restrict__ counts) {
     u32 k = k0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= k1 || glcp[k] == NOT_START || k + 1 >= K || glcp[k + 1] != NOT_START) return;
     u32 e = k + 1;
     while (e < K && glcp[e] == NOT_START) ++e;
     if (e - k <= FUSE_MAX_MEMBERS) return;                     // merged inside expand_members
     u64 g = out_base[e] - out_base[k];
-    if (g <= MERGE_MAX) small[atomicAdd(&counts[0], 1u)] = ((u64)k << 32) | e;
+    if (g <= MERGE_WARP_MAX) tiny[atomicAdd(&counts[2], 1u)] = ((u64)k << 32) | e;
+    else if (g <= MERGE_MAX) small[atomicAdd(&counts[0], 1u)] = ((u64)k << 32) | e;
     else large[atomicAdd(&counts[1], 1u)] = ((u64)k << 32) | e;
+}
+
+// One warp per group of at most 32 K suffixes: every element counts the smaller keys of its group through shuffles (the keys -- ranks of
+// the following parse suffixes -- are distinct), which is its slot, and remembers the largest of them, which is its predecessor.
+template <int K, int LO>
+__global__ void __launch_bounds__(TPB) merge_warp(const u64* __restrict__ groups, u32 ngroups, u32 k0, const u64* __restrict__ out_base,
+                                                  const u32* __restrict__ glcp, const u32* __restrict__ mem_i, const u32* __restrict__ limit,
+                                                  const u32* __restrict__ s_lcp, const u32* __restrict__ rmq, u32 rmq_blocks, u64 lead,
+                                                  u64* __restrict__ sa, u32* __restrict__ lcp, const u32* __restrict__ key, u8* __restrict__ bwt) {
+    u32 gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gi >= ngroups) return;                                  // whole warp
+    u64 g = groups[gi];
+    u32 ks = (u32)(g >> 32), ke = (u32)g;
+    u64 base = out_base[ks] - out_base[k0] + lead;
+    u32 G = (u32)(out_base[ke] - out_base[ks]);
+    if (G > 32u * K || G <= (u32)LO) return;                    // handled by another instance
+    u32 shift = limit[mem_i[ks]] - 1 - PFP_W;
+    u32 kv[K]; u64 pv[K]; u8 sv[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        u32 e = lane + 32u * k;
+        kv[k] = 0xffffffffu; pv[k] = 0; sv[k] = 0;
+        if (e < G) { kv[k] = key[base + e]; pv[k] = sa[base + e]; sv[k] = bwt[base + e]; }
+    }
+    u32 lt[K], pred[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { lt[k] = 0; pred[k] = 0; }
+#pragma unroll
+    for (int k2 = 0; k2 < K; ++k2) {
+        if (32u * k2 >= G) break;
+        for (int j = 0; j < 32; ++j) {
+            u32 kj = __shfl_sync(0xffffffffu, kv[k2], j);
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (kj < kv[k]) { ++lt[k]; pred[k] = max(pred[k], kj); }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        u32 e = lane + 32u * k;
+        if (e < G) {
+            u64 dst = base + lt[k];
+            sa[dst] = pv[k]; bwt[dst] = sv[k];
+            lcp[dst] = lt[k] ? shift + range_min(s_lcp, rmq, rmq_blocks, pred[k] + 1, kv[k]) : glcp[ks];
+        }
+    }
 }
 
 __global__ void __launch_bounds__(TPB) merge_small(const u64* __restrict__ groups, u32 k0, const u64* __restrict__ out_base, const u32* __restrict__ glcp,
                                                    const u32* __restrict__ mem_i, const u32* __restrict__ limit, const u32* __restrict__ s_lcp,
                                                    const u32* __restrict__ rmq, u32 rmq_blocks, u64 lead, u64* __restrict__ sa, u32* __restrict__ lcp,
-                                                   const u32* __restrict__ key) {
+                                                   const u32* __restrict__ key, u8* __restrict__ bwt) {
     __shared__ u64 item[MERGE_MAX];       // key << 32 | index
     __shared__ u64 pos[MERGE_MAX];
+    __shared__ u8 sym[MERGE_MAX];         // symbol preceding each suffix (written by expand_members): permuted with the suffix
     u64 g = groups[blockIdx.x];
     u32 ks = (u32)(g >> 32), ke = (u32)g;
     u64 base = out_base[ks] - out_base[k0] + lead;
@@ -272,7 +321,7 @@ __global__ void __launch_bounds__(TPB) merge_small(const u64* __restrict__ group
     u32 shift = limit[mem_i[ks]] - 1 - PFP_W;
     u32 n2 = 1; while (n2 < G) n2 <<= 1;
     for (u32 e = threadIdx.x; e < n2; e += blockDim.x) {
-        if (e < G) { item[e] = ((u64)key[base + e] << 32) | e; pos[e] = sa[base + e]; } else item[e] = ~0ull;
+        if (e < G) { item[e] = ((u64)key[base + e] << 32) | e; pos[e] = sa[base + e]; sym[e] = bwt[base + e]; } else item[e] = ~0ull;
     }
     __syncthreads();
     for (u32 k = 2; k <= n2; k <<= 1)
@@ -288,7 +337,7 @@ __global__ void __launch_bounds__(TPB) merge_small(const u64* __restrict__ group
         }
     for (u32 e = threadIdx.x; e < G; e += blockDim.x) {
         u64 it = item[e];
-        sa[base + e] = pos[(u32)it];
+        sa[base + e] = pos[(u32)it]; bwt[base + e] = sym[(u32)it];
         lcp[base + e] = e ? shift + range_min(s_lcp, rmq, rmq_blocks, (u32)(item[e - 1] >> 32) + 1, (u32)(it >> 32)) : glcp[ks];
     }
 }
@@ -558,9 +607,9 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
     delete pt;
     // ---- tile buffers: [halo | new ranks | 64 slack]; the first tile starts with the sentinel rank instead of a halo
     u64 cap = (u64)halo + max_new + 1;
-    DevBuf<u64> sa, halo_sa, small, large; DevBuf<u32> lcp, key, halo_lcp, counts; DevBuf<u8> bwt, halo_bwt;
+    DevBuf<u64> sa, halo_sa, small, large, tiny; DevBuf<u32> lcp, key, halo_lcp, counts; DevBuf<u8> bwt, halo_bwt;
     sa.alloc(cap, s); lcp.alloc(cap + 64, s); key.alloc(cap, s); bwt.alloc(cap + 64, s); halo_sa.alloc(halo + 1, s); halo_lcp.alloc(halo + 1, s);
-    halo_bwt.alloc(halo + 1, s); counts.alloc(2, s);
+    halo_bwt.alloc(halo + 1, s); counts.alloc(3, s);
     DevBuf<u8> doc;
     if (docs) doc.alloc(cap, s);
     const int expand_variant = getenv("MMB_EXPAND_VARIANT") ? atoi(getenv("MMB_EXPAND_VARIANT")) : 0;
@@ -578,7 +627,7 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
             MMB_CUDA(cudaMemcpyAsync(bwt.p, halo_bwt.p, halo_have, cudaMemcpyDeviceToDevice, s));
         }
         u32 nm = k1 - k0;
-        small.alloc((u64)nm / 2 + 1, s); large.alloc((u64)nm / 2 + 1, s); counts.zero();
+        small.alloc((u64)nm / 2 + 1, s); large.alloc((u64)nm / 2 + 1, s); tiny.alloc((u64)nm / 2 + 1, s); counts.zero();
         {
             auto launch_expand = [&](auto expand_members_k) {
                 MMB_LAUNCH(expand_members_k, ceil_div(nm, EXP_TPB), EXP_TPB, 0, s, k0, k1, (const MemberMeta*)meta.p, (const u64*)out_base.p, (const u32*)glcp.p,
@@ -593,13 +642,18 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
                 default: launch_expand(expand_members<8, 1>); break;
             }
         }
-        MMB_LAUNCH(collect_multi, ceil_div(nm, TPB), TPB, 0, s, k0, k1, K, (const u32*)glcp.p, (const u64*)out_base.p, small.p, large.p, counts.p);
-        std::vector<u32> c = to_host(counts.p, 2, s);
+        MMB_LAUNCH(collect_multi, ceil_div(nm, TPB), TPB, 0, s, k0, k1, K, (const u32*)glcp.p, (const u64*)out_base.p, tiny.p, small.p, large.p, counts.p);
+        std::vector<u32> c = to_host(counts.p, 3, s);
+        if (c[2]) {         // two instances: up to 64 suffixes (2 per lane) and up to 256 (8 per lane); each skips the groups of the other
+            auto merge_warp_2 = merge_warp<2, 0>; auto merge_warp_8 = merge_warp<8, 64>;
+            MMB_LAUNCH(merge_warp_2, ceil_div((u64)c[2] * 32, TPB), TPB, 0, s, (const u64*)tiny.p, c[2], k0, (const u64*)out_base.p, (const u32*)glcp.p, (const u32*)mem_i.p,
+                       (const u32*)ix.limit.p, (const u32*)ix.s_lcp.p, (const u32*)ix.rmq.p, ix.rmq_blocks, lead, sa.p, lcp.p, (const u32*)key.p, bwt.p);
+            MMB_LAUNCH(merge_warp_8, ceil_div((u64)c[2] * 32, TPB), TPB, 0, s, (const u64*)tiny.p, c[2], k0, (const u64*)out_base.p, (const u32*)glcp.p, (const u32*)mem_i.p,
+                       (const u32*)ix.limit.p, (const u32*)ix.s_lcp.p, (const u32*)ix.rmq.p, ix.rmq_blocks, lead, sa.p, lcp.p, (const u32*)key.p, bwt.p);
+        }
         if (c[0]) {
             MMB_LAUNCH(merge_small, c[0], TPB, 0, s, (const u64*)small.p, k0, (const u64*)out_base.p, (const u32*)glcp.p, (const u32*)mem_i.p,
-                       (const u32*)ix.limit.p, (const u32*)ix.s_lcp.p, (const u32*)ix.rmq.p, ix.rmq_blocks, lead, sa.p, lcp.p, (const u32*)key.p);
-            dim3 gb(c[0], 1);
-            MMB_LAUNCH(bwt_of_groups, gb, TPB, 0, s, (const u64*)small.p, k0, (const u64*)out_base.p, lead, text, (const u64*)sa.p, bwt.p);
+                       (const u32*)ix.limit.p, (const u32*)ix.s_lcp.p, (const u32*)ix.rmq.p, ix.rmq_blocks, lead, sa.p, lcp.p, (const u32*)key.p, bwt.p);
         }
         if (c[1]) {
             u32 nl = c[1];

@@ -302,10 +302,10 @@ __global__ void __launch_bounds__(TPB) fasta_pass(const u8* __restrict__ raw, co
 }
 
 __global__ void fasta_doc_layout(const u64* __restrict__ chunk_kept_base, const u32* __restrict__ chunk_first, u32 nfiles, u32 nchunks,
-                                 u64 total_kept, int revcomp, u64* __restrict__ doc_start, u64* __restrict__ doc_len) {
+                                 u64 total_kept, int revcomp, u64 at0, u64* __restrict__ doc_start, u64* __restrict__ doc_len) {
     // one thread: N is small (files), and each doc start depends on all earlier lengths
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    u64 at = 0;
+    u64 at = at0;
     for (u32 f = 0; f < nfiles; ++f) {
         u64 b0 = chunk_first[f] < nchunks ? chunk_kept_base[chunk_first[f]] : total_kept;
         u64 b1 = chunk_first[f + 1] < nchunks ? chunk_kept_base[chunk_first[f + 1]] : total_kept;
@@ -326,8 +326,19 @@ __global__ void fasta_terminators(const u64* __restrict__ doc_start, const u64* 
 
 }  // namespace
 
-void build_text(const u8* d_raw, const std::vector<u64>& file_off, const std::vector<u64>& file_size, bool revcomp, bool raw_mode,
-                TextLayout& out, cudaStream_t s) {
+void text_begin(const std::vector<u64>& file_size, bool revcomp, TextLayout& out, cudaStream_t s) {
+    u64 worst = 0;
+    for (u64 b : file_size) worst += b + 1;
+    worst *= revcomp ? 2 : 1;
+    out.text.alloc(worst + 128, s);     // zero slack behind the text so that vector loads near the end stay in bounds (pfp.cu stages 16-byte words up to n + 80)
+    out.n = 0; out.total_bases = 0; out.revcomp = revcomp;
+    out.h_doc_start.assign(1, 0); out.h_doc_len.clear(); out.h_rec_pos.clear(); out.h_rec_before.clear();
+}
+
+void text_append(const u8* d_raw, const std::vector<u64>& all_off, const std::vector<u64>& all_size, size_t f0, size_t f1, bool raw_mode,
+                 TextLayout& out, cudaStream_t s) {
+    std::vector<u64> file_off(all_off.begin() + f0, all_off.begin() + f1), file_size(all_size.begin() + f0, all_size.begin() + f1);
+    const bool revcomp = out.revcomp;
     u32 nfiles = (u32)file_off.size();
     std::vector<u32> chunk_first(nfiles + 1, 0);
     std::vector<u64> file_end(nfiles);
@@ -339,7 +350,7 @@ void build_text(const u8* d_raw, const std::vector<u64>& file_off, const std::ve
         file_end[f] = file_off[f] + file_size[f];
     }
     u32 nchunks = chunk_first[nfiles];
-    DevBuf<u64> d_off, d_end, d_kept_base; DevBuf<u32> d_first, d_kept, d_hdr, d_hdr_base, d_flag; DevBuf<u8> d_map, d_state;
+    DevBuf<u64> d_off, d_end, d_kept_base, d_doc_start, d_doc_len; DevBuf<u32> d_first, d_kept, d_hdr, d_hdr_base, d_flag; DevBuf<u8> d_map, d_state;
     d_off.alloc(nfiles, s); d_end.alloc(nfiles, s); d_first.alloc(nfiles + 1, s);
     MMB_CUDA(cudaMemcpyAsync(d_off.p, file_off.data(), nfiles * 8, cudaMemcpyHostToDevice, s));
     MMB_CUDA(cudaMemcpyAsync(d_end.p, file_end.data(), nfiles * 8, cudaMemcpyHostToDevice, s));
@@ -347,7 +358,7 @@ void build_text(const u8* d_raw, const std::vector<u64>& file_off, const std::ve
     d_map.alloc(nchunks, s); d_state.alloc(nchunks, s); d_kept.alloc(nchunks + 1, s); d_hdr.alloc(nchunks + 1, s);
     d_kept_base.alloc(nchunks + 1, s); d_hdr_base.alloc(nchunks + 1, s); d_flag.alloc(1, s);
     d_flag.zero(); d_kept.zero(); d_hdr.zero();
-    out.doc_start.alloc(nfiles + 1, s); out.doc_len.alloc(nfiles, s);
+    d_doc_start.alloc(nfiles + 1, s); d_doc_len.alloc(nfiles, s);
 
     if (nchunks) {
         DevBuf<u64> d_kept4, d_hdr4; d_kept4.alloc(nchunks, s); d_hdr4.alloc(nchunks, s);
@@ -362,25 +373,39 @@ void build_text(const u8* d_raw, const std::vector<u64>& file_off, const std::ve
     MMB_CUDA(cudaMemcpyAsync(&total_hdr, d_hdr_base.p + nchunks, 4, cudaMemcpyDeviceToHost, s));
     MMB_CUDA(cudaStreamSynchronize(s));
 
-    MMB_LAUNCH(fasta_doc_layout, 1, 1, 0, s, d_kept_base.p, d_first.p, nfiles, nchunks, total_kept, (int)revcomp, out.doc_start.p, out.doc_len.p);
-    out.n = (revcomp ? 2 : 1) * (total_kept + nfiles);
-    out.text.alloc(out.n + 64, s);     // slack so that vector loads near the end stay in bounds
-    MMB_CUDA(cudaMemsetAsync(out.text.p + out.n, 0, 64, s));
+    // documents of this group start where the text ends so far
+    MMB_LAUNCH(fasta_doc_layout, 1, 1, 0, s, d_kept_base.p, d_first.p, nfiles, nchunks, total_kept, (int)revcomp, out.n, d_doc_start.p, d_doc_len.p);
     DevBuf<u64> d_rec_pos, d_rec_before;
     d_rec_pos.alloc(total_hdr, s); d_rec_before.alloc(total_hdr, s);
-    MMB_LAUNCH(fasta_terminators, ceil_div(nfiles, 128), 128, 0, s, out.doc_start.p, out.doc_len.p, nfiles, (int)revcomp, out.text.p);
+    MMB_LAUNCH(fasta_terminators, ceil_div(nfiles, 128), 128, 0, s, d_doc_start.p, d_doc_len.p, nfiles, (int)revcomp, out.text.p);
     if (nchunks) {
         auto fasta_scatter_pass = fasta_pass<true>;
         MMB_LAUNCH(fasta_scatter_pass, nchunks, TPB, 0, s, d_raw, d_off.p, d_end.p, d_first.p, nfiles, d_state.p, (int)raw_mode, d_kept.p, d_hdr.p, d_flag.p,
-                   d_kept_base.p, d_hdr_base.p, out.doc_start.p, out.doc_len.p, (int)revcomp, out.text.p, d_rec_pos.p, d_rec_before.p);
+                   d_kept_base.p, d_hdr_base.p, d_doc_start.p, d_doc_len.p, (int)revcomp, out.text.p, d_rec_pos.p, d_rec_before.p);
     }
     if (to_host(d_flag.p, 1, s)[0]) throw Error(13, "FASTQ records ('+' separator line) are not supported");      // seen by the scatter pass
-    out.h_doc_start = to_host(out.doc_start.p, nfiles + 1, s);
-    out.h_doc_len = to_host(out.doc_len.p, nfiles, s);
-    out.h_rec_pos = to_host(d_rec_pos.p, total_hdr, s);
-    out.h_rec_before = to_host(d_rec_before.p, total_hdr, s);
-    out.total_bases = total_kept;
-    out.revcomp = revcomp;
+    std::vector<u64> ds = to_host(d_doc_start.p, nfiles + 1, s), dl = to_host(d_doc_len.p, nfiles, s);
+    std::vector<u64> rp = to_host(d_rec_pos.p, total_hdr, s), rb = to_host(d_rec_before.p, total_hdr, s);
+    for (u32 f = 0; f < nfiles; ++f) { out.h_doc_len.push_back(dl[f]); out.h_doc_start.push_back(ds[f + 1]); }
+    for (u32 r = 0; r < total_hdr; ++r) { out.h_rec_pos.push_back(rp[r]); out.h_rec_before.push_back(rb[r] + out.total_bases); }     // kept bases before it, over all groups
+    out.n = ds[nfiles];
+    out.total_bases += total_kept;
+}
+
+void text_finish(TextLayout& out, cudaStream_t s) {
+    size_t nfiles = out.h_doc_len.size();
+    out.doc_start.alloc(nfiles + 1, s); out.doc_len.alloc(nfiles, s);
+    MMB_CUDA(cudaMemcpyAsync(out.doc_start.p, out.h_doc_start.data(), (nfiles + 1) * 8, cudaMemcpyHostToDevice, s));
+    MMB_CUDA(cudaMemcpyAsync(out.doc_len.p, out.h_doc_len.data(), nfiles * 8, cudaMemcpyHostToDevice, s));
+    MMB_CUDA(cudaMemsetAsync(out.text.p + out.n, 0, 128, s));
+    MMB_CUDA(cudaStreamSynchronize(s));
+}
+
+void build_text(const u8* d_raw, const std::vector<u64>& file_off, const std::vector<u64>& file_size, bool revcomp, bool raw_mode,
+                TextLayout& out, cudaStream_t s) {
+    text_begin(file_size, revcomp, out, s);
+    text_append(d_raw, file_off, file_size, 0, file_off.size(), raw_mode, out, s);
+    text_finish(out, s);
 }
 
 }  // namespace mmb

@@ -21,4 +21,12 @@ struct TextLayout {
 void build_text(const u8* d_raw, const std::vector<u64>& file_off, const std::vector<u64>& file_size, bool revcomp, bool raw_mode,
                 TextLayout& out, cudaStream_t s);
 
+// The same in steps, so that the upload of later files can overlap the text build of earlier ones (engine.cu, mmb_load_fasta):
+// text_begin sizes the text for the worst case (every byte a base), text_append builds the documents of files [f0, f1) behind the ones
+// already there (it only needs the raw bytes of those files to be on the device), text_finish publishes the layout.
+void text_begin(const std::vector<u64>& file_size, bool revcomp, TextLayout& out, cudaStream_t s);
+void text_append(const u8* d_raw, const std::vector<u64>& file_off, const std::vector<u64>& file_size, size_t f0, size_t f1, bool raw_mode,
+                 TextLayout& out, cudaStream_t s);
+void text_finish(TextLayout& out, cudaStream_t s);
+
 }  // namespace mmb

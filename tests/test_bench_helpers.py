@@ -99,13 +99,13 @@ def test_parity_sample_check_runs_and_catches_a_difference(simt_lib, workload_fl
     anchor_merge vs the device-input merge) driven through the CPU unit-test build of the kernels."""
     import torch
     from mumemto_b200 import Engine
-    spec = dict(N=6, L=30000, kind="pangenome", flagset=workload_flags, desc="t")
+    spec = dict(N=5, L=30000, kind="pangenome", flagset=workload_flags, desc="t")
     eng = Engine(0, _lib=simt_lib)
-    base, parity = bench.cpu_baseline_and_parity(eng, torch.device("cpu"), spec, sample_L=5000, procs=3)
+    base, parity = bench.cpu_baseline_and_parity(eng, torch.device("cpu"), spec, sample_L=3000, procs=2)
     assert parity["result"] == "ok" and parity["checks"]["direct"]["lines"] > 5
     assert ("partitions_anchor_merge" in parity["checks"]) == (workload_flags == "strict")
     assert base["value"] > 0 and base["extrapolated"]
     monkeypatch.setattr(bench, "run_reference", lambda *a, **k: (1.0, b"20\t1,2\t+,+\n"))
     with pytest.raises(AssertionError):
-        bench.cpu_baseline_and_parity(eng, torch.device("cpu"), spec, sample_L=5000, procs=3)
+        bench.cpu_baseline_and_parity(eng, torch.device("cpu"), spec, sample_L=3000, procs=2)
     eng.close()

@@ -174,11 +174,11 @@ def test_simt_repeats_all_group_size_classes(simt_lib, oracle_bin, tmp_path, blo
     device-wide fallback above 4096), and matches with many occurrences exercise -f / -F limits."""
     rng = np.random.default_rng(17)
     unit = util.random_dna(rng, 37)
-    body = util.random_dna(rng, 1500)
+    body = util.random_dna(rng, 900)
     docs = [
-        "A" * 1300 + body + unit * 90 + "ACGT" * 40 + body[:700],
-        "A" * 300 + util.mutate(rng, body, 0.01) + unit * 60 + "C" * 150 + body[200:900],
-        util.mutate(rng, body, 0.02) + "AC" * 700 + unit * 20 + "A" * 100,
+        "A" * 700 + body + unit * 50 + "ACGT" * 40 + body[:400],
+        "A" * 300 + util.mutate(rng, body, 0.01) + unit * 30 + "C" * 150 + body[200:600],
+        util.mutate(rng, body, 0.02) + "AC" * 400 + unit * 20 + "A" * 100,
     ]
     p = [util.write_fasta(str(tmp_path / f"d{i}.fa"), [(f"d{i}", s)], width=77) for i, s in enumerate(docs)]
     simt_lib.simt_set_block_order(block_order)       # real grids run their blocks in no particular order
@@ -210,7 +210,7 @@ def test_simt_unbounded_frequency(simt_lib, oracle_bin, small, tmp_path):
             out = both(simt_lib, oracle_bin, str(tmp_path / f"{name}{i}"), paths, flags)
             if name == "rep" and i == 0:
                 assert max(len(l.split(b"\t")[1].split(b",")) for l in out[".mems"].splitlines()) > 1000
-            if i < 2:       # the same on the prefix-free-parse route: the pruned stream in one view (section 8(f).4 on the tiled route)
+            if i < 1:       # the same on the prefix-free-parse route: the pruned stream in one view (section 8(f).4 on the tiled route)
                 st = both_pfp(simt_lib, oracle_bin, str(tmp_path / f"{name}{i}"), paths, flags, tile_ranks=0)
                 assert st["pruned"] and st["pfp_tiles"] == 1
 
@@ -293,11 +293,11 @@ def test_simt_pfp_route_repeats(simt_lib, oracle_bin, tmp_path, block_order, mon
     shared-memory sort), long phrases, phrases of minimum length."""
     rng = np.random.default_rng(17)
     unit = util.random_dna(rng, 37)
-    body = util.random_dna(rng, 1500)
+    body = util.random_dna(rng, 900)
     docs = [
-        "A" * 1300 + body + unit * 90 + "ACGT" * 40 + body[:700],
-        "A" * 300 + util.mutate(rng, body, 0.01) + unit * 60 + "C" * 150 + body[200:900],
-        util.mutate(rng, body, 0.02) + "AC" * 700 + unit * 20 + "A" * 100,
+        "A" * 700 + body + unit * 50 + "ACGT" * 40 + body[:400],
+        "A" * 300 + util.mutate(rng, body, 0.01) + unit * 30 + "C" * 150 + body[200:600],
+        util.mutate(rng, body, 0.02) + "AC" * 400 + unit * 20 + "A" * 100,
     ]
     p = [util.write_fasta(str(tmp_path / f"d{i}.fa"), [(f"d{i}", s)], width=77) for i, s in enumerate(docs)]
     simt_lib.simt_set_block_order(block_order)
@@ -305,7 +305,7 @@ def test_simt_pfp_route_repeats(simt_lib, oracle_bin, tmp_path, block_order, mon
         for flags in ([], ["-f", "4", "-k", "2", "-l", "15", "-A"], ["-r", "-f", "2"]):
             both_pfp(simt_lib, oracle_bin, str(tmp_path), p, flags, tile_ranks=3000)
         if block_order == 0:
-            # the 1300-symbol run needs ~60 chunk rounds: with a limit of 12 the dictionary falls back to the doubling engine (nothing pruned)
+            # the 700-symbol run needs ~33 chunk rounds: with a limit of 12 the dictionary falls back to the doubling engine (nothing pruned)
             monkeypatch.setenv("MMB_CHUNK_ROUNDS", "12")
             st = both_pfp(simt_lib, oracle_bin, str(tmp_path), p, [], tile_ranks=3000)
             assert not st["pruned"] and st["stream_suffixes"] == st["text_symbols"] + 1
