@@ -215,13 +215,28 @@ __global__ void __launch_bounds__(TPB) fasta_chunk_maps(const u8* __restrict__ r
     if (threadIdx.x == 0) { chunk_map[blockIdx.x] = (u8)total; chunk_kept4[blockIdx.x] = kept4; chunk_hdr4[blockIdx.x] = hdr4; }
 }
 
-__global__ void fasta_chunk_states(const u8* __restrict__ chunk_map, const u64* __restrict__ chunk_kept4, const u64* __restrict__ chunk_hdr4,
-                                   const u32* __restrict__ chunk_first, u32 nfiles, int raw_mode, u8* __restrict__ chunk_state,
-                                   u32* __restrict__ chunk_kept, u32* __restrict__ chunk_hdr) {
-    u32 f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nfiles) return;
-    u32 st = raw_mode ? ST_SEQ : ST_PRE;
-    for (u32 c = chunk_first[f]; c < chunk_first[f + 1]; ++c) {
+// One WARP per file: every lane composes the maps of its slice of the file's chunks, a warp scan of the 32 slice maps gives each lane the
+// state its slice starts in, and a second walk over the slice writes the per-chunk start state and counts.
+__global__ void __launch_bounds__(128) fasta_chunk_states(const u8* __restrict__ chunk_map, const u64* __restrict__ chunk_kept4, const u64* __restrict__ chunk_hdr4,
+                                                         const u32* __restrict__ chunk_first, u32 nfiles, int raw_mode, u8* __restrict__ chunk_state,
+                                                         u32* __restrict__ chunk_kept, u32* __restrict__ chunk_hdr) {
+    u32 f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (f >= nfiles) return;                                    // whole warp
+    u32 c0 = chunk_first[f], c1 = chunk_first[f + 1];
+    u32 per = (c1 - c0 + 31) / 32;
+    u32 lo = min(c0 + lane * per, c1), hi = min(lo + per, c1);
+    u32 mine = MAP_ID;
+    if (!raw_mode) for (u32 c = lo; c < hi; ++c) mine = map_compose(mine, (u32)chunk_map[c]);
+    u32 inc = mine;
+#pragma unroll
+    for (u32 d = 1; d < 32; d <<= 1) {
+        u32 o = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc = map_compose(o, inc);
+    }
+    u32 before = __shfl_up_sync(FULL, inc, 1);                  // composition of the slices before mine
+    if (lane == 0) before = MAP_ID;
+    u32 st = raw_mode ? ST_SEQ : ((before >> (2 * ST_PRE)) & 3);        // every file starts before its first header
+    for (u32 c = lo; c < hi; ++c) {
         chunk_state[c] = (u8)st;
         chunk_kept[c] = (u32)(chunk_kept4[c] >> (16 * st)) & 0xffffu;
         chunk_hdr[c] = (u32)(chunk_hdr4[c] >> (16 * st)) & 0xffffu;
@@ -363,7 +378,7 @@ void text_append(const u8* d_raw, const std::vector<u64>& all_off, const std::ve
     if (nchunks) {
         DevBuf<u64> d_kept4, d_hdr4; d_kept4.alloc(nchunks, s); d_hdr4.alloc(nchunks, s);
         MMB_LAUNCH(fasta_chunk_maps, nchunks, TPB, 0, s, d_raw, d_off.p, d_end.p, d_first.p, nfiles, (int)raw_mode, d_map.p, d_kept4.p, d_hdr4.p);
-        MMB_LAUNCH(fasta_chunk_states, ceil_div(nfiles, 128), 128, 0, s, (const u8*)d_map.p, (const u64*)d_kept4.p, (const u64*)d_hdr4.p, d_first.p, nfiles,
+        MMB_LAUNCH(fasta_chunk_states, ceil_div((u64)nfiles * 32, 128), 128, 0, s, (const u8*)d_map.p, (const u64*)d_kept4.p, (const u64*)d_hdr4.p, d_first.p, nfiles,
                    (int)raw_mode, d_state.p, d_kept.p, d_hdr.p);
     }
     prim::exclusive_sum(d_kept.p, d_kept_base.p, nchunks + 1, s);     // entry [nchunks] = total
