@@ -9,7 +9,7 @@ CU       := $(wildcard $(CSRC)/*.cu)
 HOSTCPP  := $(wildcard $(CSRC)/library_api.cpp)
 OBJ      := $(patsubst $(CSRC)/%.cu,build/%.o,$(CU)) $(patsubst $(CSRC)/%.cpp,build/%.o,$(HOSTCPP))
 LIB      := mumemto_b200/lib/libmumemto_b200.so
-BIN      := mumemto_b200/bin/mumemto_exec mumemto_b200/bin/anchor_merge
+BIN      := mumemto_b200/bin/mumemto_exec mumemto_b200/bin/anchor_merge mumemto_b200/bin/extract_mums
 HDRS     := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 
 .PHONY: all lib simt oracle clean
@@ -35,6 +35,10 @@ mumemto_b200/bin/mumemto_exec: $(CSRC)/cli_main.cpp $(CSRC)/multi_gpu.cpp $(CSRC
 mumemto_b200/bin/anchor_merge: $(CSRC)/anchor_merge_main.cpp $(LIB) $(HDRS)
 	@mkdir -p mumemto_b200/bin
 	$(CXX) -O2 -std=c++17 -Wall -Iinclude $< -o $@ -Lmumemto_b200/lib -lmumemto_b200 -Wl,-rpath,'$$ORIGIN/../lib'
+
+mumemto_b200/bin/extract_mums: $(CSRC)/extract_mums_main.cpp
+	@mkdir -p mumemto_b200/bin
+	$(CXX) -O2 -std=c++17 -Wall $< -o $@ -lz
 
 # ---- tests only -------------------------------------------------------------------------------------------------------------
 SIMT     := tests/simt/_build/libmumemto_b200_simt.so

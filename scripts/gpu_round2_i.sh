@@ -14,7 +14,7 @@ for f in c2 c5p c4 c3; do echo == $f; head -c 250 gpurun_out/i_bench_$f.json; ta
 export MMB_MIN_WARMUP=1
 NCU_BENCH="python bench.py --workload h64_16m --route pfp --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --kernel-table-steps 0"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/i_launches_h64_16m.csv $NCU_BENCH > gpurun_out/i_ncu_list.log 2>&1
-for k in fasta_pass fasta_chunk_maps rank_words classify_segments verify_groups phrase_hash parse_lcp trigger_masks sort_groups_warp merge_small; do
+for k in fasta_pass classify_segments verify_groups phrase_hash parse_lcp trigger_masks sort_groups_warp merge_small; do
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -o gpurun_out/i_ncu_$k $NCU_BENCH > gpurun_out/i_ncu_$k.log 2>&1
 done
 NCU_M="python bench.py --workload h64_16m --route pfp --merge-mode --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --kernel-table-steps 0"
