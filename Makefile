@@ -12,8 +12,13 @@ LIB      := mumemto_b200/lib/libmumemto_b200.so
 BIN      := mumemto_b200/bin/mumemto_exec mumemto_b200/bin/anchor_merge mumemto_b200/bin/extract_mums
 HDRS     := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 
-.PHONY: all lib simt oracle clean
-all: lib $(BIN)
+PYTHON   ?= python
+PYEXT    := mumemto_b200/_mumemto_core$(shell $(PYTHON) -c "import sysconfig; print(sysconfig.get_config_var('EXT_SUFFIX'))")
+PYINC    := $(shell $(PYTHON) -c "import sysconfig, pybind11; print('-I' + sysconfig.get_paths()['include'], '-I' + pybind11.get_include())")
+
+.PHONY: all lib simt oracle clean pymodule
+all: lib $(BIN) pymodule
+pymodule: $(PYEXT)
 lib: $(LIB)
 
 build/%.o: $(CSRC)/%.cu $(HDRS)
@@ -40,6 +45,10 @@ mumemto_b200/bin/extract_mums: $(CSRC)/extract_mums_main.cpp
 	@mkdir -p mumemto_b200/bin
 	$(CXX) -O2 -std=c++17 -Wall $< -o $@ -lz
 
+# pybind11 module with the reference's Python surface (python_bindings/src/mumemto_pybind.cpp) over the library ABI of include/mumemto.h
+$(PYEXT): $(CSRC)/pybind_module.cpp include/mumemto.h $(LIB)
+	$(CXX) -O2 -std=c++17 -fPIC -shared -fvisibility=hidden -Wall -Iinclude $(PYINC) $< -o $@ -Lmumemto_b200/lib -lmumemto_b200 -Wl,-rpath,'$$ORIGIN/lib'
+
 # ---- tests only -------------------------------------------------------------------------------------------------------------
 SIMT     := tests/simt/_build/libmumemto_b200_simt.so
 simt: $(SIMT)
@@ -52,4 +61,4 @@ oracle:
 	$(MAKE) -C oracle port ref
 
 clean:
-	rm -rf build mumemto_b200/lib mumemto_b200/bin tests/simt/_build
+	rm -rf build mumemto_b200/lib mumemto_b200/bin mumemto_b200/_mumemto_core*.so tests/simt/_build

@@ -36,14 +36,16 @@ __host__ __device__ __forceinline__ u64 mix64(u64 x) {
     x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
     return x;
 }
-// Trigger test for the window T[e-9 .. e], given as its last eight bytes (x, little-endian: T[e] in the top byte) and the two bytes
-// before them (y).  Any deterministic function of the ten bytes is a valid rule (the outputs of the path do not depend on it,
-// SURVEY 8a row B); this one costs three 32-bit multiply-adds and a finaliser.
-__device__ __forceinline__ bool window_triggers(u32 x_lo, u32 x_hi, u32 y) {
-    u32 h = x_lo * 0x9E3779B1u ^ x_hi * 0x85EBCA77u ^ y * 0xC2B2AE3Du;
-    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
-    return (h >> 8) % PFP_P == 0;
-}
+// Trigger rule for the window T[e-9 .. e].  Any deterministic function of the ten bytes is a valid rule (the outputs of the path do not
+// depend on it).  This one is a polynomial hash modulo 2^32 that ROLLS from one window to the next inside a thread
+// (two multiply-adds per position instead of hashing ten bytes afresh: the first version cost ~28 instructions per position and the
+// kernel was issue-bound at 1.08 TB/s), finished by one xor-shift and one multiply; the window triggers when the result falls into the
+// lowest 1/PFP_P of the 32-bit range.
+constexpr u32 TRIG_B = 0x9E3779B1u;
+constexpr u32 trig_pow(u32 e) { u32 r = 1; for (u32 i = 0; i < e; ++i) r *= TRIG_B; return r; }
+constexpr u32 TRIG_B10 = trig_pow(PFP_W);
+constexpr u32 TRIG_LIMIT = 0xffffffffu / PFP_P;
+__device__ __forceinline__ bool hash_triggers(u32 h) { h ^= h >> 15; h *= 0x2C1B3C6Du; return h < TRIG_LIMIT; }
 
 // exclusive block scan of one u32 per thread; *total = block sum
 __device__ __forceinline__ u32 block_scan(u32 mine, u32* total) {
@@ -71,18 +73,18 @@ __global__ void __launch_bounds__(TPB) trigger_masks(const u8* __restrict__ text
         else { w[0] = w[1] = w[2] = 0; }
         uint4 c = *reinterpret_cast<const uint4*>(text + e0);
         w[3] = c.x; w[4] = c.y; w[5] = c.z; w[6] = c.w;
+#define TRIG_BYTE(b) ((w[(b) >> 2] >> (((b) & 3) * 8)) & 0xffu)
+        // T[e0+k] is byte 12+k of w[]; its window starts at byte 3+k
+        u32 h = 0;
+#pragma unroll
+        for (u32 i = 0; i < PFP_W; ++i) h = h * TRIG_B + TRIG_BYTE(3 + i);
 #pragma unroll
         for (u32 k = 0; k < 16; ++k) {
-            // T[e0+k] is byte 12+k of w[]; the window starts at byte 3+k
-            const u32 first = 3 + k, wi = first >> 2, sh = (first & 3) * 8;
-            u32 y = sh ? __funnelshift_r(w[wi], w[wi + 1], sh) : w[wi];
-            y &= 0xffffu;
-            const u32 f2 = first + 2, wj = f2 >> 2, sj = (f2 & 3) * 8;
-            u32 x_lo = sj ? __funnelshift_r(w[wj], w[wj + 1], sj) : w[wj];
-            u32 x_hi = sj ? __funnelshift_r(w[wj + 1], wj + 2 < 7 ? w[wj + 2] : 0u, sj) : w[wj + 1];
             u64 e = e0 + k;
-            if (e >= PFP_W && e < n && window_triggers(x_lo, x_hi, y)) mask |= 1u << k;
+            if (e >= PFP_W && e < n && hash_triggers(h)) mask |= 1u << k;
+            if (k < 15) h = h * TRIG_B + TRIG_BYTE(13 + k) - TRIG_BYTE(3 + k) * TRIG_B10;
         }
+#undef TRIG_BYTE
     }
     masks[(u64)blockIdx.x * TPB + threadIdx.x] = (u16)mask;
     u32 total; block_scan((u32)__popc(mask), &total);
@@ -105,20 +107,26 @@ __global__ void __launch_bounds__(TPB) phrase_starts(const u64* __restrict__ end
 }
 
 // phrase j = T'[pstart[j] .. pstart[j+1] + w - 1], length pstart[j+1] - pstart[j] + w; bytes at or past n read as 0 (text has zero slack)
-// (One thread per phrase, straight from global memory.  A variant that staged the block's text span in shared memory first -- coalesced
-// 128-bit loads, 24 KB per 128 phrases -- was SLOWER on the B200: phrase_hash 12.7 -> 15.6 ms, verify_groups 13.8 -> 25.0 ms at C2;
-// the L1 already turns the strided 8-byte reads into whole-sector traffic, and the staging costs occupancy and a barrier.)
+// PH_LANES lanes share a phrase: lane r takes the 8-byte words r, r + 8, ... (the hash is a SUM of per-word mixes, so the partial sums are
+// combined with three xor-shuffles and the value is the one a single thread would compute).  One thread per phrase read 8 bytes at a
+// stride of ~110 bytes between lanes (32 sectors per load, a warp ran as long as its longest phrase: 26 thread instructions per text
+// byte); a variant that staged the block's text span in shared memory first was slower still (12.7 -> 15.6 ms, verify 13.8 -> 25.0 ms).
+constexpr u32 PH_LANES = 8;
 __global__ void __launch_bounds__(TPB) phrase_hash(const u8* __restrict__ text, const u64* __restrict__ pstart, u32 np, u64 seed, u64* __restrict__ keys,
                                                    u32* __restrict__ vals) {
-    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= np) return;
-    u64 s = pstart[j], len = pstart[j + 1] - s + PFP_W;
-    u64 h = seed ^ mix64(len);
-    u64 k = 0;
-    for (; (k + 1) * 8 <= len; ++k) h += mix64(load8(text, s + k * 8) + (k + 1) * 0x9E3779B97F4A7C15ull + seed);
-    u32 rem = (u32)(len - k * 8);
-    if (rem) { u64 wd = load8(text, s + k * 8) & ((1ull << (8 * rem)) - 1); h += mix64(wd + (k + 1) * 0x9E3779B97F4A7C15ull + seed); }
-    keys[j] = h; vals[j] = j;
+    u32 j = (u32)(((u64)blockIdx.x * blockDim.x + threadIdx.x) / PH_LANES), r = threadIdx.x % PH_LANES;
+    u64 h = 0;
+    if (j < np) {
+        u64 s = pstart[j], len = pstart[j + 1] - s + PFP_W;
+        u64 full = len >> 3;
+        for (u64 k = r; k < full; k += PH_LANES) h += mix64(load8(text, s + k * 8) + (k + 1) * 0x9E3779B97F4A7C15ull + seed);
+        u32 rem = (u32)(len & 7);
+        if (rem && (full % PH_LANES) == r) { u64 wd = load8(text, s + full * 8) & ((1ull << (8 * rem)) - 1); h += mix64(wd + (full + 1) * 0x9E3779B97F4A7C15ull + seed); }
+        if (r == 0) h += seed ^ mix64(len);
+    }
+#pragma unroll
+    for (u32 d = PH_LANES / 2; d > 0; d >>= 1) h += __shfl_xor_sync(FULL, h, d);
+    if (j < np && r == 0) { keys[j] = h; vals[j] = j; }
 }
 
 __global__ void __launch_bounds__(TPB) hash_boundaries(const u64* __restrict__ keys, u32 np, u32* __restrict__ flag) {
@@ -137,16 +145,16 @@ __global__ void __launch_bounds__(TPB) assign_groups(const u32* __restrict__ fla
 }
 __global__ void __launch_bounds__(TPB) verify_groups(const u8* __restrict__ text, const u64* __restrict__ pstart, const u32* __restrict__ pid,
                                                      const u32* __restrict__ rep, u32 np, u32* __restrict__ mismatch) {
-    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 j = (u32)(((u64)blockIdx.x * blockDim.x + threadIdx.x) / PH_LANES), lane = threadIdx.x % PH_LANES;      // PH_LANES lanes compare one phrase with its head
     if (j >= np) return;
     u32 r = rep[pid[j]];
     if (r == j) return;
     u64 a = pstart[j], b = pstart[r], la = pstart[j + 1] - a + PFP_W, lb = pstart[r + 1] - b + PFP_W;
     bool bad = la != lb;
-    u64 k = 0;
-    for (; !bad && (k + 1) * 8 <= la; ++k) bad = load8(text, a + k * 8) != load8(text, b + k * 8);
-    u32 rem = (u32)(la - k * 8);
-    if (!bad && rem) { u64 msk = (1ull << (8 * rem)) - 1; bad = (load8(text, a + k * 8) & msk) != (load8(text, b + k * 8) & msk); }
+    u64 full = la >> 3;
+    for (u64 k = lane; !bad && k < full; k += PH_LANES) bad = load8(text, a + k * 8) != load8(text, b + k * 8);
+    u32 rem = (u32)(la & 7);
+    if (!bad && rem && (full % PH_LANES) == lane) { u64 msk = (1ull << (8 * rem)) - 1; bad = (load8(text, a + full * 8) & msk) != (load8(text, b + full * 8) & msk); }
     if (bad) *mismatch = 1;
 }
 
@@ -305,101 +313,65 @@ __global__ void __launch_bounds__(TPB) rank_words_fix_last_phrase(const u32* __r
         if (sa_d[q] == i) rk[q] |= RK_OWN;
 }
 
-// Class of every rank that is longer than w: what its segment needs (CLS_*).  The block stages the rank words of its 256 ranks plus
-// SEG_LIMIT ranks of context on both sides.  No walks (a warp would walk as far as its longest segment: 590 warp instructions per warp
-// in the first two versions): the segment of a rank is found by bit scans in a bitmap of the segment starts, and everything the class
-// depends on is a difference of two prefix sums over the staged tile --
-//   A: occurrences | whole phrases | short suffixes | saturated counts          B: suffixes n | sum of preceding symbols | sum of squares
-// (all preceding symbols equal  <=>  n * sum(x^2) == (sum x)^2).
+// Class of every rank that is longer than w: what its segment needs (CLS_*).  The block stages the rank words of its ranks plus
+// SEG_LIMIT ranks of context on both sides; the thread that finds a segment START walks the segment once and leaves its class at the
+// start's slot, then every rank looks up the class of the start to its left (a few steps on pangenome-like input).
+// (A walk-free variant -- segment bounds by bit scans in a start bitmap, aggregates as differences of block prefix sums -- was SLOWER:
+// 14.7 -> 20.2 ms at C2; three block scans with barriers cost more than the divergent walks.)
 __global__ void __launch_bounds__(TPB) classify_segments(const u32* __restrict__ rk, u32 dsize, PfpPrune prune, u32 seg_is_interval, u8* __restrict__ cls) {
-    constexpr u32 SPAN = TPB + 2 * SEG_LIMIT + 1;               // 513 staged ranks: tile index y <-> rank base + y
-    constexpr u32 WORDS = (SPAN + 31) / 32;                     // 17
+    constexpr u32 SPAN = TPB + 2 * SEG_LIMIT + 1;
+    constexpr u8 TOO_LONG = 0x80;
     __shared__ u32 tile[SPAN];
-    __shared__ u64 sum_a[SPAN], sum_b[SPAN];                    // inclusive prefix sums
-    __shared__ u32 hb_bits[WORDS + 1];
-    __shared__ u64 warp_a[TPB / 32], warp_b[TPB / 32];
-    __shared__ u64 carry_a, carry_b;
+    __shared__ u8 head_cls[SPAN];
     const i64 base = (i64)blockIdx.x * TPB - SEG_LIMIT;
-    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { carry_a = 0; carry_b = 0; hb_bits[WORDS] = 0xffffffffu; }
-    __syncthreads();
-    // three rounds of 256 consecutive tile entries (the last one holds a single entry): load, bitmap word by ballot, block prefix sums
-    for (u32 round = 0; round * TPB < SPAN; ++round) {
-        u32 y = round * TPB + threadIdx.x;
-        i64 q = base + y;
-        u32 v = RK_HB;                                          // outside the array: a segment start that owns nothing
-        if (y < SPAN && q >= 0 && q < (i64)dsize) v = rk[q];
-        if (y < SPAN) tile[y] = v;
-        unsigned starts = __ballot_sync(FULL, y >= SPAN || (v & RK_HB) != 0);      // entries past the tile read as segment starts
-        if (lane == 0 && (y >> 5) < WORDS) hb_bits[y >> 5] = starts;
-        u64 a = 0, b = 0;
-        if (y < SPAN && (v & RK_OWN)) {
-            u32 c = (v >> 9) & RK_CNT_MAX, x = v & 0x1ffu;
-            bool start = x == RK_START;
-            a = (u64)c | ((u64)(start ? 1 : 0) << 32) | ((u64)((v & RK_SHORT) ? 1 : 0) << 42) | ((u64)(c == RK_CNT_MAX ? 1 : 0) << 52);
-            u64 sym = start ? 0 : x;                            // 0 .. 255
-            b = 1ull | (sym << 10) | ((sym * sym) << 28);
-        }
-        u64 ia = a, ib = b;
-#pragma unroll
-        for (u32 d = 1; d < 32; d <<= 1) {
-            u64 oa = __shfl_up_sync(FULL, ia, d), ob = __shfl_up_sync(FULL, ib, d);
-            if (lane >= d) { ia += oa; ib += ob; }
-        }
-        if (lane == 31) { warp_a[warp] = ia; warp_b[warp] = ib; }
-        __syncthreads();
-        u64 before_a = carry_a, before_b = carry_b, all_a = 0, all_b = 0;
-        for (u32 w = 0; w < TPB / 32; ++w) { if (w < warp) { before_a += warp_a[w]; before_b += warp_b[w]; } all_a += warp_a[w]; all_b += warp_b[w]; }
-        if (y < SPAN) { sum_a[y] = before_a + ia; sum_b[y] = before_b + ib; }
-        __syncthreads();
-        if (threadIdx.x == 0) { carry_a += all_a; carry_b += all_b; }
-        __syncthreads();
+    for (u32 x = threadIdx.x; x < SPAN; x += TPB) {
+        i64 q = base + x;
+        tile[x] = (q >= 0 && q < (i64)dsize) ? rk[q] : RK_HB;       // outside the array: a segment start that owns nothing
     }
+    __syncthreads();
+    const u8 all = CLS_STREAM | CLS_REFINE | CLS_HAS_START;         // without a verdict: keep, and assume the segment may hold a whole phrase
+    const u8 general = CLS_STREAM | CLS_REFINE;
+    if (prune.enabled) {
+        for (u32 y = threadIdx.x; y < TPB + SEG_LIMIT; y += TPB) {     // every start this block's ranks can belong to
+            if (!(tile[y] & RK_HB)) continue;
+            u64 total = 0; u32 sym = 0xffffffffu; bool uniform = true, has_start = false, saturated = false, has_short = false;
+            u32 b = y, steps = 0;
+            for (;;) {
+                u32 v = tile[b];
+                if (v & RK_OWN) {
+                    u32 c = (v >> 9) & RK_CNT_MAX, bsym = v & 0x1ffu;
+                    total += c; saturated |= c == RK_CNT_MAX; has_short |= (v & RK_SHORT) != 0;
+                    if (bsym == RK_START) { has_start = true; uniform = false; }
+                    else if (sym == 0xffffffffu) sym = bsym;
+                    else if (sym != bsym) uniform = false;
+                }
+                if ((tile[b + 1] & RK_HB) || steps == SEG_LIMIT) break;
+                ++b; ++steps;
+            }
+            u8 c = 0;
+            if (!(tile[b + 1] & RK_HB)) c = TOO_LONG;                   // more than SEG_LIMIT + 1 ranks: low-complexity repeats, kept as they are
+            else {
+                if (saturated) c = general;
+                else if (total >= prune.size_lo) {
+                    if (!uniform) c = general;
+                    // -M: a segment of exactly N suffixes, all at least t = -l symbols long, is one interval of length >= -l
+                    else if (prune.merge) c = (seg_is_interval && !has_short && total == prune.ndocs) ? CLS_THRESH : general;
+                }
+                if (has_start) c |= CLS_REFINE | CLS_HAS_START;         // phrase ranks need the exact place of every whole phrase
+            }
+            head_cls[y] = c;
+        }
+    }
+    __syncthreads();
     u32 p = blockIdx.x * TPB + threadIdx.x;
     if (p >= dsize) return;
-    const u32 x = threadIdx.x + SEG_LIMIT;
-    const u32 v = tile[x];
-    if (!(v & RK_OWN)) { cls[p] = 0; return; }
-    const u8 all = CLS_STREAM | CLS_REFINE | CLS_HAS_START;     // without a verdict: keep, and assume the segment may hold a whole phrase
-    const u8 general = CLS_STREAM | CLS_REFINE;
+    u32 x = threadIdx.x + SEG_LIMIT;
+    if (!(tile[x] & RK_OWN)) { cls[p] = 0; return; }
     if (!prune.enabled) { cls[p] = all; return; }
-    // first rank of the segment: the highest start bit at or below x; last rank: one before the lowest start bit above x
-    int a_idx = -1;
-    {
-        int w = (int)(x >> 5);
-        u32 m = hb_bits[w] & (0xffffffffu >> (31 - (x & 31)));
-        for (u32 steps = 0; steps <= SEG_LIMIT / 32 + 1; ++steps) {
-            if (m) { a_idx = w * 32 + (31 - __clz((int)m)); break; }
-            if (--w < 0) break;
-            m = hb_bits[w];
-        }
-    }
-    u32 e_idx = SPAN;                                           // tile index of the next segment's start
-    {
-        u32 w = x >> 5;
-        u32 m = (x & 31) == 31 ? 0u : hb_bits[w] & (0xffffffffu << ((x & 31) + 1));
-        for (u32 steps = 0; steps <= SEG_LIMIT / 32 + 1; ++steps) {
-            if (m) { e_idx = w * 32 + (u32)__ffs((int)m) - 1; break; }
-            if (++w > WORDS) break;
-            m = hb_bits[w];
-        }
-    }
-    if (a_idx < 0 || e_idx > SPAN - 1 || e_idx - 1 - (u32)a_idx > SEG_LIMIT) { cls[p] = all; return; }      // more than SEG_LIMIT + 1 ranks: kept as it is
-    const u32 b_idx = e_idx - 1;
-    const u64 A = sum_a[b_idx] - (a_idx ? sum_a[a_idx - 1] : 0ull), B = sum_b[b_idx] - (a_idx ? sum_b[a_idx - 1] : 0ull);
-    const u64 total = A & 0xffffffffull;
-    const bool has_start = ((A >> 32) & 0x3ff) != 0, has_short = ((A >> 42) & 0x3ff) != 0, saturated = ((A >> 52) & 0x3ff) != 0;
-    const u64 cnt_n = B & 0x3ff, s1 = (B >> 10) & 0x3ffff, s2 = B >> 28;
-    const bool uniform = !has_start && cnt_n * s2 == s1 * s1;
-    u8 c = 0;
-    if (saturated) c = general;
-    else if (total >= prune.size_lo) {
-        if (!uniform) c = general;
-        // -M: a segment of exactly N suffixes, all at least t = -l symbols long, is one interval of length >= -l
-        else if (prune.merge) c = (seg_is_interval && !has_short && total == prune.ndocs) ? CLS_THRESH : general;
-    }
-    if (has_start) c |= CLS_REFINE | CLS_HAS_START;             // phrase ranks need the exact place of every whole phrase
-    cls[p] = c;
+    u32 a = x, steps = 0;
+    while (!(tile[a] & RK_HB) && steps < SEG_LIMIT) { --a; ++steps; }
+    u8 c = (tile[a] & RK_HB) ? head_cls[a] : TOO_LONG;
+    cls[p] = c == TOO_LONG ? all : c;
 }
 
 __global__ void __launch_bounds__(TPB) owned_positions(const u32* __restrict__ rk, u32 dsize, u32* __restrict__ out) {
@@ -639,12 +611,12 @@ void pfp_parse(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s
         if (attempt == 8) throw Error(73, "phrase hashing kept colliding");
         DevBuf<u64> ka, kb; DevBuf<u32> va, vb, flag, gnum, mismatch;
         ka.alloc(np, s); kb.alloc(np, s); va.alloc(np, s); vb.alloc(np, s); flag.alloc(np, s); gnum.alloc(np, s); mismatch.alloc(1, s); mismatch.zero();
-        MMB_LAUNCH(phrase_hash, ceil_div(np, TPB), TPB, 0, s, text, (const u64*)ix.pstart.p, np, mix64(attempt + 0x1234567ull), ka.p, va.p);
+        MMB_LAUNCH(phrase_hash, ceil_div((u64)np * PH_LANES, TPB), TPB, 0, s, text, (const u64*)ix.pstart.p, np, mix64(attempt + 0x1234567ull), ka.p, va.p);
         prim::sort_pairs(ka.p, kb.p, va.p, vb.p, np, 0, 64, s);
         MMB_LAUNCH(hash_boundaries, ceil_div(np, TPB), TPB, 0, s, (const u64*)kb.p, np, flag.p);
         prim::exclusive_sum(flag.p, gnum.p, np, s);
         MMB_LAUNCH(assign_groups, ceil_div(np, TPB), TPB, 0, s, (const u32*)flag.p, (const u32*)gnum.p, (const u32*)vb.p, np, pid.p, rep.p);
-        MMB_LAUNCH(verify_groups, ceil_div(np, TPB), TPB, 0, s, text, (const u64*)ix.pstart.p, (const u32*)pid.p, (const u32*)rep.p, np, mismatch.p);
+        MMB_LAUNCH(verify_groups, ceil_div((u64)np * PH_LANES, TPB), TPB, 0, s, text, (const u64*)ix.pstart.p, (const u32*)pid.p, (const u32*)rep.p, np, mismatch.p);
         u32 tail[3];
         MMB_CUDA(cudaMemcpyAsync(&tail[0], gnum.p + np - 1, 4, cudaMemcpyDeviceToHost, s));
         MMB_CUDA(cudaMemcpyAsync(&tail[1], flag.p + np - 1, 4, cudaMemcpyDeviceToHost, s));

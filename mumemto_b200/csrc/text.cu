@@ -27,7 +27,7 @@ constexpr u32 FULL = 0xffffffffu;
 enum : u32 { ST_PRE = 0, ST_BOL = 1, ST_HDR = 2, ST_SEQ = 3 };
 constexpr u32 MAP_ID = 0xE4;    // 2 bits per input state: 3->3, 2->2, 1->1, 0->0
 
-__device__ __forceinline__ bool is_marker(u8 c) { return c == '>' || c == '@'; }
+__device__ __forceinline__ u32 squeeze4(u32 m) { return ((m & 0x01010101u) * 0x01020408u) >> 24; }     // one bit per 0xff byte, byte 0 -> bit 0
 
 __device__ __forceinline__ u32 map_compose(u32 a, u32 b) {   // apply a, then b
     u32 r = 0;
@@ -85,11 +85,16 @@ __device__ __forceinline__ void load_view(const u8* __restrict__ raw, const u64*
 #pragma unroll
         for (int k = 0; k < 16; ++k) v.b[k] = (k < (int)v.nbytes) ? raw[v.begin + k] : (u8)0;
     }
+    // the four 16-bit masks, four bytes at a time: a SIMD byte compare per class and word, then the four 0xff/0x00 bytes are squeezed
+    // into four bits by one multiply (bits 0, 8, 16, 24 land on bits 24..27 of the product; no two partial products collide)
     v.nl = v.mk = v.cr = v.pl = 0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        u8 c = v.b[k];
-        v.nl |= (u32)(c == '\n') << k; v.mk |= (u32)is_marker(c) << k; v.cr |= (u32)(c == '\r') << k; v.pl |= (u32)(c == '+') << k;
+    for (int i = 0; i < 4; ++i) {
+        u32 x = ((u32)v.b[4 * i]) | ((u32)v.b[4 * i + 1] << 8) | ((u32)v.b[4 * i + 2] << 16) | ((u32)v.b[4 * i + 3] << 24);
+        v.nl |= squeeze4(__vcmpeq4(x, 0x0a0a0a0au)) << (4 * i);
+        v.mk |= squeeze4(__vcmpeq4(x, 0x3e3e3e3eu) | __vcmpeq4(x, 0x40404040u)) << (4 * i);
+        v.cr |= squeeze4(__vcmpeq4(x, 0x0d0d0d0du)) << (4 * i);
+        v.pl |= squeeze4(__vcmpeq4(x, 0x2b2b2b2bu)) << (4 * i);
     }
     u32 valid = (1u << v.nbytes) - 1;
     v.nl &= valid; v.mk &= valid; v.cr &= valid; v.pl &= valid;
@@ -136,6 +141,47 @@ __device__ __forceinline__ u32 thread_map(const ChunkView& v) {
         from_pre = (v.nl >> fm) >> 1 ? tail : ST_HDR;        // a newline after the first marker ends that header
     }
     return (from_pre << (2 * ST_PRE)) | (from_bol << (2 * ST_BOL)) | (from_hdr << (2 * ST_HDR)) | (from_seq << (2 * ST_SEQ));
+}
+
+// State before the thread's first byte when the chunk is known to start in BOL, HDR or SEQ (the scatter pass; every chunk but a file's
+// first).  Outside PRE the automaton forgets everything at a newline, so no map composition is needed: the state is the `tail` of the
+// nearest earlier thread that holds a newline -- with "beginning of line" resolved by the first byte that follows -- or the chunk's
+// start state if there is none.  One ballot and two shuffles per thread, one short walk over the warps before its own (the generic
+// composition scan of 4-state maps was a quarter of the scatter pass's instructions).
+__device__ __forceinline__ u32 block_state_before(const ChunkView& v, u32 cs) {
+    __shared__ u8 w_has_nl[TPB / 32], w_end[TPB / 32], w_first_mk[TPB / 32], w_nonempty[TPB / 32];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool has_nl = v.nl != 0;
+    u32 tail = ST_BOL;
+    if (has_nl) {
+        u32 last = 31 - (u32)__clz((int)v.nl);
+        if (last + 1 < v.nbytes) tail = ((v.mk >> (last + 1)) & 1) ? ST_HDR : ST_SEQ;
+    }
+    const u32 first_mk = v.mk & 1, nonempty = v.nbytes ? 1u : 0u;
+    const u32 nlmask = __ballot_sync(FULL, has_nl);
+    // state after the warp's last byte, when the warp holds a newline
+    const u32 jl = nlmask ? 31 - (u32)__clz((int)nlmask) : 0;
+    u32 t_last = __shfl_sync(FULL, tail, jl);
+    const u32 nxt = min(jl + 1, 31u);
+    const u32 mk_next = __shfl_sync(FULL, first_mk, nxt), ne_next = __shfl_sync(FULL, nonempty, nxt);
+    if (t_last == ST_BOL && jl < 31 && ne_next) t_last = mk_next ? ST_HDR : ST_SEQ;
+    if (lane == 0) { w_has_nl[warp] = nlmask ? 1 : 0; w_end[warp] = (u8)t_last; w_first_mk[warp] = (u8)first_mk; w_nonempty[warp] = (u8)nonempty; }
+    __syncthreads();
+    u32 sw = cs;                                                // state before the warp's first byte
+    for (u32 w = 0; w < warp; ++w) {
+        if (w_has_nl[w]) sw = w_end[w];
+        else if (sw == ST_BOL && w_nonempty[w]) sw = w_first_mk[w] ? ST_HDR : ST_SEQ;
+    }
+    const u32 mk0 = __shfl_sync(FULL, first_mk, 0);
+    const u32 prev = nlmask & ((1u << lane) - 1);
+    const u32 j = prev ? 31 - (u32)__clz((int)prev) : 0;
+    const u32 t = __shfl_sync(FULL, tail, j);
+    const u32 mk_j1 = __shfl_sync(FULL, first_mk, min(j + 1, 31u));
+    u32 st;
+    if (prev) st = (t != ST_BOL) ? t : (j + 1 == lane ? (u32)ST_BOL : (mk_j1 ? ST_HDR : ST_SEQ));
+    else st = (sw != ST_BOL) ? sw : (lane == 0 ? (u32)ST_BOL : (mk0 ? ST_HDR : ST_SEQ));
+    __syncthreads();            // the shared arrays are reused by the next call
+    return st;
 }
 
 // Which of the thread's bytes are sequence symbols (keep) and which start a header, given the state before its first byte.
@@ -268,9 +314,12 @@ __global__ void __launch_bounds__(TPB) fasta_pass(const u8* __restrict__ raw, co
     u32 st;
     if (raw_mode) st = ST_SEQ;
     else {
-        u32 total;
-        u32 prefix = block_map_scan(thread_map(v), &total);
-        st = (prefix >> (2 * (u32)chunk_state[blockIdx.x])) & 3;
+        const u32 cs = chunk_state[blockIdx.x];                // block-uniform
+        if (cs == ST_PRE) {                                     // a file's first chunk: the general composition of state maps
+            u32 total;
+            u32 prefix = block_map_scan(thread_map(v), &total);
+            st = (prefix >> (2 * ST_PRE)) & 3;
+        } else st = block_state_before(v, cs);
     }
     ByteMasks bm;
     if (raw_mode) { bm.keep = (1u << v.nbytes) - 1; bm.header = 0; bm.fastq = 0; }

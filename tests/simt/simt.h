@@ -143,6 +143,7 @@ inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
     for (int i = 0; i < 4; ++i) r |= (unsigned)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
     return r;
 }
+inline unsigned __vcmpeq4(unsigned a, unsigned b) { unsigned r = 0; for (int i = 0; i < 4; ++i) if (((a >> (8 * i)) & 0xffu) == ((b >> (8 * i)) & 0xffu)) r |= 0xffu << (8 * i); return r; }
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }
 template <class T> inline T __ldg(const T* p) { return *p; }
