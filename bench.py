@@ -505,6 +505,34 @@ ROOF = {
 }
 
 
+PEAK_GBS = 6650.0
+try:
+    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as _f:
+        PEAK_GBS = float(json.load(_f).get("hbm_gbs", PEAK_GBS))
+except Exception:
+    pass
+
+
+def ncu_traffic(kernel_name, st):
+    """DRAM traffic of a kernel per step, from its `ncu --set full` capture: profiles/ncu/traffic.json holds dram__bytes_read.sum +
+    dram__bytes_write.sum of one captured launch divided by the units that launch processed; scaled here by this run's units.  A
+    constant of the capture (taken at 64 x 16 Mbp unless noted), not measured in this run -- the source string says so."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu", "traffic.json")) as f:
+            table = json.load(f)
+    except Exception:
+        return None
+    for key, tr in table.items():
+        if key in kernel_name:
+            u = roof_units(tr["unit"], st)
+            if not u:
+                return None
+            return {"ncu_dram_bytes_per_unit": tr["dram_bytes_per_unit"], "ncu_dram_bytes_per_step": tr["dram_bytes_per_unit"] * u,
+                    "ncu_traffic_source": f"profiles/ncu/traffic.json: {tr['dram_bytes_per_unit']} B per {tr['unit']} unit from {tr['capture']} "
+                                          f"x this run's units (a constant of the capture, not measured in this run)"}
+    return None
+
+
 def roof_units(unit, st):
     return {"suffix": float(st["text_symbols"]), "stream": float(st.get("stream_suffixes") or st["text_symbols"]), "dict": float(st["pfp_dict_bytes"]),
             "phrase": float(st["pfp_phrases"])}.get(unit)
@@ -716,7 +744,11 @@ def main():
                 u = roof_units(unit, st) if bpu else None
                 if key in name and bpu and u:
                     gbs = bpu * u / (per_step * 1e-3) / 1e9
-                    entry.update({"algorithmic_bytes_per_unit": bpu, "unit": unit, "units_per_step": u, "achieved_gbs": round(gbs, 1)})
+                    entry.update({"algorithmic_bytes_per_unit": bpu, "unit": unit, "units_per_step": u, "achieved_gbs": round(gbs, 1),
+                                  "frac_of_measured_peak": round(gbs / PEAK_GBS, 4)})
+            tr = ncu_traffic(name, st)
+            if tr:
+                entry.update(tr)
             kernel_table.append(entry)
 
     # ---- end to end through the host-buffer call
@@ -799,14 +831,10 @@ def main():
         # DRAM bytes per suffix of that kernel from its ncu --set full capture (dram__bytes_read.sum + dram__bytes_write.sum of one launch
         # divided by the suffixes that launch produced); the capture and its summary are under profiles/ncu/
         traffic = None; traffic_src = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "ncu", "traffic.json")) as f:
-                tr = json.load(f).get(roof_kernel)
-            if tr and roof_launches:
-                traffic = tr["dram_bytes_per_suffix"] * float(st["text_symbols"]) * args.steps / roof_launches
-                traffic_src = f"profiles/ncu/traffic.json: {tr['dram_bytes_per_suffix']} B per suffix from {tr.get('capture', 'an ncu --set full capture')} x the suffixes of one launch (a constant of the capture, not measured in this run)"
-        except Exception:
-            pass
+        tr = ncu_traffic(roof_kernel, st)
+        if tr and roof_launches:
+            traffic = tr["ncu_dram_bytes_per_step"] * args.steps / roof_launches
+            traffic_src = tr["ncu_traffic_source"]
         bpu = roof_entry[1][0] or 0.0
         k_bytes = bpu * units
         k_achieved = (k_bytes / (roof_ms * 1e-3) / 1e9) if roof_ms > 0 else None
