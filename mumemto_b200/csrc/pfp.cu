@@ -107,46 +107,24 @@ __global__ void __launch_bounds__(TPB) phrase_starts(const u64* __restrict__ end
 }
 
 // phrase j = T'[pstart[j] .. pstart[j+1] + w - 1], length pstart[j+1] - pstart[j] + w; bytes at or past n read as 0 (text has zero slack)
-// PH_LANES lanes share a phrase: lane r takes the 16-byte chunks r, r + 8, ... (one iteration covers 128 bytes, the mean phrase is ~110),
-// each chunk read with five 32-bit loads and realigned with funnel shifts.  The hash is a SUM of per-chunk mixes (chunk index and seed
-// enter each mix), so the partial sums are combined with three xor-shuffles; bytes past the phrase end are masked to zero and the
-// length is mixed in.  History: one thread per phrase read 8 bytes at a stride of ~110 bytes between lanes and a warp ran as long as
-// its longest phrase (12.7 ms at C2); staging the block's text span in shared memory first was slower (15.6 ms); 8 lanes per phrase
-// with 8-byte words and a two-multiply 64-bit finaliser per word was slower too (14.9 ms: per-word arithmetic dominated).
+// Content hash: ONE thread per phrase, 8 bytes at a time straight from global memory, a full 64-bit finaliser per word (the hash is a
+// sum of per-word mixes).  Measured alternatives at C2 (this version: 12.7 ms): staging the block's text span in shared memory 15.6 ms;
+// 8 lanes per phrase on 8-byte words 14.9 ms; 8 lanes on 16-byte chunks with a cheaper two-multiply mix ~13.5 ms AND structurally weak
+// (differences in a chunk's last bytes only travelled upward: it collided on every seed at 4 million distinct phrases --
+// scripts/phrase_hash_quality.py reproduces that on the CPU).  The per-phrase overhead of the cooperative variants eats what their
+// coalescing wins; the verification below does profit from 8 lanes per phrase (13.8 -> 12.5 ms).
 constexpr u32 PH_LANES = 8;
-struct Chunk16 { u64 lo, hi; };
-// bytes [i, i + 16) of the text, of which the first `valid` (1..16) are kept and the rest read as zero; touches at most 19 bytes past i
-__device__ __forceinline__ Chunk16 load16(const u8* __restrict__ t, u64 i, u32 valid) {
-    const u32* w = reinterpret_cast<const u32*>(t + (i & ~3ull));
-    const u32 sh = (u32)(i & 3) * 8;
-    u32 a = w[0], b = w[1], c = w[2], d = w[3], e = w[4];
-    u32 x0 = __funnelshift_r(a, b, sh), x1 = __funnelshift_r(b, c, sh), x2 = __funnelshift_r(c, d, sh), x3 = __funnelshift_r(d, e, sh);
-    Chunk16 q;
-    q.lo = ((u64)x1 << 32) | x0; q.hi = ((u64)x3 << 32) | x2;
-    if (valid < 16) {
-        if (valid <= 8) { q.hi = 0; if (valid < 8) q.lo &= (1ull << (8 * valid)) - 1; }
-        else q.hi &= (1ull << (8 * (valid - 8))) - 1;
-    }
-    return q;
-}
 __global__ void __launch_bounds__(TPB) phrase_hash(const u8* __restrict__ text, const u64* __restrict__ pstart, u32 np, u64 seed, u64* __restrict__ keys,
                                                    u32* __restrict__ vals) {
-    u32 j = (u32)(((u64)blockIdx.x * blockDim.x + threadIdx.x) / PH_LANES), r = threadIdx.x % PH_LANES;
-    u64 h = 0;
-    if (j < np) {
-        u64 s = pstart[j], len = pstart[j + 1] - s + PFP_W;
-        u64 salt = seed + (u64)(r + 1) * 0x9E3779B97F4A7C15ull;
-        for (u64 o = (u64)r * 16; o < len; o += PH_LANES * 16, salt += PH_LANES * 0x9E3779B97F4A7C15ull) {
-            Chunk16 q = load16(text, s + o, (u32)min((u64)16, len - o));
-            u64 u = (q.lo ^ salt) * 0xbf58476d1ce4e5b9ull; u ^= u >> 32;
-            u64 v = (q.hi + u) * 0x94d049bb133111ebull; v ^= v >> 29;
-            h += v * 0x9E3779B97F4A7C15ull;
-        }
-        if (r == 0) h += seed ^ mix64(len);
-    }
-#pragma unroll
-    for (u32 d = PH_LANES / 2; d > 0; d >>= 1) h += __shfl_xor_sync(FULL, h, d);
-    if (j < np && r == 0) { keys[j] = h; vals[j] = j; }
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= np) return;
+    u64 s = pstart[j], len = pstart[j + 1] - s + PFP_W;
+    u64 h = seed ^ mix64(len);
+    u64 k = 0;
+    for (; (k + 1) * 8 <= len; ++k) h += mix64(load8(text, s + k * 8) + (k + 1) * 0x9E3779B97F4A7C15ull + seed);
+    u32 rem = (u32)(len - k * 8);
+    if (rem) { u64 wd = load8(text, s + k * 8) & ((1ull << (8 * rem)) - 1); h += mix64(wd + (k + 1) * 0x9E3779B97F4A7C15ull + seed); }
+    keys[j] = h; vals[j] = j;
 }
 
 __global__ void __launch_bounds__(TPB) hash_boundaries(const u64* __restrict__ keys, u32 np, u32* __restrict__ flag) {
@@ -171,11 +149,10 @@ __global__ void __launch_bounds__(TPB) verify_groups(const u8* __restrict__ text
     if (r == j) return;
     u64 a = pstart[j], b = pstart[r], la = pstart[j + 1] - a + PFP_W, lb = pstart[r + 1] - b + PFP_W;
     bool bad = la != lb;
-    for (u64 o = (u64)lane * 16; !bad && o < la; o += PH_LANES * 16) {
-        u32 valid = (u32)min((u64)16, la - o);
-        Chunk16 x = load16(text, a + o, valid), y = load16(text, b + o, valid);
-        bad = x.lo != y.lo || x.hi != y.hi;
-    }
+    u64 full = la >> 3;
+    for (u64 k = lane; !bad && k < full; k += PH_LANES) bad = load8(text, a + k * 8) != load8(text, b + k * 8);
+    u32 rem = (u32)(la & 7);
+    if (!bad && rem && (full % PH_LANES) == lane) { u64 msk = (1ull << (8 * rem)) - 1; bad = (load8(text, a + full * 8) & msk) != (load8(text, b + full * 8) & msk); }
     if (bad) *mismatch = 1;
 }
 
@@ -632,7 +609,7 @@ void pfp_parse(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s
         if (attempt == 8) throw Error(73, "phrase hashing kept colliding");
         DevBuf<u64> ka, kb; DevBuf<u32> va, vb, flag, gnum, mismatch;
         ka.alloc(np, s); kb.alloc(np, s); va.alloc(np, s); vb.alloc(np, s); flag.alloc(np, s); gnum.alloc(np, s); mismatch.alloc(1, s); mismatch.zero();
-        MMB_LAUNCH(phrase_hash, ceil_div((u64)np * PH_LANES, TPB), TPB, 0, s, text, (const u64*)ix.pstart.p, np, mix64(attempt + 0x1234567ull), ka.p, va.p);
+        MMB_LAUNCH(phrase_hash, ceil_div(np, TPB), TPB, 0, s, text, (const u64*)ix.pstart.p, np, mix64(attempt + 0x1234567ull), ka.p, va.p);
         prim::sort_pairs(ka.p, kb.p, va.p, vb.p, np, 0, 64, s);
         MMB_LAUNCH(hash_boundaries, ceil_div(np, TPB), TPB, 0, s, (const u64*)kb.p, np, flag.p);
         prim::exclusive_sum(flag.p, gnum.p, np, s);
