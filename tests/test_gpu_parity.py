@@ -402,3 +402,26 @@ def test_cli_partition_merge_in_one_process(ref_dir, tmp_path, mode):
     lines = open(tmp_path / "got.lengths").read().splitlines()
     assert len(lines) == 2 * len(files.paths) and lines[0].endswith(" * 150000") and lines[1].endswith(" h0 150000")
     files.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flagset", ["strict", "partial", "mem"])
+def test_midsize_pangenome_golden_md5(cuda_lib, tmp_path, flagset):
+    """64 x 4 Mbp of the benchmark generator (|T| = 5.1e8 symbols, fifty times C1): the md5 of the engine's output against the md5 of the
+    reference's own run on the same collection (tests/golden/md5_table.json `full:h64_4m:*`, recorded by scripts/make_fullsize_golden.py).
+    Skipped until that entry exists."""
+    import hashlib
+    import bench
+    entry = util.load_golden_table().get(f"full:h64_4m:{flagset}")
+    if not entry:
+        pytest.skip("no golden entry for h64_4m")
+    imgs = bench.make_collection(bench.WORKLOADS["h64_4m"], seed=1)
+    paths = []
+    for i, im in enumerate(imgs):
+        p = str(tmp_path / f"h{i}.fa"); im.tofile(p); paths.append(p)
+    st = api.find_files(paths, str(tmp_path / "out"), _lib=cuda_lib, **util.flags_to_kwargs(entry["flags"]))
+    assert st["route"] == 2 and st["pruned"]
+    ext = ".mems" if flagset == "mem" else ".mums"
+    with open(str(tmp_path / "out") + ext, "rb") as f:
+        data = f.read()
+    assert len(data) == entry["bytes"][ext] and hashlib.md5(data).hexdigest() == entry["md5"][ext]
