@@ -68,6 +68,19 @@ def test_edge_inputs_vs_oracle(cuda_lib, oracle_bin, tmp_path):
         assert open(g + ".lengths").read() == open(o + ".lengths").read()
 
 
+def test_text_long_lines_and_headers(cuda_lib, oracle_bin, tmp_path):
+    """Chunks without a newline, headers longer than a chunk, records meeting chunk boundaries (the scatter pass takes the state before a
+    thread's bytes from the nearest earlier newline; these shapes have none nearby)."""
+    from test_simt_pipeline import _long_line_inputs
+    p = _long_line_inputs(tmp_path, np.random.default_rng(8), 60000)
+    for i, flags in enumerate(([], ["-r", "-f", "2"], ["-k", "-1"])):
+        o, g = str(tmp_path / f"o{i}"), str(tmp_path / f"g{i}")
+        util.run_cli(oracle_bin, ["-o", o, *flags, *p])
+        run_gpu(cuda_lib, p, g, flags)
+        assert util.outputs(g) == util.outputs(o), flags
+        assert open(g + ".lengths").read() == open(o + ".lengths").read()
+
+
 @pytest.mark.parametrize("seed,N,L,snp", [(21, 2, 50000, 0.001), (22, 9, 30000, 0.03), (23, 33, 8000, 0.01), (24, 70, 3000, 0.02)])
 def test_random_collections_vs_oracle(cuda_lib, oracle_bin, tmp_path, seed, N, L, snp):
     """N = 2 ... 70 documents (70 exercises the multi-word document counters), shallow and deep LCPs."""

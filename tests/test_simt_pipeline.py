@@ -51,6 +51,31 @@ def test_simt_edge_inputs(simt_lib, oracle_bin, tmp_path):
         both(simt_lib, oracle_bin, str(tmp_path), p, flags)
 
 
+def _long_line_inputs(tmp_path, rng, n):
+    """FASTA shapes where whole 4 KiB chunks hold no newline: single-line sequences, a header longer than a chunk, CRLF on long lines,
+    records that end exactly at / one byte around a chunk boundary, a chunk that is all header followed by a marker-free chunk."""
+    core = util.random_dna(rng, n)
+    p = []
+    p.append(util.write_fasta(str(tmp_path / "oneline.fa"), [("a", core)], width=10 ** 9))
+    p.append(util.write_fasta(str(tmp_path / "crlf_long.fa"), [("b", util.mutate(rng, core, 0.01)[: n // 2]), ("b2", core[n // 2:])], width=9000, newline="\r\n"))
+    with open(tmp_path / "longhdr.fa", "w") as f:          # header of 5000 characters with markers inside, then lines of 4095 / 4096 / 4097 bytes
+        m = util.mutate(rng, core, 0.02)
+        f.write(">" + "h>@+ " * 1000 + "\n" + m[:4095] + "\n" + m[4095:8191] + "\n" + m[8191:12288] + "\n>x\n" + m[12288:])
+    p.append(str(tmp_path / "longhdr.fa"))
+    with open(tmp_path / "edge.fa", "w") as f:             # first record ends so that the next header starts at byte 4096 exactly
+        m = util.mutate(rng, core, 0.01)
+        head = ">e\n"
+        f.write(head + m[:4096 - len(head) - 1] + "\n" + ">e2 " + "d" * 4090 + "\n" + m[4096:] + "\n\n")
+    p.append(str(tmp_path / "edge.fa"))
+    return p
+
+
+def test_simt_text_long_lines_and_headers(simt_lib, oracle_bin, tmp_path):
+    p = _long_line_inputs(tmp_path, np.random.default_rng(8), 14000)
+    for flags in ([], ["-r", "-f", "2"]):
+        both(simt_lib, oracle_bin, str(tmp_path), p, flags)
+
+
 def test_simt_gz_and_duplicates(simt_lib, oracle_bin, small, tmp_path):
     import gzip, shutil
     gz = str(tmp_path / "h0.fa.gz")
