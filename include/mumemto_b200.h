@@ -57,7 +57,12 @@ typedef struct mmb_options {
     uint8_t route;               /* 0 auto; 1 direct suffix sorting of the text (|T| < 2^31); 2 prefix-free parse (dictionary + parse), any |T| < 2^40 with -F below 2^20 */
     uint8_t keep_arrays;         /* 1: keep SA/LCP of the whole stream for mmb_copy_arrays even on the tiled (route 2) path */
     uint8_t no_prune;            /* 1: enumerate every suffix on route 2 (no segment pruning; results are identical) */
-    uint8_t reserved[5];
+    uint8_t shard_count;         /* > 1 = this call reports only the matches of shard `shard_index` of `shard_count` contiguous slices of
+                                    the suffix order (cut at segment boundaries, which no reportable interval crosses); the outputs of the shards,
+                                    concatenated in shard order, are the bytes of the unsharded call.  Needs the pruned prefix-free-parse route
+                                    (forced); not with merge / keep_arrays / no_prune.  0 or 1 = everything */
+    uint8_t shard_index;
+    uint8_t reserved[3];
     uint64_t tile_ranks;         /* route 2: ranks per stream tile, 0 = default (2^30 in mmb_find = ~18 GB of tile buffers; 2^26 in mmb_find_from_arrays) */
     uint32_t trim_min_len;       /* 0 = off (the reference's output, bit-exact).  > 0: multi-MUM rows are post-processed like the reference's
                                     `mumemto trim` (mumemto/trim_mums.py:51-86): shortened by their overhang past the end of a sequence,

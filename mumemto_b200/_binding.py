@@ -19,7 +19,7 @@ u8p = C.POINTER(C.c_uint8)
 class Options(C.Structure):
     _fields_ = [("min_match_len", C.c_uint32), ("num_distinct_docs", C.c_int32), ("rare_freq", C.c_int32), ("max_mem_freq", C.c_int32),
                 ("merge", C.c_uint8), ("anchor_merge", C.c_uint8), ("cli_normalise", C.c_uint8), ("want_text", C.c_uint8),
-                ("route", C.c_uint8), ("keep_arrays", C.c_uint8), ("no_prune", C.c_uint8), ("reserved", C.c_uint8 * 5), ("tile_ranks", C.c_uint64), ("trim_min_len", C.c_uint32), ("reserved2", C.c_uint32)]
+                ("route", C.c_uint8), ("keep_arrays", C.c_uint8), ("no_prune", C.c_uint8), ("shard_count", C.c_uint8), ("shard_index", C.c_uint8), ("reserved", C.c_uint8 * 3), ("tile_ranks", C.c_uint64), ("trim_min_len", C.c_uint32), ("reserved2", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -171,9 +171,11 @@ class Engine:
     ROUTES = {"auto": 0, "direct": 1, "pfp": 2}
 
     def find(self, min_match_len=20, num_distinct_docs=0, rare_freq=1, max_mem_freq=0, merge=False, anchor_merge=False, cli_normalise=True,
-             want_text=True, route="auto", keep_arrays=False, tile_ranks=0, no_prune=False, trim_min_len=0):
+             want_text=True, route="auto", keep_arrays=False, tile_ranks=0, no_prune=False, trim_min_len=0, shard=None):
+        """shard = (index, count): only the matches of that slice of the suffix order; outputs concatenate in index order."""
         o = Options(min_match_len, num_distinct_docs, rare_freq, max_mem_freq, int(merge), int(anchor_merge), int(cli_normalise), int(want_text),
-                    self.ROUTES[route], int(keep_arrays), int(no_prune), (C.c_uint8 * 5)(), int(tile_ranks), int(trim_min_len), 0)
+                    self.ROUTES[route], int(keep_arrays), int(no_prune), shard[1] if shard else 0, shard[0] if shard else 0, (C.c_uint8 * 3)(),
+                    int(tile_ranks), int(trim_min_len), 0)
         self._check(self.lib.mmb_find(self.h, C.byref(o)))
         return self.stats()
 
@@ -181,7 +183,7 @@ class Engine:
                          max_mem_freq=0, merge=False, anchor_merge=False, cli_normalise=True, want_text=True, tile_ranks=0):
         """Detection over pre-computed arrays in the reference's file format (uint8 arrays: 5-byte LE SA / LCP entries, BWT bytes)."""
         o = Options(min_match_len, num_distinct_docs, rare_freq, max_mem_freq, int(merge), int(anchor_merge), int(cli_normalise), int(want_text),
-                    0, 0, 0, (C.c_uint8 * 5)(), int(tile_ranks), 0, 0)
+                    0, 0, 0, 0, 0, (C.c_uint8 * 3)(), int(tile_ranks), 0, 0)
         dl = np.ascontiguousarray(doc_lengths, dtype=np.uint64)
         self._keep_arrays = (dl, sa5, lcp5, bwt)
         self._check(self.lib.mmb_find_from_arrays(self.h, dl.ctypes.data_as(C.POINTER(C.c_uint64)), len(dl), int(revcomp), _ptr(sa5), _ptr(lcp5),

@@ -111,8 +111,9 @@ def write_outputs(engine, prefix, paths=None, binary=False, anchor_merge=False, 
 
 
 def find_files(paths, prefix, min_match_len=20, num_distinct_docs=0, rare_freq=1, max_mem_freq=0, revcomp=True, binary=False, merge=False,
-               anchor_merge=False, arrays_out=False, device=0, route="auto", tile_ranks=0, no_prune=False, trim_min_len=0, _lib=None):
-    """`mumemto_exec [flags] -o prefix paths...` through the Python binding (the C++ CLI in csrc/cli_main.cpp is the drop-in)."""
+               anchor_merge=False, arrays_out=False, device=0, route="auto", tile_ranks=0, no_prune=False, trim_min_len=0, shard=None, _lib=None):
+    """`mumemto_exec [flags] -o prefix paths...` through the Python binding (the C++ CLI in csrc/cli_main.cpp is the drop-in).
+    shard = (index, count): this call writes only the slice `index` of the match list; `cat` of the slices = the whole."""
     uniq, seen = [], set()
     for p in paths:
         ap = os.path.normpath(os.path.abspath(p))
@@ -124,7 +125,8 @@ def find_files(paths, prefix, min_match_len=20, num_distinct_docs=0, rare_freq=1
         if binary and rare_freq != 1:
             binary = False
         st = e.find(min_match_len=min_match_len, num_distinct_docs=num_distinct_docs, rare_freq=rare_freq, max_mem_freq=max_mem_freq,
-                    merge=merge, anchor_merge=anchor_merge, want_text=not binary, route=route, keep_arrays=arrays_out, tile_ranks=tile_ranks, no_prune=no_prune, trim_min_len=trim_min_len)
+                    merge=merge, anchor_merge=anchor_merge, want_text=not binary, route=route, keep_arrays=arrays_out, tile_ranks=tile_ranks, no_prune=no_prune, trim_min_len=trim_min_len,
+                    shard=shard)
         N = e.num_docs
         k = num_distinct_docs
         k = 2 if k < -N else (N + k if k <= 0 else (2 if k == 1 else min(k, N)))

@@ -514,7 +514,12 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
         if (unbounded && !prune_ok && (opts->route == 2 || n + 1 >= (1ull << 31)))
             throw Error(31, "unbounded total frequency (-f 0 with -F 0) needs the whole suffix stream in one view: not together with keep_arrays / no_prune on the prefix-free-parse route");
         e->prm.whole_stream = 0;
-        bool use_pfp = (opts->route == 2 || (opts->route == 0 && n + 1 >= (1ull << 31)));
+        const u32 shards = opts->shard_count > 1 ? opts->shard_count : 1;
+        if (shards > 1) {
+            if (opts->shard_index >= shards) throw Error(32, "shard_index must be below shard_count");
+            if (merge || !prune_ok || opts->route == 1) throw Error(32, "a sharded call needs the pruned prefix-free-parse route: not with merge, keep_arrays, no_prune or route = 1");
+        }
+        bool use_pfp = (opts->route == 2 || shards > 1 || (opts->route == 0 && n + 1 >= (1ull << 31)));
         Timer tparse(s); float ms_parse = 0;
         if (opts->route == 0 && !use_pfp && !unbounded && n >= (1u << 16)) {      // unbounded + auto: the direct route whenever it fits
             tparse.start();
@@ -558,7 +563,10 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
             prune.enabled = (opts->keep_arrays || opts->no_prune) ? 0 : 1;
             prune.min_len = e->prm.min_len; prune.size_lo = std::max<u32>(2, e->prm.num_distinct); prune.merge = merge ? 1 : 0; prune.ndocs = N;
             prune.doc_coarse = e->doc_coarse.p; prune.coarse_shift = e->coarse_shift; prune.doc_start = e->text.doc_start.p;
+            prune.shard_index = shards > 1 ? opts->shard_index : 0; prune.shard_count = shards;
             pfp_finish(e->text.text.p, n, ix, pp, s, prune);
+            if (shards > 1 && (!ix.pruned || ix.full_stream))
+                throw Error(32, "a sharded call needs segment pruning, and this collection could not be pruned (-l below 11, or a very long low-complexity phrase)");
             pp = PfpParse();
             e->stats.ms_sa = t.stop() + ms_parse;
             e->stats.ms_lcp = 0;

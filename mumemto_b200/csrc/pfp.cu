@@ -372,6 +372,36 @@ __global__ void __launch_bounds__(TPB) classify_segments(const u32* __restrict__
     cls[p] = c == TOO_LONG ? all : c;
 }
 
+// Sharding by suffix-order slice: slice bounds are moved forward to the next segment start (no reportable interval
+// crosses a segment boundary, pfp.h fact 1), then every segment outside [lo, hi) loses its place in the stream; it keeps its refinement
+// only when it holds a whole phrase (phrase ranks are global).  The first out-of-slice rank after the slice's last segment becomes the
+// stand-in that closes it with the true boundary LCP, exactly like a pruned neighbour.
+__global__ void __launch_bounds__(TPB) shard_snap(const u32* __restrict__ rk, u32 dsize, u32 raw_lo, u32 raw_hi, u32* __restrict__ bounds) {
+    __shared__ u32 found;
+    const u32 raw = blockIdx.x == 0 ? raw_lo : raw_hi;
+    u32 result = dsize;
+    if (raw == 0) result = 0;
+    else if (raw < dsize) {
+        for (u32 base = raw; base < dsize; base += TPB) {
+            if (threadIdx.x == 0) found = 0xffffffffu;
+            __syncthreads();
+            u32 p = base + threadIdx.x;
+            if (p < dsize && (rk[p] & RK_HB)) atomicMin(&found, p);
+            __syncthreads();
+            u32 f = found;
+            __syncthreads();
+            if (f != 0xffffffffu) { result = f; break; }
+        }
+    }
+    if (threadIdx.x == 0) bounds[blockIdx.x] = result;
+}
+__global__ void __launch_bounds__(TPB) shard_mask(const u32* __restrict__ bounds, u32 dsize, u8* __restrict__ cls) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= dsize || (p >= bounds[0] && p < bounds[1])) return;
+    u8 c = cls[p];
+    cls[p] = (c & CLS_HAS_START) ? (u8)(CLS_REFINE | CLS_HAS_START) : (u8)0;
+}
+
 __global__ void __launch_bounds__(TPB) owned_positions(const u32* __restrict__ rk, u32 dsize, u32* __restrict__ out) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < dsize) out[p] = (rk[p] & RK_OWN) ? p + 1 : 0u;
@@ -691,6 +721,13 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
             pinfo.release(); count.release();
             DevBuf<u8> cls, refine; cls.alloc(dsize, s); refine.alloc(dsize, s);
             MMB_LAUNCH(classify_segments, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)ix.rk.p, dsize, prune, (u32)(t == prune.min_len ? 1 : 0), cls.p);
+            if (prune.shard_count > 1) {
+                DevBuf<u32> bounds; bounds.alloc(2, s);
+                u32 raw_lo = (u32)((u64)dsize * prune.shard_index / prune.shard_count), raw_hi = (u32)((u64)dsize * (prune.shard_index + 1) / prune.shard_count);
+                if (prune.shard_index + 1 == prune.shard_count) raw_hi = dsize;
+                MMB_LAUNCH(shard_snap, 2, TPB, 0, s, (const u32*)ix.rk.p, dsize, raw_lo, raw_hi, bounds.p);
+                MMB_LAUNCH(shard_mask, ceil_div(dsize, TPB), TPB, 0, s, (const u32*)bounds.p, dsize, cls.p);
+            }
             ix.prev_owned.alloc(dsize, s);
             {
                 DevBuf<u32> own_pos; own_pos.alloc(dsize, s);

@@ -91,6 +91,7 @@ struct PfpPrune {
     u32 size_lo = 2;        // smallest interval size that can qualify
     u32 merge = 0;          // -M
     u32 ndocs = 0;
+    u32 shard_index = 0, shard_count = 1;   // only the segments of this slice of the dictionary suffix order are streamed
     // -M: position -> document lookup (device pointers; coarse table + document starts, as DetectParams::doc_coarse)
     const u16* doc_coarse = nullptr; u32 coarse_shift = 0; const u64* doc_start = nullptr;
 };

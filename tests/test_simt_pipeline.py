@@ -374,3 +374,59 @@ def test_simt_anchor_merge_is_the_fold_not_a_kway_min(simt_lib, ref_dir, tmp_pat
     got = util.outputs(str(tmp_path / "gm"))
     assert got == util.outputs(str(tmp_path / "om"))
     assert got[".mums"] == b"20\t130,7,440,40\t+,-,-,+\n"          # a K-way min over the latest-started sources would report 90
+
+
+@pytest.mark.parametrize("flags", [[], ["-k", "-1"], ["-f", "3", "-F", "100"], ["-f", "0", "-k", "2"], ["-b"]])
+def test_simt_sharded_collection(simt_lib, oracle_bin, tmp_path, flags):
+    """one collection, the suffix order cut into K slices at segment boundaries; every slice reports its own matches and the
+    outputs concatenated in slice order are the bytes of the unsharded run (= the oracle's)."""
+    paths = util.appendix_a(str(tmp_path / "in"), N=6, L=4000, seed=23, identical_ends=True, snp=0.01, width=70)
+    o = str(tmp_path / "o")
+    util.run_cli(oracle_bin, ["-o", o, *[f for f in flags if f != "-b"], *paths])
+    want = util.outputs(o)
+    ext = ".mems" if "-f" in flags else ".mums"
+    for k in (2, 3, 7):
+        got, rows, streamed = b"", 0, 0
+        for i in range(k):
+            g = str(tmp_path / f"g{k}_{i}")
+            try:
+                st = api.find_files(paths, g, shard=(i, k), _lib=simt_lib, **util.flags_to_kwargs(flags))
+            except RuntimeError as e:               # -b with an empty slice is an error like an empty result (include/mem_finder.hpp:461-462)
+                assert "-b" in flags and "zero MUMs" in str(e)
+                continue
+            assert st["route"] == 2 and st["pruned"]
+            streamed += st["stream_suffixes"]
+            if "-b" in flags:
+                import mumemto_b200.merge_mums as mm
+                l, s, d = mm.read_table(g + ".bumbl")
+                got += "".join(f"{l[r]}\t{','.join(map(str, s[r]))}\t{','.join('+' if x else '-' for x in d[r])}\n" for r in range(len(l))).encode()
+            else:
+                got += util.outputs(g)[ext]
+        assert got == want[ext], (flags, k)
+    with pytest.raises(Exception, match="sharded"):
+        api.find_files(paths, str(tmp_path / "bad"), shard=(0, 2), merge=True, anchor_merge=True, _lib=simt_lib)
+    with pytest.raises(Exception, match="shard_index"):
+        api.find_files(paths, str(tmp_path / "bad"), shard=(2, 2), _lib=simt_lib)
+
+
+def test_simt_sharded_collection_repeats(simt_lib, oracle_bin, tmp_path):
+    """The same on tandem repeats / low-complexity runs: segments longer than the classifier's window, multi-member groups, many
+    occurrences per match; slice bounds fall inside long runs and must move to the next segment start."""
+    rng = np.random.default_rng(17)
+    unit, body = util.random_dna(rng, 37), util.random_dna(rng, 900)
+    docs = ["A" * 700 + body + unit * 50 + "ACGT" * 40 + body[:400],
+            "A" * 300 + util.mutate(rng, body, 0.01) + unit * 30 + "C" * 150 + body[200:600],
+            util.mutate(rng, body, 0.02) + "AC" * 400 + unit * 20 + "A" * 100]
+    p = [util.write_fasta(str(tmp_path / f"d{i}.fa"), [(f"d{i}", s)], width=77) for i, s in enumerate(docs)]
+    for flags, ks in (([], (2, 5)), (["-f", "4", "-k", "2", "-l", "15"], (3,))):
+        o = str(tmp_path / "o")
+        util.run_cli(oracle_bin, ["-o", o, *flags, *p])
+        want = util.outputs(o)
+        ext = ".mems" if "-f" in flags else ".mums"
+        for k in ks:
+            got = b""
+            for i in range(k):
+                g = str(tmp_path / f"g{k}_{i}")
+                api.find_files(p, g, shard=(i, k), _lib=simt_lib, **util.flags_to_kwargs(flags))
+                got += util.outputs(g)[ext]
+            assert got == want[ext], (flags, k)
