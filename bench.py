@@ -548,6 +548,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline AND the parity-sample check (profiling runs only)")
     ap.add_argument("--route", default=os.environ.get("MMB_ROUTE", "auto"), choices=["auto", "direct", "pfp"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sharded", action="store_true", help="N > 1: ONE collection (the N = 1 workload) on N GPUs, every rank reports its slice of the suffix "
+                    "order (SURVEY 8e(2)); strong scaling.  Without it N > 1 runs the partition-merge workload (one partition per GPU)")
     ap.add_argument("--merge-mode", action="store_true", help="N = 1 only: run the partition flags (-M -n) without an exchange, to time that mode")
     ap.add_argument("--tile-ranks", type=int, default=0, help="ranks per stream tile on the PFP route (0 = engine default)")
     ap.add_argument("--roofline-kernel", default=None, help="kernel (name substring) whose launches are timed with CUDA events for the roofline line")
@@ -557,7 +559,8 @@ def main():
     ap.add_argument("--dump-output", default=None, help="write the .mums/.mems bytes of the last end-to-end step to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1 and args.workload == "c2":
+    sharded = world > 1 and args.sharded
+    if world > 1 and args.workload == "c2" and not sharded:
         args.workload = "c5"            # several GPUs: the partition-merge configuration, one 32-genome partition per GPU
     spec = WORKLOADS[args.workload]
     flagset = spec.get("flagset", "strict")
@@ -590,7 +593,7 @@ def main():
     eng = Engine(device=local, stream=stream.cuda_stream)
 
     # ---- synthetic input: N = 1 -> the named collection; N > 1 -> one partition per rank sharing the anchor document
-    multi = world > 1
+    multi = world > 1 and not sharded           # partition-merge mode; `sharded`: every rank holds the whole N = 1 collection
     cache = os.environ.get("MMB_CACHE_DIR")      # optional: keep the generated FASTA images between runs on the same box
     cache_file = os.path.join(cache, f"{args.workload}_r{rank}_w{world}.npy") if cache else None
     imgs = None
@@ -599,7 +602,7 @@ def main():
         sz = np.load(cache_file + ".sizes.npy")
         at0 = np.concatenate([[0], np.cumsum(sz)[:-1]])
         imgs = [data[o:o + n] for o, n in zip(at0, sz)]
-    imgs = imgs or make_collection(spec, seed=1 + 1000 * rank, anchor_seed=(12345 if (multi and spec["kind"] == "pangenome") else None),
+    imgs = imgs or make_collection(spec, seed=1 + 1000 * (rank if multi else 0), anchor_seed=(12345 if (multi and spec["kind"] == "pangenome") else None),
                            first_index=0) if not (multi and spec["kind"] == "independent") else make_collection(spec, seed=1)
     if multi and spec["kind"] == "independent":
         # partitions of the Appendix-A collection cannot share an anchor unless it is the same h0: rank r keeps h0 + its own variants
@@ -631,6 +634,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
     merge_flags = multi or args.merge_mode
     opts = dict(merge=merge_flags, anchor_merge=merge_flags, route=args.route, tile_ranks=args.tile_ranks, **find_kw)
+    if sharded:
+        opts["shard"] = (rank, world)
 
     from mumemto_b200 import partition
     tdev = torch.device("cuda", local)
@@ -653,8 +658,11 @@ def main():
         st = eng.find(want_text=True, **opts)
         if multi:
             exchange(record)
+        if sharded:         # the final gather of the output slices (the only exchange of this mode), inside the timed step
+            slices_out[0], slices_out[1] = partition.gather_slices(eng, dist, world, tdev)
         return st
 
+    slices_out = [None, 0]
     out_host = None
     merged_host = None
 
@@ -662,6 +670,13 @@ def main():
         nonlocal out_host, merged_host
         eng.load_fasta_bytes(pinned_imgs)
         eng.find(want_text=True, **opts)
+        if sharded:         # every rank uploaded the whole collection; the slices are gathered on the devices and rank 0 reads them back
+            allb, n = partition.gather_slices(eng, dist, world, tdev)
+            if rank == 0:
+                if out_host is None or out_host.numel() < n:
+                    out_host = torch.empty(max(n + n // 8, 1), dtype=torch.uint8).pin_memory()
+                out_host[:n].copy_(allb, non_blocking=False)
+            return n
         n = eng.lib.mmb_text_size(eng.h)
         if out_host is None or out_host.numel() < n:
             out_host = torch.empty(max(n, 1), dtype=torch.uint8).pin_memory()
@@ -770,6 +785,12 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = total_bases / float(te.item())
 
+    total_matches = int(st["num_matches"])
+    if sharded:
+        tm = torch.tensor([total_matches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tm)
+        total_matches = int(tm.item())
+
     # ---- checks off the clock (rank 0): sampled lines against the sequences, md5 of the whole output against the reference's run on the
     # full workload when that is on record, and the byte-for-byte parity sample against the reference executed here
     verified = 0
@@ -839,12 +860,13 @@ def main():
         k_bytes = bpu * units
         k_achieved = (k_bytes / (roof_ms * 1e-3) / 1e9) if roof_ms > 0 else None
         line = {"metric": "input bases/sec end-to-end (FASTA->.mums)", "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
-                "warmup": n_warm, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "warmup": n_warm, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic", "config": {"workload": spec["desc"], "name": args.workload, "flags": FLAGSETS[flagset][0] + (["-M", "-n"] if merge_flags else []),
                                                 "l2": "flushed between steps (256 MiB write)",
-                                                "partitioning": "1 collection" if not multi else f"{world} partitions sharing anchor h0, -M -n, 1 per GPU"},
+                                                "partitioning": (f"1 collection on every GPU, {world} slices of the suffix order (1 per GPU), output slices gathered in order [SURVEY 8e(2)]" if sharded
+                                                                 else "1 collection" if not multi else f"{world} partitions sharing anchor h0, -M -n, 1 per GPU")},
                 "value_region": "device: FASTA images resident in HBM -> formatted output bytes in HBM (CUDA events); e2e adds the host<->device copies; e2e_cli (when present) is process start -> closed file",
-                "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(sum(sizes)), "d2h_bytes_per_step": int(out_bytes)},
+                "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(sum(sizes)) * (world if sharded else 1), "d2h_bytes_per_step": int(out_bytes)},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": k_achieved, "peak": peak, "unit": "GB/s",
                              "frac": (k_achieved / peak) if k_achieved else None, "traffic": traffic, "traffic_source": traffic_src,
@@ -855,7 +877,7 @@ def main():
                              "whole_path": {"achieved": achieved, "frac": achieved / peak, "algorithmic_bytes_per_base": 60.0},
                              "kernels": kernel_table},
                 "stages_ms": {k: v / args.steps for k, v in stage.items()}, "step_ms": step_ms, "per_step_stages": per_step_stages, "e2e_stages_ms": e2e_stage,
-                "matches": int(st["num_matches"]), "verified_sample_lines": int(verified), "output_md5": output_md5, "golden_full_size": golden_check,
+                "matches": int(total_matches), "verified_sample_lines": int(verified), "output_md5": output_md5, "golden_full_size": golden_check,
                 "parity_sample": parity["result"] if parity else None, "parity_sample_detail": parity,
                 "sa_rounds": int(st["sa_rounds"]), "sa_sorted_elements": int(st["sa_sorted_elements"]),
                 "text_symbols": int(st["text_symbols"]), "wall_s_timed_region": t_wall, "clocks": sampler.summary(),

@@ -50,6 +50,7 @@ struct Options {
     int device = 0;
     int gpus = 1;           // --gpus N: partition-merge over N GPUs in this process (anchor = first sequence), NCCL all-gather + device merge
     int partitions = 0;     // --partitions P (with one GPU): the same workflow with the partitions run one after the other
+    int shards = 0;         // --shards K: ONE collection, the suffix order in K slices (one per GPU with --gpus K; one after the other on one GPU)
     int trim = 0;           // --trim[=MINLEN]: post-process multi-MUMs like `mumemto trim` (mumemto/trim_mums.py); 0 = off
 };
 
@@ -86,6 +87,8 @@ static int usage() {
         "\t                                split into N groups (one per GPU, -M -n), one NCCL all-gather, merge on the device;\n"
         "\t                                writes PREFIX.mums / PREFIX.athresh like `anchor_merge` (rows in anchor order)\n"
         "\t    --partitions      [INT]     the same workflow with P partitions run one after the other on one GPU\n"
+        "\t    --shards          [INT]     ONE collection on K GPUs (--gpus K) or in K passes on one GPU: every GPU holds the whole collection and\n"
+        "\t                                reports its slice of the suffix order; the slices are written in order = the single-GPU bytes\n"
         "\t    --trim[=INT]                shorten multi-MUMs that run past the end of a sequence and drop those shorter than INT (default 20)\n"
         "\t                                afterwards, like `mumemto trim`; off by default (the reference's output, bit for bit)\n\n");
     return 0;
@@ -118,7 +121,7 @@ int main(int argc, char** argv) {
         {"arrays-in", required_argument, nullptr, 'a'}, {"keep-temp-files", no_argument, nullptr, 'K'}, {"window", required_argument, nullptr, 'w'},
         {"rare", required_argument, nullptr, 'f'}, {"binary", no_argument, nullptr, 'b'}, {"merge", no_argument, nullptr, 'M'},
         {"anchor", no_argument, nullptr, 'n'}, {"use-gsacak", no_argument, nullptr, 'g'}, {"device", required_argument, nullptr, 'd'},
-        {"gpus", required_argument, nullptr, 1000}, {"partitions", required_argument, nullptr, 1001}, {"trim", optional_argument, nullptr, 1002},
+        {"gpus", required_argument, nullptr, 1000}, {"partitions", required_argument, nullptr, 1001}, {"trim", optional_argument, nullptr, 1002}, {"shards", required_argument, nullptr, 1003},
         {nullptr, 0, nullptr, 0}};
     Options o;
     int c;
@@ -142,6 +145,7 @@ int main(int argc, char** argv) {
             case 'd': o.device = std::atoi(optarg); break;
             case 1000: o.gpus = std::atoi(optarg); break;
             case 1001: o.partitions = std::atoi(optarg); break;
+            case 1003: o.shards = std::atoi(optarg); break;
             case 1002: o.trim = optarg ? std::atoi(optarg) : 20; break;
             case 'p': case 'P': case 'K':
                 fatal("-p/-P/-K use stage files of the CPU algorithm (.dict/.parse); the GPU engine has no such stages");
@@ -224,6 +228,21 @@ int main(int argc, char** argv) {
     std::vector<fio::Source> sources;
     try { sources = fio::probe(inputs); } catch (const std::exception& ex) { fatal(ex.what()); }
     mark("probe input files");
+    if (o.shards > 1) {
+        // one collection, K slices of the suffix order (multi_gpu.cpp: run_sharded)
+        if (o.merge || o.arrays_out || !o.arrays_in.empty() || o.partitions > 1) fatal("--shards cannot be combined with -M, -A, -a or --partitions");
+        std::fprintf(stderr, " done.  (%.3f sec)\n", lap());
+        mgpu::ShardRequest rq;
+        rq.sources = &sources; rq.gpus = std::max(1, o.gpus); rq.shards = o.shards; rq.first_device = o.device; rq.use_rcomp = o.use_rcomp;
+        rq.binary = o.binary && o.rare_freq == 1; rq.min_match_len = (uint32_t)o.min_match_len; rq.num_distinct_docs = o.num_distinct_docs;
+        rq.rare_freq = o.rare_freq; rq.max_mem_freq = o.max_mem_freq; rq.trim_min_len = (o.rare_freq == 1 && o.trim > 0) ? (uint32_t)o.trim : 0;
+        rq.output_prefix = o.output_prefix;
+        std::string err;
+        status(o.rare_freq == 1 ? "finding multi-MUMs: one slice of the suffix order per GPU" : "finding multi-MEMs: one slice of the suffix order per GPU");
+        if (!mgpu::run_sharded(rq, err)) fatal(err);
+        std::fprintf(stderr, " done.  (%.3f sec)\n", lap());
+        return 0;
+    }
     if (o.gpus > 1 || o.partitions > 1) {
         // partition-merge inside this process (multi_gpu.cpp): replaces `mumemto_exec -M -n` x P + `anchor_merge` of the reference
         // workflow (mumemto/merge_mums.py:171-183 -> src/merge_candidates.cpp:170-255)

@@ -224,4 +224,96 @@ bool run(const Request& rq, std::string& error) {
     }
 }
 
+bool run_sharded(const ShardRequest& rq, std::string& error) {
+    try {
+        int ndev = 0;
+        cu(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount");
+        const std::vector<fio::Source>& src = *rq.sources;
+        if (rq.shards < 2 || rq.shards > 255) throw Fail("--shards must be between 2 and 255");
+        if (rq.gpus < 1 || rq.first_device < 0 || rq.first_device + rq.gpus > ndev)
+            throw Fail("--gpus " + std::to_string(rq.gpus) + " from device " + std::to_string(rq.first_device) + ": only " + std::to_string(ndev) + " CUDA devices");
+        if (rq.gpus > 1 && rq.gpus != rq.shards) throw Fail("--shards must equal --gpus when several GPUs are used (one slice per GPU)");
+        const bool mum_mode = rq.rare_freq == 1;
+        const int K = rq.shards;
+        struct Slice {
+            int device = 0; std::string error; std::vector<char> text; uint64_t n = 0, nd = 0;
+            std::vector<uint32_t> len; std::vector<int64_t> off; std::vector<uint8_t> plus; std::string lengths_lines; float ms = 0; uint64_t streamed = 0;
+        };
+        std::vector<Slice> sl(K);
+        for (int k = 0; k < K; ++k) sl[k].device = rq.first_device + (rq.gpus > 1 ? k : 0);
+        auto work = [&](int k) {
+            Slice& me = sl[k];
+            mmb_engine* e = nullptr;
+            try {
+                cu(cudaSetDevice(me.device), "cudaSetDevice");
+                mm(mmb_create(me.device, nullptr, &e));
+                std::vector<const fio::Source*> all;
+                for (auto& f : src) all.push_back(&f);
+                fio::DeviceImages img = fio::upload(all, me.device);
+                int rc = mmb_load_fasta_device(e, img.d_raw, img.offsets.data(), img.sizes.data(), img.sizes.size(), rq.use_rcomp ? 1 : 0);
+                img.release();
+                mm(rc);
+                mmb_options mo; mmb_default_options(&mo);
+                mo.min_match_len = rq.min_match_len; mo.num_distinct_docs = rq.num_distinct_docs; mo.rare_freq = rq.rare_freq; mo.max_mem_freq = rq.max_mem_freq;
+                mo.cli_normalise = 1; mo.want_text = (mum_mode && rq.binary) ? 0 : 1; mo.trim_min_len = mum_mode ? rq.trim_min_len : 0;
+                mo.shard_count = (uint8_t)K; mo.shard_index = (uint8_t)k;
+                mm(mmb_find(e, &mo));
+                mmb_stats st; mmb_get_stats(e, &st);
+                me.ms = st.ms_total; me.streamed = st.stream_suffixes;
+                me.n = mmb_num_matches(e); me.nd = mmb_num_docs(e);
+                if (mo.want_text) { me.text.resize(mmb_text_size(e)); if (!me.text.empty()) mm(mmb_copy_text(e, me.text.data())); }
+                else if (me.n) {
+                    me.len.resize(me.n); me.off.resize(me.n * me.nd); me.plus.resize(me.n * me.nd);
+                    mm(mmb_copy_mums(e, me.len.data(), me.off.data(), me.plus.data()));
+                }
+                if (k == 0)
+                    for (size_t d = 0; d < src.size(); ++d) {
+                        std::string cp = std::filesystem::canonical(src[d].path).string();
+                        uint64_t total = 0; size_t nr = mmb_num_records(e, d);
+                        for (size_t r = 0; r < nr; ++r) { uint64_t len; mmb_record(e, d, r, nullptr, &len); total += len; }
+                        me.lengths_lines += cp + " * " + std::to_string(total) + "\n";
+                        for (size_t r = 0; r < nr; ++r) { const char* name; uint64_t len; mmb_record(e, d, r, &name, &len); me.lengths_lines += cp + " " + name + " " + std::to_string(len) + "\n"; }
+                    }
+            } catch (const std::exception& ex) { me.error = ex.what(); }
+            if (e) mmb_destroy(e);
+        };
+        if (rq.gpus > 1) {
+            std::vector<std::thread> th;
+            for (int k = 0; k < K; ++k) th.emplace_back(work, k);
+            for (auto& t : th) t.join();
+        } else for (int k = 0; k < K; ++k) work(k);
+        for (auto& s : sl) if (!s.error.empty()) throw Fail(s.error);
+
+        uint64_t total = 0;
+        for (auto& s : sl) total += s.n;
+        if (mum_mode && rq.binary) {
+            if (total == 0) throw Fail("no multi-MUMs found: nothing to write in binary format");
+            uint64_t ns = sl[0].nd, nm = total;
+            long n = (long)ns, kk = rq.num_distinct_docs;
+            kk = kk < -n ? 2 : (kk <= 0 ? n + kk : (kk == 1 ? 2 : std::min(kk, n)));
+            uint16_t flags = (uint16_t)(0x8000 | (kk < n ? 0x2000 : 0));
+            std::vector<uint8_t> bits((nm * ns + 7) / 8, 0);
+            uint64_t at = 0;
+            for (auto& s : sl) for (uint64_t i = 0; i < s.n * ns; ++i, ++at) if (s.plus[i]) bits[at >> 3] |= (uint8_t)(0x80u >> (at & 7));
+            std::ofstream b(rq.output_prefix + ".bumbl", std::ios::binary);
+            b.write((char*)&flags, 2); b.write((char*)&ns, 8); b.write((char*)&nm, 8);
+            for (auto& s : sl) b.write((char*)s.len.data(), (std::streamsize)(s.n * 4));
+            for (auto& s : sl) b.write((char*)s.off.data(), (std::streamsize)(s.n * ns * 8));
+            b.write((char*)bits.data(), (std::streamsize)bits.size());
+        } else {
+            std::ofstream o(rq.output_prefix + (mum_mode ? ".mums" : ".mems"), std::ios::binary);
+            if (!o) throw Fail("cannot write " + rq.output_prefix);
+            for (auto& s : sl) o.write(s.text.data(), (std::streamsize)s.text.size());
+        }
+        { std::ofstream Lf(rq.output_prefix + ".lengths"); Lf << sl[0].lengths_lines; }
+        std::fprintf(stderr, "\n\t%d slices of the suffix order:", K);
+        for (int k = 0; k < K; ++k) std::fprintf(stderr, " [%d] %llu matches, %llu ranks streamed, %.1f ms;", k, (unsigned long long)sl[k].n, (unsigned long long)sl[k].streamed, sl[k].ms);
+        std::fprintf(stderr, "\n\tFound %llu matches!", (unsigned long long)total);
+        return true;
+    } catch (const std::exception& ex) {
+        error = ex.what();
+        return false;
+    }
+}
+
 }  // namespace mgpu

@@ -32,4 +32,19 @@ std::vector<std::vector<size_t>> make_partitions(size_t nfiles, size_t parts);
 // Returns false with `error` set on failure.
 bool run(const Request& rq, std::string& error);
 
+// ONE collection over several GPUs: every GPU holds the whole collection and reports the matches of its slice of the
+// suffix order (mmb_options.shard_index / shard_count; slices are cut at segment boundaries, which no reportable interval crosses); the
+// slices are written one after the other, so PREFIX.mums / .mems / .bumbl are the bytes of the single-GPU run.  No collective: the only
+// exchange is the final gather of output bytes through the host.  With gpus == 1 the slices run one after the other (tests).
+struct ShardRequest {
+    const std::vector<fio::Source>* sources = nullptr;
+    int gpus = 1, shards = 2, first_device = 0;
+    bool use_rcomp = true, binary = false;
+    uint32_t min_match_len = 20;
+    int num_distinct_docs = 0, rare_freq = 1, max_mem_freq = 0;
+    uint32_t trim_min_len = 0;
+    std::string output_prefix;
+};
+bool run_sharded(const ShardRequest& rq, std::string& error);
+
 }  // namespace mgpu

@@ -93,3 +93,24 @@ def partition_merge(engine, dist, world, device, fetch=True):
     """Everything after the per-rank find(): exchange + merge.  Every rank ends up with the merged result."""
     parts = gather_partitions(local_partition(engine, device), dist, world)
     return merge_gathered(engine, parts, fetch=fetch)
+
+
+def gather_slices(engine, dist, world, device):
+    """SURVEY 8e(2), one collection sharded over ranks by slice of the suffix order: the output bytes of every rank's slice, in rank order
+    (= the bytes of the unsharded run).  One size exchange and ONE all-gather of the padded text slices; returns (bytes tensor on
+    `device` holding all slices back to back, total length)."""
+    n = int(engine.lib.mmb_text_size(engine.h))
+    sizes = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(sizes, torch.tensor([n], dtype=torch.int64, device=device))
+    sizes = sizes.tolist()
+    stride = (max(sizes) + 15) & ~15
+    mine = torch.zeros(max(stride, 16), dtype=torch.uint8, device=device)
+    if n:
+        if device.type == "cuda":
+            mine[:n].copy_(torch.as_tensor(_DevArray(engine.lib.mmb_text_device(engine.h), (n,), "|u1"), device=device))
+        else:
+            mine[:n].copy_(torch.from_numpy(np.frombuffer(engine.text(), dtype=np.uint8).copy()))
+    everything = torch.empty(world * mine.numel(), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(everything, mine)
+    out = torch.cat([everything[r * mine.numel(): r * mine.numel() + sizes[r]] for r in range(world)]) if sum(sizes) else everything[:0]
+    return out, int(sum(sizes))

@@ -438,3 +438,31 @@ def test_midsize_pangenome_golden_md5(cuda_lib, tmp_path, flagset):
     with open(str(tmp_path / "out") + ext, "rb") as f:
         data = f.read()
     assert len(data) == entry["bytes"][ext] and hashlib.md5(data).hexdigest() == entry["md5"][ext]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["passes", "gpus"])
+def test_cli_sharded_collection(ref_dir, tmp_path, mode):
+    """`mumemto_exec --shards K` -- ONE collection, every GPU (or pass) reports its slice of the suffix order, slices written
+    in order.  The files must be the bytes the reference writes for the whole collection (strict, -k -1, MEMs, .bumbl)."""
+    import bench
+    import subprocess
+    import torch
+    K = 3
+    extra = []
+    if mode == "gpus":
+        if torch.cuda.device_count() < 2:
+            pytest.skip("needs two GPUs")
+        K = min(torch.cuda.device_count(), 4)
+        extra = ["--gpus", str(K)]
+    files = bench.SampleFiles(dict(N=12, L=120000, kind="pangenome"))
+    for i, flags in enumerate(([], ["-k", "-1"], ["-f", "3", "-F", "100"], ["-b"])):
+        ref, got = str(tmp_path / f"ref{i}"), str(tmp_path / f"got{i}")
+        subprocess.run([os.path.join(ref_dir, "mumemto_exec"), "-o", ref, *flags, *files.paths], check=True, capture_output=True)
+        util.run_cli(os.path.join(BIN, "mumemto_exec"), ["-o", got, "--shards", str(K), *extra, *flags, *files.paths])
+        a, b = util.outputs(got), util.outputs(ref)
+        assert a == b and sum(map(len, b.values())) > 1000, flags
+        assert open(got + ".lengths").read() == open(ref + ".lengths").read()
+    r = util.run_cli(os.path.join(BIN, "mumemto_exec"), ["-o", str(tmp_path / "bad"), "--shards", "2", "-M", "-n", *files.paths], check=False)
+    assert r.returncode == 1 and b"--shards cannot be combined" in r.stderr
+    files.close()

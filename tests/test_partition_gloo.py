@@ -58,3 +58,41 @@ def test_partition_merge_over_gloo(simt_lib, oracle_bin, tmp_path, groups):
     util.run_cli(oracle_bin, ["-o", str(tmp_path / "all"), "-M", "-n", *paths])
     assert sorted(want_mums.splitlines()) == sorted(open(tmp_path / "all.mums", "rb").read().splitlines())
     assert want_thr == open(tmp_path / "all.athresh", "rb").read()
+
+
+SHARD_WORKER = r'''
+import os, sys, ctypes, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+from mumemto_b200 import _binding, partition
+from mumemto_b200._binding import Engine
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+lib = _binding.declare(ctypes.CDLL(os.path.join({root!r}, "tests", "simt", "_build", "libmumemto_b200_simt.so")))
+paths = [os.path.join({data!r}, "h%d.fa" % i) for i in range({n})]
+e = Engine(_lib=lib)
+e.load_fasta_files(paths)
+st = e.find(shard=(rank, world), **{kw!r})
+assert st["route"] == 2 and st["pruned"]
+out, n = partition.gather_slices(e, dist, world, torch.device("cpu"))
+open(os.path.join({out!r}, "sharded_rank%d.out" % rank), "wb").write(out.numpy()[:n].tobytes())
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world,flags", [(2, []), (3, ["-f", "3", "-F", "100"])])
+def test_sharded_collection_over_gloo(simt_lib, oracle_bin, tmp_path, world, flags):
+    """SURVEY 8e(2) host logic at world_size 2 / 3: every rank holds the whole collection and finds the matches of its slice of the suffix
+    order; one size exchange + one all-gather of the output slices; every rank ends up with the bytes of the single-process run."""
+    data = str(tmp_path / "data")
+    paths = util.appendix_a(data, N=5, L=3000, seed=13, identical_ends=True, snp=0.015, width=70)
+    script = tmp_path / "worker.py"
+    script.write_text(SHARD_WORKER.format(root=ROOT, data=data, out=str(tmp_path), n=len(paths), kw=util.flags_to_kwargs(flags)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29520 + world))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(29530 + world), str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    util.run_cli(oracle_bin, ["-o", str(tmp_path / "all"), *flags, *paths])
+    want = open(str(tmp_path / "all") + (".mems" if flags else ".mums"), "rb").read()
+    assert len(want) > 100
+    for rank in range(world):
+        assert open(tmp_path / f"sharded_rank{rank}.out", "rb").read() == want
