@@ -62,27 +62,41 @@ __device__ __forceinline__ u32 block_scan(u32 mine, u32* total) {
     return before + inc - mine;
 }
 
-// Pass 1: every thread reads the 28 bytes around its 16 positions once (one 128-bit load + three words), tests the 16 windows from
-// registers and keeps the result as a 16-bit mask; the block's trigger count goes to block_count.
+// Pass 1: every thread reads the bytes around its 16 positions once (the window's history rounded up to whole words + one 128-bit load),
+// tests the 16 windows from registers and keeps the result as a 16-bit mask; the block's trigger count goes to block_count.
+constexpr u32 TRIG_HIST = (PFP_W - 1 + 3) / 4 * 4;      // bytes of history before the thread's first position, a multiple of 4
+constexpr u32 TRIG_WORDS = TRIG_HIST / 4 + 4;
 __global__ void __launch_bounds__(TPB) trigger_masks(const u8* __restrict__ text, u64 n, u16* __restrict__ masks, u32* __restrict__ block_count) {
     u64 e0 = (u64)blockIdx.x * SCAN_BLOCK + (u64)threadIdx.x * 16;
     u32 mask = 0;
     if (e0 < n) {
-        u32 w[7];                                       // bytes e0-12 .. e0+15 (the text allocation is 16-byte aligned with 64 bytes of slack)
-        if (e0) { const u32* q = reinterpret_cast<const u32*>(text + e0 - 12); w[0] = q[0]; w[1] = q[1]; w[2] = q[2]; }
-        else { w[0] = w[1] = w[2] = 0; }
+        u32 w[TRIG_WORDS];                              // bytes e0 - TRIG_HIST .. e0 + 15 (the text allocation is 16-byte aligned with 64 bytes of slack)
+        if (e0 >= TRIG_HIST) {
+            const u32* q = reinterpret_cast<const u32*>(text + e0 - TRIG_HIST);
+#pragma unroll
+            for (u32 i = 0; i < TRIG_HIST / 4; ++i) w[i] = q[i];
+        } else {                                        // the first thread(s) of the text: positions before 0 read as zero
+#pragma unroll
+            for (u32 i = 0; i < TRIG_HIST / 4; ++i) {
+                u32 v = 0;
+#pragma unroll
+                for (u32 b = 0; b < 4; ++b) { u64 at = e0 + 4 * i + b; if (at >= TRIG_HIST) v |= (u32)text[at - TRIG_HIST] << (8 * b); }
+                w[i] = v;
+            }
+        }
         uint4 c = *reinterpret_cast<const uint4*>(text + e0);
-        w[3] = c.x; w[4] = c.y; w[5] = c.z; w[6] = c.w;
+        w[TRIG_HIST / 4] = c.x; w[TRIG_HIST / 4 + 1] = c.y; w[TRIG_HIST / 4 + 2] = c.z; w[TRIG_HIST / 4 + 3] = c.w;
 #define TRIG_BYTE(b) ((w[(b) >> 2] >> (((b) & 3) * 8)) & 0xffu)
-        // T[e0+k] is byte 12+k of w[]; its window starts at byte 3+k
+        // T[e0+k] is byte TRIG_HIST + k of w[]; its window starts PFP_W - 1 bytes earlier
+        constexpr u32 first = TRIG_HIST - (PFP_W - 1);
         u32 h = 0;
 #pragma unroll
-        for (u32 i = 0; i < PFP_W; ++i) h = h * TRIG_B + TRIG_BYTE(3 + i);
+        for (u32 i = 0; i < PFP_W; ++i) h = h * TRIG_B + TRIG_BYTE(first + i);
 #pragma unroll
         for (u32 k = 0; k < 16; ++k) {
             u64 e = e0 + k;
             if (e >= PFP_W && e < n && hash_triggers(h)) mask |= 1u << k;
-            if (k < 15) h = h * TRIG_B + TRIG_BYTE(13 + k) - TRIG_BYTE(3 + k) * TRIG_B10;
+            if (k < 15) h = h * TRIG_B + TRIG_BYTE(first + PFP_W + k) - TRIG_BYTE(first + k) * TRIG_B10;
         }
 #undef TRIG_BYTE
     }
@@ -696,7 +710,7 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
         // segments get coarser (t = min(-l, key symbols)), at C2 the stream grows by 7.6 % and the sort saves 5.3 ms: 330.8 -> 328.5 ms;
         // 16 symbols lose (the stream doubles: 352.8 ms).  -M keeps all 21: its threshold-only segments need t = -l.  MMB_KEY_SYMBOLS
         // overrides (never below w + 2: the pruned route needs t > w).
-        if (!prune.merge && cpk > 18) cpk = 18;
+        { const u32 narrow = std::max(18u, PFP_W + 2); if (!prune.merge && cpk > narrow) cpk = narrow; }      // with w = 19 this is 21: no narrowing
         if (const char* ks = getenv("MMB_KEY_SYMBOLS")) { u32 v = (u32)atoi(ks); if (v >= PFP_W + 2 && v <= 64 / bits) cpk = v; }
         DevBuf<u8> d_lut; d_lut.alloc(256, s);
         MMB_CUDA(cudaMemcpyAsync(d_lut.p, lut.data(), 256, cudaMemcpyHostToDevice, s));

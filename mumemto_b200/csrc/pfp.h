@@ -16,7 +16,12 @@
 
 namespace mmb {
 
-constexpr u32 PFP_W = 10;           // window (reference default -w 10)
+constexpr u32 PFP_W = 19;           // window.  The reference defaults to -w 10; the outputs do not depend on it, the cost does:
+                                    // a dictionary suffix is valid when it is longer than w, so with w = 19 every valid suffix has at least
+                                    // 20 = the default -l symbols and its segment is decided by the key alone.  With w = 10 the positions
+                                    // 11..19 symbols before a phrase end (9 % of the text) formed huge undecidable groups (all text positions
+                                    // sharing an 11-, 12- or 13-mer that ends in a trigger window: ~3000 / 760 / 190 suffixes each) that made
+                                    // up more than half of the pruned stream and all of its large merges.
 constexpr u32 PFP_P = 100;          // modulus (reference default -m 100)
 
 // -M on the pruned route, collections of at most 64 documents: which documents the occurrences of a phrase lie in.

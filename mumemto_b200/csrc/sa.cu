@@ -211,13 +211,11 @@ __global__ void __launch_bounds__(TPB) sort_groups_block(const Group* __restrict
     __syncthreads();
     for (u32 k = 2; k <= n2; k <<= 1) {
         for (u32 j = k >> 1; j > 0; j >>= 1) {
-            for (u32 e = threadIdx.x; e < n2; e += blockDim.x) {
-                u32 partner = e ^ j;
-                if (partner > e) {
-                    u64 a = item[e], b = item[partner];
-                    bool up = (e & k) == 0;
-                    if ((a > b) == up) { item[e] = b; item[partner] = a; }
-                }
+            for (u32 t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {     // one thread per compare-exchange pair
+                u32 e = ((t & ~(j - 1)) << 1) | (t & (j - 1)), partner = e | j;
+                u64 a = item[e], b = item[partner];
+                bool up = (e & k) == 0;
+                if ((a > b) == up) { item[e] = b; item[partner] = a; }
             }
             __syncthreads();
         }
@@ -423,14 +421,12 @@ __global__ void __launch_bounds__(TPB) sort_dgroups_block(const Group* __restric
     __syncthreads();
     for (u32 k = 2; k <= n2; k <<= 1) {
         for (u32 j = k >> 1; j > 0; j >>= 1) {
-            for (u32 e = threadIdx.x; e < n2; e += blockDim.x) {
-                u32 partner = e ^ j;
-                if (partner > e) {
-                    u64 a = key[e], b = key[partner]; u16 ia = idx[e], ib = idx[partner];
-                    bool up = (e & k) == 0;
-                    bool gt = a > b || (a == b && ia > ib);
-                    if (gt == up) { key[e] = b; key[partner] = a; idx[e] = ib; idx[partner] = ia; }
-                }
+            for (u32 t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {     // one thread per compare-exchange pair
+                u32 e = ((t & ~(j - 1)) << 1) | (t & (j - 1)), partner = e | j;
+                u64 a = key[e], b = key[partner]; u16 ia = idx[e], ib = idx[partner];
+                bool up = (e & k) == 0;
+                bool gt = a > b || (a == b && ia > ib);
+                if (gt == up) { key[e] = b; key[partner] = a; idx[e] = ib; idx[partner] = ia; }
             }
             __syncthreads();
         }

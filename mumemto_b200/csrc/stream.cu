@@ -326,12 +326,10 @@ __global__ void __launch_bounds__(TPB) merge_small(const u64* __restrict__ group
     __syncthreads();
     for (u32 k = 2; k <= n2; k <<= 1)
         for (u32 j = k >> 1; j > 0; j >>= 1) {
-            for (u32 e = threadIdx.x; e < n2; e += blockDim.x) {
-                u32 partner = e ^ j;
-                if (partner > e) {
-                    u64 a = item[e], b = item[partner];
-                    if ((a > b) == ((e & k) == 0)) { item[e] = b; item[partner] = a; }
-                }
+            for (u32 t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {     // one thread per compare-exchange PAIR (no idle partner half)
+                u32 e = ((t & ~(j - 1)) << 1) | (t & (j - 1)), partner = e | j;
+                u64 a = item[e], b = item[partner];
+                if ((a > b) == ((e & k) == 0)) { item[e] = b; item[partner] = a; }
             }
             __syncthreads();
         }
@@ -644,6 +642,7 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
         }
         MMB_LAUNCH(collect_multi, ceil_div(nm, TPB), TPB, 0, s, k0, k1, K, (const u32*)glcp.p, (const u64*)out_base.p, tiny.p, small.p, large.p, counts.p);
         std::vector<u32> c = to_host(counts.p, 3, s);
+        if (getenv("MMB_DEBUG")) fprintf(stderr, "[stream] tile members %u fresh ranks %llu: multi-member groups by size: <=256: %u, <=2048: %u, larger: %u\n", nm, (unsigned long long)fresh, c[2], c[0], c[1]);
         if (c[2]) {         // two instances: up to 64 suffixes (2 per lane) and up to 256 (8 per lane); each skips the groups of the other
             auto merge_warp_2 = merge_warp<2, 0>; auto merge_warp_8 = merge_warp<8, 64>;
             MMB_LAUNCH(merge_warp_2, ceil_div((u64)c[2] * 32, TPB), TPB, 0, s, (const u64*)tiny.p, c[2], k0, (const u64*)out_base.p, (const u32*)glcp.p, (const u32*)mem_i.p,
@@ -666,7 +665,8 @@ void stream_suffixes(const u8* text, const PfpIndex& ix, u64 tile_ranks, u32 hal
             dim3 grid(nl, 32);
             MMB_LAUNCH(large_gather, grid, TPB, 0, s, (const u64*)large.p, (const u64*)fbase.p, k0, (const u64*)out_base.p, lead, (const u64*)sa.p,
                        (const u32*)key.p, fk_a.p, fv_a.p);
-            prim::sort_pairs64(fk_a.p, fk_b.p, fv_a.p, fv_b.p, ftotal, 0, 64, s);
+            int seq_bits = 1; while ((1ull << seq_bits) < (u64)nl) ++seq_bits;      // keys are (group number << 32 | rank): the bits above are zero
+            prim::sort_pairs64(fk_a.p, fk_b.p, fv_a.p, fv_b.p, ftotal, 0, 32 + seq_bits, s);
             MMB_LAUNCH(large_scatter, ceil_div(ftotal, TPB), TPB, 0, s, (const u64*)large.p, (const u64*)fbase.p, ftotal, k0, (const u64*)out_base.p,
                        (const u32*)glcp.p, (const u32*)mem_i.p, (const u32*)ix.limit.p, (const u32*)ix.s_lcp.p, (const u32*)ix.rmq.p, ix.rmq_blocks, lead,
                        (const u64*)fk_b.p, (const u64*)fv_b.p, sa.p, lcp.p);
