@@ -566,7 +566,7 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
             prune.shard_index = shards > 1 ? opts->shard_index : 0; prune.shard_count = shards;
             pfp_finish(e->text.text.p, n, ix, pp, s, prune);
             if (shards > 1 && (!ix.pruned || ix.full_stream))
-                throw Error(32, "a sharded call needs segment pruning, and this collection could not be pruned (-l below 20, or a very long low-complexity phrase)");
+                throw Error(32, "a sharded call needs segment pruning, and this collection could not be pruned (-l below 11, or a very long low-complexity phrase)");
             pp = PfpParse();
             e->stats.ms_sa = t.stop() + ms_parse;
             e->stats.ms_lcp = 0;
@@ -579,7 +579,7 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
             // ranks per stream tile: 17 B per rank of tile buffers; C2 measured 745 / 731 / 722 ms per step at 2^28 / 2^29 / 2^30
             u64 tile_ranks = opts->tile_ranks ? opts->tile_ranks : (1ull << 30);
             if (hi == 0) {          // unbounded: one tile or nothing
-                if (!ix.pruned || ix.full_stream) throw Error(31, "unbounded total frequency (-f 0 with -F 0): the suffix stream could not be pruned (-l below 20, or a very long low-complexity phrase); use the direct route (text below 2^31 symbols)");
+                if (!ix.pruned || ix.full_stream) throw Error(31, "unbounded total frequency (-f 0 with -F 0): the suffix stream could not be pruned (-l below 11, or a very long low-complexity phrase); use the direct route (text below 2^31 symbols)");
                 tile_ranks = 1ull << 62; halo = 0; e->prm.whole_stream = 1;
             }
             struct Consumer : TileConsumer {

@@ -720,7 +720,9 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
         MMB_LAUNCH(dict_keys, ceil_div(dsize, TPB), TPB, 0, s, (const u8*)ix.dict.p, (const u32*)ix.limit.p, dsize, (const u8*)d_lut.p, bits, cpk, ka.p, va.p);
         // Pruned route: needs the longer-than-w flag in the key (cpk > w) and a segment prefix of at least w + 1 symbols.
         const u32 t = std::min(prune.min_len, cpk);
-        const bool try_pruned = cpk > PFP_W && t > PFP_W && !getenv("MMB_NO_PRUNE");
+        // t may be at or below w: every owned suffix has more than w >= t symbols then (none is "short"), and a suffix of at most w symbols
+        // that shares its first t symbols with owned ones sits inside their segment without owning anything (validated by the fuzzer)
+        const bool try_pruned = cpk > PFP_W && t > 10 && !getenv("MMB_NO_PRUNE");
         if (try_pruned) {
             prim::sort_pairs(ka.p, kb.p, va.p, ix.sa_d.p, dsize, 0, (int)(bits * cpk), s);
             ka.release(); va.release();

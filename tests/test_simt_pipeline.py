@@ -418,7 +418,7 @@ def test_simt_sharded_collection_repeats(simt_lib, oracle_bin, tmp_path):
             "A" * 300 + util.mutate(rng, body, 0.01) + unit * 30 + "C" * 150 + body[200:600],
             util.mutate(rng, body, 0.02) + "AC" * 400 + unit * 20 + "A" * 100]
     p = [util.write_fasta(str(tmp_path / f"d{i}.fa"), [(f"d{i}", s)], width=77) for i, s in enumerate(docs)]
-    for flags, ks in (([], (2, 5)), (["-f", "4", "-k", "2", "-l", "21"], (3,))):
+    for flags, ks in (([], (2, 5)), (["-f", "4", "-k", "2", "-l", "15"], (3,))):
         o = str(tmp_path / "o")
         util.run_cli(oracle_bin, ["-o", o, *flags, *p])
         want = util.outputs(o)
