@@ -3,7 +3,8 @@
 NVCC     ?= /usr/local/cuda/bin/nvcc
 CXX      ?= g++
 ARCH     := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS  := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden,-Wall,-Wno-unknown-pragmas --expt-relaxed-constexpr
+EXTRA_NVFLAGS ?=
+NVFLAGS  := $(ARCH) $(EXTRA_NVFLAGS) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden,-Wall,-Wno-unknown-pragmas --expt-relaxed-constexpr
 CSRC     := mumemto_b200/csrc
 CU       := $(wildcard $(CSRC)/*.cu)
 HOSTCPP  := $(wildcard $(CSRC)/library_api.cpp)

@@ -710,8 +710,8 @@ void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t 
         // segments get coarser (t = min(-l, key symbols)), at C2 the stream grows by 7.6 % and the sort saves 5.3 ms: 330.8 -> 328.5 ms;
         // 16 symbols lose (the stream doubles: 352.8 ms).  -M keeps all 21: its threshold-only segments need t = -l.  MMB_KEY_SYMBOLS
         // overrides (never below w + 2: the pruned route needs t > w).
-        { const u32 narrow = std::max(18u, PFP_W + 2); if (!prune.merge && cpk > narrow) cpk = narrow; }      // with w = 19 this is 21: no narrowing
-        if (const char* ks = getenv("MMB_KEY_SYMBOLS")) { u32 v = (u32)atoi(ks); if (v >= PFP_W + 2 && v <= 64 / bits) cpk = v; }
+        { const u32 narrow = std::max(18u, PFP_W + 1); if (!prune.merge && cpk > narrow) cpk = narrow; }      // the key must hold symbol w (longer-than-w flag)
+        if (const char* ks = getenv("MMB_KEY_SYMBOLS")) { u32 v = (u32)atoi(ks); if (v >= PFP_W + 1 && v <= 64 / bits) cpk = v; }
         DevBuf<u8> d_lut; d_lut.alloc(256, s);
         MMB_CUDA(cudaMemcpyAsync(d_lut.p, lut.data(), 256, cudaMemcpyHostToDevice, s));
         MMB_CUDA(cudaStreamSynchronize(s));       // lut lives on this stack frame

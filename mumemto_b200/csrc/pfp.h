@@ -16,12 +16,19 @@
 
 namespace mmb {
 
-constexpr u32 PFP_W = 19;           // window.  The reference defaults to -w 10; the outputs do not depend on it, the cost does:
-                                    // a dictionary suffix is valid when it is longer than w, so with w = 19 every valid suffix has at least
-                                    // 20 = the default -l symbols and its segment is decided by the key alone.  With w = 10 the positions
-                                    // 11..19 symbols before a phrase end (9 % of the text) formed huge undecidable groups (all text positions
-                                    // sharing an 11-, 12- or 13-mer that ends in a trigger window: ~3000 / 760 / 190 suffixes each) that made
-                                    // up more than half of the pruned stream and all of its large merges.
+#ifndef MMB_PFP_W
+#define MMB_PFP_W 15
+#endif
+constexpr u32 PFP_W = MMB_PFP_W;    // window.  The reference defaults to -w 10; the outputs do not depend on it, the cost does.
+                                    // A dictionary suffix is valid when it is longer than w.  The text positions whose valid suffix has L < -l
+                                    // symbols cannot be pruned from the key; grouped by content they are ALL text positions sharing an L-mer that
+                                    // ends in a trigger window: about 2 N |genome| / 4^L suffixes per group (64 x 100 Mbp: 3050 for L = 11, 763
+                                    // for 12, 190 for 13, 48 for 14, 12 for 15, 3 for 16).  With w = 10 the groups of L = 11..13 survived every
+                                    // size rule, made up more than half of the pruned stream (684 M ranks at C2) and caused all of its large
+                                    // merges.  From w = 15 on the smallest valid suffix has 16 symbols and such groups fall under the size
+                                    // rule.  Measured at C2 / C4 / one C5 partition (ms): w = 10: 330.7 / 392.4 / 223.5; w = 19: 305.4 / 341.8 /
+                                    // 203.5; w = 17: 301.4 / 339.0 / 204.7; w = 15: 297.2 / 336.4 / 205.9 (a smaller w = a smaller dictionary:
+                                    // phrases overlap by w; and w <= 17 lets the initial sort use 18-symbol keys = 7 radix passes).
 constexpr u32 PFP_P = 100;          // modulus (reference default -m 100)
 
 // -M on the pruned route, collections of at most 64 documents: which documents the occurrences of a phrase lie in.
