@@ -325,65 +325,90 @@ __global__ void __launch_bounds__(TPB) rank_words_fix_last_phrase(const u32* __r
         if (sa_d[q] == i) rk[q] |= RK_OWN;
 }
 
-// Class of every rank that is longer than w: what its segment needs (CLS_*).  The block stages the rank words of its ranks plus
-// SEG_LIMIT ranks of context on both sides; the thread that finds a segment START walks the segment once and leaves its class at the
-// start's slot, then every rank looks up the class of the start to its left (a few steps on pangenome-like input).
-// (A walk-free variant -- segment bounds by bit scans in a start bitmap, aggregates as differences of block prefix sums -- was SLOWER:
-// 14.7 -> 20.2 ms at C2; three block scans with barriers cost more than the divergent walks.)
+// Class of every rank that is longer than w: what its segment needs (CLS_*).  The block stages the rank words of its 256 ranks plus
+// SEG_LIMIT ranks of context on both sides.  A segment that lies inside the 32 ranks of one warp (nearly all do: segments are a few
+// ranks long) is classified without any walk: its bounds come from bit scans of the warp's segment-start ballot, and everything the
+// class depends on is a difference of two warp prefix sums --
+//   A: occurrences | whole phrases | short suffixes | saturated counts          B: suffixes n | sum of preceding symbols | sum of squares
+// (all preceding symbols equal  <=>  n * sum(x^2) == (sum x)^2).  Only the lanes whose segment crosses the warp's window walk it, left
+// to its start and right to its end, as every rank did in the first versions (590 warp instructions per warp, 18 per dictionary
+// position: a warp walked as far as its longest segment, twice).  A block-level walk-free variant (start bitmap + three block prefix
+// sums with barriers) had measured slower than the walks: 14.7 -> 20.2 ms at C2.
+__device__ __forceinline__ u8 segment_class(u64 total, bool uniform, bool has_start, bool has_short, bool saturated, const PfpPrune& prune, u32 seg_is_interval) {
+    const u8 general = CLS_STREAM | CLS_REFINE;
+    u8 c = 0;
+    if (saturated) c = general;
+    else if (total >= prune.size_lo) {
+        if (!uniform) c = general;
+        // -M: a segment of exactly N suffixes, all at least t = -l symbols long, is one interval of length >= -l
+        else if (prune.merge) c = (seg_is_interval && !has_short && total == prune.ndocs) ? CLS_THRESH : general;
+    }
+    if (has_start) c |= CLS_REFINE | CLS_HAS_START;             // phrase ranks need the exact place of every whole phrase
+    return c;
+}
 __global__ void __launch_bounds__(TPB) classify_segments(const u32* __restrict__ rk, u32 dsize, PfpPrune prune, u32 seg_is_interval, u8* __restrict__ cls) {
     constexpr u32 SPAN = TPB + 2 * SEG_LIMIT + 1;
-    constexpr u8 TOO_LONG = 0x80;
     __shared__ u32 tile[SPAN];
-    __shared__ u8 head_cls[SPAN];
     const i64 base = (i64)blockIdx.x * TPB - SEG_LIMIT;
-    for (u32 x = threadIdx.x; x < SPAN; x += TPB) {
-        i64 q = base + x;
-        tile[x] = (q >= 0 && q < (i64)dsize) ? rk[q] : RK_HB;       // outside the array: a segment start that owns nothing
+    for (u32 y = threadIdx.x; y < SPAN; y += TPB) {
+        i64 q = base + y;
+        tile[y] = (q >= 0 && q < (i64)dsize) ? rk[q] : RK_HB;       // outside the array: a segment start that owns nothing
     }
     __syncthreads();
     const u8 all = CLS_STREAM | CLS_REFINE | CLS_HAS_START;         // without a verdict: keep, and assume the segment may hold a whole phrase
-    const u8 general = CLS_STREAM | CLS_REFINE;
-    if (prune.enabled) {
-        for (u32 y = threadIdx.x; y < TPB + SEG_LIMIT; y += TPB) {     // every start this block's ranks can belong to
-            if (!(tile[y] & RK_HB)) continue;
-            u64 total = 0; u32 sym = 0xffffffffu; bool uniform = true, has_start = false, saturated = false, has_short = false;
-            u32 b = y, steps = 0;
-            for (;;) {
-                u32 v = tile[b];
-                if (v & RK_OWN) {
-                    u32 c = (v >> 9) & RK_CNT_MAX, bsym = v & 0x1ffu;
-                    total += c; saturated |= c == RK_CNT_MAX; has_short |= (v & RK_SHORT) != 0;
-                    if (bsym == RK_START) { has_start = true; uniform = false; }
-                    else if (sym == 0xffffffffu) sym = bsym;
-                    else if (sym != bsym) uniform = false;
-                }
-                if ((tile[b + 1] & RK_HB) || steps == SEG_LIMIT) break;
-                ++b; ++steps;
-            }
-            u8 c = 0;
-            if (!(tile[b + 1] & RK_HB)) c = TOO_LONG;                   // more than SEG_LIMIT + 1 ranks: low-complexity repeats, kept as they are
-            else {
-                if (saturated) c = general;
-                else if (total >= prune.size_lo) {
-                    if (!uniform) c = general;
-                    // -M: a segment of exactly N suffixes, all at least t = -l symbols long, is one interval of length >= -l
-                    else if (prune.merge) c = (seg_is_interval && !has_short && total == prune.ndocs) ? CLS_THRESH : general;
-                }
-                if (has_start) c |= CLS_REFINE | CLS_HAS_START;         // phrase ranks need the exact place of every whole phrase
-            }
-            head_cls[y] = c;
-        }
+    const u32 p = blockIdx.x * TPB + threadIdx.x, x = threadIdx.x + SEG_LIMIT, lane = threadIdx.x & 31, wbase = x - lane;
+    const u32 v = tile[x];
+    if (!prune.enabled) { if (p < dsize) cls[p] = (v & RK_OWN) ? all : (u8)0; return; }       // uniform over the grid
+    // ---- the warp's window: tile[wbase .. wbase + 32)
+    const unsigned hb = __ballot_sync(FULL, (v & RK_HB) != 0);
+    const bool next_hb = (tile[wbase + 32] & RK_HB) != 0;
+    const unsigned le = hb & (0xffffffffu >> (31 - lane));
+    const int a = le ? 31 - __clz((int)le) : -1;                                    // lane of the segment's first rank, -1: before the window
+    const unsigned gt = lane == 31 ? 0u : hb & (0xffffffffu << (lane + 1));
+    const int e = gt ? __ffs((int)gt) - 1 : (next_hb ? 32 : 33);                    // lane of the next segment's first rank, 33: beyond the window
+    u64 sa = 0, sb = 0;
+    if (v & RK_OWN) {
+        u32 c = (v >> 9) & RK_CNT_MAX, sym = v & 0x1ffu;
+        bool start = sym == RK_START;
+        sa = (u64)c | ((u64)(start ? 1 : 0) << 32) | ((u64)((v & RK_SHORT) ? 1 : 0) << 42) | ((u64)(c == RK_CNT_MAX ? 1 : 0) << 52);
+        if (!start) sb = 1ull | ((u64)sym << 10) | ((u64)(sym * sym) << 28);
     }
-    __syncthreads();
-    u32 p = blockIdx.x * TPB + threadIdx.x;
+#pragma unroll
+    for (u32 d = 1; d < 32; d <<= 1) {
+        u64 oa = __shfl_up_sync(FULL, sa, d), ob = __shfl_up_sync(FULL, sb, d);
+        if (lane >= d) { sa += oa; sb += ob; }
+    }
+    const int last = min(max(e - 1, 0), 31), before = max(a - 1, 0);
+    u64 A = __shfl_sync(FULL, sa, last), B = __shfl_sync(FULL, sb, last);
+    const u64 A0 = __shfl_sync(FULL, sa, before), B0 = __shfl_sync(FULL, sb, before);
+    if (a > 0) { A -= A0; B -= B0; }
     if (p >= dsize) return;
-    u32 x = threadIdx.x + SEG_LIMIT;
-    if (!(tile[x] & RK_OWN)) { cls[p] = 0; return; }
-    if (!prune.enabled) { cls[p] = all; return; }
-    u32 a = x, steps = 0;
-    while (!(tile[a] & RK_HB) && steps < SEG_LIMIT) { --a; ++steps; }
-    u8 c = (tile[a] & RK_HB) ? head_cls[a] : TOO_LONG;
-    cls[p] = c == TOO_LONG ? all : c;
+    if (!(v & RK_OWN)) { cls[p] = 0; return; }
+    if (a >= 0 && e <= 32) {
+        const u64 n = B & 0x3ff, s1 = (B >> 10) & 0x3ffff, s2 = B >> 28;
+        const bool has_start = ((A >> 32) & 0x3ff) != 0;
+        cls[p] = segment_class(A & 0xffffffffull, !has_start && n * s2 == s1 * s1, has_start, ((A >> 42) & 0x3ff) != 0, ((A >> 52) & 0x3ff) != 0, prune, seg_is_interval);
+        return;
+    }
+    // ---- the segment crosses the window: walk to its start, then over it (at most SEG_LIMIT + 1 ranks; longer ones are kept as they are)
+    u32 s0 = x, steps = 0;
+    while (!(tile[s0] & RK_HB) && steps < SEG_LIMIT) { --s0; ++steps; }
+    if (!(tile[s0] & RK_HB)) { cls[p] = all; return; }
+    u64 total = 0; u32 sym = 0xffffffffu; bool uniform = true, has_start = false, saturated = false, has_short = false;
+    u32 b = s0; steps = 0;
+    for (;;) {
+        u32 w = tile[b];
+        if (w & RK_OWN) {
+            u32 c = (w >> 9) & RK_CNT_MAX, bsym = w & 0x1ffu;
+            total += c; saturated |= c == RK_CNT_MAX; has_short |= (w & RK_SHORT) != 0;
+            if (bsym == RK_START) { has_start = true; uniform = false; }
+            else if (sym == 0xffffffffu) sym = bsym;
+            else if (sym != bsym) uniform = false;
+        }
+        if ((tile[b + 1] & RK_HB) || steps == SEG_LIMIT) break;
+        ++b; ++steps;
+    }
+    cls[p] = (tile[b + 1] & RK_HB) ? segment_class(total, uniform, has_start, has_short, saturated, prune, seg_is_interval) : all;
 }
 
 // Sharding by suffix-order slice: slice bounds are moved forward to the next segment start (no reportable interval
