@@ -326,14 +326,15 @@ __global__ void __launch_bounds__(TPB) rank_words_fix_last_phrase(const u32* __r
 }
 
 // Class of every rank that is longer than w: what its segment needs (CLS_*).  The block stages the rank words of its 256 ranks plus
-// SEG_LIMIT ranks of context on both sides.  A segment that lies inside the 32 ranks of one warp (nearly all do: segments are a few
-// ranks long) is classified without any walk: its bounds come from bit scans of the warp's segment-start ballot, and everything the
-// class depends on is a difference of two warp prefix sums --
+// SEG_LIMIT ranks of context on both sides, as 17 windows of 32 entries.  No walks: every warp computes, for its windows, the ballot of
+// segment starts and the warp prefix sums of two packed aggregates --
 //   A: occurrences | whole phrases | short suffixes | saturated counts          B: suffixes n | sum of preceding symbols | sum of squares
-// (all preceding symbols equal  <=>  n * sum(x^2) == (sum x)^2).  Only the lanes whose segment crosses the warp's window walk it, left
-// to its start and right to its end, as every rank did in the first versions (590 warp instructions per warp, 18 per dictionary
-// position: a warp walked as far as its longest segment, twice).  A block-level walk-free variant (start bitmap + three block prefix
-// sums with barriers) had measured slower than the walks: 14.7 -> 20.2 ms at C2.
+// (all preceding symbols equal  <=>  n * sum(x^2) == (sum x)^2) -- and leaves them in shared memory with the window totals; a rank then
+// finds the bounds of its segment by bit scans over the start bits and reads its aggregates as differences of prefix sums (plus whole
+// window totals when the segment spans windows).  History: every rank walking its segment (18 warp instructions per dictionary position:
+// a warp walked as far as its longest segment, twice) 14.7 ms at C2; a first walk-free variant with BLOCK-wide 64-bit scans and their
+// barriers 20.2 ms; warp prefix sums with a fallback walk for segments crossing a 32-rank window 13.2 ms (about half of the segments
+// cross one: with 64 haplotypes a segment is 10..30 ranks long).
 __device__ __forceinline__ u8 segment_class(u64 total, bool uniform, bool has_start, bool has_short, bool saturated, const PfpPrune& prune, u32 seg_is_interval) {
     const u8 general = CLS_STREAM | CLS_REFINE;
     u8 c = 0;
@@ -347,8 +348,12 @@ __device__ __forceinline__ u8 segment_class(u64 total, bool uniform, bool has_st
     return c;
 }
 __global__ void __launch_bounds__(TPB) classify_segments(const u32* __restrict__ rk, u32 dsize, PfpPrune prune, u32 seg_is_interval, u8* __restrict__ cls) {
-    constexpr u32 SPAN = TPB + 2 * SEG_LIMIT + 1;
+    constexpr u32 SPAN = TPB + 2 * SEG_LIMIT + 1;               // 513 staged ranks: tile index y <-> rank base + y
+    constexpr u32 NWIN = (SPAN + 31) / 32;                      // 17 windows of 32 tile entries
     __shared__ u32 tile[SPAN];
+    __shared__ u64 pa[NWIN * 32], pb[NWIN * 32];                // inclusive prefix sums of A / B inside each window
+    __shared__ u64 wa[NWIN], wb[NWIN];                          // window totals
+    __shared__ u32 hbm[NWIN + 1];                               // segment-start bits of each window; [NWIN] = all ones
     const i64 base = (i64)blockIdx.x * TPB - SEG_LIMIT;
     for (u32 y = threadIdx.x; y < SPAN; y += TPB) {
         i64 q = base + y;
@@ -356,59 +361,57 @@ __global__ void __launch_bounds__(TPB) classify_segments(const u32* __restrict__
     }
     __syncthreads();
     const u8 all = CLS_STREAM | CLS_REFINE | CLS_HAS_START;         // without a verdict: keep, and assume the segment may hold a whole phrase
-    const u32 p = blockIdx.x * TPB + threadIdx.x, x = threadIdx.x + SEG_LIMIT, lane = threadIdx.x & 31, wbase = x - lane;
-    const u32 v = tile[x];
-    if (!prune.enabled) { if (p < dsize) cls[p] = (v & RK_OWN) ? all : (u8)0; return; }       // uniform over the grid
-    // ---- the warp's window: tile[wbase .. wbase + 32)
-    const unsigned hb = __ballot_sync(FULL, (v & RK_HB) != 0);
-    const bool next_hb = (tile[wbase + 32] & RK_HB) != 0;
-    const unsigned le = hb & (0xffffffffu >> (31 - lane));
-    const int a = le ? 31 - __clz((int)le) : -1;                                    // lane of the segment's first rank, -1: before the window
-    const unsigned gt = lane == 31 ? 0u : hb & (0xffffffffu << (lane + 1));
-    const int e = gt ? __ffs((int)gt) - 1 : (next_hb ? 32 : 33);                    // lane of the next segment's first rank, 33: beyond the window
-    u64 sa = 0, sb = 0;
-    if (v & RK_OWN) {
-        u32 c = (v >> 9) & RK_CNT_MAX, sym = v & 0x1ffu;
-        bool start = sym == RK_START;
-        sa = (u64)c | ((u64)(start ? 1 : 0) << 32) | ((u64)((v & RK_SHORT) ? 1 : 0) << 42) | ((u64)(c == RK_CNT_MAX ? 1 : 0) << 52);
-        if (!start) sb = 1ull | ((u64)sym << 10) | ((u64)(sym * sym) << 28);
-    }
-#pragma unroll
-    for (u32 d = 1; d < 32; d <<= 1) {
-        u64 oa = __shfl_up_sync(FULL, sa, d), ob = __shfl_up_sync(FULL, sb, d);
-        if (lane >= d) { sa += oa; sb += ob; }
-    }
-    const int last = min(max(e - 1, 0), 31), before = max(a - 1, 0);
-    u64 A = __shfl_sync(FULL, sa, last), B = __shfl_sync(FULL, sb, last);
-    const u64 A0 = __shfl_sync(FULL, sa, before), B0 = __shfl_sync(FULL, sb, before);
-    if (a > 0) { A -= A0; B -= B0; }
-    if (p >= dsize) return;
-    if (!(v & RK_OWN)) { cls[p] = 0; return; }
-    if (a >= 0 && e <= 32) {
-        const u64 n = B & 0x3ff, s1 = (B >> 10) & 0x3ffff, s2 = B >> 28;
-        const bool has_start = ((A >> 32) & 0x3ff) != 0;
-        cls[p] = segment_class(A & 0xffffffffull, !has_start && n * s2 == s1 * s1, has_start, ((A >> 42) & 0x3ff) != 0, ((A >> 52) & 0x3ff) != 0, prune, seg_is_interval);
-        return;
-    }
-    // ---- the segment crosses the window: walk to its start, then over it (at most SEG_LIMIT + 1 ranks; longer ones are kept as they are)
-    u32 s0 = x, steps = 0;
-    while (!(tile[s0] & RK_HB) && steps < SEG_LIMIT) { --s0; ++steps; }
-    if (!(tile[s0] & RK_HB)) { cls[p] = all; return; }
-    u64 total = 0; u32 sym = 0xffffffffu; bool uniform = true, has_start = false, saturated = false, has_short = false;
-    u32 b = s0; steps = 0;
-    for (;;) {
-        u32 w = tile[b];
-        if (w & RK_OWN) {
-            u32 c = (w >> 9) & RK_CNT_MAX, bsym = w & 0x1ffu;
-            total += c; saturated |= c == RK_CNT_MAX; has_short |= (w & RK_SHORT) != 0;
-            if (bsym == RK_START) { has_start = true; uniform = false; }
-            else if (sym == 0xffffffffu) sym = bsym;
-            else if (sym != bsym) uniform = false;
+    const u32 p = blockIdx.x * TPB + threadIdx.x, x = threadIdx.x + SEG_LIMIT, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (!prune.enabled) { if (p < dsize) cls[p] = (tile[x] & RK_OWN) ? all : (u8)0; return; }       // uniform over the grid
+    // ---- phase 1: per window of 32 entries the start bits and the warp prefix sums of
+    //   A: occurrences | whole phrases << 32 | short suffixes << 42 | saturated counts << 52      B: n | sum x << 10 | sum x^2 << 28
+    for (u32 win = warp; win < NWIN; win += TPB / 32) {
+        const u32 y = win * 32 + lane;
+        const u32 v = y < SPAN ? tile[y] : RK_HB;
+        const unsigned hb = __ballot_sync(FULL, (v & RK_HB) != 0);
+        u64 sa = 0, sb = 0;
+        if (v & RK_OWN) {
+            u32 c = (v >> 9) & RK_CNT_MAX, sym = v & 0x1ffu;
+            bool start = sym == RK_START;
+            sa = (u64)c | ((u64)(start ? 1 : 0) << 32) | ((u64)((v & RK_SHORT) ? 1 : 0) << 42) | ((u64)(c == RK_CNT_MAX ? 1 : 0) << 52);
+            if (!start) sb = 1ull | ((u64)sym << 10) | ((u64)(sym * sym) << 28);
         }
-        if ((tile[b + 1] & RK_HB) || steps == SEG_LIMIT) break;
-        ++b; ++steps;
+#pragma unroll
+        for (u32 d = 1; d < 32; d <<= 1) {
+            u64 oa = __shfl_up_sync(FULL, sa, d), ob = __shfl_up_sync(FULL, sb, d);
+            if (lane >= d) { sa += oa; sb += ob; }
+        }
+        pa[y] = sa; pb[y] = sb;
+        if (lane == 31) { wa[win] = sa; wb[win] = sb; }
+        if (lane == 0) hbm[win] = hb;
     }
-    cls[p] = (tile[b + 1] & RK_HB) ? segment_class(total, uniform, has_start, has_short, saturated, prune, seg_is_interval) : all;
+    if (threadIdx.x == 0) hbm[NWIN] = 0xffffffffu;
+    __syncthreads();
+    if (p >= dsize) return;
+    if (!(tile[x] & RK_OWN)) { cls[p] = 0; return; }
+    // ---- phase 2: bounds of the rank's segment by bit scans over the start bits, its aggregates from the prefix sums
+    const u32 kx = x >> 5, lx = x & 31;
+    int k = (int)kx;
+    u32 m = hbm[k] & (0xffffffffu >> (31 - lx));
+    while (!m && k > 0 && kx - (u32)k <= SEG_LIMIT / 32) { --k; m = hbm[k]; }
+    if (!m) { cls[p] = all; return; }
+    const u32 a = (u32)k * 32 + (31 - (u32)__clz((int)m));                          // first rank of the segment
+    k = (int)kx;
+    m = lx == 31 ? 0u : hbm[k] & (0xffffffffu << (lx + 1));
+    while (!m) { ++k; m = hbm[k]; }                                                 // hbm[NWIN] ends the search
+    const u32 e = (u32)k * 32 + (u32)__ffs((int)m) - 1;                             // first rank of the next segment
+    if (x - a > SEG_LIMIT || e - a > SEG_LIMIT + 1) { cls[p] = all; return; }       // more than SEG_LIMIT + 1 ranks: low-complexity repeats, kept as they are
+    const u32 ka = a >> 5, ke = (e - 1) >> 5;
+    u64 A = pa[e - 1], B = pb[e - 1];
+    const u64 A0 = (a & 31) ? pa[a - 1] : 0ull, B0 = (a & 31) ? pb[a - 1] : 0ull;
+    if (ka == ke) { A -= A0; B -= B0; }
+    else {
+        A += wa[ka] - A0; B += wb[ka] - B0;
+        for (u32 w = ka + 1; w < ke; ++w) { A += wa[w]; B += wb[w]; }
+    }
+    const u64 n = B & 0x3ff, s1 = (B >> 10) & 0x3ffff, s2 = B >> 28;
+    const bool has_start = ((A >> 32) & 0x3ff) != 0;
+    cls[p] = segment_class(A & 0xffffffffull, !has_start && n * s2 == s1 * s1, has_start, ((A >> 42) & 0x3ff) != 0, ((A >> 52) & 0x3ff) != 0, prune, seg_is_interval);
 }
 
 // Sharding by suffix-order slice: slice bounds are moved forward to the next segment start (no reportable interval

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, visit S (1 GPU): classify_segments through warp prefix sums (walks only for segments that cross a warp's window)
+# round 2, visit S, T (1 GPU): classify_segments through warp prefix sums
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/s_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/s_pytest.log
 tail -n 3 gpurun_out/s_pytest.log
