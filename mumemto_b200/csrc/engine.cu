@@ -163,6 +163,7 @@ struct mmb_engine {
     std::vector<std::vector<RecordInfo>> records;
     DevBuf<u8> raw;                     // device copy of the input images (host-load path)
     DevBuf<u16> doc_coarse;             // document of every 2^coarse_shift-th text position (DetectParams::doc_coarse)
+    PfpTriggers trig;                   // trigger masks of the text prefix, scanned while the upload was still running (load_common)
     u32 coarse_shift = 0;
 
     SuffixArray sa;
@@ -290,13 +291,20 @@ void load_common(mmb_engine* e, const u8* d_raw, const u8* const* host_imgs, con
                  bool revcomp, bool raw_mode, const std::vector<UploadGroup>* groups = nullptr) {
     if (off.size() < 2) throw Error(41, "Multiple FASTA inputs required. Perhaps split a multi-FASTA into multiple files?");
     e->found = false; e->loaded = false;
+    e->trig.reset();
     Timer t(e->stream); t.start();
     if (groups && groups->size() > 1) {
         // the text build of the files that have arrived runs while the copy stream is still uploading the next ones
+        // ... and so does the first pass of the prefix-free parse: the stream would otherwise idle between groups (the copy is the slower side)
         text_begin(size, revcomp, e->text, e->stream);
+        u64 worst = 0;
+        for (u64 b : size) worst += (b + 1) * (revcomp ? 2 : 1);
+        const char* amin = getenv("MMB_TRIGGER_AHEAD_MIN");                     // tests lower it; small texts may take the direct route anyway
+        if (worst >= (amin ? (u64)atoll(amin) : (1ull << 24))) pfp_triggers_begin(worst, e->trig, e->stream);
         for (const UploadGroup& g : *groups) {
             MMB_CUDA(cudaStreamWaitEvent(e->stream, g.ready, 0));
             text_append(d_raw, off, size, g.f0, g.f1, raw_mode, e->text, e->stream);
+            pfp_triggers_extend(e->text.text.p, e->text.n, e->trig, e->stream);
         }
         text_finish(e->text, e->stream);
     } else {
@@ -321,7 +329,8 @@ void upload(mmb_engine* e, const u8* const* imgs, const u64* sizes, size_t n, st
     if (!e->copy_stream) MMB_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     MMB_CUDA(cudaStreamSynchronize(e->stream));        // nothing of an earlier call may still read the buffer the copy stream is about to fill
     MMB_CUDA(cudaMemsetAsync(e->raw.p + at, 0, 64, e->copy_stream));
-    constexpr u64 GROUP_BYTES = 256ull << 20;
+    const char* gb = getenv("MMB_UPLOAD_GROUP_BYTES");                            // tests make the groups small
+    const u64 GROUP_BYTES = gb ? (u64)atoll(gb) : (256ull << 20);
     size_t f0 = 0; u64 acc = 0;
     for (size_t i = 0; i < n; ++i) {
         if (sizes[i]) MMB_CUDA(cudaMemcpyAsync(e->raw.p + off[i], imgs[i], sizes[i], cudaMemcpyHostToDevice, e->copy_stream));
@@ -523,7 +532,7 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
         Timer tparse(s); float ms_parse = 0;
         if (opts->route == 0 && !use_pfp && !unbounded && n >= (1u << 16)) {      // unbounded + auto: the direct route whenever it fits
             tparse.start();
-            pfp_parse(e->text.text.p, n, ix, pp, s); parsed = true;
+            pfp_parse(e->text.text.p, n, ix, pp, s, &e->trig); parsed = true;
             ms_parse = tparse.stop();
             use_pfp = (u64)ix.dsize * 3 <= n;
             if (!use_pfp) { ix = PfpIndex(); pp = PfpParse(); }
@@ -533,6 +542,7 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
         e->stats.pfp_phrases = e->stats.pfp_distinct_phrases = e->stats.pfp_dict_bytes = e->stats.pfp_tiles = 0;
         e->stats.stream_suffixes = n + 1; e->stats.pruned = 0; e->stats.threshold_segments = 0;
         if (!use_pfp) {
+            e->trig.reset();
             t.start();
             build_suffix_array(e->text.text.p, n, e->sa, s);
             e->stats.ms_sa = t.stop() + ms_parse;
@@ -557,7 +567,7 @@ int mmb_find(mmb_engine* e, const mmb_options* opts) {
         } else {
             e->sa.sa.release(); e->sa.isa.release(); e->lcp.release();
             t.start();
-            if (!parsed) pfp_parse(e->text.text.p, n, ix, pp, s);
+            if (!parsed) pfp_parse(e->text.text.p, n, ix, pp, s, &e->trig);
             // segment pruning (pfp.h): off when the caller wants the whole suffix stream back
             PfpPrune prune;
             prune.enabled = (opts->keep_arrays || opts->no_prune) ? 0 : 1;

@@ -66,8 +66,9 @@ __device__ __forceinline__ u32 block_scan(u32 mine, u32* total) {
 // tests the 16 windows from registers and keeps the result as a 16-bit mask; the block's trigger count goes to block_count.
 constexpr u32 TRIG_HIST = (PFP_W - 1 + 3) / 4 * 4;      // bytes of history before the thread's first position, a multiple of 4
 constexpr u32 TRIG_WORDS = TRIG_HIST / 4 + 4;
-__global__ void __launch_bounds__(TPB) trigger_masks(const u8* __restrict__ text, u64 n, u16* __restrict__ masks, u32* __restrict__ block_count) {
-    u64 e0 = (u64)blockIdx.x * SCAN_BLOCK + (u64)threadIdx.x * 16;
+__global__ void __launch_bounds__(TPB) trigger_masks(const u8* __restrict__ text, u64 n, u32 block0, u16* __restrict__ masks, u32* __restrict__ block_count) {
+    const u32 blk = blockIdx.x + block0;                // blocks below block0 were scanned ahead of the parse (PfpTriggers)
+    u64 e0 = (u64)blk * SCAN_BLOCK + (u64)threadIdx.x * 16;
     u32 mask = 0;
     if (e0 < n) {
         u32 w[TRIG_WORDS];                              // bytes e0 - TRIG_HIST .. e0 + 15 (the text allocation is 16-byte aligned with 64 bytes of slack)
@@ -100,9 +101,9 @@ __global__ void __launch_bounds__(TPB) trigger_masks(const u8* __restrict__ text
         }
 #undef TRIG_BYTE
     }
-    masks[(u64)blockIdx.x * TPB + threadIdx.x] = (u16)mask;
+    masks[(u64)blk * TPB + threadIdx.x] = (u16)mask;
     u32 total; block_scan((u32)__popc(mask), &total);
-    if (threadIdx.x == 0) block_count[blockIdx.x] = total;
+    if (threadIdx.x == 0) block_count[blk] = total;
 }
 
 // Pass 2: positions of the set bits, in text order.
@@ -646,7 +647,22 @@ void build_pfp_index(const u8* text, u64 n, PfpIndex& ix, cudaStream_t s) {
 }
 
 // stages 1-3: triggers, phrase identity, dictionary (cheap; tells how repetitive the collection is)
-void pfp_parse(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s) {
+void pfp_triggers_begin(u64 worst_symbols, PfpTriggers& tr, cudaStream_t s) {
+    tr.reset();
+    u64 blocks = (worst_symbols + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    if (blocks == 0 || blocks > 0x7fffffffull) return;
+    tr.masks.alloc(blocks * TPB, s); tr.bcount.alloc(blocks + 1, s);
+    tr.capacity_blocks = blocks;
+}
+void pfp_triggers_extend(const u8* text, u64 prefix_symbols, PfpTriggers& tr, cudaStream_t s) {
+    if (!tr.capacity_blocks) return;
+    u32 full = (u32)std::min<u64>(prefix_symbols / SCAN_BLOCK, tr.capacity_blocks);      // blocks whose positions all lie inside the finished prefix
+    if (full <= tr.blocks_done) return;
+    MMB_LAUNCH(trigger_masks, full - tr.blocks_done, TPB, 0, s, text, prefix_symbols, tr.blocks_done, tr.masks.p, tr.bcount.p);
+    tr.blocks_done = full; tr.text = text;
+}
+
+void pfp_parse(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s, PfpTriggers* ahead) {
     ix.n = n;
     if (n < PFP_W + 2) throw Error(70, "text too short for the prefix-free parse route");
     // ---- 1. triggers
@@ -654,10 +670,16 @@ void pfp_parse(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s
     u64 nblk64 = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     if (nblk64 > 0x7fffffffull) throw Error(71, "text too long");
     u32 nblk = (u32)nblk64;
-    DevBuf<u32> bcount, bbase; bcount.alloc(nblk + 1, s); bbase.alloc(nblk + 1, s);
+    DevBuf<u32> bcount, bbase; DevBuf<u16> masks;
+    u32 done = 0;
+    if (ahead && ahead->text == text && ahead->blocks_done && ahead->blocks_done <= nblk && ahead->capacity_blocks >= nblk) {
+        masks = std::move(ahead->masks); bcount = std::move(ahead->bcount); done = ahead->blocks_done;     // scanned while the upload was running
+    } else { bcount.alloc(nblk + 1, s); masks.alloc((u64)nblk * TPB, s); }
+    if (ahead) ahead->reset();
+    if (getenv("MMB_DEBUG")) fprintf(stderr, "[pfp] trigger blocks scanned ahead of the parse: %u of %u\n", done, nblk);
+    bbase.alloc(nblk + 1, s);
     MMB_CUDA(cudaMemsetAsync(bcount.p + nblk, 0, 4, s));
-    DevBuf<u16> masks; masks.alloc((u64)nblk * TPB, s);
-    MMB_LAUNCH(trigger_masks, nblk, TPB, 0, s, text, n, masks.p, bcount.p);
+    if (done < nblk) MMB_LAUNCH(trigger_masks, nblk - done, TPB, 0, s, text, n, done, masks.p, bcount.p);
     prim::exclusive_sum(bcount.p, bbase.p, nblk + 1, s);
     u64 ntrig = to_host(bbase.p + nblk, 1, s)[0];
     if (ntrig + 2 >= 0xfffffff0ull) throw Error(72, "too many phrases");

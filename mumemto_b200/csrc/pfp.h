@@ -109,9 +109,20 @@ struct PfpPrune {
 };
 
 
+// Trigger masks computed AHEAD of the parse, while the collection is still being uploaded (engine.cu: load_common): a window only looks
+// backwards, so every 4096-position block that lies inside the finished prefix of the text can be scanned as soon as that prefix exists.
+// pfp_parse takes over what is there and scans the rest.
+struct PfpTriggers {
+    DevBuf<u16> masks; DevBuf<u32> bcount;
+    u64 capacity_blocks = 0; u32 blocks_done = 0; const u8* text = nullptr;
+    void reset() { masks.release(); bcount.release(); capacity_blocks = 0; blocks_done = 0; text = nullptr; }
+};
+void pfp_triggers_begin(u64 worst_symbols, PfpTriggers& tr, cudaStream_t s);
+void pfp_triggers_extend(const u8* text, u64 prefix_symbols, PfpTriggers& tr, cudaStream_t s);
+
 void build_pfp_index(const u8* text, u64 n, PfpIndex& out, cudaStream_t s);
 // The same in two steps: parse + dictionary (stages 1-3, cheap) and everything else; `auto` routing looks at ix.dsize in between.
-void pfp_parse(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s);
+void pfp_parse(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s, PfpTriggers* ahead = nullptr);
 void pfp_finish(const u8* text, u64 n, PfpIndex& ix, PfpParse& pp, cudaStream_t s, const PfpPrune& prune = PfpPrune());
 
 // One window of the suffix stream in rank order, with `halo` ranks of the previous window in front of it.

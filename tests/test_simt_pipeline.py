@@ -430,3 +430,17 @@ def test_simt_sharded_collection_repeats(simt_lib, oracle_bin, tmp_path):
                 api.find_files(p, g, shard=(i, k), _lib=simt_lib, **util.flags_to_kwargs(flags))
                 got += util.outputs(g)[ext]
             assert got == want[ext], (flags, k)
+
+
+def test_simt_triggers_scanned_ahead_of_the_parse(simt_lib, oracle_bin, tmp_path, monkeypatch):
+    """Host-image loads arrive in upload groups; the text of the finished groups is built AND its trigger windows are scanned while later
+    groups are still in flight (engine.cu load_common, pfp.cu PfpTriggers).  Tiny groups here, so that the parse takes over a prefix that
+    was scanned ahead in several steps (block-aligned and not) and scans the rest itself; results must not change."""
+    monkeypatch.setenv("MMB_UPLOAD_GROUP_BYTES", "3000")
+    monkeypatch.setenv("MMB_TRIGGER_AHEAD_MIN", "0")
+    paths = util.appendix_a(str(tmp_path / "in"), N=7, L=2900, seed=31, identical_ends=True, snp=0.01, width=70)
+    for flags in ([], ["-f", "3", "-F", "50", "-k", "2"], ["-M", "-n"]):
+        st = both_pfp(simt_lib, oracle_bin, str(tmp_path), paths, flags, tile_ranks=0)
+        assert st["route"] == 2
+    monkeypatch.setenv("MMB_UPLOAD_GROUP_BYTES", "9000")        # two files per group; and the direct route must simply drop the masks
+    both(simt_lib, oracle_bin, str(tmp_path), paths, [])
