@@ -113,6 +113,11 @@ def main():
             elif 0.25 <= variant < 0.35:
                 os.environ["MMB_CHUNK_ROUNDS"] = str(int(rng.integers(1, 4)))
             lib.simt_set_block_order(int(rng.integers(0, 3)))           # block scheduling order of the SIMT harness: forward, reverse, shuffled
+            # host-image loads in small upload groups, with the trigger scan running ahead of the parse on the finished text prefix
+            for k in ("MMB_UPLOAD_GROUP_BYTES", "MMB_TRIGGER_AHEAD_MIN"):
+                os.environ.pop(k, None)
+            if rng.random() < 0.3:
+                os.environ["MMB_UPLOAD_GROUP_BYTES"] = str(int(rng.integers(200, 6000))); os.environ["MMB_TRIGGER_AHEAD_MIN"] = "0"
             if os.path.exists(REF) and rng.random() < 0.15 and "-A" not in flags and not ("-f" in flags and flags[flags.index("-f") + 1] == "0" and "-F" not in flags):
                 # array input: the reference's own -A dump, then its own -a run against ours
                 import subprocess
@@ -166,6 +171,19 @@ def main():
                     bad += 1; print("MISMATCH status", it, flags, route, tile, ok_o, ok_g, "" if ok_g else err[:200]); shutil.copytree(d, f"/tmp/fuzz_fail_{seed}_{it}")
             elif ok_o and util.outputs(g) != util.outputs(o):
                 bad += 1; print("MISMATCH output", it, flags, route, tile, no_prune, os.environ.get("MMB_NO_PRUNE"), os.environ.get("MMB_CHUNK_ROUNDS")); shutil.copytree(d, f"/tmp/fuzz_fail_{seed}_{it}")
+            elif ok_o and rng.random() < 0.25 and not any(f in flags for f in ("-M", "-A", "-b")) and not no_prune:
+                # one collection in K slices of the suffix order: the slices' outputs concatenate to the whole
+                K = int(rng.integers(2, 6)); ext = ".mems" if "-f" in flags and flags[flags.index("-f") + 1] != "1" else ".mums"
+                try:
+                    got = b""
+                    for i in range(K):
+                        api.find_files(paths, g + f"_s{i}", tile_ranks=tile, shard=(i, K), _lib=lib, **kw)
+                        got += util.outputs(g + f"_s{i}").get(ext, b"")
+                    if got != util.outputs(o).get(ext, b""):
+                        bad += 1; print("MISMATCH sharded", it, flags, K, tile); shutil.copytree(d, f"/tmp/fuzz_fail_{seed}_{it}")
+                except Exception as ex:
+                    if "sharded call needs" not in str(ex) and "too short" not in str(ex):
+                        bad += 1; print("ERROR sharded", it, flags, K, str(ex)[:200]); shutil.copytree(d, f"/tmp/fuzz_fail_{seed}_{it}")
         finally:
             shutil.rmtree(d, ignore_errors=True)
         if (it + 1) % 50 == 0:
